@@ -1,0 +1,259 @@
+"""TEST INFRASTRUCTURE — ctypes loader for the CPU oracle.  Not product code.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  It loads
+
+  * oracle/libwt_oracle.so        — our plain-C++ restatement (oracle/wt_oracle.cpp), fp32 + fp64 twin
+  * oracle/_ref/libwt_ref_*.so    — the reference's own camera.cpp / render-engine.h / GLM and its
+                                    water-grid.vert text compiled as C++ (oracle/Makefile); optional,
+                                    present wherever `make -C oracle ref` ran (it needs /root/reference)
+
+and exposes both behind the same numpy-level interface so tests can compare them bit for bit.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+c_float_p = C.POINTER(C.c_float)
+c_double_p = C.POINTER(C.c_double)
+
+
+class Camera(C.Structure):
+    """Camera ctor arguments (reference src/camera.h:49, src/render-engine.cpp:52)."""
+    _fields_ = [("fov_deg", C.c_float), ("aspect", C.c_float), ("z_near", C.c_float), ("z_far", C.c_float),
+                ("pos", C.c_float * 3), ("yaw_deg", C.c_float), ("pitch_deg", C.c_float)]
+
+
+def _grid_struct(ft):
+    class Grid(C.Structure):
+        _fields_ = [("has_grid", C.c_int), ("n_intersections", C.c_int), ("corners", ft * 16),
+                    ("view", ft * 16), ("proj", ft * 16), ("view_proj", ft * 16), ("view_only_yaw", ft * 16),
+                    ("cam_forward", ft * 3), ("aimpoint_1", ft * 3), ("aimpoint_2", ft * 3), ("aimpoint_final", ft * 3),
+                    ("projector_pitch_deg", ft), ("projector_y", ft), ("range", ft * 4)]
+    return Grid
+
+
+GridF32 = _grid_struct(C.c_float)
+GridF64 = _grid_struct(C.c_double)
+
+
+class Uniforms(C.Structure):
+    """Water-program uniforms in scope (water-grid.vert:37-64, water-grid.frag:39-47)."""
+    _fields_ = [("bottomLeft", C.c_float * 4), ("bottomRight", C.c_float * 4), ("topLeft", C.c_float * 4), ("topRight", C.c_float * 4),
+                ("cameraPosition", C.c_float * 3), ("gerstnerWaveCount", C.c_uint), ("gridLength", C.c_uint),
+                ("heightmapDisplacementScale", C.c_float), ("heightmapSampleScale", C.c_float),
+                ("verticalBounceWaveDisplacement", C.c_float),
+                ("viewMatOnlyYaw", C.c_float * 16), ("viewProjection", C.c_float * 16),
+                ("waveAnimationTimeInSeconds", C.c_float),
+                ("sunPosition", C.c_float * 3), ("sunShininess", C.c_float), ("sunStrength", C.c_float)]
+
+
+class RefVertUniforms(C.Structure):
+    _fields_ = [("bottomLeft", C.c_float * 4), ("bottomRight", C.c_float * 4), ("topLeft", C.c_float * 4), ("topRight", C.c_float * 4),
+                ("cameraPosition", C.c_float * 3), ("gerstnerWaveCount", C.c_uint), ("gridLength", C.c_uint),
+                ("heightmapDisplacementScale", C.c_float), ("heightmapSampleScale", C.c_float),
+                ("verticalBounceWaveDisplacement", C.c_float),
+                ("viewMatOnlyYaw", C.c_float * 16), ("viewProjection", C.c_float * 16),
+                ("waveAnimationTimeInSeconds", C.c_float)]
+
+
+class Textures(C.Structure):
+    _fields_ = [("heightmap_rgba", C.c_void_p), ("hm_w", C.c_int), ("hm_h", C.c_int),
+                ("sky_faces", C.c_void_p * 6), ("sky_n", C.c_int)]
+
+
+# numpy dtype of one shader-side wave record: A, w, phi, Q_i, Dx, Dz
+WAVE_UNIFORM_DTYPE = np.dtype([("A", "f4"), ("w", "f4"), ("phi", "f4"), ("Q_i", "f4"), ("Dx", "f4"), ("Dz", "f4")])
+REF_VERT_OUT_DTYPE = np.dtype([("gl_Position", "f4", 4), ("heightmap_colour", "f4", 4), ("normal", "f4", 3),
+                               ("normalVecInViewSpaceOnlyYaw", "f4", 3), ("viewVecRaw", "f4", 3),
+                               ("xyPositionNDCSpaceHeight0", "f4", 2)])
+
+
+def build(ref: bool = True) -> None:
+    """Compile the oracle (and, when /root/reference is present, oracle/_ref) with oracle/Makefile."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-C", HERE, "-s"] + targets, check=True)
+
+
+def _load(path):
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+class Oracle:
+    """Our restatement.  fp32 is the parity oracle, fp64 the truth twin."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "libwt_oracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.wto_total_amplitude.restype = C.c_float
+        L.wto_steepness_Q_i.restype = C.c_float
+        L.wto_steepness_Q_i.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint]
+        L.wto_bounce_displacement.restype = C.c_float
+        L.wto_bounce_displacement.argtypes = [C.c_float, C.c_float]
+        L.wto_sun_position.argtypes = [C.c_float, c_float_p]
+        L.wto_project_grid_f32.argtypes = [C.POINTER(Camera), C.c_float, C.POINTER(GridF32)]
+        L.wto_project_grid_f64.argtypes = [C.POINTER(Camera), C.c_double, C.POINTER(GridF64)]
+        common = [C.POINTER(Uniforms), C.c_void_p, C.POINTER(Textures), C.c_void_p, C.c_longlong,
+                  C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong]
+        L.wto_eval_f32.argtypes = common + [C.c_void_p] * 4
+        L.wto_eval_f64.argtypes = common + [C.c_void_p] * 4
+
+    # --- host-side scalar rules -------------------------------------------------------------
+    def num_threads(self) -> int:
+        return int(self.lib.wto_num_threads())
+
+    def set_num_threads(self, n: int) -> None:
+        self.lib.wto_set_num_threads(int(n))
+
+    def total_amplitude(self, amplitudes) -> np.float32:
+        a = np.ascontiguousarray(amplitudes, dtype=np.float32)
+        return np.float32(self.lib.wto_total_amplitude(a.ctypes.data_as(c_float_p), C.c_uint(a.size)))
+
+    def steepness_Q_i(self, Q, w, A, count) -> np.float32:
+        return np.float32(self.lib.wto_steepness_Q_i(float(Q), float(w), float(A), int(count)))
+
+    def bounce_displacement(self, amplitude, phase) -> np.float32:
+        return np.float32(self.lib.wto_bounce_displacement(float(amplitude), float(phase)))
+
+    def sun_position(self, hours) -> np.ndarray:
+        out = np.zeros(3, np.float32)
+        self.lib.wto_sun_position(float(hours), out.ctypes.data_as(c_float_p))
+        return out
+
+    def wave_uniforms(self, waves: np.ndarray) -> np.ndarray:
+        """(W,6) reference-native rows [A, w, phi, Q, Dx, Dz] -> shader-side records with Q_i
+        (src/render-engine.cpp:1073, Count() == W)."""
+        waves = np.asarray(waves, np.float32).reshape(-1, 6)
+        out = np.zeros(len(waves), WAVE_UNIFORM_DTYPE)
+        for i, (A, w, phi, Q, dx, dz) in enumerate(waves):
+            out[i] = (A, w, phi, self.steepness_Q_i(Q, w, A, len(waves)), dx, dz)
+        return out
+
+    # --- projected grid -----------------------------------------------------------------------
+    def project_grid(self, cam: Camera, displaceable_amplitude, f64: bool = False):
+        if f64:
+            g = GridF64()
+            st = self.lib.wto_project_grid_f64(C.byref(cam), C.c_double(float(displaceable_amplitude)), C.byref(g))
+        else:
+            g = GridF32()
+            st = self.lib.wto_project_grid_f32(C.byref(cam), C.c_float(float(displaceable_amplitude)), C.byref(g))
+        return st, g
+
+    # --- per-vertex evaluation ----------------------------------------------------------------
+    def eval(self, u: Uniforms, wave_uniforms: np.ndarray, heightmap_rgba: np.ndarray, sky_faces=None,
+             ids=None, rows=None, cols=None, shade: bool = False, extra: bool = False, f64: bool = False):
+        """Returns dict(pos (n,4), normal (n,4), shade (n,4)|None, extra (n,16)|None)."""
+        L = int(u.gridLength)
+        wu = np.ascontiguousarray(wave_uniforms)
+        assert wu.dtype == WAVE_UNIFORM_DTYPE and len(wu) >= u.gerstnerWaveCount
+        hm = np.ascontiguousarray(heightmap_rgba, np.uint8)
+        assert hm.ndim == 3 and hm.shape[2] == 4
+        tx = Textures()
+        tx.heightmap_rgba = hm.ctypes.data
+        tx.hm_h, tx.hm_w = hm.shape[0], hm.shape[1]
+        keep = [hm, wu]
+        if sky_faces is not None:
+            sky = np.ascontiguousarray(sky_faces, np.uint8)
+            assert sky.ndim == 4 and sky.shape[0] == 6 and sky.shape[1] == sky.shape[2] and sky.shape[3] == 4
+            for f in range(6):
+                tx.sky_faces[f] = sky[f].ctypes.data
+            tx.sky_n = sky.shape[1]
+            keep.append(sky)
+        if ids is not None:
+            ids_a = np.ascontiguousarray(ids, np.int64)
+            n = ids_a.size
+            ids_p, r0, r1, c0, c1 = ids_a.ctypes.data, 0, 0, 0, 0
+        else:
+            r0, r1 = rows if rows is not None else (0, L)
+            c0, c1 = cols if cols is not None else (0, L)
+            n = (r1 - r0) * (c1 - c0)
+            ids_p = None
+        dt = np.float64 if f64 else np.float32
+        pos = np.empty((n, 4), dt)
+        nrm = np.empty((n, 4), dt)
+        shd = np.empty((n, 4), dt) if shade else None
+        ext = np.empty((n, 16), dt) if extra else None
+        fn = self.lib.wto_eval_f64 if f64 else self.lib.wto_eval_f32
+        st = fn(C.byref(u), wu.ctypes.data, C.byref(tx), ids_p, n, r0, r1, c0, c1, pos.ctypes.data, nrm.ctypes.data,
+                shd.ctypes.data if shade else None, ext.ctypes.data if extra else None)
+        if st != 0:
+            raise RuntimeError(f"oracle eval failed: {st}")
+        return {"pos": pos, "normal": nrm, "shade": shd, "extra": ext}
+
+
+class Ref:
+    """The reference itself (camera.cpp / render-engine.h / GLM / water-grid.vert as C++)."""
+
+    def __init__(self):
+        self.proj = _load(os.path.join(HERE, "_ref", "libwt_ref_proj.so"))
+        self.vert = _load(os.path.join(HERE, "_ref", "libwt_ref_vert.so"))
+        if self.proj is not None:
+            P = self.proj
+            P.wtref_total_amplitude.restype = C.c_float
+            P.wtref_steepness_Q_i.restype = C.c_float
+            P.wtref_steepness_Q_i.argtypes = [C.c_float, C.c_float, C.c_float, C.c_uint]
+            P.wtref_bounce_displacement.restype = C.c_float
+            P.wtref_bounce_displacement.argtypes = [C.c_float, C.c_float]
+            P.wtref_sun_position.argtypes = [C.c_float, c_float_p]
+            P.wtref_project_grid.argtypes = [C.POINTER(Camera), C.c_float, C.POINTER(GridF32)]
+        if self.vert is not None:
+            V = self.vert
+            V.wtref_vert_set_uniforms.argtypes = [C.POINTER(RefVertUniforms), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+            V.wtref_vert_run.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
+
+    @property
+    def available(self) -> bool:
+        return self.proj is not None and self.vert is not None
+
+    def max_waves(self) -> int:
+        return int(self.vert.wtref_max_waves())
+
+    def total_amplitude(self, amplitudes) -> np.float32:
+        a = np.ascontiguousarray(amplitudes, dtype=np.float32)
+        return np.float32(self.proj.wtref_total_amplitude(a.ctypes.data_as(c_float_p), C.c_uint(a.size)))
+
+    def steepness_Q_i(self, Q, w, A, count) -> np.float32:
+        return np.float32(self.proj.wtref_steepness_Q_i(float(Q), float(w), float(A), int(count)))
+
+    def bounce_displacement(self, amplitude, phase) -> np.float32:
+        return np.float32(self.proj.wtref_bounce_displacement(float(amplitude), float(phase)))
+
+    def sun_position(self, hours) -> np.ndarray:
+        out = np.zeros(3, np.float32)
+        self.proj.wtref_sun_position(float(hours), out.ctypes.data_as(c_float_p))
+        return out
+
+    def project_grid(self, cam: Camera, displaceable_amplitude):
+        g = GridF32()
+        st = self.proj.wtref_project_grid(C.byref(cam), C.c_float(float(displaceable_amplitude)), C.byref(g))
+        return st, g
+
+    def vert_run(self, u: Uniforms, wave_uniforms: np.ndarray, heightmap_rgba: np.ndarray, ids=None, id_range=None):
+        """Runs the compiled shader main() and returns the REF_VERT_OUT_DTYPE records.  World-space
+        position is not a shader output; callers obtain it by passing viewProjection = identity, for
+        which gl_Position == position exactly."""
+        ru = RefVertUniforms()
+        for name, _ in RefVertUniforms._fields_:
+            setattr(ru, name, getattr(u, name))
+        wu = np.ascontiguousarray(wave_uniforms)
+        hm = np.ascontiguousarray(heightmap_rgba, np.uint8)
+        st = self.vert.wtref_vert_set_uniforms(C.byref(ru), wu.ctypes.data, hm.ctypes.data, hm.shape[1], hm.shape[0])
+        if st != 0:
+            raise RuntimeError("reference shader: too many waves for the compiled array bound")
+        if ids is not None:
+            ids_a = np.ascontiguousarray(ids, np.int32)
+            out = np.empty(ids_a.size, REF_VERT_OUT_DTYPE)
+            self.vert.wtref_vert_run(ids_a.ctypes.data, 0, ids_a.size, out.ctypes.data)
+        else:
+            b, e = id_range
+            out = np.empty(e - b, REF_VERT_OUT_DTYPE)
+            self.vert.wtref_vert_run(None, b, e - b, out.ctypes.data)
+        return out

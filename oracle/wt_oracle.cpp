@@ -1,0 +1,548 @@
+// TEST INFRASTRUCTURE — not product code.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may build, load or call this file.  The product
+// (wave_tool_b200/) never links it and has no CPU fallback.
+//
+// CPU restatement ("port") of the per-vertex ocean-surface path of TexelBox/wave-tool, in plain
+// C++17 with no GLM, templated on the scalar type: T = float is the parity oracle (same fp32
+// operation order as the reference + GLM 0.9.9.8, built with -ffp-contract=off), T = double is
+// the "truth" twin used for error budgeting.
+//
+// PINNING: the reference ships no tests or golden vectors for this path.  This
+// restatement is pinned instead against the reference ITSELF run in the build container:
+// oracle/_ref/libwt_ref_{proj,vert}.so, compiled by oracle/Makefile from the reference's own
+// camera.cpp, render-engine.h, GLM and the water-grid.vert shader TEXT (as C++), see
+// tests/test_oracle_vs_ref.py (bit-exact) and the committed vectors under tests/golden/.
+//
+// Each function cites the reference lines it follows (paths relative to /root/reference).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "gl_sampler.h"
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// Minimal vector/matrix algebra.  The ORDER of floating-point operations restates GLM 0.9.9.8
+// (deps/glm/glm, the reference's only math dependency) so that T=float reproduces it bit for bit.
+// ----------------------------------------------------------------------------------------------
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> struct V4 { T x, y, z, w; };
+template <typename T> struct M4 { V4<T> c[4]; };   // column-major, c[j] = column j (glm::mat4[j])
+
+template <typename T> V3<T> operator+(V3<T> a, V3<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+template <typename T> V3<T> operator-(V3<T> a, V3<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+template <typename T> V3<T> operator*(V3<T> a, T s) { return {a.x * s, a.y * s, a.z * s}; }
+template <typename T> V3<T> operator*(T s, V3<T> a) { return {s * a.x, s * a.y, s * a.z}; }
+template <typename T> V4<T> operator+(V4<T> a, V4<T> b) { return {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+template <typename T> V4<T> operator-(V4<T> a, V4<T> b) { return {a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+template <typename T> V4<T> operator*(V4<T> a, V4<T> b) { return {a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w}; }
+template <typename T> V4<T> operator*(V4<T> a, T s) { return {a.x * s, a.y * s, a.z * s, a.w * s}; }
+template <typename T> V4<T> operator/(V4<T> a, T s) { return {a.x / s, a.y / s, a.z / s, a.w / s}; }
+template <typename T> V3<T> xyz(V4<T> a) { return {a.x, a.y, a.z}; }
+
+// glm/detail/func_geometric.inl:48-55 — tmp = a*b; tmp.x + tmp.y + tmp.z
+template <typename T> T dot(V3<T> a, V3<T> b) { T tx = a.x * b.x, ty = a.y * b.y, tz = a.z * b.z; return tx + ty + tz; }
+// glm/detail/func_geometric.inl:68-79
+template <typename T> V3<T> cross(V3<T> x, V3<T> y) {
+    return {x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y};
+}
+// glm/detail/func_geometric.inl:82-90 with inversesqrt = 1/sqrt (func_exponential.inl:44-50)
+template <typename T> V3<T> normalize(V3<T> v) { T inv = (T)1 / std::sqrt(dot(v, v)); return v * inv; }
+// glm/detail/func_geometric.inl:104-110 — I - N * dot(N, I) * 2
+template <typename T> V3<T> reflect(V3<T> I, V3<T> N) { T d = dot(N, I); return I - (N * d) * (T)2; }
+// glm/detail/func_common.inl:526-538 — x * (1 - a) + y * a
+template <typename T> T mix(T x, T y, T a) { return x * ((T)1 - a) + y * a; }
+template <typename T> V3<T> mix(V3<T> x, V3<T> y, T a) { return {mix(x.x, y.x, a), mix(x.y, y.y, a), mix(x.z, y.z, a)}; }
+template <typename T> V4<T> mix(V4<T> x, V4<T> y, T a) { return {mix(x.x, y.x, a), mix(x.y, y.y, a), mix(x.z, y.z, a), mix(x.w, y.w, a)}; }
+template <typename T> T clampT(T x, T lo, T hi) { return std::min(std::max(x, lo), hi); }
+template <typename T> T radians(T d) { return d * (T)0.01745329251994329576923690768489L; }
+template <typename T> T degrees(T r) { return r * (T)57.295779513082320876798154814105L; }
+template <typename T> T gmod(T x, T y) { return x - y * std::floor(x / y); }   // glm::mod
+
+// glm/detail/type_mat4x4.inl:536-572 — (m0*v0 + m1*v1) + (m2*v2 + m3*v3)
+template <typename T> V4<T> mul(const M4<T>& m, V4<T> v) {
+    V4<T> a0 = m.c[0] * v.x + m.c[1] * v.y;
+    V4<T> a1 = m.c[2] * v.z + m.c[3] * v.w;
+    return a0 + a1;
+}
+// glm/detail/type_mat4x4.inl:630-648 — ((A0*b0 + A1*b1) + A2*b2) + A3*b3 per result column
+template <typename T> M4<T> mul(const M4<T>& a, const M4<T>& b) {
+    M4<T> r;
+    for (int j = 0; j < 4; ++j) r.c[j] = a.c[0] * b.c[j].x + a.c[1] * b.c[j].y + a.c[2] * b.c[j].z + a.c[3] * b.c[j].w;
+    return r;
+}
+template <typename T> T& at(M4<T>& m, int col, int row) { return (&m.c[col].x)[row]; }
+template <typename T> T at(const M4<T>& m, int col, int row) { return (&m.c[col].x)[row]; }
+
+// glm/detail/func_matrix.inl:294-352 — cofactor inverse, 2x2 sub-determinants shared between columns
+template <typename T> M4<T> inverse(const M4<T>& m) {
+    auto e = [&](int c, int r) { return at(m, c, r); };
+    // sub[k][j]: 2x2 minors built from rows (ra, rb) of columns (2,3), (1,3), (1,2)
+    auto minor3 = [&](int ra, int rb, T out[3]) {
+        out[0] = e(2, ra) * e(3, rb) - e(3, ra) * e(2, rb);
+        out[1] = e(1, ra) * e(3, rb) - e(3, ra) * e(1, rb);
+        out[2] = e(1, ra) * e(2, rb) - e(2, ra) * e(1, rb);
+    };
+    T c0[3], c1[3], c2[3], c3[3], c4[3], c5[3];
+    minor3(2, 3, c0);   // Coef00,02,03
+    minor3(1, 3, c1);   // Coef04,06,07
+    minor3(1, 2, c2);   // Coef08,10,11
+    minor3(0, 3, c3);   // Coef12,14,15
+    minor3(0, 2, c4);   // Coef16,18,19
+    minor3(0, 1, c5);   // Coef20,22,23
+    auto fac = [](const T c[3]) { return V4<T>{c[0], c[0], c[1], c[2]}; };
+    V4<T> F0 = fac(c0), F1 = fac(c1), F2 = fac(c2), F3 = fac(c3), F4 = fac(c4), F5 = fac(c5);
+    V4<T> v0{e(1, 0), e(0, 0), e(0, 0), e(0, 0)};
+    V4<T> v1{e(1, 1), e(0, 1), e(0, 1), e(0, 1)};
+    V4<T> v2{e(1, 2), e(0, 2), e(0, 2), e(0, 2)};
+    V4<T> v3{e(1, 3), e(0, 3), e(0, 3), e(0, 3)};
+    V4<T> i0 = v1 * F0 - v2 * F1 + v3 * F2;
+    V4<T> i1 = v0 * F0 - v2 * F3 + v3 * F4;
+    V4<T> i2 = v0 * F1 - v1 * F3 + v3 * F5;
+    V4<T> i3 = v0 * F2 - v1 * F4 + v2 * F5;
+    V4<T> sa{(T)1, (T)-1, (T)1, (T)-1}, sb{(T)-1, (T)1, (T)-1, (T)1};
+    M4<T> inv{{i0 * sa, i1 * sb, i2 * sa, i3 * sb}};
+    V4<T> row0{inv.c[0].x, inv.c[1].x, inv.c[2].x, inv.c[3].x};
+    V4<T> d0 = m.c[0] * row0;
+    T det = (d0.x + d0.y) + (d0.z + d0.w);
+    T ood = (T)1 / det;
+    for (int j = 0; j < 4; ++j) inv.c[j] = inv.c[j] * ood;
+    return inv;
+}
+
+// glm/ext/matrix_clip_space.inl:249-262 (perspectiveRH_NO; glm::perspective's default)
+template <typename T> M4<T> perspective(T fovy, T aspect, T zn, T zf) {
+    T th = std::tan(fovy / (T)2);
+    M4<T> r;
+    std::memset(&r, 0, sizeof(r));
+    at(r, 0, 0) = (T)1 / (aspect * th);
+    at(r, 1, 1) = (T)1 / th;
+    at(r, 2, 2) = -(zf + zn) / (zf - zn);
+    at(r, 2, 3) = -(T)1;
+    at(r, 3, 2) = -((T)2 * zf * zn) / (zf - zn);
+    return r;
+}
+// glm/ext/matrix_transform.inl:99-118 (lookAtRH)
+template <typename T> M4<T> look_at(V3<T> eye, V3<T> center, V3<T> up) {
+    V3<T> f = normalize(center - eye);
+    V3<T> s = normalize(cross(f, up));
+    V3<T> u = cross(s, f);
+    M4<T> r;
+    std::memset(&r, 0, sizeof(r));
+    at(r, 0, 0) = s.x; at(r, 1, 0) = s.y; at(r, 2, 0) = s.z;
+    at(r, 0, 1) = u.x; at(r, 1, 1) = u.y; at(r, 2, 1) = u.z;
+    at(r, 0, 2) = -f.x; at(r, 1, 2) = -f.y; at(r, 2, 2) = -f.z;
+    at(r, 3, 0) = -dot(s, eye); at(r, 3, 1) = -dot(u, eye); at(r, 3, 2) = dot(f, eye);
+    at(r, 3, 3) = (T)1;
+    return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Camera — src/camera.cpp:47-146
+// ----------------------------------------------------------------------------------------------
+template <typename T> struct Camera {
+    T fov, aspect, zn, zf, yaw, pitch;
+    V3<T> pos, forward, right, up, up_init;
+    M4<T> view, proj;
+    // camera.cpp:47-54 (ctor: yaw/pitch stored raw)
+    Camera(T fov_, T aspect_, T zn_, T zf_, V3<T> pos_, T yaw_, T pitch_)
+        : fov(fov_), aspect(aspect_), zn(zn_), zf(zf_), yaw(yaw_), pitch(pitch_), pos(pos_) {
+        up_init = {(T)0, (T)1, (T)0};
+        update_basis();
+        proj = perspective(radians(fov), aspect, zn, zf);   // camera.cpp:140-142
+    }
+    void update_basis() {   // camera.cpp:130-138
+        T cy = std::cos(radians(yaw)), sy = std::sin(radians(yaw));
+        T cp = std::cos(radians(pitch)), sp = std::sin(radians(pitch));
+        forward = normalize(V3<T>{cy * cp, sp, sy * cp});
+        right = normalize(cross(forward, up_init));
+        up = normalize(cross(right, forward));
+        update_view();
+    }
+    void update_view() { view = look_at(pos, pos + forward, up); }   // camera.cpp:144-146
+    void set_rotation(T yaw_deg, T pitch_deg) {                        // camera.cpp:93-98
+        yaw = gmod(yaw_deg, (T)360);
+        pitch = clampT(pitch_deg, (T)-89, (T)89);
+        update_basis();
+    }
+    void translate(V3<T> d) { pos = pos + d; update_view(); }         // camera.cpp:100-104
+};
+
+// ----------------------------------------------------------------------------------------------
+// utils::linePlaneIntersection — src/render-engine.h:111-124 (infinite line; false iff n.dir == 0)
+// ----------------------------------------------------------------------------------------------
+template <typename T> bool line_plane(V3<T>& out, V3<T> p0, V3<T> p1, V4<T> plane /*a,b,c,d*/) {
+    V3<T> n{plane.x, plane.y, plane.z};
+    V3<T> dir = normalize(p1 - p0);
+    T denom = dot(n, dir);
+    if ((T)0 == denom) return false;
+    T t = (plane.w - dot(n, p0)) / denom;
+    out = p0 + t * dir;
+    return true;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// C interface (ctypes).  f32 = oracle, f64 = truth twin.  Layouts are shared with tests/.
+// ----------------------------------------------------------------------------------------------
+extern "C" {
+
+struct wto_camera { float fov_deg, aspect, z_near, z_far, pos[3], yaw_deg, pitch_deg; };
+
+struct wto_grid_f32 {
+    int has_grid, n_intersections;
+    float corners[4][4];   // [0]=bottomLeft [1]=topLeft [2]=bottomRight [3]=topRight
+    float view[16], proj[16], view_proj[16], view_only_yaw[16];
+    float cam_forward[3], aimpoint_1[3], aimpoint_2[3], aimpoint_final[3];
+    float projector_pitch_deg, projector_y;
+    float range[4];
+};
+struct wto_grid_f64 {
+    int has_grid, n_intersections;
+    double corners[4][4];
+    double view[16], proj[16], view_proj[16], view_only_yaw[16];
+    double cam_forward[3], aimpoint_1[3], aimpoint_2[3], aimpoint_final[3];
+    double projector_pitch_deg, projector_y;
+    double range[4];
+};
+
+}  // extern "C"
+
+namespace {
+
+template <typename T, typename OUT>
+int project_grid(const wto_camera& ci, T D, OUT* o) {
+    std::memset(o, 0, sizeof(*o));
+    auto put16 = [](auto* dst, const M4<T>& m) { for (int j = 0; j < 4; ++j) for (int r = 0; r < 4; ++r) dst[4 * j + r] = at(m, j, r); };
+    auto put3 = [](auto* dst, V3<T> v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; };
+
+    Camera<T> cam((T)ci.fov_deg, (T)ci.aspect, (T)ci.z_near, (T)ci.z_far, V3<T>{(T)ci.pos[0], (T)ci.pos[1], (T)ci.pos[2]},
+                  (T)ci.yaw_deg, (T)ci.pitch_deg);
+    // src/render-engine.cpp:278-286
+    Camera<T> yaw_only = cam;
+    yaw_only.set_rotation(yaw_only.yaw, (T)0);
+    M4<T> vp = mul(cam.proj, cam.view);
+    M4<T> ivp = inverse(vp);
+    put16(o->view, cam.view); put16(o->proj, cam.proj); put16(o->view_proj, vp); put16(o->view_only_yaw, yaw_only.view);
+    put3(o->cam_forward, cam.forward);
+
+    // :807-809 planes y = +D, 0, -D
+    V4<T> upper{(T)0, (T)1, (T)0, D}, base{(T)0, (T)1, (T)0, (T)0}, lower{(T)0, (T)1, (T)0, -D};
+
+    // :815-838 padded NDC cube -> world
+    V4<T> fc[8];
+    for (int i = 0; i < 8; ++i) {
+        V4<T> ndc{(i & 4) ? (T)1 : (T)-1, (i & 2) ? (T)1 : (T)-1, (i & 1) ? (T)1 : (T)-1, (T)1};
+        ndc.x *= (T)1.2f;   // SAFETY_PADDING_SCALAR is the float literal 1.2f (:828)
+        ndc.y *= (T)1.2f;
+        V4<T> w = mul(ivp, ndc);
+        fc[i] = w / w.w;
+    }
+    // :842-853
+    static const int E[12][2] = {{0, 1}, {0, 2}, {0, 4}, {1, 3}, {1, 5}, {2, 3}, {2, 6}, {3, 7}, {4, 5}, {4, 6}, {5, 7}, {6, 7}};
+    std::vector<V4<T>> pts;
+    for (auto& e : E) {   // :860-883
+        V3<T> p0 = xyz(fc[e[0]]), p1 = xyz(fc[e[1]]);
+        T lo = std::min(p0.y, p1.y), hi = std::max(p0.y, p1.y);
+        V3<T> hit;
+        if (lo <= upper.w && upper.w <= hi && line_plane(hit, p0, p1, upper)) pts.push_back({hit.x, hit.y, hit.z, (T)1});
+        if (lo <= lower.w && lower.w <= hi && line_plane(hit, p0, p1, lower)) pts.push_back({hit.x, hit.y, hit.z, (T)1});
+    }
+    for (auto& c : fc)    // :887-891
+        if (lower.w <= c.y && c.y <= upper.w) pts.push_back(c);
+    o->n_intersections = (int)pts.size();
+    if (pts.empty()) return 1;   // :894
+    o->has_grid = 1;
+
+    // :905-917
+    Camera<T> projector = cam;
+    T cam_y = cam.pos.y;
+    bool underwater = cam_y < (T)0;
+    T min_y = D + (T)1;
+    if (cam_y < min_y) {
+        if (underwater) projector.translate({(T)0, min_y - (T)2 * cam_y, (T)0});
+        else projector.translate({(T)0, min_y - cam_y, (T)0});
+    }
+    // :920-926
+    V3<T> fs = cam.forward;
+    const T EPS = (T)0.001f;
+    if (std::fabs(fs.y) < EPS) fs.y = (fs.y >= (T)0 ? (T)1 : (T)-1) * EPS;
+    // :929-939
+    V3<T> aim1{(T)0, (T)0, (T)0};
+    bool looking_down = fs.y < (T)0;
+    if (looking_down != underwater) {
+        line_plane(aim1, cam.pos, cam.pos + fs, base);
+    } else {
+        V3<T> mirrored = reflect(fs, V3<T>{(T)0, (T)1, (T)0});
+        line_plane(aim1, cam.pos, cam.pos + mirrored, base);
+    }
+    // :943-954
+    V3<T> aim2 = cam.pos + (T)1 * cam.forward;
+    aim2.y = (T)0;
+    T a = std::fabs(fs.y);
+    V3<T> aim = mix(aim2, aim1, a);
+    put3(o->aimpoint_1, aim1); put3(o->aimpoint_2, aim2); put3(o->aimpoint_final, aim);
+    // :957-963
+    V3<T> pf = normalize(aim - projector.pos);
+    V3<T> pf_xz = normalize(V3<T>{pf.x, (T)0, pf.z});
+    T pitch_deg = -degrees(std::acos(dot(pf, pf_xz)));
+    projector.set_rotation(projector.yaw, pitch_deg);
+    o->projector_pitch_deg = projector.pitch;
+    o->projector_y = projector.pos.y;
+    // :967-979
+    M4<T> pvp = mul(projector.proj, projector.view);
+    for (auto& p : pts) {
+        p.y = (T)0;
+        V4<T> c = mul(pvp, p);
+        p = c / c.w;
+    }
+    // :982-992 (else-if scan, as written in the reference)
+    T x_min = pts[0].x, x_max = pts[0].x, y_min = pts[0].y, y_max = pts[0].y;
+    for (size_t i = 1; i < pts.size(); ++i) {
+        if (pts[i].x < x_min) x_min = pts[i].x; else if (pts[i].x > x_max) x_max = pts[i].x;
+        if (pts[i].y < y_min) y_min = pts[i].y; else if (pts[i].y > y_max) y_max = pts[i].y;
+    }
+    o->range[0] = x_min; o->range[1] = x_max; o->range[2] = y_min; o->range[3] = y_max;
+    // :1002-1008
+    M4<T> range;
+    std::memset(&range, 0, sizeof(range));
+    at(range, 0, 0) = x_max - x_min; at(range, 1, 1) = y_max - y_min; at(range, 2, 2) = (T)1;
+    at(range, 3, 0) = x_min; at(range, 3, 1) = y_min; at(range, 3, 3) = (T)1;
+    M4<T> pm = mul(inverse(mul(cam.proj, projector.view)), range);   // camera projection × projector view
+    // :1012-1036
+    static const T UV[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+    for (int i = 0; i < 4; ++i) {
+        V4<T> p0 = mul(pm, V4<T>{UV[i][0], UV[i][1], (T)-1, (T)1});
+        p0 = p0 / p0.w;
+        V4<T> p1 = mul(pm, V4<T>{UV[i][0], UV[i][1], (T)1, (T)1});
+        p1 = p1 / p1.w;
+        V3<T> hit{(T)0, (T)0, (T)0};
+        if (!line_plane(hit, xyz(p0), xyz(p1), base)) return -2;
+        o->corners[i][0] = hit.x; o->corners[i][1] = hit.y; o->corners[i][2] = hit.z; o->corners[i][3] = (T)1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Uniform block of the water program — the subset water-grid.vert:37-64 and the in-scope lines of
+// water-grid.frag consume; upload sites src/render-engine.cpp:1057-1110.  All fp32, as uploaded.
+struct wto_uniforms {
+    float bottomLeft[4], bottomRight[4], topLeft[4], topRight[4];
+    float cameraPosition[3];
+    unsigned gerstnerWaveCount;
+    unsigned gridLength;
+    float heightmapDisplacementScale, heightmapSampleScale;
+    float verticalBounceWaveDisplacement;
+    float viewMatOnlyYaw[16];
+    float viewProjection[16];
+    float waveAnimationTimeInSeconds;
+    float sunPosition[3];
+    float sunShininess, sunStrength;
+};
+struct wto_wave { float A, w, phi, Q_i, Dx, Dz; };   // per-wave uniforms, render-engine.cpp:1076-1080
+
+struct wto_textures {
+    const uint8_t* heightmap_rgba; int hm_w, hm_h;   // GL row order
+    const uint8_t* sky_faces[6]; int sky_n;           // may be all-NULL when shading is not requested
+};
+
+}  // extern "C"
+
+namespace {
+
+template <typename T> struct Surface {
+    const wto_uniforms& u;
+    const wto_wave* waves;
+    wt_gl::Image2D hm;
+    V4<T> BL, BR, TL, TR;
+    T t, bounce, hm_disp, hm_scale;
+
+    Surface(const wto_uniforms& u_, const wto_wave* w_, const wto_textures& tx) : u(u_), waves(w_) {
+        hm = {tx.heightmap_rgba, tx.hm_w, tx.hm_h};
+        auto v4 = [](const float* p) { return V4<T>{(T)p[0], (T)p[1], (T)p[2], (T)p[3]}; };
+        BL = v4(u.bottomLeft); BR = v4(u.bottomRight); TL = v4(u.topLeft); TR = v4(u.topRight);
+        t = (T)u.waveAnimationTimeInSeconds; bounce = (T)u.verticalBounceWaveDisplacement;
+        hm_disp = (T)u.heightmapDisplacementScale; hm_scale = (T)u.heightmapSampleScale;
+    }
+    // water-grid.vert:87-91
+    V4<T> grid(T uu, T vv) const { return mix(mix(BL, BR, uu), mix(TL, TR, uu), vv); }
+    // water-grid.vert:74-85 — argument is the UNdisplaced (x,z); sin for height, cos for horizontal
+    V3<T> gerstner(T x, T z) const {
+        V3<T> P{x, (T)0, z};
+        for (unsigned i = 0; i < u.gerstnerWaveCount; ++i) {
+            T A = (T)waves[i].A, w = (T)waves[i].w, phi = (T)waves[i].phi, Q = (T)waves[i].Q_i;
+            T Dx = (T)waves[i].Dx, Dz = (T)waves[i].Dz;
+            T dxz = Dx * x + Dz * z;                 // dot(vec2, vec2): tmp.x + tmp.y
+            T k = w * dxz + phi * t;
+            T c = Q * std::cos(k);
+            V3<T> d{Dx * c, std::sin(k), Dz * c};
+            P = P + A * d;
+        }
+        return P;
+    }
+    // water-grid.vert:93-104 (sample at the DISPLACED position, t-coordinate uses -z)
+    void sample_hm(V3<T> P, T texel[4]) const {
+        wt_gl::texture2d_mirrored_linear<T>(hm, hm_scale * P.x, hm_scale * (-P.z), texel);
+    }
+    // water-grid.vert:106-111
+    T hm_displacement(const T texel[4]) const { return hm_disp * ((T)2 * (texel[0] - (T)0.5)); }
+    // the position pipeline of water-grid.vert:135-147 (also used for the 4 neighbours, :164-182)
+    V3<T> displaced(T uu, T vv, T texel_out[4]) const {
+        V4<T> g = grid(uu, vv);
+        V3<T> P = gerstner(g.x, g.z);
+        T tx[4];
+        sample_hm(P, tx);
+        P.y += hm_displacement(tx);
+        P.y += bounce;
+        if (texel_out) std::memcpy(texel_out, tx, sizeof(tx));
+        return P;
+    }
+};
+
+// Per-vertex outputs.  pos4 = (x,y,z,1) world position (water-grid.vert `position`),
+// nrm4 = (normal.xyz, fresnel or 0), shade4 = (sky.rgb, sun), extra16 = clip(4) ndc0(2) viewVecRaw(3)
+// normalVecInViewSpaceOnlyYaw(3) heightmap_colour(4).
+template <typename T>
+void eval_vertex(const Surface<T>& S, const M4<T>& VP, const M4<T>& VY, const wt_gl::CubeRGBA8* sky, long long col, long long row,
+                 T* pos4, T* nrm4, T* shade4, T* extra16) {
+    const wto_uniforms& u = S.u;
+    // water-grid.vert:123-125.  Exact-integer (col,row) semantics: identical to the shader's float
+    // mod()/integer division for gridLength <= 4096 and well-defined beyond.
+    T du = (T)1 / (T)(u.gridLength - 1);
+    T dv = du;
+    T uu = (T)col * du, vv = (T)row * dv;
+
+    T texel[4];
+    V3<T> P = S.displaced(uu, vv, texel);                                   // :135-147
+    V4<T> clip = mul(VP, V4<T>{P.x, P.y, P.z, (T)1});                        // :150
+    V4<T> clip0 = mul(VP, V4<T>{P.x, (T)0, P.z, (T)1});                      // :153
+    T ndc0x = clip0.x / clip0.w, ndc0y = clip0.y / clip0.w;                  // :154
+    V3<T> cam{(T)u.cameraPosition[0], (T)u.cameraPosition[1], (T)u.cameraPosition[2]};
+    V3<T> view_raw = cam - P;                                               // :158
+    // :164-182 neighbours at uv -/+ (du,0), uv -/+ (0,dv), full pipeline each
+    V3<T> Pmu = S.displaced(uu - du, vv, nullptr);
+    V3<T> Ppu = S.displaced(uu + du, vv, nullptr);
+    V3<T> Pmv = S.displaced(uu, vv - dv, nullptr);
+    V3<T> Ppv = S.displaced(uu, vv + dv, nullptr);
+    V3<T> n = normalize(cross(Ppu - Pmu, Ppv - Pmv));                       // :187
+    V3<T> view_n = normalize(view_raw);
+    if (dot(n, view_n) < (T)0) n = n * (T)-1;                               // :190
+    V4<T> ny4 = mul(VY, V4<T>{n.x, n.y, n.z, (T)0});                         // :193
+    V3<T> ny = normalize(xyz(ny4));
+
+    pos4[0] = P.x; pos4[1] = P.y; pos4[2] = P.z; pos4[3] = (T)1;
+    nrm4[0] = n.x; nrm4[1] = n.y; nrm4[2] = n.z; nrm4[3] = (T)0;
+    if (extra16) {
+        extra16[0] = clip.x; extra16[1] = clip.y; extra16[2] = clip.z; extra16[3] = clip.w;
+        extra16[4] = ndc0x; extra16[5] = ndc0y;
+        extra16[6] = view_raw.x; extra16[7] = view_raw.y; extra16[8] = view_raw.z;
+        extra16[9] = ny.x; extra16[10] = ny.y; extra16[11] = ny.z;
+        for (int c = 0; c < 4; ++c) extra16[12 + c] = texel[c];
+    }
+    if (shade4) {
+        // water-grid.frag:71-73,95-111 evaluated at the vertex with the un-interpolated varyings
+        T len = std::sqrt(dot(view_raw, view_raw));                         // length(), frag:71
+        V3<T> vv3{view_raw.x / len, view_raw.y / len, view_raw.z / len};     // frag:73 (vec3 / float)
+        V3<T> R = reflect(V3<T>{-vv3.x, -vv3.y, -vv3.z}, n);                // frag:95
+        T sky_c[4] = {0, 0, 0, 0};
+        if (sky && sky->face[0]) wt_gl::texture_cube_clamp_linear<T>(*sky, R.x, R.y, R.z, sky_c);   // frag:96
+        V3<T> sun{(T)u.sunPosition[0], (T)u.sunPosition[1], (T)u.sunPosition[2]};
+        T sd = clampT(dot(R, sun), (T)0, (T)1);
+        T sun_term = (T)u.sunStrength * (T)1 * std::pow(sd, (T)u.sunShininess);   // frag:99-100
+        T cos_theta = dot(n, vv3);                                          // frag:110
+        T fres = (T)0.02f + ((T)1 - (T)0.02f) * std::pow((T)1 - cos_theta, (T)5);   // frag:107-111
+        shade4[0] = sky_c[0]; shade4[1] = sky_c[1]; shade4[2] = sky_c[2]; shade4[3] = sun_term;
+        nrm4[3] = fres;
+    }
+}
+
+template <typename T>
+int eval_vertices(const wto_uniforms* u, const wto_wave* waves, const wto_textures* tx, const long long* ids, long long n,
+                  long long row0, long long row1, long long col0, long long col1, T* pos4, T* nrm4, T* shade4, T* extra16) {
+    if (u->gridLength < 2) return -1;
+    Surface<T> S(*u, waves, *tx);
+    M4<T> VP, VY;
+    for (int j = 0; j < 4; ++j) for (int r = 0; r < 4; ++r) { at(VP, j, r) = (T)u->viewProjection[4 * j + r]; at(VY, j, r) = (T)u->viewMatOnlyYaw[4 * j + r]; }
+    wt_gl::CubeRGBA8 cube{{tx->sky_faces[0], tx->sky_faces[1], tx->sky_faces[2], tx->sky_faces[3], tx->sky_faces[4], tx->sky_faces[5]}, tx->sky_n};
+    const long long L = u->gridLength;
+    const long long ncol = col1 - col0;
+    const long long total = ids ? n : (row1 - row0) * ncol;
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long long k = 0; k < total; ++k) {
+        long long col, row;
+        if (ids) { col = ids[k] % L; row = ids[k] / L; }
+        else { row = row0 + k / ncol; col = col0 + k % ncol; }
+        eval_vertex<T>(S, VP, VY, &cube, col, row, pos4 + 4 * k, nrm4 + 4 * k, shade4 ? shade4 + 4 * k : nullptr,
+                       extra16 ? extra16 + 16 * k : nullptr);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wto_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void wto_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+int wto_project_grid_f32(const wto_camera* cam, float displaceable_amplitude, wto_grid_f32* out) {
+    return project_grid<float>(*cam, displaceable_amplitude, out);
+}
+int wto_project_grid_f64(const wto_camera* cam, double displaceable_amplitude, wto_grid_f64* out) {
+    return project_grid<double>(*cam, displaceable_amplitude, out);
+}
+
+// host-side scalar rules of the boundary
+float wto_total_amplitude(const float* A, unsigned n) {   // render-engine.h:156-157 (running fp32 sum)
+    float s = 0.0f;
+    for (unsigned i = 0; i < n; ++i) s += A[i];
+    return s;
+}
+float wto_steepness_Q_i(float Q, float w, float A, unsigned count) {   // render-engine.cpp:1073
+    return (w * A) != 0.0f ? Q / (w * A * count) : 0.0f;
+}
+void wto_sun_position(float hours, float out3[3]) {   // render-engine.cpp:289-291
+    float days = hours / 24.0f;
+    float theta = days * 6.283185307179586476925286766559f - 1.5707963267948966192313216916398f;
+    out3[0] = std::cos(theta); out3[1] = std::sin(theta); out3[2] = 0.0f;
+}
+float wto_bounce_displacement(float amplitude, float phase) {   // render-engine.cpp:299-300
+    float shift = phase * 6.283185307179586476925286766559f;
+    return amplitude * std::sin(shift);
+}
+
+// ids != NULL: evaluate the n listed vertex ids (id = row * gridLength + col);
+// ids == NULL: evaluate the region rows [row0,row1) x cols [col0,col1), row-major.
+int wto_eval_f32(const wto_uniforms* u, const wto_wave* waves, const wto_textures* tx, const long long* ids, long long n,
+                 long long row0, long long row1, long long col0, long long col1, float* pos4, float* nrm4, float* shade4, float* extra16) {
+    return eval_vertices<float>(u, waves, tx, ids, n, row0, row1, col0, col1, pos4, nrm4, shade4, extra16);
+}
+int wto_eval_f64(const wto_uniforms* u, const wto_wave* waves, const wto_textures* tx, const long long* ids, long long n,
+                 long long row0, long long row1, long long col0, long long col1, double* pos4, double* nrm4, double* shade4, double* extra16) {
+    return eval_vertices<double>(u, waves, tx, ids, n, row0, row1, col0, col1, pos4, nrm4, shade4, extra16);
+}
+
+}  // extern "C"
