@@ -1,0 +1,211 @@
+/*
+ * wavetool_b200.h — C ABI of the B200-native water-surface evaluator.
+ *
+ * Drop-in boundary for ONE path of TexelBox/wave-tool: "set the water program's uniforms, then
+ * glDrawElements" (reference src/render-engine.cpp:1045-1122), fed by the projected-grid builder
+ * (src/render-engine.cpp:797-1042).  The reference has no plugin/FFI API; every entry point below
+ * cites the reference code it replaces.  Plain C: pointers and sizes only, no C++/torch types, no
+ * exceptions or stdout across the boundary.  Every call returns an int status:
+ *     WT_OK (0)        success
+ *     WT_NO_GRID (1)   the frustum misses the displaceable volume: the reference draws no water this
+ *                      frame (render-engine.cpp:894) — not an error
+ *     < 0              error; wt_last_error(ctx) (or wt_last_error(NULL) for ctx-less calls) describes it
+ *
+ * Ownership: the caller owns every host array (copied during the call) and every output device
+ * buffer; a wt_ctx owns its wave table, textures and scratch.  A ctx is bound to one CUDA device and
+ * is not thread-safe: one ctx per GPU per host thread.  Device work is stream-ordered on the stream
+ * the caller passes (a cudaStream_t, passed as void*); no hidden synchronisation except in the
+ * *_host convenience calls, which say so.
+ *
+ * There is no CPU fallback: device entry points fail with WT_ERR_NO_DEVICE when no CUDA device is
+ * usable.  The host-math entry points (wt_camera_matrices, wt_project_grid, wt_build_frame, ...) are
+ * pure CPU code by design — they are the reference's own CPU prologue (4 points per frame).
+ */
+#ifndef WAVETOOL_B200_H_
+#define WAVETOOL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WT_OK 0
+#define WT_NO_GRID 1
+#define WT_ERR_INVALID_ARGUMENT (-1)
+#define WT_ERR_CUDA (-2)
+#define WT_ERR_NO_DEVICE (-3)
+#define WT_ERR_NOT_READY (-4)   /* waves / heightmap / skybox not set before an evaluation that needs them */
+#define WT_ERR_DEGENERATE (-5)  /* a projector ray is parallel to the base plane (reference asserts, render-engine.cpp:1034) */
+
+#define WT_MAX_WAVES 1000u      /* reference: GerstnerWave::MAX_COUNT = 4 (render-engine.h:132); generalised here */
+
+/* evaluation flags */
+#define WT_FLAG_SHADE 0x1u            /* also evaluate the vertex-evaluable fragment terms (water-grid.frag:71-73,95-111) */
+#define WT_FLAG_CHECKSUM 0x2u         /* fold the outputs into the wt_checksum record passed to the call */
+#define WT_FLAG_FAST_PHASE 0x4u       /* pre-folded 2-FMA wave phase (not bit-faithful to the reference's fp32 phase) */
+#define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
+
+typedef struct wt_ctx wt_ctx;
+
+/* geometry::GerstnerWave — reference src/render-engine.h:130-167 (the reference-native 5-tuple). */
+typedef struct wt_wave {
+    float amplitude_A;        /* >= 0, height of crest above the equilibrium plane */
+    float frequency_w;        /* >= 0, ~2/L */
+    float phaseConstant_phi;  /* >= 0, speed * w */
+    float steepness_Q;        /* in [0,1]; the shader-side Q_i is derived by wt_set_waves (render-engine.cpp:1073) */
+    float dir_x, dir_z;       /* xzDirection_D, unit length +-1e-3 */
+} wt_wave;
+
+/* Camera constructor arguments — reference src/camera.h:49, src/render-engine.cpp:52.
+ * yaw/pitch are stored raw, as the constructor does (camera.cpp:47-54); defaults -90 / 0. */
+typedef struct wt_camera {
+    float fov_deg, aspect, z_near, z_far;
+    float pos[3];
+    float yaw_deg, pitch_deg;
+} wt_camera;
+
+/* The RenderEngine public fields the path reads — reference src/render-engine.h:224-238. */
+typedef struct wt_params {
+    float heightmapDisplacementScale;   /* default 1.0  */
+    float heightmapSampleScale;         /* default 0.02 */
+    float verticalBounceWaveAmplitude;  /* default 0.1  */
+    float verticalBounceWavePhase;      /* default 0.0, in [0,1] */
+    float waveAnimationTimeInSeconds;   /* default 0.0  */
+    float timeOfDayInHours;             /* default 9.0  */
+    float sunShininess;                 /* default 50.0 */
+    float sunStrength;                  /* default 1.0  */
+} wt_params;
+
+/* One draw call's uniform set, as uploaded at render-engine.cpp:1057-1110 (in-scope subset;
+ * names follow the GLSL uniforms of water-grid.vert:37-64 / water-grid.frag:39-47).
+ * Matrices are column-major like glm::value_ptr. */
+typedef struct wt_frame {
+    float bottomLeftGridPointInWorld[4];
+    float bottomRightGridPointInWorld[4];
+    float topLeftGridPointInWorld[4];
+    float topRightGridPointInWorld[4];
+    float viewProjection[16];
+    float viewMatOnlyYaw[16];
+    float cameraPosition[3];
+    float waveAnimationTimeInSeconds;
+    float verticalBounceWaveDisplacement;
+    float heightmapDisplacementScale;
+    float heightmapSampleScale;
+    float sunShininess;
+    float sunPosition[3];
+    float sunStrength;
+} wt_frame;
+
+/* Order-independent digest of one evaluation (sums of IEEE-754 bit patterns, mod 2^64). */
+typedef struct wt_checksum {
+    uint64_t position_bits;   /* sum over vertices of bits(x)+bits(y)+bits(z) */
+    uint64_t normal_bits;     /* sum over vertices of bits(nx)+bits(ny)+bits(nz)+bits(w) */
+    uint64_t shade_bits;      /* sum over vertices of the four shade words (0 without WT_FLAG_SHADE) */
+    float min_y, max_y;       /* extrema of position.y */
+    uint64_t vertices;        /* number of vertices folded in */
+} wt_checksum;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library / error reporting
+ * ------------------------------------------------------------------------------------------- */
+const char* wt_version(void);
+const char* wt_last_error(const wt_ctx* ctx);   /* ctx may be NULL: last error of a ctx-less call on this thread */
+int wt_device_count(void);                      /* number of usable CUDA devices (0 on a CPU-only host) */
+
+/* ---------------------------------------------------------------------------------------------
+ * Host math — the reference's CPU prologue, bit-faithful fp32 (same operation order as the
+ * reference + GLM 0.9.9.8).  No GPU needed.
+ * ------------------------------------------------------------------------------------------- */
+
+/* RenderEngine defaults (render-engine.h:224-238) and the default camera (render-engine.cpp:52). */
+void wt_default_params(wt_params* out);
+void wt_default_camera(wt_camera* out, float aspect);
+/* The reference's hard-coded wave set (render-engine.cpp:46-49); writes 4 waves. */
+void wt_default_waves(wt_wave out[4]);
+
+/* Camera::getViewMat/getProjectionMat and the per-frame products of render-engine.cpp:278-285.
+ * Any output pointer may be NULL. */
+int wt_camera_matrices(const wt_camera* cam, float view[16], float proj[16], float view_proj[16],
+                       float view_only_yaw[16], float forward[3]);
+
+/* GerstnerWave::TotalAmplitude() as the constructors accumulate it (render-engine.h:156-157). */
+float wt_total_amplitude(const wt_wave* waves, unsigned count);
+/* steepness_Q_i of render-engine.cpp:1073 with Count() == count. */
+float wt_steepness_Q_i(const wt_wave* wave, unsigned count);
+/* sunPosition of render-engine.cpp:289-291. */
+void wt_sun_position(float time_of_day_hours, float out[3]);
+/* verticalBounceWaveDisplacement of render-engine.cpp:299-300. */
+float wt_bounce_displacement(float amplitude, float phase);
+
+/* Projected-grid builder, render-engine.cpp:797-1042.  displaceable_amplitude is
+ * TotalAmplitude() + heightmapDisplacementScale + verticalBounceWaveAmplitude (:803).
+ * corners[0..3] = bottomLeft, topLeft, bottomRight, topRight (the order of waterGridCornerPoints,
+ * :1012-1015).  Returns WT_OK, WT_NO_GRID (:894) or WT_ERR_DEGENERATE (:1034). */
+int wt_project_grid(const wt_camera* cam, float displaceable_amplitude, float corners[4][4]);
+
+/* Everything RenderEngine::render() computes on the CPU for the water draw, in one call:
+ * matrices (:278-285), sun (:289-291), bounce (:299-300), projected grid (:797-1042) -> wt_frame. */
+int wt_build_frame(const wt_camera* cam, const wt_params* params, float total_wave_amplitude, wt_frame* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device context
+ * ------------------------------------------------------------------------------------------- */
+int wt_create(wt_ctx** out, int cuda_device);
+void wt_destroy(wt_ctx* ctx);
+
+/* Replaces the per-wave uniform upload loop (render-engine.cpp:1067-1081): derives Q_i with
+ * Count() == count and stages the table for the kernels.  count in [0, WT_MAX_WAVES]. */
+int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count);
+
+/* Replaces load2DTexture + create2DTexture (render-engine.cpp:1308-1322, texture.cpp:54-72):
+ * tightly packed RGBA8, rows ALREADY in GL order (i.e. flipped as stbi_set_flip_vertically_on_load
+ * does), sampled GL_LINEAR / GL_MIRRORED_REPEAT / LOD 0 with exact fp32 weights. */
+int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int width, int height);
+
+/* Replaces the skybox cubemap binding (render-engine.cpp:90-110, :1092-1094): six n x n RGBA8 faces
+ * in GL order +x,-x,+y,-y,+z,-z; GL_LINEAR, GL_CLAMP_TO_EDGE, non-seamless. */
+int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n);
+
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation — replaces glDrawElements on the water program (render-engine.cpp:1115) for the
+ * vertex stage (water-grid.vert:114-194) and, with WT_FLAG_SHADE, the vertex-evaluable fragment
+ * terms (water-grid.frag:71-73,95-111).
+ *
+ * Vertex id layout is the shader's (water-grid.vert:115-125): id = row * grid_len + col, row 0 =
+ * bottom.  Rows [row_begin,row_end) are evaluated (row sharding; the +-1-row normal stencil is
+ * recomputed locally); output element k = (row - row_begin) * grid_len + col of each buffer:
+ *     d_position  float4  (x, y, z, 1)                          world-space `position`
+ *     d_normal    float4  (nx, ny, nz, fresnel_f_theta | 0)      `normal` after the view-facing flip
+ *     d_shade     float4  (sky.r, sky.g, sky.b, sun specular)    only with WT_FLAG_SHADE (else may be NULL)
+ * d_checksum (device pointer to ONE wt_checksum, zero-initialised by the call) is only touched with
+ * WT_FLAG_CHECKSUM.  `frame` is a HOST pointer; it is consumed before the call returns.
+ * ------------------------------------------------------------------------------------------- */
+int wt_eval_frame(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsigned row_begin, unsigned row_end,
+                  void* d_position, void* d_normal, void* d_shade, void* d_checksum, unsigned flags, void* cuda_stream);
+
+/* A batch of n_frames independent frames (animation; frame sharding takes a subset per GPU).
+ * Frame f writes slot (f % ring_depth) of each ring buffer (slot stride = (row_end-row_begin)*grid_len
+ * float4) and, with WT_FLAG_CHECKSUM, d_checksums[f].  Stream-ordered, returns without synchronising. */
+int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsigned grid_len, unsigned row_begin,
+                  unsigned row_end, void* d_position_ring, void* d_normal_ring, void* d_shade_ring, unsigned ring_depth,
+                  void* d_checksums, unsigned flags, void* cuda_stream);
+
+/* Host-buffer convenience (synchronous): evaluates into ctx-owned device scratch and copies the
+ * requested outputs to HOST memory.  Any of h_position/h_normal/h_shade/h_checksum may be NULL. */
+int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsigned row_begin, unsigned row_end,
+                       float* h_position, float* h_normal, float* h_shade, wt_checksum* h_checksum, unsigned flags);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helpers (used by bench.py; they launch real kernels on the ctx's device)
+ * ------------------------------------------------------------------------------------------- */
+/* Number of kernels this ctx has launched so far (evaluation + helper kernels). */
+uint64_t wt_launch_count(const wt_ctx* ctx);
+/* Micro-benchmarks for the roofline denominators: kind 0 = MUFU (sin+cos pairs/s),
+ * 1 = FP32 FMA (FLOP/s), 2 = HBM float4 store stream (bytes/s).  Synchronous; result in *per_second. */
+int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVETOOL_B200_H_ */

@@ -1,0 +1,99 @@
+"""The PRODUCT's host prologue (C ABI: wt_camera_matrices / wt_project_grid / wt_build_frame / scalar
+rules, wave_tool_b200/csrc/wt_host.cpp) against the golden vectors produced by the reference's own
+code.  Bit-exact.  No GPU needed: this is the part the reference itself runs on the CPU."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from tests.common import GOLDEN, Scene
+from wave_tool_b200 import api, scenes
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_projector_and_matrices_match_reference_bits():
+    z = np.load(os.path.join(GOLDEN, "projector.npz"))
+    for i in range(len(z["names"])):
+        cam = api.Camera.from_buffer_copy(z["cameras"][i].tobytes())
+        st, corners = api.project_grid(cam, float(z["D"][i]))
+        assert st == z["status"][i], z["names"][i]
+        if st == api.WT_OK:
+            assert np.array_equal(bits(corners).ravel(), bits(z["corners"][i]).ravel()), z["names"][i]
+        m = api.camera_matrices(cam)
+        mats = np.concatenate([m["view"], m["proj"], m["view_proj"], m["view_only_yaw"]])
+        assert np.array_equal(bits(mats), bits(z["matrices"][i])), z["names"][i]
+        assert np.array_equal(bits(m["forward"]), bits(z["forward"][i]))
+
+
+def test_scalar_rules_match_reference_bits():
+    z = np.load(os.path.join(GOLDEN, "scalars.npz"))
+    L = api.lib()
+    for (q, w, a), n, expect in zip(z["q_in"], z["q_count"], z["q_out"]):
+        wave = api.Wave(a, w, 0.0, q, 1.0, 0.0)
+        got = np.float32(L.wt_steepness_Q_i(C.byref(wave), int(n)))
+        assert bits(got) == bits(expect)
+    for h, expect in zip(z["hours"], z["sun"]):
+        out = np.zeros(3, np.float32)
+        L.wt_sun_position(float(h), out.ctypes.data)
+        assert np.array_equal(bits(out), bits(expect))
+    for p, expect in zip(z["phases"], z["bounce"]):
+        assert bits(np.float32(L.wt_bounce_displacement(0.1, float(p)))) == bits(expect)
+    waves = np.zeros((256, 6), np.float32)
+    waves[:, 0] = z["amps"]
+    assert bits(np.float32(api.total_amplitude(waves))) == bits(z["amp_total"])
+
+
+def test_defaults_are_the_reference_defaults():
+    p = api.default_params()
+    assert (p.heightmapDisplacementScale, p.verticalBounceWaveAmplitude, p.timeOfDayInHours, p.sunShininess) == (1.0, np.float32(0.1), 9.0, 50.0)
+    assert abs(p.heightmapSampleScale - 0.02) < 1e-9
+    c = api.default_camera(1.0)
+    assert (c.fov_deg, c.z_far, c.yaw_deg, c.pitch_deg, tuple(c.pos)) == (72.0, 100.0, -90.0, 0.0, (0.0, 4.0, 70.0))
+    w = api.default_waves()
+    assert w.shape == (4, 6) and np.float32(api.total_amplitude(w)) == np.float32(np.float32(0.06) + np.float32(0.1))
+    assert abs(np.hypot(w[1, 4], w[1, 5]) - 1.0) < 1e-6
+
+
+def test_build_frame_equals_oracle_uniforms(oracle, heightmap):
+    """wt_build_frame (product) and the oracle derive the draw call's uniforms independently from the
+    same camera/params: every float must agree bit for bit."""
+    for name, kw in scenes.EDGE_CAMERAS.items():
+        p = scenes.animation_params(37)
+        sc = Scene(scenes.seeded_waves(32, cfg=5), scenes.camera(**kw), p, 64, heightmap)
+        st, f = sc.frame()
+        st_o, u, _ = sc.oracle_uniforms(oracle)
+        assert st == st_o, name
+        if st != api.WT_OK:
+            assert st == api.WT_NO_GRID
+            continue
+        pairs = [(f.bottomLeftGridPointInWorld, u.bottomLeft), (f.bottomRightGridPointInWorld, u.bottomRight),
+                 (f.topLeftGridPointInWorld, u.topLeft), (f.topRightGridPointInWorld, u.topRight),
+                 (f.viewProjection, u.viewProjection), (f.viewMatOnlyYaw, u.viewMatOnlyYaw), (f.cameraPosition, u.cameraPosition),
+                 (f.sunPosition, u.sunPosition)]
+        for a, b in pairs:
+            assert np.array_equal(bits(a[:]), bits(b[:])), name
+        for a, b in [(f.waveAnimationTimeInSeconds, u.waveAnimationTimeInSeconds), (f.verticalBounceWaveDisplacement, u.verticalBounceWaveDisplacement),
+                     (f.heightmapDisplacementScale, u.heightmapDisplacementScale), (f.heightmapSampleScale, u.heightmapSampleScale),
+                     (f.sunShininess, u.sunShininess), (f.sunStrength, u.sunStrength)]:
+            assert bits(np.float32(a)) == bits(np.float32(b)), name
+
+
+def test_null_arguments_are_reported_not_crashed():
+    L = api.lib()
+    assert L.wt_project_grid(None, C.c_float(1.0), None) == api.WT_ERR_INVALID_ARGUMENT
+    assert b"NULL" in L.wt_last_error(None)
+    assert L.wt_build_frame(None, None, C.c_float(1.0), None) == api.WT_ERR_INVALID_ARGUMENT
+
+
+def test_unorm8_reciprocal_trick_is_exact():
+    """The kernel converts RGBA8 texels with q = c*r; q += fma(-q,255,c)*r (wt_kernels.cuh:unorm8);
+    emulate that in numpy (fp64 holds the fp32 FMA exactly) and compare with IEEE c/255."""
+    c = np.arange(256, dtype=np.float32)
+    r = np.float32(1) / np.float32(255)
+    q = (c * r).astype(np.float32)
+    rem = (c.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
+    q2 = (q.astype(np.float64) + rem.astype(np.float64) * np.float64(r)).astype(np.float32)
+    assert np.array_equal(q2, c / np.float32(255))

@@ -1,0 +1,117 @@
+"""The oracle restatement (oracle/wt_oracle.cpp) against the committed golden vectors, which are
+outputs of the reference's own code (tests/golden/make_golden.py).  Bit-exact: the oracle performs
+the same fp32 operations in the same order as the reference + GLM."""
+import os
+
+import numpy as np
+
+from tests.common import GOLDEN
+from oracle import oracle as orc
+from wave_tool_b200 import scenes
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_projector_matches_reference_bits(oracle):
+    z = np.load(os.path.join(GOLDEN, "projector.npz"))
+    assert len(z["names"]) >= 30
+    for i in range(len(z["names"])):
+        cam = orc.Camera.from_buffer_copy(z["cameras"][i].tobytes())
+        st, g = oracle.project_grid(cam, z["D"][i])
+        assert st == z["status"][i], z["names"][i]
+        assert np.array_equal(bits(g.corners), bits(z["corners"][i])), z["names"][i]
+        mats = np.concatenate([np.array(m, np.float32) for m in (g.view, g.proj, g.view_proj, g.view_only_yaw)])
+        assert np.array_equal(bits(mats), bits(z["matrices"][i])), z["names"][i]
+        assert np.array_equal(bits(g.cam_forward), bits(z["forward"][i]))
+    assert (z["status"] == 1).sum() >= 3      # the "no water this frame" cases are covered (render-engine.cpp:894)
+
+
+def test_default_scene_known_answers(oracle):
+    """Known-answer values of the default scene recorded in SURVEY.md §8a."""
+    cam = orc.Camera.from_buffer_copy(bytes(scenes.camera()))
+    st, g = oracle.project_grid(cam, np.float32(1.26))
+    assert st == 0 and g.n_intersections == 8
+    assert abs(g.projector_pitch_deg - (-38.66378)) < 1e-4 and g.projector_y == 4.0
+    np.testing.assert_allclose(np.array(g.range), [-1.4891324, 1.48913217, -0.322296411, 1.0137701], rtol=0, atol=1e-6)
+    c = np.array(g.corners).reshape(4, 4)
+    np.testing.assert_allclose(c[0, [0, 2]], [-5.35869646, 66.8567657], atol=1e-5)
+    np.testing.assert_allclose(c[1, [0, 2]], [-87.1667862, -29.9878922], atol=1e-5)
+    np.testing.assert_allclose(c[3, [0, 2]], [87.1667709, -29.9878922], atol=1e-5)
+
+
+def test_scalar_rules(oracle):
+    z = np.load(os.path.join(GOLDEN, "scalars.npz"))
+    q = np.array([oracle.steepness_Q_i(a, b, c, int(n)) for (a, b, c), n in zip(z["q_in"], z["q_count"])], np.float32)
+    assert np.array_equal(bits(q), bits(z["q_out"]))
+    assert np.all(q[:4] == 0.0)
+    sun = np.array([oracle.sun_position(h) for h in z["hours"]], np.float32)
+    assert np.array_equal(bits(sun), bits(z["sun"]))
+    b = np.array([oracle.bounce_displacement(0.1, p) for p in z["phases"]], np.float32)
+    assert np.array_equal(bits(b), bits(z["bounce"]))
+    assert bits(oracle.total_amplitude(z["amps"])) == bits(z["amp_total"])
+
+
+def _oracle_uniforms(oracle, cam, waves, t, L):
+    total = oracle.total_amplitude(waves[:, 0])
+    D = np.float32(np.float32(total + np.float32(1.0)) + np.float32(0.1))
+    st, g = oracle.project_grid(cam, D)
+    assert st == 0
+    u = orc.Uniforms()
+    c = np.array(g.corners, np.float32).reshape(4, 4)
+    u.bottomLeft[:] = c[0]; u.topLeft[:] = c[1]; u.bottomRight[:] = c[2]; u.topRight[:] = c[3]
+    u.cameraPosition[:] = cam.pos[:]
+    u.gerstnerWaveCount = len(waves); u.gridLength = L
+    u.heightmapDisplacementScale = 1.0; u.heightmapSampleScale = 0.02
+    u.verticalBounceWaveDisplacement = float(oracle.bounce_displacement(0.1, float(np.float32(np.fmod(t / 3.0, 1.0)))))
+    u.viewMatOnlyYaw[:] = g.view_only_yaw[:]; u.viewProjection[:] = g.view_proj[:]
+    u.waveAnimationTimeInSeconds = t
+    return u, oracle.wave_uniforms(waves)
+
+
+def _check_vert(oracle, heightmap, u, wu, ids, out, world):
+    o = oracle.eval(u, wu, heightmap, ids=ids, extra=True)
+    assert np.array_equal(bits(o["pos"]), bits(world)), "world position"
+    assert np.array_equal(bits(o["normal"][:, :3]), bits(out["normal"])), "normal"
+    assert np.array_equal(bits(o["extra"][:, 0:4]), bits(out["gl_Position"])), "gl_Position"
+    assert np.array_equal(bits(o["extra"][:, 4:6]), bits(out["xyPositionNDCSpaceHeight0"])), "ndc"
+    assert np.array_equal(bits(o["extra"][:, 6:9]), bits(out["viewVecRaw"])), "viewVecRaw"
+    assert np.array_equal(bits(o["extra"][:, 9:12]), bits(out["normalVecInViewSpaceOnlyYaw"])), "yaw normal"
+    assert np.array_equal(bits(o["extra"][:, 12:16]), bits(out["heightmap_colour"])), "heightmap colour"
+
+
+def test_vertex_shader_default_scene(oracle, heightmap):
+    z = np.load(os.path.join(GOLDEN, "vert_default.npz"))
+    cam = orc.Camera.from_buffer_copy(bytes(scenes.camera()))
+    waves = scenes.default_waves()
+    for t in (0.0, 1.5):
+        u, wu = _oracle_uniforms(oracle, cam, waves, t, 513)
+        _check_vert(oracle, heightmap, u, wu, z["ids"], z[f"out_t{t}"], z[f"world_t{t}"])
+    # SURVEY.md §8a known answers (vertex 51337 and the flipped centre vertex 131584, H2)
+    u, wu = _oracle_uniforms(oracle, cam, waves, 0.0, 513)
+    o = oracle.eval(u, wu, heightmap, ids=[51337, 131584])
+    np.testing.assert_allclose(o["pos"][0, :3], [-18.04618, 0.1935035, 47.9418], atol=2e-5)
+    np.testing.assert_allclose(o["normal"][0, :3], [-0.1282277, 0.981949, 0.1390464], atol=1e-6)
+    np.testing.assert_allclose(o["normal"][1, :3], [0.1800599, -0.9607528, 0.2110267], atol=1e-6)
+
+
+def test_vertex_shader_seeded8(oracle, heightmap):
+    z = np.load(os.path.join(GOLDEN, "vert_seeded8.npz"))
+    waves = scenes.seeded_waves(8, cfg=2)
+    assert np.array_equal(bits(waves), bits(z["waves"])), "seeded wave set is not reproducible"
+    cam = orc.Camera.from_buffer_copy(bytes(scenes.camera()))
+    u, wu = _oracle_uniforms(oracle, cam, waves, 0.5, 1024)
+    _check_vert(oracle, heightmap, u, wu, z["ids"], z["out"], z["world"])
+
+
+def test_fp64_twin_close_to_fp32(oracle, heightmap):
+    """Error budget: the fp32 oracle vs the fp64 truth twin fed the SAME fp32 uniforms."""
+    cam = orc.Camera.from_buffer_copy(bytes(scenes.camera()))
+    waves = scenes.seeded_waves(8, cfg=2)
+    u, wu = _oracle_uniforms(oracle, cam, waves, 0.5, 1024)
+    ids = np.arange(0, 1024 * 1024, 997)
+    a = oracle.eval(u, wu, heightmap, ids=ids)
+    b = oracle.eval(u, wu, heightmap, ids=ids, f64=True)
+    err = np.abs(a["pos"][:, :3] - b["pos"][:, :3]).max()
+    assert err < 1e-4, err          # within the parity tolerance for sum(A) = 1

@@ -1,0 +1,70 @@
+"""Direct bit-for-bit comparison of the oracle restatement with the reference's own code compiled
+headless (oracle/_ref).  Runs wherever oracle/_ref exists (build container: rebuilt from
+/root/reference; GPU box: the prebuilt .so travels with the snapshot); skipped otherwise."""
+import numpy as np
+
+from oracle import oracle as orc
+from tests.common import Scene
+from wave_tool_b200 import api, scenes
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_random_cameras_bit_exact(oracle, ref):
+    rng = np.random.default_rng(7)
+    n_grid = 0
+    for _ in range(300):
+        cam = scenes.camera(pos=(rng.uniform(-200, 200), rng.uniform(-20, 120), rng.uniform(-200, 200)),
+                            yaw=rng.uniform(-360, 720), pitch=rng.uniform(-89, 89), fov=rng.uniform(15, 105),
+                            aspect=rng.choice([1.0, 16 / 9, 0.75]))
+        ocam = orc.Camera.from_buffer_copy(bytes(cam))
+        D = np.float32(rng.uniform(0.05, 4.0))
+        st_o, g_o = oracle.project_grid(ocam, D)
+        st_r, g_r = ref.project_grid(ocam, D)
+        assert st_o == st_r
+        assert bytes(g_o) == bytes(g_r)
+        n_grid += st_o == 0
+    assert 50 < n_grid < 300      # both outcomes exercised
+
+
+def test_vertex_shader_random_scenes_bit_exact(oracle, ref, heightmap):
+    rng = np.random.default_rng(11)
+    for case in range(6):
+        W = [1, 3, 4, 8, 37, 256][case]
+        L = [2, 17, 513, 640, 1024, 4096][case]
+        waves = scenes.default_waves()[:W] if W <= 4 else scenes.seeded_waves(W, cfg=case)
+        p = api.default_params()
+        p.waveAnimationTimeInSeconds = float(rng.uniform(0, 20))
+        p.verticalBounceWavePhase = float(rng.uniform(0, 1))
+        p.heightmapSampleScale = float(rng.choice([0.02, 0.13, 1.7]))
+        p.heightmapDisplacementScale = float(rng.choice([1.0, 0.25, 0.0]))
+        cam = scenes.camera(**list(scenes.EDGE_CAMERAS.values())[case])
+        sc = Scene(waves, cam, p, L, heightmap)
+        st, u, wu = sc.oracle_uniforms(oracle)
+        assert st == 0
+        ids = np.unique(np.concatenate([rng.integers(0, L * L, 400), [0, L - 1, L * (L - 1), L * L - 1]]))
+        o = oracle.eval(u, wu, heightmap, ids=ids, extra=True)
+        r = ref.vert_run(u, wu, heightmap, ids=ids)
+        assert np.array_equal(bits(o["normal"][:, :3]), bits(r["normal"])), case
+        assert np.array_equal(bits(o["extra"][:, 0:4]), bits(r["gl_Position"])), case
+        assert np.array_equal(bits(o["extra"][:, 6:9]), bits(r["viewVecRaw"])), case
+        assert np.array_equal(bits(o["extra"][:, 9:12]), bits(r["normalVecInViewSpaceOnlyYaw"])), case
+        assert np.array_equal(bits(o["extra"][:, 12:16]), bits(r["heightmap_colour"])), case
+        u.viewProjection[:] = np.eye(4, dtype=np.float32).ravel()
+        rw = ref.vert_run(u, wu, heightmap, ids=ids)
+        assert np.array_equal(bits(o["pos"]), bits(rw["gl_Position"])), case
+
+
+def test_integer_vertex_id_semantics_match_shader_up_to_4096(oracle, ref, heightmap):
+    """water-grid.vert:125 derives (col,row) with a float mod(); exact for gridLength <= 4096 (2^24 ids).
+    The oracle/kernels use exact integers — identical there, and well defined beyond."""
+    L = 4096
+    sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), api.default_params(), L, heightmap)
+    st, u, wu = sc.oracle_uniforms(oracle)
+    ids = np.array([L * L - 1, L * L - L, L * 4095 + 4094, 16777215, 12345678, 4095, 4096, 8191], np.int64)
+    u.viewProjection[:] = np.eye(4, dtype=np.float32).ravel()
+    o = oracle.eval(u, wu, heightmap, ids=ids)
+    r = ref.vert_run(u, wu, heightmap, ids=ids)
+    assert np.array_equal(bits(o["pos"]), bits(r["gl_Position"]))

@@ -1,0 +1,255 @@
+"""ctypes view of the C ABI (include/wavetool_b200.h) plus a small convenience class.
+
+This is harness code for tests/ and bench.py: the product is the shared library.  Nothing here
+computes surface values on the CPU, and nothing here touches oracle/ — if the CUDA library is
+missing or no B200 is visible, device calls raise (there is no fallback path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+WT_OK, WT_NO_GRID = 0, 1
+WT_ERR_INVALID_ARGUMENT, WT_ERR_CUDA, WT_ERR_NO_DEVICE, WT_ERR_NOT_READY, WT_ERR_DEGENERATE = -1, -2, -3, -4, -5
+WT_MAX_WAVES = 1000
+FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER = 0x1, 0x2, 0x4, 0x8
+
+# every symbol include/wavetool_b200.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTED_SYMBOLS = [
+    "wt_version", "wt_last_error", "wt_device_count",
+    "wt_default_params", "wt_default_camera", "wt_default_waves", "wt_camera_matrices",
+    "wt_total_amplitude", "wt_steepness_Q_i", "wt_sun_position", "wt_bounce_displacement",
+    "wt_project_grid", "wt_build_frame",
+    "wt_create", "wt_destroy", "wt_set_waves", "wt_set_heightmap_rgba8", "wt_set_skybox_rgba8",
+    "wt_eval_frame", "wt_eval_batch", "wt_eval_frame_host", "wt_launch_count", "wt_measure_peak",
+]
+
+
+class Wave(C.Structure):
+    _fields_ = [("amplitude_A", C.c_float), ("frequency_w", C.c_float), ("phaseConstant_phi", C.c_float),
+                ("steepness_Q", C.c_float), ("dir_x", C.c_float), ("dir_z", C.c_float)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fov_deg", C.c_float), ("aspect", C.c_float), ("z_near", C.c_float), ("z_far", C.c_float),
+                ("pos", C.c_float * 3), ("yaw_deg", C.c_float), ("pitch_deg", C.c_float)]
+
+
+class Params(C.Structure):
+    _fields_ = [("heightmapDisplacementScale", C.c_float), ("heightmapSampleScale", C.c_float),
+                ("verticalBounceWaveAmplitude", C.c_float), ("verticalBounceWavePhase", C.c_float),
+                ("waveAnimationTimeInSeconds", C.c_float), ("timeOfDayInHours", C.c_float),
+                ("sunShininess", C.c_float), ("sunStrength", C.c_float)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("bottomLeftGridPointInWorld", C.c_float * 4), ("bottomRightGridPointInWorld", C.c_float * 4),
+                ("topLeftGridPointInWorld", C.c_float * 4), ("topRightGridPointInWorld", C.c_float * 4),
+                ("viewProjection", C.c_float * 16), ("viewMatOnlyYaw", C.c_float * 16),
+                ("cameraPosition", C.c_float * 3), ("waveAnimationTimeInSeconds", C.c_float),
+                ("verticalBounceWaveDisplacement", C.c_float), ("heightmapDisplacementScale", C.c_float),
+                ("heightmapSampleScale", C.c_float), ("sunShininess", C.c_float),
+                ("sunPosition", C.c_float * 3), ("sunStrength", C.c_float)]
+
+
+class Checksum(C.Structure):
+    _fields_ = [("position_bits", C.c_uint64), ("normal_bits", C.c_uint64), ("shade_bits", C.c_uint64),
+                ("min_y", C.c_float), ("max_y", C.c_float), ("vertices", C.c_uint64)]
+
+    def as_tuple(self):
+        return (self.position_bits, self.normal_bits, self.shade_bits, self.min_y, self.max_y, self.vertices)
+
+
+CHECKSUM_DTYPE = np.dtype([("position_bits", "u8"), ("normal_bits", "u8"), ("shade_bits", "u8"),
+                           ("min_y", "f4"), ("max_y", "f4"), ("vertices", "u8")])
+assert CHECKSUM_DTYPE.itemsize == C.sizeof(Checksum) == 40
+
+_lib = None
+
+
+class WaveToolError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"wavetool_b200 status {status}: {msg}")
+        self.status = status
+
+
+def lib(build_if_missing: bool = True) -> C.CDLL:
+    """Loads wave_tool_b200/libwavetool_b200.so (building it in-tree first if it is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB_PATH):
+        raise WaveToolError(WT_ERR_NO_DEVICE, f"{_build.LIB_PATH} is missing: the CUDA extension is required (no CPU fallback)")
+    L = C.CDLL(_build.LIB_PATH)
+    L.wt_version.restype = C.c_char_p
+    L.wt_last_error.restype = C.c_char_p
+    L.wt_last_error.argtypes = [C.c_void_p]
+    L.wt_default_params.argtypes = [C.POINTER(Params)]
+    L.wt_default_camera.argtypes = [C.POINTER(Camera), C.c_float]
+    L.wt_default_waves.argtypes = [C.POINTER(Wave)]
+    L.wt_camera_matrices.argtypes = [C.POINTER(Camera)] + [C.c_void_p] * 5
+    L.wt_total_amplitude.restype = C.c_float
+    L.wt_total_amplitude.argtypes = [C.c_void_p, C.c_uint]
+    L.wt_steepness_Q_i.restype = C.c_float
+    L.wt_steepness_Q_i.argtypes = [C.POINTER(Wave), C.c_uint]
+    L.wt_sun_position.argtypes = [C.c_float, C.c_void_p]
+    L.wt_bounce_displacement.restype = C.c_float
+    L.wt_bounce_displacement.argtypes = [C.c_float, C.c_float]
+    L.wt_project_grid.argtypes = [C.POINTER(Camera), C.c_float, C.c_void_p]
+    L.wt_build_frame.argtypes = [C.POINTER(Camera), C.POINTER(Params), C.c_float, C.POINTER(Frame)]
+    L.wt_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    L.wt_destroy.argtypes = [C.c_void_p]
+    L.wt_set_waves.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+    L.wt_set_heightmap_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.wt_set_skybox_rgba8.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int]
+    L.wt_eval_frame.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_uint, C.c_void_p]
+    L.wt_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_uint, C.c_void_p, C.c_uint, C.c_void_p]
+    L.wt_eval_frame_host.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_uint]
+    L.wt_launch_count.restype = C.c_uint64
+    L.wt_launch_count.argtypes = [C.c_void_p]
+    L.wt_measure_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(status, ctx=None):
+    if status < 0:
+        raise WaveToolError(status, (lib().wt_last_error(ctx) or b"").decode())
+    return status
+
+
+# ------------------------------------------------------------------------------------------------
+# host math wrappers
+# ------------------------------------------------------------------------------------------------
+def default_params() -> Params:
+    p = Params()
+    lib().wt_default_params(C.byref(p))
+    return p
+
+
+def default_camera(aspect: float = 1.0) -> Camera:
+    c = Camera()
+    lib().wt_default_camera(C.byref(c), aspect)
+    return c
+
+
+def waves_array(rows) -> np.ndarray:
+    """(W,6) float32 rows [A, w, phi, Q, Dx, Dz] — the memory layout of wt_wave[W]."""
+    a = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 6)
+    return a
+
+
+def default_waves() -> np.ndarray:
+    w = (Wave * 4)()
+    lib().wt_default_waves(w)
+    return np.frombuffer(w, dtype=np.float32).reshape(4, 6).copy()
+
+
+def total_amplitude(waves: np.ndarray) -> float:
+    w = waves_array(waves)
+    return float(lib().wt_total_amplitude(w.ctypes.data, len(w)))
+
+
+def camera_matrices(cam: Camera):
+    out = [np.zeros(16, np.float32) for _ in range(4)] + [np.zeros(3, np.float32)]
+    _check(lib().wt_camera_matrices(C.byref(cam), *[o.ctypes.data for o in out]))
+    return {"view": out[0], "proj": out[1], "view_proj": out[2], "view_only_yaw": out[3], "forward": out[4]}
+
+
+def project_grid(cam: Camera, displaceable_amplitude: float):
+    corners = np.zeros((4, 4), np.float32)
+    st = _check(lib().wt_project_grid(C.byref(cam), C.c_float(displaceable_amplitude), corners.ctypes.data))
+    return st, corners
+
+
+def build_frame(cam: Camera, params: Params, total_wave_amplitude: float):
+    f = Frame()
+    st = _check(lib().wt_build_frame(C.byref(cam), C.byref(params), C.c_float(total_wave_amplitude), C.byref(f)))
+    return st, f
+
+
+# ------------------------------------------------------------------------------------------------
+# device context
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """Owns a wt_ctx.  Raises WaveToolError(WT_ERR_NO_DEVICE) when no B200 is visible."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        self._lib = lib()
+        _check(self._lib.wt_create(C.byref(self._h), device))
+        self.device = device
+        self.n_waves = 0
+
+    def close(self):
+        if self._h:
+            self._lib.wt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_waves(self, waves: np.ndarray):
+        w = waves_array(waves)
+        _check(self._lib.wt_set_waves(self._h, w.ctypes.data, len(w)), self._h)
+        self.n_waves = len(w)
+
+    def set_heightmap(self, rgba: np.ndarray):
+        a = np.ascontiguousarray(rgba, np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 4
+        _check(self._lib.wt_set_heightmap_rgba8(self._h, a.ctypes.data, a.shape[1], a.shape[0]), self._h)
+
+    def set_skybox(self, faces: np.ndarray):
+        a = np.ascontiguousarray(faces, np.uint8)
+        assert a.ndim == 4 and a.shape[0] == 6 and a.shape[1] == a.shape[2] and a.shape[3] == 4
+        ptrs = (C.c_void_p * 6)(*[a[f].ctypes.data for f in range(6)])
+        _check(self._lib.wt_set_skybox_rgba8(self._h, ptrs, a.shape[1]), self._h)
+
+    def eval_frame(self, frame: Frame, grid_len: int, d_pos: int, d_normal: int, d_shade: int = 0, d_checksum: int = 0,
+                   flags: int = 0, rows=None, stream: int = 0):
+        """Device-pointer entry point (ints are raw device addresses, e.g. torch.Tensor.data_ptr())."""
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        return _check(self._lib.wt_eval_frame(self._h, C.byref(frame), grid_len, r0, r1, d_pos, d_normal, d_shade or None,
+                                              d_checksum or None, flags, stream or None), self._h)
+
+    def eval_batch(self, frames, grid_len: int, d_pos_ring: int, d_normal_ring: int, d_shade_ring: int = 0, ring_depth: int = 2,
+                   d_checksums: int = 0, flags: int = 0, rows=None, stream: int = 0):
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        arr = (Frame * len(frames))(*frames) if not isinstance(frames, C.Array) else frames
+        return _check(self._lib.wt_eval_batch(self._h, arr, len(arr), grid_len, r0, r1, d_pos_ring, d_normal_ring, d_shade_ring or None,
+                                              ring_depth, d_checksums or None, flags, stream or None), self._h)
+
+    def eval_frame_host(self, frame: Frame, grid_len: int, flags: int = 0, rows=None, want_pos=True, want_normal=True,
+                        want_checksum=False):
+        """Host-buffer entry point: returns numpy arrays (n,4) copied back from the device."""
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        n = (r1 - r0) * grid_len
+        pos = np.empty((n, 4), np.float32) if want_pos else None
+        nrm = np.empty((n, 4), np.float32) if want_normal else None
+        shd = np.empty((n, 4), np.float32) if (flags & FLAG_SHADE) else None
+        cks = Checksum() if want_checksum else None
+        _check(self._lib.wt_eval_frame_host(self._h, C.byref(frame), grid_len, r0, r1,
+                                            pos.ctypes.data if want_pos else None, nrm.ctypes.data if want_normal else None,
+                                            shd.ctypes.data if shd is not None else None,
+                                            C.byref(cks) if cks is not None else None, flags), self._h)
+        return {"pos": pos, "normal": nrm, "shade": shd, "checksum": cks}
+
+    def launch_count(self) -> int:
+        return int(self._lib.wt_launch_count(self._h))
+
+    def measure_peak(self, kind: int) -> float:
+        v = C.c_double()
+        _check(self._lib.wt_measure_peak(self._h, kind, C.byref(v)), self._h)
+        return v.value

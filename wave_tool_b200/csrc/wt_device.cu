@@ -1,0 +1,443 @@
+// Device context and the evaluation entry points of the C ABI (include/wavetool_b200.h).
+//
+// Replaces the host side of the reference's water draw call: uniform upload + glDrawElements
+// (src/render-engine.cpp:1045-1122).  There is NO CPU fallback: every entry point here needs a CUDA
+// device and fails with WT_ERR_NO_DEVICE / WT_ERR_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "wt_internal.h"
+#include "wt_kernels.cuh"
+
+namespace wt {
+
+static thread_local std::string g_thread_error;
+
+int set_thread_error(int code, const char* msg) {
+    g_thread_error = msg ? msg : "";
+    return code;
+}
+
+}  // namespace wt
+
+using namespace wt;
+
+struct wt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    // wave tables (host copies; handed to the kernels as __grid_constant__ parameters per launch)
+    unsigned n_waves = 0;
+    bool waves_set = false;
+    std::vector<WaveK> tab_exact, tab_fast, tab_raw;
+    // textures
+    float* d_hm_r = nullptr;
+    int hm_w = 0, hm_h = 0;
+    uchar4* d_sky = nullptr;
+    int sky_n = 0;
+    // scratch for the *_host entry points
+    float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
+    size_t s_elems = 0;
+    wt_checksum* s_cks = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(wt_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    set_thread_error(code, msg.c_str());
+    return code;
+}
+
+#define WT_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(ctx, WT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Launch planning for surface_tile_kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int V_ROWS = 4;   // rows evaluated per thread per marching step
+
+struct Plan {
+    int S = 128, strip_cols = 126, n_strips = 1, rows_per_chunk = 1, n_chunks = 1;
+    size_t smem = 0;
+};
+
+template <typename K>
+int ctas_per_sm(K kernel, int S, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, S, smem) != cudaSuccess) n = 0;
+    return std::max(n, 1);
+}
+
+// Chooses the strip width S (threads per CTA, each owning one column incl. 2 halo columns) and the
+// rows per chunk so that  (a) few lanes idle,  (b) the CTAs fill whole waves of the 148 SMs,
+// (c) the +2 halo rows and the round-up to V rows cost little.  Cost model: every resident CTA slot
+// is busy for (marching steps * V) rows; a partially filled wave costs as much as a full one.
+template <typename K>
+Plan make_plan(K kernel, int sm_count, int L, int rows) {
+    Plan best;
+    double best_cost = 1e300;
+    for (int S = 64; S <= 256; S += 32) {
+        const size_t smem = (size_t)2 * (V_ROWS + 1) * S * sizeof(float4);
+        const int per_sm = ctas_per_sm(kernel, S, smem);
+        const long long slots = (long long)sm_count * per_sm;
+        const int n_strips = (L + (S - 2) - 1) / (S - 2);
+        const int strip_cols = (L + n_strips - 1) / n_strips;
+        const int max_chunks = std::max(1, rows / 8);
+        for (int waves = 1; waves <= 4; ++waves) {
+            int n_chunks = (int)std::min<long long>(max_chunks, std::max<long long>(1, waves * slots / n_strips));
+            int rpc = (rows + n_chunks - 1) / n_chunks;
+            // make rpc + 2 a multiple of V so no marching step is partly wasted
+            rpc = ((rpc + 2 + V_ROWS - 1) / V_ROWS) * V_ROWS - 2;
+            if (rpc < 2) rpc = 2;
+            n_chunks = (rows + rpc - 1) / rpc;
+            const long long ctas = (long long)n_strips * n_chunks;
+            const long long rounds = (ctas + slots - 1) / slots;
+            const int steps = (rpc + 2 + V_ROWS - 1) / V_ROWS;
+            // time ~ rounds * (threads resident per SM) * rows marched per CTA
+            const double cost = (double)rounds * per_sm * S * steps * V_ROWS;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.S = S; best.strip_cols = strip_cols; best.n_strips = n_strips;
+                best.rows_per_chunk = rpc; best.n_chunks = n_chunks; best.smem = smem;
+            }
+        }
+    }
+    return best;
+}
+
+int wave_capacity(unsigned n) { return n <= 16 ? 16 : n <= 64 ? 64 : n <= 256 ? 256 : 1000; }
+
+template <int CAP>
+void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
+    std::memset(&t, 0, sizeof(t));
+    std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
+}
+
+template <int CAP, bool EXACT, bool SHADE>
+cudaError_t launch_tile(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    auto kernel = surface_tile_kernel<CAP, V_ROWS, EXACT, SHADE>;
+    static thread_local struct { int L = -1, rows = -1, dev = -1; Plan p; } cache;   // per instantiation
+    const int rows = a.row_end - a.row_begin;
+    if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cache.p = make_plan(kernel, ctx->sm_count, a.L, rows);
+        cache.L = a.L; cache.rows = rows; cache.dev = ctx->device;
+    }
+    const Plan& p = cache.p;
+    a.strip_cols = p.strip_cols;
+    a.rows_per_chunk = p.rows_per_chunk;
+    static thread_local WaveTable<CAP> table;
+    fill_table(table, tab);
+    for (size_t i = 0; i < tab.size(); ++i) table.w[i].phi = tab[i].phi * a.t;   // fl(phi * t), water-grid.vert:78
+    kernel<<<dim3(p.n_strips, p.n_chunks), p.S, p.smem, stream>>>(a, table);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+template <int CAP, bool SHADE>
+cudaError_t launch_reference_order(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    static thread_local WaveTable<CAP> table;
+    fill_table(table, tab);
+    const long long n = (long long)(a.row_end - a.row_begin) * a.L;
+    int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    surface_reference_order_kernel<CAP, SHADE><<<std::max(blocks, 1), 256, 0, stream>>>(a, table);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+template <int CAP>
+cudaError_t dispatch_cap(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
+    const bool shade = flags & WT_FLAG_SHADE;
+    if (flags & WT_FLAG_REFERENCE_ORDER)
+        return shade ? launch_reference_order<CAP, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<CAP, false>(ctx, a, ctx->tab_raw, stream);
+    if (flags & WT_FLAG_FAST_PHASE)
+        return shade ? launch_tile<CAP, false, true>(ctx, a, ctx->tab_fast, stream) : launch_tile<CAP, false, false>(ctx, a, ctx->tab_fast, stream);
+    return shade ? launch_tile<CAP, true, true>(ctx, a, ctx->tab_exact, stream) : launch_tile<CAP, true, false>(ctx, a, ctx->tab_exact, stream);
+}
+
+int validate_eval(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
+                  void* d_cks, unsigned flags) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (!frame) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "frame is NULL");
+    if (L < 2) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "grid_len must be >= 2 (water-grid.vert:53)");
+    if (L > 32768) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "grid_len must be <= 32768");
+    if (r0 >= r1 || r1 > L) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "need 0 <= row_begin < row_end <= grid_len");
+    if (!d_pos || !d_nrm) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "position/normal output buffers are NULL");
+    if ((flags & WT_FLAG_SHADE) && !d_shade) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_SHADE needs a shade buffer");
+    if ((flags & WT_FLAG_CHECKSUM) && !d_cks) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_CHECKSUM needs a checksum buffer");
+    if (!ctx->waves_set) return fail(ctx, WT_ERR_NOT_READY, "wt_set_waves has not been called");
+    if (!ctx->d_hm_r) return fail(ctx, WT_ERR_NOT_READY, "wt_set_heightmap_rgba8 has not been called (the reference draws no water without a heightmap, program.cpp:721)");
+    return WT_OK;
+}
+
+EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
+                   void* d_cks, unsigned flags) {
+    EvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.blx = f.bottomLeftGridPointInWorld[0]; a.blz = f.bottomLeftGridPointInWorld[2];
+    a.brx = f.bottomRightGridPointInWorld[0]; a.brz = f.bottomRightGridPointInWorld[2];
+    a.tlx = f.topLeftGridPointInWorld[0]; a.tlz = f.topLeftGridPointInWorld[2];
+    a.trx = f.topRightGridPointInWorld[0]; a.trz = f.topRightGridPointInWorld[2];
+    a.t = f.waveAnimationTimeInSeconds;
+    a.bounce = f.verticalBounceWaveDisplacement;
+    a.hm_disp = f.heightmapDisplacementScale;
+    a.hm_scale = f.heightmapSampleScale;
+    a.camx = f.cameraPosition[0]; a.camy = f.cameraPosition[1]; a.camz = f.cameraPosition[2];
+    a.du = 1.0f / (float)(L - 1);   // water-grid.vert:123 (IEEE division on the host)
+    a.sunx = f.sunPosition[0]; a.suny = f.sunPosition[1]; a.sunz = f.sunPosition[2];
+    a.sun_shininess = f.sunShininess;
+    a.sun_strength = f.sunStrength;
+    a.n_waves = (int)ctx->n_waves;
+    a.hm_r = ctx->d_hm_r; a.hm_w = ctx->hm_w; a.hm_h = ctx->hm_h;
+    a.hm_pow2 = ((ctx->hm_w & (ctx->hm_w - 1)) == 0) && ((ctx->hm_h & (ctx->hm_h - 1)) == 0);
+    a.sky = ctx->d_sky; a.sky_n = ctx->sky_n;
+    a.pos = (float4*)d_pos; a.nrm = (float4*)d_nrm; a.shade = (float4*)d_shade;
+    a.cks = (flags & WT_FLAG_CHECKSUM) ? (wt_checksum*)d_cks : nullptr;
+    a.L = (int)L; a.row_begin = (int)r0; a.row_end = (int)r1;
+    return a;
+}
+
+cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
+    switch (wave_capacity(ctx->n_waves)) {
+        case 16: return dispatch_cap<16>(ctx, a, flags, stream);
+        case 64: return dispatch_cap<64>(ctx, a, flags, stream);
+        case 256: return dispatch_cap<256>(ctx, a, flags, stream);
+        default: return dispatch_cap<1000>(ctx, a, flags, stream);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wt_version(void) { return "wavetool_b200 0.1.0 (sm_100a)"; }
+
+const char* wt_last_error(const wt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_thread_error.c_str(); }
+
+int wt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int wt_create(wt_ctx** out, int device) {
+    if (!out) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_create: out is NULL");
+    *out = nullptr;
+    int n = wt_device_count();
+    if (n <= 0) return fail(nullptr, WT_ERR_NO_DEVICE, "wt_create: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_create: device index out of range");
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    WT_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(nullptr, WT_ERR_NO_DEVICE, "wt_create: device is not sm_100 (kernels are built for sm_100a only)");
+    wt_ctx* ctx = new wt_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    WT_CUDA(nullptr, cudaMalloc(&ctx->s_cks, sizeof(wt_checksum)));
+    *out = ctx;
+    return WT_OK;
+}
+
+void wt_destroy(wt_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    cudaFree(ctx->d_hm_r);
+    cudaFree(ctx->d_sky);
+    cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
+    delete ctx;
+}
+
+int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_set_waves: ctx is NULL");
+    if (count > WT_MAX_WAVES) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_waves: count exceeds WT_MAX_WAVES");
+    if (count && !waves) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_waves: waves is NULL");
+    for (unsigned i = 0; i < count; ++i) {   // the reference's constructor asserts, render-engine.h:147-154
+        const wt_wave& w = waves[i];
+        float len = std::sqrt(w.dir_x * w.dir_x + w.dir_z * w.dir_z);
+        if (!(w.amplitude_A >= 0.0f) || !(w.frequency_w >= 0.0f) || !(w.phaseConstant_phi >= 0.0f) || !(w.steepness_Q >= 0.0f && w.steepness_Q <= 1.0f) ||
+            !(len >= 1.0f - 0.001f && len <= 1.0f + 0.001f))
+            return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_waves: wave " + std::to_string(i) + " violates the GerstnerWave constraints (render-engine.h:147-154)");
+    }
+    ctx->tab_exact.assign(count, WaveK{});
+    ctx->tab_fast.assign(count, WaveK{});
+    ctx->tab_raw.assign(count, WaveK{});
+    for (unsigned i = 0; i < count; ++i) {
+        const wt_wave& w = waves[i];
+        const float Qi = wt_steepness_Q_i(&w, count);   // render-engine.cpp:1073
+        // horizontal coefficient A*Q_i*D folded in double and rounded once (the shader rounds three
+        // times: A * (D * (Q_i * cos)); the difference is <= 2 ulp of a term bounded by Q/(w*count))
+        const float cX = (float)((double)w.amplitude_A * (double)Qi * (double)w.dir_x);
+        const float cZ = (float)((double)w.amplitude_A * (double)Qi * (double)w.dir_z);
+        ctx->tab_exact[i] = {w.dir_x, w.dir_z, w.frequency_w, w.phaseConstant_phi, cX, w.amplitude_A, cZ, 0.f};
+        ctx->tab_fast[i] = {(float)((double)w.frequency_w * w.dir_x), (float)((double)w.frequency_w * w.dir_z), w.frequency_w, w.phaseConstant_phi, cX, w.amplitude_A, cZ, 0.f};
+        ctx->tab_raw[i] = {w.dir_x, w.dir_z, w.frequency_w, w.phaseConstant_phi, Qi, w.amplitude_A, 0.f, 0.f};
+    }
+    ctx->n_waves = count;
+    ctx->waves_set = true;
+    return WT_OK;
+}
+
+int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int w, int h) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_set_heightmap_rgba8: ctx is NULL");
+    if (!rgba || w <= 0 || h <= 0 || w > 16384 || h > 16384) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_heightmap_rgba8: bad image");
+    DeviceGuard g(ctx->device);
+    // water-grid.vert:106-111 reads only .r; stage it as the exact unorm value c/255.0f
+    std::vector<float> r((size_t)w * h);
+    for (size_t i = 0; i < r.size(); ++i) r[i] = (float)rgba[4 * i] / 255.0f;
+    cudaFree(ctx->d_hm_r);
+    ctx->d_hm_r = nullptr;
+    WT_CUDA(ctx, cudaMalloc(&ctx->d_hm_r, r.size() * sizeof(float)));
+    WT_CUDA(ctx, cudaMemcpy(ctx->d_hm_r, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->hm_w = w; ctx->hm_h = h;
+    return WT_OK;
+}
+
+int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: ctx is NULL");
+    if (!faces || n <= 0 || n > 16384) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: bad cubemap");
+    for (int f = 0; f < 6; ++f) if (!faces[f]) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: face pointer is NULL");
+    DeviceGuard g(ctx->device);
+    cudaFree(ctx->d_sky);
+    ctx->d_sky = nullptr;
+    const size_t face_bytes = (size_t)n * n * 4;
+    WT_CUDA(ctx, cudaMalloc(&ctx->d_sky, 6 * face_bytes));
+    for (int f = 0; f < 6; ++f) WT_CUDA(ctx, cudaMemcpy((uint8_t*)ctx->d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice));
+    ctx->sky_n = n;
+    return WT_OK;
+}
+
+int wt_eval_frame(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
+                  void* d_cks, unsigned flags, void* stream_) {
+    int st = validate_eval(ctx, frame, L, r0, r1, d_pos, d_nrm, d_shade, d_cks, flags);
+    if (st != WT_OK) return st;
+    DeviceGuard g(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EvalArgs a = make_args(ctx, *frame, L, r0, r1, d_pos, d_nrm, d_shade, d_cks, flags);
+    if (a.cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
+    if (a.cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    WT_CUDA(ctx, cudaGetLastError());
+    return WT_OK;
+}
+
+int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsigned L, unsigned r0, unsigned r1, void* d_pos_ring,
+                  void* d_nrm_ring, void* d_shade_ring, unsigned ring_depth, void* d_checksums, unsigned flags, void* stream_) {
+    if (n_frames == 0) return WT_OK;
+    if (ring_depth == 0) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_eval_batch: ring_depth must be >= 1");
+    int st = validate_eval(ctx, frames, L, r0, r1, d_pos_ring, d_nrm_ring, d_shade_ring, d_checksums, flags);
+    if (st != WT_OK) return st;
+    DeviceGuard g(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool cks = flags & WT_FLAG_CHECKSUM;
+    if (cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    const size_t slot = (size_t)(r1 - r0) * L;
+    for (unsigned f = 0; f < n_frames; ++f) {
+        const size_t off = (size_t)(f % ring_depth) * slot;
+        EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
+                               d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
+        WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
+    }
+    if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    WT_CUDA(ctx, cudaGetLastError());
+    return WT_OK;
+}
+
+int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, float* h_pos, float* h_nrm, float* h_shade,
+                       wt_checksum* h_cks, unsigned flags) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (L < 2 || r0 >= r1 || r1 > L) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "need grid_len >= 2 and 0 <= row_begin < row_end <= grid_len");
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)(r1 - r0) * L;
+    if (n > ctx->s_elems) {
+        cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade);
+        ctx->s_pos = ctx->s_nrm = ctx->s_shade = nullptr;
+        ctx->s_elems = 0;
+        WT_CUDA(ctx, cudaMalloc(&ctx->s_pos, n * sizeof(float4)));
+        WT_CUDA(ctx, cudaMalloc(&ctx->s_nrm, n * sizeof(float4)));
+        WT_CUDA(ctx, cudaMalloc(&ctx->s_shade, n * sizeof(float4)));
+        ctx->s_elems = n;
+    }
+    if (h_cks) flags |= WT_FLAG_CHECKSUM; else flags &= ~WT_FLAG_CHECKSUM;
+    int st = wt_eval_frame(ctx, frame, L, r0, r1, ctx->s_pos, ctx->s_nrm, ctx->s_shade, ctx->s_cks, flags, nullptr);
+    if (st != WT_OK) return st;
+    if (h_pos) WT_CUDA(ctx, cudaMemcpy(h_pos, ctx->s_pos, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (h_nrm) WT_CUDA(ctx, cudaMemcpy(h_nrm, ctx->s_nrm, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (h_shade && (flags & WT_FLAG_SHADE)) WT_CUDA(ctx, cudaMemcpy(h_shade, ctx->s_shade, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (h_cks) WT_CUDA(ctx, cudaMemcpy(h_cks, ctx->s_cks, sizeof(wt_checksum), cudaMemcpyDeviceToHost));
+    WT_CUDA(ctx, cudaDeviceSynchronize());
+    return WT_OK;
+}
+
+uint64_t wt_launch_count(const wt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second) {
+    if (!ctx || !per_second) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_measure_peak: NULL argument");
+    DeviceGuard g(ctx->device);
+    cudaEvent_t e0, e1;
+    WT_CUDA(ctx, cudaEventCreate(&e0));
+    WT_CUDA(ctx, cudaEventCreate(&e1));
+    float* sink = nullptr;
+    WT_CUDA(ctx, cudaMalloc(&sink, 256));
+    double best = 0.0;
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    if (kind == 0 || kind == 1) {
+        const int iters = 4096;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0);
+            if (kind == 0) peak_mufu_kernel<<<blocks, threads>>>(sink, iters);
+            else peak_fma_kernel<<<blocks, threads>>>(sink, iters);
+            cudaEventRecord(e1);
+            WT_CUDA(ctx, cudaEventSynchronize(e1));
+            ctx->launches++;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            // kind 0: sin+cos PAIRS per second (2 MUFU ops each); kind 1: FLOP/s (2 per FMA)
+            double work = (double)blocks * threads * 8.0 * iters * (kind == 0 ? 1.0 : 2.0);
+            if (rep > 0) best = std::max(best, work / (ms * 1e-3));
+        }
+    } else if (kind == 2) {
+        const size_t n = (size_t)1 << 26;   // 64 Mi float4 = 1 GiB
+        float4* buf = nullptr;
+        WT_CUDA(ctx, cudaMalloc(&buf, n * sizeof(float4)));
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0);
+            peak_store_kernel<<<ctx->sm_count * 16, 256>>>(buf, n);
+            cudaEventRecord(e1);
+            WT_CUDA(ctx, cudaEventSynchronize(e1));
+            ctx->launches++;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0) best = std::max(best, (double)n * sizeof(float4) / (ms * 1e-3));
+        }
+        cudaFree(buf);
+    } else {
+        cudaFree(sink);
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_measure_peak: kind must be 0, 1 or 2");
+    }
+    cudaFree(sink);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *per_second = best;
+    return WT_OK;
+}
+
+}  // extern "C"
