@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — vertex-waves/s of the fused water-surface kernel (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one frame of the workload per GPU (frame sharding: global frame f runs on rank f mod N,
+no data-path collective; weak scaling).  Default workload = BASELINE.json configs[2], the one the
+metric ("ms per 4096^2 grid frame", ">=70% of roofline at a 4096^2 grid with 64 waves") is quoted on:
+4096x4096 projected grid, 64 seeded Gerstner waves + heightmap detail, finite-difference normals and the
+Fresnel / sky-cubemap / sun-specular terms, default camera.  Synthetic data (seeded waves, procedural
+heightmap and cubemap).  Rank 0 prints ONE JSON line.
+
+Timing: W >= 3 untimed warm-up steps, then EXACTLY K steps bracketed by barrier + synchronize, timed
+with CUDA events on the stream the kernels are launched on, max over ranks.  Every step writes
+805 MB of fresh output (>> the 126 MB L2) into a 2-deep ring, so no step can be served from L2.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (grid_len, n_waves, cfg seed, shade, description)
+    "cfg3": (4096, 64, 3, True, "configs[2]: 4096x4096 grid, 64 waves, normals + Fresnel/sky-cubemap/sun-specular terms"),
+    "cfg2": (1024, 8, 2, False, "configs[1]: 1024x1024 projected grid, 8 Gerstner waves + heightmap noise, animation frames"),
+    "cfg4": (8192, 256, 4, False, "configs[3]: 8192x8192 grid, 256 waves, frame batch sharded by frame"),
+}
+TRANSCENDENTALS_PER_VERTEX_WAVE = 2      # 1 sin + 1 cos (water-grid.vert:78-81), SURVEY.md §8d
+FLOP_PER_VERTEX_WAVE = 15
+SKYBOX_N = 2048                           # reference: 2048^2 faces (render-engine.h:191)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05] or self.rows
+        for _, line in rows:
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
+    """The reference's own CPU implementation of the path on the host cores: the reference
+    water-grid.vert shader text compiled as C++ (oracle/_ref, kind 'reference') when it was built,
+    else the oracle port (kind 'port').  Bounded sample: whole rows of the SAME frame until about
+    `seconds_target` seconds of wall time have been spent."""
+    from oracle import oracle as orc                      # cpu_baseline leg: the one place bench.py may use oracle/
+    from tests.common import Scene
+    from wave_tool_b200 import scenes
+    O = orc.Oracle()
+    R = orc.Ref()
+    hm = scenes.procedural_heightmap(512)
+    sc = Scene(scenes.seeded_waves(W, cfg=cfg), scenes.camera(), scenes.animation_params(75), L, hm)
+    st, u, wu = sc.oracle_uniforms(O)
+    use_ref = R.available and L <= 4096 and W <= R.max_waves()
+    rows_done, t_spent, chunk = 0, 0.0, 8
+    cores = O.num_threads()
+    while t_spent < seconds_target and rows_done + chunk <= L:
+        t0 = time.perf_counter()
+        if use_ref:
+            R.vert_run(u, wu, hm, id_range=(rows_done * L, (rows_done + chunk) * L))
+        else:
+            O.eval(u, wu, hm, rows=(rows_done, rows_done + chunk))
+        dt = time.perf_counter() - t0
+        t_spent += dt
+        rows_done += chunk
+        if t_spent + 2 * dt > max_seconds:
+            break
+        if dt < 1.0:
+            chunk = min(chunk * 2, 256)
+    vw = rows_done * L * W
+    return {"value": vw / t_spent, "unit": "vertex-waves/s", "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"rows [0,{rows_done}) of one {L}x{L} frame with {W} waves (vertex stage: positions + 4-neighbour normals), "
+                      f"{t_spent:.1f} s wall, OpenMP over vertices, g++ -O2 -ffp-contract=off",
+            "seconds": t_spent, "vertex_waves": vw}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L, W, cfg, shade, desc = WORKLOADS[args.workload]
+    vals = []
+    per_step = max(2.0, min(12.0, 60.0 / max(1, args.steps + args.warmup)))
+    base = None
+    for i in range(args.warmup + args.steps):
+        base = cpu_reference_rate(L, W, cfg, seconds_target=per_step, max_seconds=per_step * 2.5)
+        if i >= args.warmup:
+            vals.append(base)
+    total_vw = sum(b["vertex_waves"] for b in vals)
+    total_s = sum(b["seconds"] for b in vals)
+    value = total_vw / total_s
+    cb = dict(base)
+    cb["value"] = value
+    cb.pop("seconds", None); cb.pop("vertex_waves", None)
+    line = {"impl": "reference", "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "grid_len": L, "waves": W, "note": "each step is a bounded row sample of one frame on the host cores"},
+            "cpu_baseline": cb, "e2e": {"value": value, "unit": "vertex-waves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ms_per_frame_extrapolated": 1e3 * (L * L * W) / value}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from wave_tool_b200 import api, scenes, shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    L, W, cfg, shade, desc = WORKLOADS[args.workload]
+    K, Wm = args.steps, max(3, args.warmup)
+    flags = api.FLAG_SHADE if shade else 0
+    if args.fast_phase:
+        flags |= api.FLAG_FAST_PHASE
+
+    # ---- setup (untimed): context, wave table, textures, output ring ----------------------------
+    waves = scenes.seeded_waves(W, cfg=cfg)
+    cam = scenes.camera()
+    ctx = api.Context(local_rank)
+    ctx.set_waves(waves)
+    ctx.set_heightmap(scenes.procedural_heightmap(512))
+    if shade:
+        ctx.set_skybox(scenes.procedural_skybox(SKYBOX_N))
+    n = L * L
+    ring = 2
+    pos = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
+    nrm = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
+    shd = torch.empty((ring * n, 4), dtype=torch.float32, device=dev) if shade else None
+    total_frames = (Wm + K) * n_gpus
+    my_frames = shard.frame_shard(total_frames, rank, n_gpus)          # global frame indices of this rank
+    frames = scenes.frames_for_animation(cam, waves, first=rank, count=Wm + K, stride=n_gpus)
+    cks = torch.zeros((Wm + K) * 40, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    # roofline denominators measured on this very device (untimed)
+    mufu_pairs = ctx.measure_peak(0)
+    fma_flops = ctx.measure_peak(1)
+    store_bps = ctx.measure_peak(2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def launch(lo, hi, with_cks=False):
+        arr = (api.Frame * (hi - lo))(*frames[lo:hi])
+        ctx.eval_batch(arr, L, pos.data_ptr(), nrm.data_ptr(), shd.data_ptr() if shade else 0, ring,
+                       cks.data_ptr() + 40 * lo if with_cks else 0, flags=flags | (api.FLAG_CHECKSUM if with_cks else 0), stream=sp)
+
+    # ---- device-timed region: W warm-up steps, then exactly K steps ------------------------------
+    launch(0, Wm)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.15 if sampler else 0.0)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record(stream)
+    launch(Wm, Wm + K)
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    launches = ctx.launch_count() - l0
+    ms_local = e0.elapsed_time(e1)
+    ms = shard.max_over_ranks(ms_local, dev) if world > 1 else ms_local
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    vw_per_frame = n * W
+    value = n_gpus * K * vw_per_frame / (ms * 1e-3)
+    ms_per_step = ms / K
+
+    # ---- end-to-end through the C ABI with HOST inputs/outputs -----------------------------------
+    # per step: camera+params (host structs) -> wt_build_frame (host prologue) -> wt_eval_frame with the
+    # digest -> device->host read of the 40-byte result into pinned memory, synchronised every step.
+    pinned = torch.empty(40, dtype=torch.uint8).pin_memory()
+    total_amp = api.total_amplitude(waves)
+    h2d = C.sizeof(api.Frame) + 32 * W            # the uniforms + wave table every launch carries to the device
+    d2h = 40
+
+    def e2e_step(k):
+        f = my_frames[Wm + k] if Wm + k < len(my_frames) else my_frames[-1]
+        st, fr = api.build_frame(cam, scenes.animation_params(f), total_amp)
+        slot = k % ring
+        ctx.eval_frame(fr, L, pos.data_ptr() + slot * n * 16, nrm.data_ptr() + slot * n * 16, (shd.data_ptr() + slot * n * 16) if shade else 0,
+                       cks.data_ptr(), flags=flags | api.FLAG_CHECKSUM, stream=sp)
+        pinned.copy_(cks[:40], non_blocking=True)
+        stream.synchronize()
+
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        e2e_step(k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = shard.max_over_ranks(e2e_s, dev) if world > 1 else e2e_s
+    e2e_value = n_gpus * K * vw_per_frame / e2e_s
+
+    # full read-back variant: every output byte copied to pinned host memory each step (PCIe-bound)
+    rb = None
+    if args.readback and rank == 0:
+        hp = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        hn = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        hs = torch.empty((n, 4), dtype=torch.float32).pin_memory() if shade else None
+        t0 = time.perf_counter()
+        reps = min(K, 3)
+        for k in range(reps):
+            e2e_step(k)
+            hp.copy_(pos[:n], non_blocking=True); hn.copy_(nrm[:n], non_blocking=True)
+            if shade:
+                hs.copy_(shd[:n], non_blocking=True)
+            stream.synchronize()
+        dt = time.perf_counter() - t0
+        rb = {"value": reps * vw_per_frame / dt, "unit": "vertex-waves/s", "d2h_bytes_per_step": n * 16 * (3 if shade else 2), "n_gpus": 1}
+
+    # gather the per-frame digests of the timed frames (the only collective; after the timed region)
+    digests = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K]
+    if world > 1:
+        launch(Wm, Wm + K, with_cks=True)
+        torch.cuda.synchronize()
+        allr = shard.all_gather_checksums(cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K], dev)
+        digest_of_digests = shard.combine_checksums(allr.ravel())
+    else:
+        launch(Wm, Wm + K, with_cks=True)
+        torch.cuda.synchronize()
+        digest_of_digests = shard.combine_checksums(cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        kernel_ms = ms_local / K                                    # one evaluation kernel per step
+        trans_per_s = vw_per_frame * TRANSCENDENTALS_PER_VERTEX_WAVE / (kernel_ms * 1e-3)
+        sfu_peak = 2.0 * mufu_pairs                                  # measured MUFU-only micro-kernel, this device, this run
+        out_bytes = n * 16 * (3 if shade else 2)
+        hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        compute_bound = (vw_per_frame * 2 / sfu_peak) >= (out_bytes / (hbm_peak * 1e9))
+        roof_sfu = {"bound": "sfu", "achieved": trans_per_s / 1e9, "peak": sfu_peak / 1e9, "unit": "Gtranscendental/s",
+                    "frac": trans_per_s / sfu_peak, "traffic": traffic,
+                    "peak_source": "MUFU-only micro-kernel (sin+cos) measured on this device in this run (wt_measure_peak); "
+                                   "nominal 16/clk/SM x 148 SM x clocks.max.sm",
+                    "nominal_peak": 16 * 148 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6 / 1e9,
+                    "algorithmic_per_launch": {"vertex_waves": vw_per_frame, "transcendentals": vw_per_frame * 2,
+                                               "flop": vw_per_frame * FLOP_PER_VERTEX_WAVE, "bytes_written": out_bytes}}
+        roof_hbm = {"bound": "hbm", "achieved": out_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": out_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, of measured)" if peaks else "fallback 6650 GB/s",
+                    "store_stream_measured_gbs": store_bps / 1e9}
+        line = {
+            "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": n_gpus, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "grid_len": L, "waves": W, "shade": shade, "frames_per_step_per_gpu": 1,
+                       "parallelism": f"frame-sharded x{n_gpus} (frame f on rank f mod N), no data-path collective",
+                       "l2": "each step writes %d MB of fresh output into a 2-deep ring (> 126 MB L2)" % (out_bytes // 2 ** 20),
+                       "phase": "fast (pre-folded FMA)" if args.fast_phase else "bit-faithful fp32 phase"},
+            "ms_per_frame": ms_per_step,
+            "roofline": roof_sfu if compute_bound else roof_hbm,
+            "roofline_secondary": roof_hbm if compute_bound else roof_sfu,
+            "fp32_fma_peak_measured_tflops": fma_flops / 1e12,
+            "e2e": {"value": e2e_value, "unit": "vertex-waves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "host camera/params -> wt_build_frame -> wt_eval_frame(+digest) -> 40-byte digest read back to pinned host memory, synchronised every step"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "digest_of_timed_frames": {k: (int(v) if not isinstance(v, float) else v) for k, v in digest_of_digests.items()},
+        }
+        if rb:
+            line["e2e_full_readback"] = rb
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_rate(L, W, cfg)
+            cb.pop("seconds", None); cb.pop("vertex_waves", None)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3")
+    ap.add_argument("--fast-phase", action="store_true", help="use the pre-folded (not bit-faithful) wave phase")
+    ap.add_argument("--readback", action="store_true", help="also time full output read-back to pinned host memory")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

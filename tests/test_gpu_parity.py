@@ -1,0 +1,345 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs (and against the committed golden vectors of the reference's own code).
+
+Tolerances are BASELINE.json's: positions within 1e-4 x total wave amplitude, normals within 1e-3 rad
+(tests/common.py).  Everything that involves no transcendental is required to be BIT-EXACT."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import GOLDEN, Scene, angle_between, compare, numpy_checksum, reference_heightmap
+from wave_tool_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def gpu_eval(ctx, frame, L, flags=0, rows=None, checksum=False):
+    """Evaluate through wt_eval_frame into torch-owned device buffers; return numpy copies."""
+    torch = torch_mod()
+    r0, r1 = rows if rows is not None else (0, L)
+    n = (r1 - r0) * L
+    pos = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    nrm = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    shd = torch.empty((n, 4), dtype=torch.float32, device="cuda") if flags & api.FLAG_SHADE else None
+    cks = torch.zeros(40, dtype=torch.uint8, device="cuda") if checksum else None
+    f = flags | (api.FLAG_CHECKSUM if checksum else 0)
+    st = ctx.eval_frame(frame, L, pos.data_ptr(), nrm.data_ptr(), shd.data_ptr() if shd is not None else 0,
+                        cks.data_ptr() if cks is not None else 0, flags=f, rows=(r0, r1), stream=torch.cuda.current_stream().cuda_stream)
+    assert st == api.WT_OK
+    torch.cuda.synchronize()
+    out = {"pos": pos.cpu().numpy(), "normal": nrm.cpu().numpy(), "shade": shd.cpu().numpy() if shd is not None else None}
+    if checksum:
+        out["checksum"] = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[0]
+    return out
+
+
+def rows_to_ids(rows, L):
+    return np.concatenate([np.arange(r * L, (r + 1) * L, dtype=np.int64) for r in rows])
+
+
+def take_rows(full, rows, L, row_begin=0):
+    idx = np.concatenate([np.arange((r - row_begin) * L, (r - row_begin + 1) * L) for r in rows])
+    return {k: (v[idx] if isinstance(v, np.ndarray) and v.ndim == 2 else v) for k, v in full.items()}
+
+
+@pytest.fixture(scope="module")
+def hm():
+    return reference_heightmap()
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[0]: the reference default scene (513^2 grid, the 4 hard-coded wave slots)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("t", [0.0, 1.5])
+def test_cfg1_default_scene_full_grid(oracle, hm, t):
+    p = scenes.animation_params(int(round(t * 60)))
+    sc = Scene(scenes.default_waves(), scenes.camera(), p, 513, hm)
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    got = gpu_eval(ctx, frame, 513)
+    want = sc.oracle_eval(oracle)
+    stats = compare(got, want, sc, label=f"cfg1 t={t}")
+    print("cfg1", t, stats)
+    # the committed golden vectors of the reference's own shader (bit-exact with the oracle on CPU)
+    z = np.load(os.path.join(GOLDEN, "vert_default.npz"))
+    ids = z["ids"]
+    gold = {"pos": z[f"world_t{t}"], "normal": np.concatenate([z[f"out_t{t}"]["normal"], np.zeros((len(ids), 1), np.float32)], 1)}
+    compare({"pos": got["pos"][ids], "normal": got["normal"][ids]}, gold, sc, label="cfg1 golden")
+
+
+def test_cfg1_reference_order_kernel(oracle, hm):
+    """The straight transliteration (5 evaluations per vertex, libdevice sincosf, IEEE sqrt/div) must
+    sit much closer to the oracle than the tolerance: only sinf/cosf implementations differ."""
+    sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(90), 513, hm)
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    got = gpu_eval(ctx, frame, 513, flags=api.FLAG_REFERENCE_ORDER)
+    want = sc.oracle_eval(oracle)
+    stats = compare(got, want, sc, pos_tol=2e-6, normal_tol=2e-4, label="cfg1 reference-order")
+    print("cfg1 reference-order", stats)
+
+
+def test_no_transcendentals_means_bit_exact(oracle, hm):
+    """With zero waves the path is bilinear placement + heightmap bump + bounce only — no sin/cos — so
+    positions must match the oracle BIT FOR BIT (same fp32 operations in the same order), on every
+    projector edge case."""
+    for name, kw in scenes.EDGE_CAMERAS.items():
+        sc = Scene(np.zeros((0, 6), np.float32), scenes.camera(**kw), scenes.animation_params(17), 257, hm)
+        st, frame = sc.frame()
+        if st == api.WT_NO_GRID:
+            assert name == "looking_up_no_grid"
+            continue
+        ctx = sc.make_context()
+        got = gpu_eval(ctx, frame, 257)
+        want = sc.oracle_eval(oracle)
+        assert np.array_equal(got["pos"].view(np.uint32), want["pos"].view(np.uint32)), name
+        ang = angle_between(got["normal"][:, :3], want["normal"][:, :3])
+        flipped = angle_between(got["normal"][:, :3], -want["normal"][:, :3])
+        assert np.minimum(ang, flipped).max() < 2e-6, name      # rsqrt vs 1/sqrt: a few ulp of length only
+        assert (ang > 1e-3).sum() <= 2, name
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[1]: 1024^2 grid, 8 Gerstner waves + heightmap noise, animation
+# --------------------------------------------------------------------------------------------------
+def test_cfg2_animation_frames_and_batch(oracle, hm):
+    torch = torch_mod()
+    L, waves, cam = 1024, scenes.seeded_waves(8, cfg=2), scenes.camera()
+    frame_ids = [0, 1, 499, 999]
+    frames = [api.build_frame(cam, scenes.animation_params(f), api.total_amplitude(waves))[1] for f in frame_ids]
+    sc = Scene(waves, cam, scenes.animation_params(0), L, hm)
+    ctx = sc.make_context()
+    singles = []
+    for f, frame in zip(frame_ids, frames):
+        sc.params = scenes.animation_params(f)
+        got = gpu_eval(ctx, frame, L, checksum=True)
+        want = sc.oracle_eval(oracle)
+        stats = compare(got, want, sc, label=f"cfg2 frame {f}")
+        print("cfg2 frame", f, stats)
+        assert tuple(got["checksum"])[:3] == numpy_checksum(got["pos"], got["normal"], None)[:3]
+        assert got["checksum"]["min_y"] == got["pos"][:, 1].min() and got["checksum"]["max_y"] == got["pos"][:, 1].max()
+        assert got["checksum"]["vertices"] == L * L
+        singles.append(got)
+    # the golden vectors of the reference's own shader for this configuration (t = 0.5 -> frame 30)
+    z = np.load(os.path.join(GOLDEN, "vert_seeded8.npz"))
+    sc.params = scenes.animation_params(30)
+    got = gpu_eval(ctx, sc.frame()[1], L)
+    gold = {"pos": z["world"], "normal": np.concatenate([z["out"]["normal"], np.zeros((len(z["ids"]), 1), np.float32)], 1)}
+    compare({"pos": got["pos"][z["ids"]], "normal": got["normal"][z["ids"]]}, gold, sc, label="cfg2 golden")
+    # wt_eval_batch: ring of 2 buffers + per-frame digests == the single-frame calls, bit for bit
+    n = L * L
+    ring_p = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
+    ring_n = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
+    cks = torch.zeros(40 * len(frames), dtype=torch.uint8, device="cuda")
+    ctx.eval_batch(frames, L, ring_p.data_ptr(), ring_n.data_ptr(), 0, 2, cks.data_ptr(), flags=api.FLAG_CHECKSUM,
+                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    digests = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
+    for k, s in enumerate(singles):
+        assert digests[k] == s["checksum"], k
+    last = len(frames) - 1
+    assert np.array_equal(ring_p[(last % 2) * n:(last % 2 + 1) * n].cpu().numpy(), singles[last]["pos"])
+    assert np.array_equal(ring_n[((last - 1) % 2) * n:((last - 1) % 2 + 1) * n].cpu().numpy(), singles[last - 1]["normal"])
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[2]: 4096^2 grid, 64 waves, normals + Fresnel / sky cubemap / sun specular
+# --------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cfg3(hm):
+    sc = Scene(scenes.seeded_waves(64, cfg=3), scenes.camera(), scenes.animation_params(75), 4096, hm, skybox=scenes.procedural_skybox(512))
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    return sc, frame, ctx
+
+
+def test_cfg3_shaded_vs_oracle_on_sampled_rows(oracle, cfg3):
+    sc, frame, ctx = cfg3
+    L = sc.L
+    rows = [0, 1, 2, 117, 118, 119, 120, 121, 1500, 2047, 2048, 3333, 4093, 4094, 4095]
+    got = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE, checksum=True)
+    want = sc.oracle_eval(oracle, shade=True, ids=rows_to_ids(rows, L))
+    stats = compare(take_rows(got, rows, L), want, sc, shade=True, label="cfg3")
+    print("cfg3", stats)
+    assert tuple(got["checksum"])[:3] == numpy_checksum(got["pos"], got["normal"], got["shade"])[:3]
+    # columns too: the strip seams of the tile kernel (every column of a few rows was covered above;
+    # here a full-height slice of columns around likely seams)
+    cols = np.array([0, 1, 2, 155, 156, 157, 158, 159, 160, 161, 2046, 2047, 2048, 4093, 4094, 4095])
+    ids = (np.arange(L)[:, None] * L + cols[None, :]).ravel()
+    want = sc.oracle_eval(oracle, shade=True, ids=ids)
+    sub = {k: got[k][ids] for k in ("pos", "normal", "shade")}
+    compare(sub, want, sc, shade=True, label="cfg3 columns")
+
+
+def test_cfg3_full_grid_vs_reference_order_kernel(cfg3):
+    """Full 4096^2 coverage: the tile kernel against the reference-order kernel (itself checked against
+    the oracle above and in cfg1) — every vertex, every strip/chunk seam."""
+    sc, frame, ctx = cfg3
+    a = gpu_eval(ctx, frame, sc.L, flags=api.FLAG_SHADE)
+    b = gpu_eval(ctx, frame, sc.L, flags=api.FLAG_SHADE | api.FLAG_REFERENCE_ORDER)
+    stats = compare(a, b, sc, shade=True, label="cfg3 tile vs reference-order")
+    print("cfg3 full", stats)
+
+
+def test_cfg3_fast_phase_variant_within_tolerance(oracle, cfg3):
+    sc, frame, ctx = cfg3
+    L = sc.L
+    rows = [0, 1, 2000, 4095]
+    got = gpu_eval(ctx, frame, L, flags=api.FLAG_FAST_PHASE)
+    want = sc.oracle_eval(oracle, ids=rows_to_ids(rows, L))
+    stats = compare(take_rows(got, rows, L), want, sc, label="cfg3 fast-phase")
+    print("cfg3 fast-phase", stats)
+
+
+def test_row_sharded_equals_unsharded_bit_exact(cfg3):
+    """Row sharding: every vertex is a pure function of (col,row) — 8 row shards give
+    the very same bits as one evaluation, and their digests fold into the unsharded digest."""
+    from wave_tool_b200 import shard
+    sc, frame, ctx = cfg3
+    L = 1024     # same scene, smaller grid (memory/time)
+    full = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE, checksum=True)
+    parts = []
+    for r in range(8):
+        b, e = shard.row_shard(L, r, 8)
+        part = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE, rows=(b, e), checksum=True)
+        for k in ("pos", "normal", "shade"):
+            assert np.array_equal(part[k].view(np.uint32), full[k][b * L:e * L].view(np.uint32)), (r, k)
+        parts.append(part["checksum"])
+    c = shard.combine_checksums(np.array(parts))
+    f = full["checksum"]
+    assert (c["position_bits"], c["normal_bits"], c["shade_bits"], c["vertices"]) == (f["position_bits"], f["normal_bits"], f["shade_bits"], f["vertices"])
+    assert c["min_y"] == f["min_y"] and c["max_y"] == f["max_y"]
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[3]: 8192^2 grid, 256 waves (row bands only — 2.15 GB per full frame)
+# --------------------------------------------------------------------------------------------------
+def test_cfg4_8192_grid_256_waves_row_bands(oracle, hm):
+    L = 8192
+    sc = Scene(scenes.seeded_waves(256, cfg=4), scenes.camera(), scenes.animation_params(1023), L, hm)
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    for band in [(0, 6), (4090, 4100), (8186, 8192)]:
+        got = gpu_eval(ctx, frame, L, rows=band)
+        rows = [band[0], band[1] - 1]
+        want = sc.oracle_eval(oracle, ids=rows_to_ids(rows, L))
+        stats = compare(take_rows(got, rows, L, row_begin=band[0]), want, sc, label=f"cfg4 rows {band}")
+        print("cfg4", band, stats)
+
+
+# --------------------------------------------------------------------------------------------------
+# configs[4]: 16384^2 grid, 32 waves, horizon-grazing / high-altitude projector edge cases
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(scenes.EDGE_CAMERAS))
+def test_cfg5_edge_cameras_16384(oracle, hm, name):
+    L = 16384
+    sc = Scene(scenes.seeded_waves(32, cfg=5), scenes.camera(**scenes.EDGE_CAMERAS[name]), scenes.animation_params(11), L, hm)
+    st, frame = sc.frame()
+    st_o, _, _ = sc.oracle_uniforms(oracle)
+    assert st == st_o
+    if st == api.WT_NO_GRID:      # render-engine.cpp:894: surfaced as a status, not an error
+        assert name == "looking_up_no_grid"
+        return
+    ctx = sc.make_context()
+    for band in [(0, 4), (8190, 8194), (16380, 16384)]:
+        got = gpu_eval(ctx, frame, L, rows=band)
+        rows = [band[0] + 1]
+        ids = rows_to_ids(rows, L)
+        want = sc.oracle_eval(oracle, ids=ids)
+        truth = sc.oracle_eval(oracle, ids=ids, f64=True)
+        sub = take_rows(got, rows, L, row_begin=band[0])
+        # far from the origin the fp32 reference arithmetic itself is coarser than the
+        # tolerance (ulp of the coordinates); report both, gate on the stated tolerance wherever the
+        # fp32 oracle is itself within tolerance of the fp64 truth, else on the oracle's own error.
+        tol = 1e-4 * sc.total_amplitude
+        o_err = np.abs(want["pos"][:, :3].astype(np.float64) - truth["pos"][:, :3]).max(axis=1)
+        g_err = np.abs(sub["pos"][:, :3].astype(np.float64) - want["pos"][:, :3]).max(axis=1)
+        assert np.all(g_err <= np.maximum(tol, o_err)), (name, band, g_err.max(), o_err.max())
+        ang = angle_between(sub["normal"][:, :3], want["normal"][:, :3])
+        ang = np.minimum(ang, angle_between(sub["normal"][:, :3], -want["normal"][:, :3]))
+        o_ang = angle_between(want["normal"][:, :3], truth["normal"][:, :3].astype(np.float32))
+        o_ang = np.minimum(o_ang, angle_between(want["normal"][:, :3], -truth["normal"][:, :3].astype(np.float32)))
+        assert np.all(ang <= np.maximum(1e-3, o_ang)), (name, band, ang.max())
+        print("cfg5", name, band, dict(pos_max=float(g_err.max()), oracle_vs_truth=float(o_err.max()), normal_max=float(ang.max()),
+                                       normal_oracle_vs_truth=float(o_ang.max()), over_tol=int((g_err > tol).sum())))
+
+
+# --------------------------------------------------------------------------------------------------
+# boundary behaviour
+# --------------------------------------------------------------------------------------------------
+def test_ragged_and_tiny_grids(oracle, hm):
+    for L in (2, 3, 5, 31, 64, 127, 130, 255, 257, 1000):
+        sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), L, hm)
+        st, frame = sc.frame()
+        ctx = sc.make_context()
+        got = gpu_eval(ctx, frame, L)
+        want = sc.oracle_eval(oracle)
+        compare(got, want, sc, label=f"L={L}")
+
+
+def test_wave_count_tiers(oracle, hm):
+    for W in (0, 1, 4, 16, 17, 64, 65, 256, 257, 1000):
+        waves = scenes.seeded_waves(W, cfg=9) if W else np.zeros((0, 6), np.float32)
+        sc = Scene(waves, scenes.camera(), scenes.animation_params(5), 96, hm)
+        st, frame = sc.frame()
+        ctx = sc.make_context()
+        got = gpu_eval(ctx, frame, 96)
+        want = sc.oracle_eval(oracle)
+        tol = None if W else 1e-12
+        compare(got, want, sc, pos_tol=tol, label=f"W={W}")
+
+
+def test_non_power_of_two_heightmap(oracle):
+    hm = scenes.procedural_heightmap(200)[:150]      # 200 x 150 texels
+    sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), 300, hm)
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    compare(gpu_eval(ctx, frame, 300), sc.oracle_eval(oracle), sc, label="npot heightmap")
+
+
+def test_error_statuses(hm):
+    torch = torch_mod()
+    ctx = api.Context(0)
+    buf = torch.empty((64, 4), dtype=torch.float32, device="cuda")
+    st, frame = api.build_frame(scenes.camera(), api.default_params(), 0.16)
+    with pytest.raises(api.WaveToolError) as e:
+        ctx.eval_frame(frame, 8, buf.data_ptr(), buf.data_ptr())
+    assert e.value.status == api.WT_ERR_NOT_READY
+    ctx.set_waves(scenes.default_waves())
+    with pytest.raises(api.WaveToolError) as e:      # no heightmap -> the reference draws no water (program.cpp:721)
+        ctx.eval_frame(frame, 8, buf.data_ptr(), buf.data_ptr())
+    assert e.value.status == api.WT_ERR_NOT_READY
+    ctx.set_heightmap(hm)
+    for bad in [dict(grid_len=1), dict(grid_len=8, rows=(5, 5)), dict(grid_len=8, rows=(0, 9))]:
+        with pytest.raises(api.WaveToolError) as e:
+            ctx.eval_frame(frame, bad["grid_len"], buf.data_ptr(), buf.data_ptr(), rows=bad.get("rows"))
+        assert e.value.status == api.WT_ERR_INVALID_ARGUMENT
+    with pytest.raises(api.WaveToolError):            # shading requested without a shade buffer
+        ctx.eval_frame(frame, 8, buf.data_ptr(), buf.data_ptr(), flags=api.FLAG_SHADE)
+    bad_wave = scenes.default_waves()
+    bad_wave[0, 4] = 3.0                               # |D| != 1 (render-engine.h:152-154)
+    with pytest.raises(api.WaveToolError):
+        ctx.set_waves(bad_wave)
+    with pytest.raises(api.WaveToolError):
+        api.Context(10 ** 6)
+    assert ctx.eval_frame(frame, 8, buf.data_ptr(), buf.data_ptr()) == api.WT_OK
+
+
+def test_host_buffer_entry_point(oracle, hm):
+    sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 513, hm, skybox=scenes.procedural_skybox(64))
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    out = ctx.eval_frame_host(frame, 513, flags=api.FLAG_SHADE, want_checksum=True)
+    want = sc.oracle_eval(oracle, shade=True)
+    compare(out, want, sc, shade=True, label="host entry point")
+    assert out["checksum"].as_tuple()[:3] == numpy_checksum(out["pos"], out["normal"], out["shade"])[:3]
+    assert ctx.launch_count() >= 3
