@@ -105,6 +105,7 @@ class Oracle:
                   C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong]
         L.wto_eval_f32.argtypes = common + [C.c_void_p] * 4
         L.wto_eval_f64.argtypes = common + [C.c_void_p] * 4
+        L.wto_shade_f32.argtypes = [C.POINTER(Uniforms), C.POINTER(Textures), C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
 
     # --- host-side scalar rules -------------------------------------------------------------
     def num_threads(self) -> int:
@@ -187,6 +188,23 @@ class Oracle:
         if st != 0:
             raise RuntimeError(f"oracle eval failed: {st}")
         return {"pos": pos, "normal": nrm, "shade": shd, "extra": ext}
+
+
+    def shade(self, u: Uniforms, sky_faces, pos4: np.ndarray, nrm4: np.ndarray):
+        """water-grid.frag:71-73,95-111 at caller-supplied vertices -> (shade (n,4), fresnel (n,))."""
+        tx = Textures()
+        keep = None
+        if sky_faces is not None:
+            keep = np.ascontiguousarray(sky_faces, np.uint8)
+            for f in range(6):
+                tx.sky_faces[f] = keep[f].ctypes.data
+            tx.sky_n = keep.shape[1]
+        p = np.ascontiguousarray(pos4, np.float32)
+        n = np.ascontiguousarray(nrm4, np.float32)
+        shade = np.empty((len(p), 4), np.float32)
+        fres = np.empty(len(p), np.float32)
+        self.lib.wto_shade_f32(C.byref(u), C.byref(tx), len(p), p.ctypes.data, n.ctypes.data, shade.ctypes.data, fres.ctypes.data)
+        return shade, fres
 
 
 class Ref:

@@ -410,6 +410,23 @@ template <typename T> struct Surface {
     }
 };
 
+// water-grid.frag:71-73,95-111 evaluated at a vertex with the un-interpolated varyings
+// (viewVecRaw, normal).  shade4 = (sky.rgb, sun specular), *fresnel = fresnel_f_theta.
+template <typename T>
+void shade_vertex(const wto_uniforms& u, const wt_gl::CubeRGBA8* sky, V3<T> view_raw, V3<T> n, T* shade4, T* fresnel) {
+    T len = std::sqrt(dot(view_raw, view_raw));                         // length(), frag:71
+    V3<T> vv3{view_raw.x / len, view_raw.y / len, view_raw.z / len};     // frag:73 (vec3 / float)
+    V3<T> R = reflect(V3<T>{-vv3.x, -vv3.y, -vv3.z}, n);                // frag:95
+    T sky_c[4] = {0, 0, 0, 0};
+    if (sky && sky->face[0]) wt_gl::texture_cube_clamp_linear<T>(*sky, R.x, R.y, R.z, sky_c);   // frag:96
+    V3<T> sun{(T)u.sunPosition[0], (T)u.sunPosition[1], (T)u.sunPosition[2]};
+    T sd = clampT(dot(R, sun), (T)0, (T)1);
+    T sun_term = (T)u.sunStrength * (T)1 * std::pow(sd, (T)u.sunShininess);   // frag:99-100
+    T cos_theta = dot(n, vv3);                                          // frag:110
+    *fresnel = (T)0.02f + ((T)1 - (T)0.02f) * std::pow((T)1 - cos_theta, (T)5);   // frag:107-111
+    shade4[0] = sky_c[0]; shade4[1] = sky_c[1]; shade4[2] = sky_c[2]; shade4[3] = sun_term;
+}
+
 // Per-vertex outputs.  pos4 = (x,y,z,1) world position (water-grid.vert `position`),
 // nrm4 = (normal.xyz, fresnel or 0), shade4 = (sky.rgb, sun), extra16 = clip(4) ndc0(2) viewVecRaw(3)
 // normalVecInViewSpaceOnlyYaw(3) heightmap_colour(4).
@@ -450,21 +467,7 @@ void eval_vertex(const Surface<T>& S, const M4<T>& VP, const M4<T>& VY, const wt
         extra16[9] = ny.x; extra16[10] = ny.y; extra16[11] = ny.z;
         for (int c = 0; c < 4; ++c) extra16[12 + c] = texel[c];
     }
-    if (shade4) {
-        // water-grid.frag:71-73,95-111 evaluated at the vertex with the un-interpolated varyings
-        T len = std::sqrt(dot(view_raw, view_raw));                         // length(), frag:71
-        V3<T> vv3{view_raw.x / len, view_raw.y / len, view_raw.z / len};     // frag:73 (vec3 / float)
-        V3<T> R = reflect(V3<T>{-vv3.x, -vv3.y, -vv3.z}, n);                // frag:95
-        T sky_c[4] = {0, 0, 0, 0};
-        if (sky && sky->face[0]) wt_gl::texture_cube_clamp_linear<T>(*sky, R.x, R.y, R.z, sky_c);   // frag:96
-        V3<T> sun{(T)u.sunPosition[0], (T)u.sunPosition[1], (T)u.sunPosition[2]};
-        T sd = clampT(dot(R, sun), (T)0, (T)1);
-        T sun_term = (T)u.sunStrength * (T)1 * std::pow(sd, (T)u.sunShininess);   // frag:99-100
-        T cos_theta = dot(n, vv3);                                          // frag:110
-        T fres = (T)0.02f + ((T)1 - (T)0.02f) * std::pow((T)1 - cos_theta, (T)5);   // frag:107-111
-        shade4[0] = sky_c[0]; shade4[1] = sky_c[1]; shade4[2] = sky_c[2]; shade4[3] = sun_term;
-        nrm4[3] = fres;
-    }
+    if (shade4) shade_vertex<T>(u, sky, view_raw, n, shade4, nrm4 + 3);
 }
 
 template <typename T>
@@ -543,6 +546,21 @@ int wto_eval_f32(const wto_uniforms* u, const wto_wave* waves, const wto_texture
 int wto_eval_f64(const wto_uniforms* u, const wto_wave* waves, const wto_textures* tx, const long long* ids, long long n,
                  long long row0, long long row1, long long col0, long long col1, double* pos4, double* nrm4, double* shade4, double* extra16) {
     return eval_vertices<double>(u, waves, tx, ids, n, row0, row1, col0, col1, pos4, nrm4, shade4, extra16);
+}
+
+// The in-scope fragment terms alone, evaluated at caller-supplied vertices: pos4/nrm4 are (n,4) arrays
+// (e.g. a kernel's own outputs); writes shade4 (n,4) and fresnel (n).  Lets a test check the shading
+// FUNCTION tightly, independent of how errors of the normal propagate through pow(., shininess).
+int wto_shade_f32(const wto_uniforms* u, const wto_textures* tx, long long n, const float* pos4, const float* nrm4, float* shade4, float* fresnel) {
+    wt_gl::CubeRGBA8 cube{{tx->sky_faces[0], tx->sky_faces[1], tx->sky_faces[2], tx->sky_faces[3], tx->sky_faces[4], tx->sky_faces[5]}, tx->sky_n};
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < n; ++k) {
+        V3<float> P{pos4[4 * k], pos4[4 * k + 1], pos4[4 * k + 2]};
+        V3<float> cam{u->cameraPosition[0], u->cameraPosition[1], u->cameraPosition[2]};
+        V3<float> nn{nrm4[4 * k], nrm4[4 * k + 1], nrm4[4 * k + 2]};
+        shade_vertex<float>(*u, &cube, cam - P, nn, shade4 + 4 * k, fresnel + k);
+    }
+    return 0;
 }
 
 }  // extern "C"
