@@ -275,7 +275,10 @@ def test_cfg5_edge_cameras_16384(oracle, hm, name):
         o_ang = angle_between(want["normal"][:, :3], truth["normal"][:, :3].astype(np.float32))
         o_ang = np.minimum(o_ang, angle_between(want["normal"][:, :3], -truth["normal"][:, :3].astype(np.float32)))
         assert ang.max() <= max(1e-3, 2.0 * o_ang.max()), (name, band, ang.max(), o_ang.max())
-        assert np.quantile(ang, 0.999) <= 1e-3, (name, band, np.quantile(ang, 0.999))
+        # the same rule on the bulk of the distribution (measured here: on the near-field band of the default
+        # camera the fp32 oracle's own 99.9 % quantile vs fp64 truth is 2.6e-3 rad, its median 2.7e-4 rad)
+        for q in (0.5, 0.999):
+            assert np.quantile(ang, q) <= max(1e-3 if q > 0.9 else 1e-4, 2.0 * np.quantile(o_ang, q)), (name, band, q, np.quantile(ang, q), np.quantile(o_ang, q))
         print("cfg5", name, band, dict(pos_max=float(g_err.max()), oracle_vs_truth=float(o_err.max()), normal_max=float(ang.max()),
                                        normal_oracle_vs_truth=float(o_ang.max()), over_tol=int((g_err > tol).sum())))
 
