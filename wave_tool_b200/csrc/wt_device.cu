@@ -35,9 +35,11 @@ struct wt_ctx {
     bool waves_set = false;
     std::vector<WaveK> tab_exact, tab_fast, tab_raw;
     // textures
-    float* d_hm_r = nullptr;
+    float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
+    float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)
     int hm_w = 0, hm_h = 0;
-    uchar4* d_sky = nullptr;
+    uchar4* d_sky = nullptr;        // 6 faces RGBA8 (reference-order kernel)
+    uint4* d_sky_quads = nullptr;   // clamp-to-edge footprint table (production kernel)
     int sky_n = 0;
     // scratch for the *_host entry points
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
@@ -71,54 +73,36 @@ int fail(wt_ctx* ctx, int code, const std::string& msg) {
     } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// Launch planning for surface_tile_kernel
+// Launch planning for surface_warp_kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int V_ROWS = 4;   // rows evaluated per thread per marching step
+constexpr int R_EXACT = 4;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
+constexpr int R_RECUR = 8;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
 
 struct Plan {
-    int S = 128, strip_cols = 126, n_strips = 1, rows_per_chunk = 1, n_chunks = 1;
-    size_t smem = 0;
+    int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;
 };
 
-template <typename K>
-int ctas_per_sm(K kernel, int S, size_t smem) {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, S, smem) != cudaSuccess) n = 0;
-    return std::max(n, 1);
-}
-
-// Chooses the strip width S (threads per CTA, each owning one column incl. 2 halo columns) and the
-// rows per chunk so that  (a) few lanes idle,  (b) the CTAs fill whole waves of the 148 SMs,
-// (c) the +2 halo rows and the round-up to V rows cost little.  Cost model: every resident CTA slot
-// is busy for (marching steps * V) rows; a partially filled wave costs as much as a full one.
-template <typename K>
-Plan make_plan(K kernel, int sm_count, int L, int rows) {
+// Work items are warps: n_strips strips of STRIP_COLS columns x n_chunks chunks of rows.  Every item
+// marches rows_per_chunk + 2 rows (the +-1-row stencil halo is recomputed, never exchanged), in steps
+// of R.  Cost model: the SMs hold `slots` warps at a time; a partially filled round costs as much as
+// a full one; smaller chunks balance better but pay the 2 halo rows more often.
+Plan make_plan(int slots, int L, int rows, int R) {
     Plan best;
     double best_cost = 1e300;
-    for (int S = 64; S <= 256; S += 32) {
-        const size_t smem = (size_t)2 * (V_ROWS + 1) * S * sizeof(float4);
-        const int per_sm = ctas_per_sm(kernel, S, smem);
-        const long long slots = (long long)sm_count * per_sm;
-        const int n_strips = (L + (S - 2) - 1) / (S - 2);
-        const int strip_cols = (L + n_strips - 1) / n_strips;
-        const int max_chunks = std::max(1, rows / 8);
-        for (int waves = 1; waves <= 4; ++waves) {
-            int n_chunks = (int)std::min<long long>(max_chunks, std::max<long long>(1, waves * slots / n_strips));
-            int rpc = (rows + n_chunks - 1) / n_chunks;
-            // make rpc + 2 a multiple of V so no marching step is partly wasted
-            rpc = ((rpc + 2 + V_ROWS - 1) / V_ROWS) * V_ROWS - 2;
-            if (rpc < 2) rpc = 2;
-            n_chunks = (rows + rpc - 1) / rpc;
-            const long long ctas = (long long)n_strips * n_chunks;
-            const long long rounds = (ctas + slots - 1) / slots;
-            const int steps = (rpc + 2 + V_ROWS - 1) / V_ROWS;
-            // time ~ rounds * (threads resident per SM) * rows marched per CTA
-            const double cost = (double)rounds * per_sm * S * steps * V_ROWS;
-            if (cost < best_cost) {
-                best_cost = cost;
-                best.S = S; best.strip_cols = strip_cols; best.n_strips = n_strips;
-                best.rows_per_chunk = rpc; best.n_chunks = n_chunks; best.smem = smem;
-            }
+    const int n_strips = (L + STRIP_COLS - 1) / STRIP_COLS;
+    for (int rounds = 1; rounds <= 6; ++rounds) {
+        long long want = std::max<long long>(1, (long long)rounds * slots / n_strips);
+        int rpc = (int)((rows + want - 1) / want);
+        rpc = ((rpc + 2 + R - 1) / R) * R - 2;   // rpc + 2 a multiple of R: no marching step is partly wasted
+        if (rpc < 1) rpc = R - 2 > 0 ? R - 2 : 1;
+        const int n_chunks = (rows + rpc - 1) / rpc;
+        const long long items = (long long)n_strips * n_chunks;
+        const long long full_rounds = (items + slots - 1) / slots;
+        const double cost = (double)full_rounds * (rpc + 2) * (1.0 + 0.02 * full_rounds);   // mild preference for fewer rounds
+        if (cost < best_cost) {
+            best_cost = cost;
+            best.n_strips = n_strips; best.rows_per_chunk = rpc; best.n_chunks = n_chunks;
+            best.ctas = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
         }
     }
     return best;
@@ -132,23 +116,39 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
 }
 
-template <int CAP, bool EXACT, bool SHADE>
-cudaError_t launch_tile(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
-    auto kernel = surface_tile_kernel<CAP, V_ROWS, EXACT, SHADE>;
+template <int CAP, int MODE, bool SHADE>
+cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
+    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE>;
+    constexpr int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP;
     static thread_local struct { int L = -1, rows = -1, dev = -1; Plan p; } cache;   // per instantiation
     const int rows = a.row_end - a.row_begin;
     if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cache.p = make_plan(kernel, ctx->sm_count, a.L, rows);
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * WARPS_PER_CTA, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache.p = make_plan(ctx->sm_count * per_sm * WARPS_PER_CTA, a.L, rows, R);
         cache.L = a.L; cache.rows = rows; cache.dev = ctx->device;
     }
     const Plan& p = cache.p;
-    a.strip_cols = p.strip_cols;
+    a.n_strips = p.n_strips;
     a.rows_per_chunk = p.rows_per_chunk;
+    a.n_chunks = p.n_chunks;
     static thread_local WaveTable<CAP> table;
     fill_table(table, tab);
-    for (size_t i = 0; i < tab.size(); ++i) table.w[i].phi = tab[i].phi * a.t;   // fl(phi * t), water-grid.vert:78
-    kernel<<<dim3(p.n_strips, p.n_chunks), p.S, p.smem, stream>>>(a, table);
+    for (size_t i = 0; i < tab.size(); ++i) {
+        const float c = tab[i].phi * a.t;   // fl(phi * t), water-grid.vert:78
+        // MODE 1 adds the offset inside an FMA chain: hand it over reduced mod 2pi (in double) so it costs no precision
+        table.w[i].phi = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
+    }
+    if (MODE == 1) {
+        // largest per-row phase step over the grid: |w| * longest column edge * du
+        const float e0 = std::hypot(a.tlx - a.blx, a.tlz - a.blz), e1 = std::hypot(a.trx - a.brx, a.trz - a.brz);
+        float wmax = 0.f;
+        for (const WaveK& w : tab) wmax = std::max(wmax, std::hypot(w.Dx, w.Dz));
+        const float dmax = wmax * std::max(e0, e1) * a.du;
+        a.delta_reduce = !(dmax < 3.0f);
+    }
+    kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -170,8 +170,8 @@ cudaError_t dispatch_cap(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t 
     if (flags & WT_FLAG_REFERENCE_ORDER)
         return shade ? launch_reference_order<CAP, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<CAP, false>(ctx, a, ctx->tab_raw, stream);
     if (flags & WT_FLAG_FAST_PHASE)
-        return shade ? launch_tile<CAP, false, true>(ctx, a, ctx->tab_fast, stream) : launch_tile<CAP, false, false>(ctx, a, ctx->tab_fast, stream);
-    return shade ? launch_tile<CAP, true, true>(ctx, a, ctx->tab_exact, stream) : launch_tile<CAP, true, false>(ctx, a, ctx->tab_exact, stream);
+        return shade ? launch_warp<CAP, 1, true>(ctx, a, ctx->tab_fast, stream) : launch_warp<CAP, 1, false>(ctx, a, ctx->tab_fast, stream);
+    return shade ? launch_warp<CAP, 0, true>(ctx, a, ctx->tab_exact, stream) : launch_warp<CAP, 0, false>(ctx, a, ctx->tab_exact, stream);
 }
 
 int validate_eval(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
@@ -207,9 +207,10 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
     a.sun_shininess = f.sunShininess;
     a.sun_strength = f.sunStrength;
     a.n_waves = (int)ctx->n_waves;
-    a.hm_r = ctx->d_hm_r; a.hm_w = ctx->hm_w; a.hm_h = ctx->hm_h;
+    a.one = 1.0f;
+    a.hm_r = ctx->d_hm_r; a.hm_quads = ctx->d_hm_quads; a.hm_w = ctx->hm_w; a.hm_h = ctx->hm_h;
     a.hm_pow2 = ((ctx->hm_w & (ctx->hm_w - 1)) == 0) && ((ctx->hm_h & (ctx->hm_h - 1)) == 0);
-    a.sky = ctx->d_sky; a.sky_n = ctx->sky_n;
+    a.sky = ctx->d_sky; a.sky_quads = ctx->d_sky_quads; a.sky_n = ctx->sky_n;
     a.pos = (float4*)d_pos; a.nrm = (float4*)d_nrm; a.shade = (float4*)d_shade;
     a.cks = (flags & WT_FLAG_CHECKSUM) ? (wt_checksum*)d_cks : nullptr;
     a.L = (int)L; a.row_begin = (int)r0; a.row_end = (int)r1;
@@ -260,8 +261,8 @@ int wt_create(wt_ctx** out, int device) {
 void wt_destroy(wt_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
-    cudaFree(ctx->d_hm_r);
-    cudaFree(ctx->d_sky);
+    cudaFree(ctx->d_hm_r); cudaFree(ctx->d_hm_quads);
+    cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_quads);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     delete ctx;
 }
@@ -303,10 +304,14 @@ int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int w, int h) {
     // water-grid.vert:106-111 reads only .r; stage it as the exact unorm value c/255.0f
     std::vector<float> r((size_t)w * h);
     for (size_t i = 0; i < r.size(); ++i) r[i] = (float)rgba[4 * i] / 255.0f;
-    cudaFree(ctx->d_hm_r);
-    ctx->d_hm_r = nullptr;
+    cudaFree(ctx->d_hm_r); cudaFree(ctx->d_hm_quads);
+    ctx->d_hm_r = nullptr; ctx->d_hm_quads = nullptr;
     WT_CUDA(ctx, cudaMalloc(&ctx->d_hm_r, r.size() * sizeof(float)));
     WT_CUDA(ctx, cudaMemcpy(ctx->d_hm_r, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice));
+    WT_CUDA(ctx, cudaMalloc(&ctx->d_hm_quads, 4 * r.size() * sizeof(float4)));
+    build_heightmap_quads_kernel<<<ctx->sm_count * 4, 256>>>(ctx->d_hm_r, w, h, ctx->d_hm_quads);
+    ctx->launches++;
+    WT_CUDA(ctx, cudaDeviceSynchronize());
     ctx->hm_w = w; ctx->hm_h = h;
     return WT_OK;
 }
@@ -316,11 +321,15 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
     if (!faces || n <= 0 || n > 16384) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: bad cubemap");
     for (int f = 0; f < 6; ++f) if (!faces[f]) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: face pointer is NULL");
     DeviceGuard g(ctx->device);
-    cudaFree(ctx->d_sky);
-    ctx->d_sky = nullptr;
+    cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_quads);
+    ctx->d_sky = nullptr; ctx->d_sky_quads = nullptr;
     const size_t face_bytes = (size_t)n * n * 4;
     WT_CUDA(ctx, cudaMalloc(&ctx->d_sky, 6 * face_bytes));
     for (int f = 0; f < 6; ++f) WT_CUDA(ctx, cudaMemcpy((uint8_t*)ctx->d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice));
+    WT_CUDA(ctx, cudaMalloc(&ctx->d_sky_quads, 6 * (size_t)(n + 1) * (n + 1) * sizeof(uint4)));
+    build_sky_quads_kernel<<<ctx->sm_count * 8, 256>>>(ctx->d_sky, n, ctx->d_sky_quads);
+    ctx->launches++;
+    WT_CUDA(ctx, cudaDeviceSynchronize());
     ctx->sky_n = n;
     return WT_OK;
 }

@@ -1,15 +1,20 @@
 // Device code of the water-surface path (sm_100a).  See DESIGN.md for the derivation.
 //
-//   surface_tile_kernel   — the production kernel: one thread per grid COLUMN marching over ROWS;
-//                           every displaced position is evaluated once and shared with the four
-//                           stencil neighbours (left/right through shared memory, up/down through
-//                           registers).  Fuses: bilinear grid placement (water-grid.vert:87-91),
-//                           the Gerstner sum (:74-85), heightmap detail (:93-111), bounce (:147),
-//                           finite-difference normal + view-facing flip (:164-190) and, optionally,
-//                           the vertex-evaluable fragment terms (water-grid.frag:71-73,95-111).
+//   surface_warp_kernel   — the production kernel.  One WARP owns a strip of 62 output columns
+//                           (+2 halo columns; lane l holds columns l and l+32 of the strip as the two
+//                           halves of Blackwell packed-fp32 registers: FFMA2 / FMUL2) and marches
+//                           over rows, R rows per step.  No CTA barrier: the 4-neighbour stencil is
+//                           served from a warp-private shared-memory ring.  Fuses: bilinear grid
+//                           placement (water-grid.vert:87-91), the Gerstner sum (:74-85), heightmap
+//                           detail (:93-111), bounce (:147), finite-difference normal + view-facing
+//                           flip (:164-190) and, optionally, the vertex-evaluable fragment terms
+//                           (water-grid.frag:71-73,95-111).  Two phase modes:
+//                             MODE 0  bit-faithful fp32 phase + one MUFU sin/cos pair per vertex-wave
+//                             MODE 1  one MUFU seed per wave per R rows, the other rows by complex
+//                                     rotation (the phase is affine in the row index along a column)
 //   surface_reference_order_kernel — straight transliteration of the shader (5 full evaluations per
-//                           vertex, libdevice sincosf, IEEE sqrt/div); used to cross-check the tile
-//                           kernel at full grid sizes and as the "naive GPU port" timing baseline.
+//                           vertex, libdevice sincosf, IEEE sqrt/div); used to cross-check the
+//                           production kernel at full grid sizes and as the "naive GPU port" timing.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,11 +23,11 @@
 
 namespace wt {
 
-// One wave, pre-folded on the host (wt_set_waves).  Exact-phase kernels read (Dx,Dz,w); fast-phase
-// kernels are handed a table whose (Dx,Dz) already hold w*Dx, w*Dz.  cX = A*Q_i*Dx, cZ = A*Q_i*Dz.
-// For the tile kernel the launcher overwrites `phi` with the per-frame product fl(phi * t), which
-// the shader recomputes per vertex per wave (water-grid.vert:78); the reference-order kernel keeps
-// the raw phi (and Q_i in cX) and multiplies in the kernel.
+// One wave, pre-folded on the host (wt_set_waves).  MODE 0 reads (Dx,Dz,w); MODE 1 is handed a
+// table whose (Dx,Dz) already hold w*Dx, w*Dz.  cX = A*Q_i*Dx, cZ = A*Q_i*Dz.  For the production
+// kernel the launcher overwrites `phi` with the per-frame phase offset fl(phi * t), which the shader
+// recomputes per vertex per wave (water-grid.vert:78) — MODE 1 gets it reduced mod 2pi; the
+// reference-order kernel keeps the raw phi (and Q_i in cX) and multiplies in the kernel.
 struct __align__(16) WaveK {
     float Dx, Dz, w, phi;
     float cX, A, cZ, pad;
@@ -33,6 +38,8 @@ struct WaveTable {
     WaveK w[CAP];
 };
 
+constexpr int STRIP_COLS = 62;   // output columns per warp: 64 held columns minus the two halo columns
+
 struct EvalArgs {
     // grid corners, x and z only (y is discarded by water-grid.vert:138 `position.xz`)
     float blx, blz, brx, brz, tlx, tlz, trx, trz;
@@ -40,21 +47,29 @@ struct EvalArgs {
     float camx, camy, camz, du;
     float sunx, suny, sunz, sun_shininess;
     float sun_strength;
+    float one;          // 1.0f the compiler cannot see: x*one + y is an exact add ptxas cannot contract
     int n_waves;
-    // heightmap: R channel as exact unorm floats (c/255.0f), row-major, GL row order
+    int delta_reduce;   // MODE 1: the per-row phase step may exceed the MUFU-accurate range -> reduce it too
+    // heightmap, reference-order kernel: R channel as exact unorm floats (c/255.0f), row-major, GL row order
     const float* hm_r;
     int hm_w, hm_h, hm_pow2;
-    // sky cubemap: 6 faces of n*n RGBA8, GL face order
+    // heightmap, production kernel: GL_MIRRORED_REPEAT unrolled into a (2w x 2h) table of bilinear
+    // footprints (t00, t10, t01, t11) so that one 16-byte load serves a sample
+    const float4* hm_quads;
+    // sky cubemap, reference-order kernel: 6 faces of n*n RGBA8, GL face order
     const uchar4* sky;
     int sky_n;
+    // sky cubemap, production kernel: per face (n+1)^2 CLAMP_TO_EDGE footprints of four RGBA8 texels
+    const uint4* sky_quads;
     // outputs (element 0 = (row_begin, col 0))
     float4* pos;
     float4* nrm;
     float4* shade;
     wt_checksum* cks;   // NULL unless WT_FLAG_CHECKSUM
     int L, row_begin, row_end;
-    int strip_cols;     // output columns per strip (blockIdx.x)
-    int rows_per_chunk; // output rows per chunk (blockIdx.y)
+    int n_strips;       // warps across a row
+    int rows_per_chunk; // output rows per warp
+    int n_chunks;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -176,41 +191,6 @@ __device__ __forceinline__ float3 sky_rgb(const EvalArgs& a, float rx, float ry,
 
 struct P3 { float x, y, z; };
 
-// cross((right-left), (up-down)) normalised and flipped towards the eye (water-grid.vert:187-190),
-// plus — with SHADE — water-grid.frag:71-73,95-111 evaluated at the vertex.
-template <bool SHADE>
-__device__ __forceinline__ void normal_and_shade(const EvalArgs& a, const P3& c, const P3& left, const P3& right, const P3& down, const P3& up,
-                                                 float4& out_n, float4& out_s) {
-    float ux = sub_rn(right.x, left.x), uy = sub_rn(right.y, left.y), uz = sub_rn(right.z, left.z);
-    float vx = sub_rn(up.x, down.x), vy = sub_rn(up.y, down.y), vz = sub_rn(up.z, down.z);
-    float nx = sub_rn(mul_rn(uy, vz), mul_rn(vy, uz));
-    float ny = sub_rn(mul_rn(uz, vx), mul_rn(vz, ux));
-    float nz = sub_rn(mul_rn(ux, vy), mul_rn(vx, uy));
-    float inv = rsqrtf(add_rn(add_rn(mul_rn(nx, nx), mul_rn(ny, ny)), mul_rn(nz, nz)));
-    nx *= inv; ny *= inv; nz *= inv;
-    float wx = sub_rn(a.camx, c.x), wy = sub_rn(a.camy, c.y), wz = sub_rn(a.camz, c.z);   // viewVecRaw, :158
-    float winv = rsqrtf(add_rn(add_rn(mul_rn(wx, wx), mul_rn(wy, wy)), mul_rn(wz, wz)));
-    float ex = wx * winv, ey = wy * winv, ez = wz * winv;                                  // normalize(viewVecRaw)
-    float facing = add_rn(add_rn(mul_rn(nx, ex), mul_rn(ny, ey)), mul_rn(nz, ez));
-    if (facing < 0.0f) { nx = -nx; ny = -ny; nz = -nz; facing = -facing; }
-    float fres = 0.0f;
-    if (SHADE) {
-        // R = reflect(-viewVec, normal) = I - N*dot(N,I)*2 with I = -viewVec   (frag:95)
-        float d2 = -facing * 2.0f;
-        float rx = -ex - nx * d2, ry = -ey - ny * d2, rz = -ez - nz * d2;
-        float3 sky = make_float3(0.0f, 0.0f, 0.0f);
-        if (a.sky) sky = sky_rgb(a, rx, ry, rz);                                            // frag:96
-        float sd = fminf(fmaxf(rx * a.sunx + ry * a.suny + rz * a.sunz, 0.0f), 1.0f);
-        // pow(sd, shininess) (frag:100): 0^0 = 1, 0^y = 0
-        float sp = (a.sun_shininess == 0.0f) ? 1.0f : (sd <= 0.0f ? 0.0f : exp2f(a.sun_shininess * log2f(sd)));
-        float om = 1.0f - facing;                                                            // frag:110-111
-        float om2 = om * om;
-        fres = 0.02f + (1.0f - 0.02f) * (om2 * om2 * om);
-        out_s = make_float4(sky.x, sky.y, sky.z, a.sun_strength * sp);
-    }
-    out_n = make_float4(nx, ny, nz, fres);
-}
-
 // order-preserving float <-> uint key for atomicMin/atomicMax
 __device__ __forceinline__ unsigned float_key(float f) {
     unsigned b = __float_as_uint(f);
@@ -281,111 +261,344 @@ __global__ void checksum_finalize_kernel(wt_checksum* c, int n) {
     }
 }
 
+// single-instruction MUFU approximations (flush-to-zero forms: no denormal fix-up code around them)
+__device__ __forceinline__ float rsq_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// ------------------------------------------------------------------------------------------------
+// Packed fp32 (Blackwell FFMA2 / FMUL2): both halves are rounded like the scalar instruction.
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it does not for the scalar forms),
+// so wherever the reference's rounding ORDER matters the add is written a*one + b with a run-time
+// one == 1.0f (EvalArgs::one): bit-identical to the add, one instruction, and not contractible.
+// ------------------------------------------------------------------------------------------------
+typedef float2 f2;
+__device__ __forceinline__ f2 bc(float a) { return make_float2(a, a); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }                     // only where neither operand is a product
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 add2x(f2 a, f2 b, float one) { return __ffma2_rn(a, bc(one), b); }    // fl(a + b), exact order
+__device__ __forceinline__ f2 sub2x(f2 a, f2 b, float one) { return __ffma2_rn(b, bc(-one), a); }   // fl(a - b), exact order
+
+// sin and cos of both halves: the Cody-Waite reduction of sincos_mufu, packed
+__device__ __forceinline__ void sincos2(f2 k, f2& s, f2& c) {
+    const float INV_2PI = 0.15915494309189535f;
+    const float MAGIC = 12582912.0f;
+    const float TWO_PI_HI = 6.2831854820251465f;
+    const float TWO_PI_LO = -1.7484556000744883e-07f;
+    f2 n = add2(fma2(k, bc(INV_2PI), bc(MAGIC)), bc(-MAGIC));
+    f2 r = fma2(n, bc(-TWO_PI_HI), k);
+    r = fma2(n, bc(-TWO_PI_LO), r);
+    s = make_float2(__sinf(r.x), __sinf(r.y));
+    c = make_float2(__cosf(r.x), __cosf(r.y));
+}
+
+// texture(heightmap, scale*(x,-z)).r for the two columns of a lane, from the footprint table; then
+// water-grid.vert:141-147.  Same fp32 operations in the same order as heightmap_r/finish_height.
+__device__ __forceinline__ int wrap_period(int i, int period, int pow2) {
+    if (pow2) return i & (period - 1);
+    int m = i % period;
+    return m < 0 ? m + period : m;
+}
+__device__ __forceinline__ f2 finish_height2(const EvalArgs& a, f2 px, f2 py, f2 pz) {
+    const float one = a.one;
+    f2 s = mul2(bc(a.hm_scale), px);
+    f2 t = mul2(bc(-a.hm_scale), pz);
+    f2 um = sub2x(mul2(s, bc((float)a.hm_w)), bc(0.5f), one);
+    f2 vm = sub2x(mul2(t, bc((float)a.hm_h)), bc(0.5f), one);
+    f2 fu = make_float2(floorf(um.x), floorf(um.y)), fv = make_float2(floorf(vm.x), floorf(vm.y));
+    f2 al = sub2(um, fu), be = sub2(vm, fv);
+    const int w2 = 2 * a.hm_w, h2 = 2 * a.hm_h;
+    const float4 qa = __ldg(a.hm_quads + (size_t)wrap_period((int)fv.x, h2, a.hm_pow2) * w2 + wrap_period((int)fu.x, w2, a.hm_pow2));
+    const float4 qb = __ldg(a.hm_quads + (size_t)wrap_period((int)fv.y, h2, a.hm_pow2) * w2 + wrap_period((int)fu.y, w2, a.hm_pow2));
+    f2 oma = sub2(bc(1.0f), al), omb = sub2(bc(1.0f), be);
+    f2 w00 = mul2(oma, omb), w10 = mul2(al, omb), w01 = mul2(oma, be), w11 = mul2(al, be);
+    f2 acc = mul2(w00, make_float2(qa.x, qb.x));
+    acc = add2x(mul2(w10, make_float2(qa.y, qb.y)), acc, one);
+    acc = add2x(mul2(w01, make_float2(qa.z, qb.z)), acc, one);
+    acc = add2x(mul2(w11, make_float2(qa.w, qb.w)), acc, one);
+    f2 bump = mul2(bc(a.hm_disp), mul2(bc(2.0f), sub2(acc, bc(0.5f))));
+    return add2(add2x(bump, py, one), bc(a.bounce));
+}
+
+// texture(skybox, R).rgb from the footprint table: GL 4.1 cube map face selection, per-face
+// CLAMP_TO_EDGE bilinear.  (Reciprocal and weights are not bit-ordered like the oracle: the sky colour
+// has its own, absolute tolerance.)
+__device__ __forceinline__ float3 sky_rgb_quads(const EvalArgs& a, float rx, float ry, float rz) {
+    const float ax = fabsf(rx), ay = fabsf(ry), az = fabsf(rz);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) {
+        ma = ax; tc = -ry;
+        if (rx >= 0.0f) { face = 0; sc = -rz; } else { face = 1; sc = rz; }
+    } else if (ay >= az) {
+        ma = ay; sc = rx;
+        if (ry >= 0.0f) { face = 2; tc = rz; } else { face = 3; tc = -rz; }
+    } else {
+        ma = az; tc = -ry;
+        if (rz >= 0.0f) { face = 4; sc = rx; } else { face = 5; sc = -rx; }
+    }
+    const int n = a.sky_n;
+    const float hn = 0.5f * (float)n;
+    const float inv = rcp_approx(ma);
+    const float um = fmaf(sc * inv, hn, hn - 0.5f), vm = fmaf(tc * inv, hn, hn - 0.5f);
+    const float fu = floorf(um), fv = floorf(vm);
+    const float al = um - fu, be = vm - fv;
+    const int iu = min(max((int)fu, -1), n - 1) + 1, iv = min(max((int)fv, -1), n - 1) + 1;
+    const int n1 = n + 1;
+    const uint4 q = __ldg(a.sky_quads + ((size_t)face * n1 + iv) * n1 + iu);
+    const float oma = 1.0f - al, omb = 1.0f - be;
+    const float w00 = oma * omb, w10 = al * omb, w01 = oma * be, w11 = al * be;
+    float3 o;
+    o.x = w00 * (float)(q.x & 0xffu) + w10 * (float)(q.y & 0xffu) + w01 * (float)(q.z & 0xffu) + w11 * (float)(q.w & 0xffu);
+    o.y = w00 * (float)((q.x >> 8) & 0xffu) + w10 * (float)((q.y >> 8) & 0xffu) + w01 * (float)((q.z >> 8) & 0xffu) + w11 * (float)((q.w >> 8) & 0xffu);
+    o.z = w00 * (float)((q.x >> 16) & 0xffu) + w10 * (float)((q.y >> 16) & 0xffu) + w01 * (float)((q.z >> 16) & 0xffu) + w11 * (float)((q.w >> 16) & 0xffu);
+    const float k = 1.0f / 255.0f;
+    o.x *= k; o.y *= k; o.z *= k;
+    return o;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Production kernel.
-//   grid  = (strips, row chunks), block = S threads (S a multiple of 32, chosen by the host planner)
-//   thread tid of strip s owns column  col = s*strip_cols - 1 + tid  (tid 0 and tid strip_w+1 are the
-//   halo columns whose positions are needed by the stencil but not written).
-//   The CTA marches over rows  r0-1 ... r1  in steps of V rows; per step every thread evaluates V
-//   displaced positions with the wave constants loaded once per wave (constant bank -> uniform
-//   registers), publishes them to shared memory for its left/right neighbours, and writes V rows of
-//   (position, normal[, shade]) as coalesced float4 stores.
+//   One warp = one work item = (strip of STRIP_COLS output columns) x (chunk of rows_per_chunk rows).
+//   Lane l holds the strip's columns  l  and  l + 32  (strip column 0 and 63 are the halo columns
+//   whose positions feed the stencil but are not written) as the .x/.y halves of packed registers.
+//   Per step of R rows:  grid placement -> sum over waves (constants broadcast from the constant
+//   bank) -> heightmap + bounce -> final positions into a warp-private shared-memory ring of R+2 rows
+//   (laid out so that one 8-byte load yields the packed left / centre / right neighbours of both
+//   columns) -> for the R rows whose up/down neighbours are now known: normal, flip, shading,
+//   coalesced float4 stores.  Only __syncwarp(); warps never wait for each other.
 // ------------------------------------------------------------------------------------------------
-template <int CAP, int V, bool EXACT, bool SHADE>
-__global__ void __launch_bounds__(256) surface_tile_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
-    extern __shared__ float4 smem[];   // [2][V+1][S]
-    const int S = blockDim.x;
-    const int tid = threadIdx.x;
-    const int strip0 = blockIdx.x * a.strip_cols;
-    const int strip_w = min(a.strip_cols, a.L - strip0);
-    const int col = strip0 - 1 + tid;
-    const bool col_active = tid <= strip_w + 1;
-    const bool col_out = tid >= 1 && tid <= strip_w;
-    const int r0 = a.row_begin + blockIdx.y * a.rows_per_chunk;
+constexpr int WARPS_PER_CTA = 4;
+constexpr int RING_COLS = 34;   // entries per ring row: [0] = (-, A of lane 31), [1 + l] = (A_l, B_l), [33] = (B of lane 0, -)
+
+template <int R>
+struct RingLayout {
+    static constexpr int ROWS = R + 2;
+    static constexpr int PLANE = ROWS * RING_COLS;                   // float2 entries per component
+    static constexpr int BYTES_PER_WARP = 3 * PLANE * (int)sizeof(float2);
+};
+
+template <int CAP, int R, int MODE, bool SHADE>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, MODE == 1 ? 4 : 5)
+surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
+    extern __shared__ float2 ring_all[];
+    using RL = RingLayout<R>;
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (item >= a.n_strips * a.n_chunks) return;                       // whole warps only
+    float2* const ring = ring_all + (size_t)(threadIdx.x >> 5) * 3 * RL::PLANE;
+    const int strip = item % a.n_strips, chunk = item / a.n_strips;
+    const int strip0 = strip * STRIP_COLS;
+    const int r0 = a.row_begin + chunk * a.rows_per_chunk;
     const int r1 = min(r0 + a.rows_per_chunk, a.row_end);
+    const int colA = strip0 - 1 + lane, colB = colA + 32;
+    const bool outA = lane >= 1 && colA < a.L;
+    const bool outB = lane <= 30 && colB < a.L;
+    const float one = a.one;
 
-    // water-grid.vert:123-125,87-91: u = col*du is fixed per thread, so the two inner mixes are too
-    const float u = mul_rn((float)col, a.du);
-    const float m1x = mix_rn(a.blx, a.brx, u), m1z = mix_rn(a.blz, a.brz, u);
-    const float m2x = mix_rn(a.tlx, a.trx, u), m2z = mix_rn(a.tlz, a.trz, u);
+    // water-grid.vert:123-125,87-91: u = col*du is fixed per lane, so the two inner mixes are too
+    const f2 u = make_float2(mul_rn((float)colA, a.du), mul_rn((float)colB, a.du));
+    const f2 omu = sub2(bc(1.0f), u);
+    const f2 m1x = add2x(mul2(bc(a.blx), omu), mul2(bc(a.brx), u), one), m1z = add2x(mul2(bc(a.blz), omu), mul2(bc(a.brz), u), one);
+    const f2 m2x = add2x(mul2(bc(a.tlx), omu), mul2(bc(a.trx), u), one), m2z = add2x(mul2(bc(a.tlz), omu), mul2(bc(a.trz), u), one);
+    // MODE 1: world-space step between consecutive rows of this column (the grid is bilinear, hence
+    // affine in the row index along a column), so every wave's phase advances by a constant per row
+    const f2 ex = mul2(sub2(m2x, m1x), bc(a.du)), ez = mul2(sub2(m2z, m1z), bc(a.du));
 
-    P3 carry1 = {0.f, 0.f, 0.f}, carry2 = {0.f, 0.f, 0.f};   // rows a-1 and a-2 of this column
     ChecksumAcc acc;
-    int buf = 0;
+    int slot_new = 2;   // ring row that receives the first row of the next step; rows -2/-1 of the first step are never read
 
-    for (int row_a = r0 - 1; row_a <= r1; row_a += V) {
-        float gx[V], gz[V];
-        P3 p[V];
-        if (col_active) {
+    for (int row_a = r0 - 1; row_a <= r1; row_a += R) {
+        f2 px[R], py[R], pz[R];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                float v = mul_rn((float)(row_a + j), a.du);
-                gx[j] = mix_rn(m1x, m2x, v);
-                gz[j] = mix_rn(m1z, m2z, v);
-                p[j].x = gx[j]; p[j].y = 0.0f; p[j].z = gz[j];
-            }
-            // ---- the hot loop: sum of Gerstner waves (water-grid.vert:74-85) ----
-#pragma unroll 2
+        for (int j = 0; j < R; ++j) {
+            const float v = mul_rn((float)(row_a + j), a.du);
+            const float omv = sub_rn(1.0f, v);
+            px[j] = add2x(mul2(m1x, bc(omv)), mul2(m2x, bc(v)), one);
+            pz[j] = add2x(mul2(m1z, bc(omv)), mul2(m2z, bc(v)), one);
+            py[j] = bc(0.0f);
+        }
+        // ---- the hot loop: sum of Gerstner waves (water-grid.vert:74-85) ----
+        if (MODE == 0) {
+            f2 gx[R], gz[R];
+#pragma unroll
+            for (int j = 0; j < R; ++j) { gx[j] = px[j]; gz[j] = pz[j]; }
+#pragma unroll 1
             for (int i = 0; i < a.n_waves; ++i) {
-                const WaveK wk = wt.w[i];
-                const float c = wk.phi;   // the host stored fl(phaseConstant_phi * t) here for this launch
+                const WaveK wk = wt.w[i];   // phi holds fl(phaseConstant_phi * t) for this launch
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    float k;
-                    if (EXACT) {
-                        // frequency_w * dot(D, xz) + phi * t, every operation rounded as GLSL/GLM does
-                        k = add_rn(mul_rn(wk.w, add_rn(mul_rn(wk.Dx, gx[j]), mul_rn(wk.Dz, gz[j]))), c);
-                    } else {
-                        k = __fmaf_rn(wk.Dx, gx[j], __fmaf_rn(wk.Dz, gz[j], c));   // table holds w*D
-                    }
-                    float s, co;
-                    sincos_mufu(k, s, co);
-                    p[j].x = __fmaf_rn(wk.cX, co, p[j].x);
-                    p[j].y = __fmaf_rn(wk.A, s, p[j].y);
-                    p[j].z = __fmaf_rn(wk.cZ, co, p[j].z);
+                for (int j = 0; j < R; ++j) {
+                    // frequency_w * dot(D, xz) + phi * t, every operation rounded as GLSL/GLM does
+                    const f2 d = add2x(mul2(bc(wk.Dx), gx[j]), mul2(bc(wk.Dz), gz[j]), one);
+                    const f2 k = add2x(mul2(bc(wk.w), d), bc(wk.phi), one);
+                    f2 s, c;
+                    sincos2(k, s, c);
+                    px[j] = fma2(bc(wk.cX), c, px[j]);
+                    py[j] = fma2(bc(wk.A), s, py[j]);
+                    pz[j] = fma2(bc(wk.cZ), c, pz[j]);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < V; ++j) p[j].y = finish_height(a, p[j].x, p[j].y, p[j].z);
         } else {
+            const f2 gx0 = px[0], gz0 = pz[0];
+#pragma unroll 1
+            for (int i = 0; i < a.n_waves; ++i) {
+                const WaveK wk = wt.w[i];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
+                f2 s, c, sd, cd;
+                sincos2(fma2(bc(wk.Dx), gx0, fma2(bc(wk.Dz), gz0, bc(wk.phi))), s, c);
+                const f2 dk = fma2(bc(wk.Dx), ex, mul2(bc(wk.Dz), ez));
+                if (a.delta_reduce) {
+                    sincos2(dk, sd, cd);
+                } else {
+                    sd = make_float2(__sinf(dk.x), __sinf(dk.y));
+                    cd = make_float2(__cosf(dk.x), __cosf(dk.y));
+                }
+                px[0] = fma2(bc(wk.cX), c, px[0]);
+                py[0] = fma2(bc(wk.A), s, py[0]);
+                pz[0] = fma2(bc(wk.cZ), c, pz[0]);
 #pragma unroll
-            for (int j = 0; j < V; ++j) p[j] = {0.f, 0.f, 0.f};
-        }
-
-        // publish rows row_a-1 (slot 0, the carried row) .. row_a+V-1 (slot V) of this column
-        float4* sb = smem + (size_t)buf * (V + 1) * S;
-        sb[tid] = make_float4(carry1.x, carry1.y, carry1.z, 0.f);
-#pragma unroll
-        for (int j = 0; j < V; ++j) sb[(j + 1) * S + tid] = make_float4(p[j].x, p[j].y, p[j].z, 0.f);
-        __syncthreads();
-
-        // outputs for rows row_a-1 .. row_a+V-2
-        if (col_out) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const int row = row_a - 1 + j;
-                if (row >= r0 && row < r1) {
-                    const P3& c = (j == 0) ? carry1 : p[j - 1];
-                    const P3& up = p[j];
-                    const P3& down = (j == 0) ? carry2 : ((j == 1) ? carry1 : p[j - 2 < 0 ? 0 : j - 2]);
-                    float4 l4 = sb[j * S + tid - 1], r4 = sb[j * S + tid + 1];
-                    P3 left = {l4.x, l4.y, l4.z}, right = {r4.x, r4.y, r4.z};
-                    float4 on, os;
-                    normal_and_shade<SHADE>(a, c, left, right, down, up, on, os);
-                    const size_t o = (size_t)(row - a.row_begin) * a.L + col;
-                    float4 op = make_float4(c.x, c.y, c.z, 1.0f);
-                    __stcs(a.pos + o, op);
-                    __stcs(a.nrm + o, on);
-                    if (SHADE) __stcs(a.shade + o, os);
-                    if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(os); }
+                for (int j = 1; j < R; ++j) {
+                    // e^{i(k + dk)} = e^{ik} e^{i dk}
+                    const f2 c2 = fma2(c, cd, mul2(make_float2(-s.x, -s.y), sd));
+                    s = fma2(s, cd, mul2(c, sd));
+                    c = c2;
+                    px[j] = fma2(bc(wk.cX), c, px[j]);
+                    py[j] = fma2(bc(wk.A), s, py[j]);
+                    pz[j] = fma2(bc(wk.cZ), c, pz[j]);
                 }
             }
         }
-        carry2 = p[V - 2];
-        carry1 = p[V - 1];
-        buf ^= 1;
+        // ---- heightmap detail + bounce, final positions into the ring ----
+        __syncwarp();   // the previous step's readers are done with the rows being overwritten
+        {
+            int slot = slot_new;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                py[j] = finish_height2(a, px[j], py[j], pz[j]);
+                float2* const row = ring + slot * RING_COLS;
+                row[1 + lane] = px[j];
+                row[RL::PLANE + 1 + lane] = py[j];
+                row[2 * RL::PLANE + 1 + lane] = pz[j];
+                if (lane == 31) {
+                    row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
+                }
+                if (lane == 0) {
+                    row[33] = make_float2(px[j].y, 0.f); row[RL::PLANE + 33] = make_float2(py[j].y, 0.f); row[2 * RL::PLANE + 33] = make_float2(pz[j].y, 0.f);
+                }
+                slot = slot + 1 == RL::ROWS ? 0 : slot + 1;
+            }
+        }
+        __syncwarp();
+
+        // ---- outputs for rows row_a-1 .. row_a+R-2 (their up/down neighbours are in the ring now) ----
+        int sd_ = slot_new - 2 < 0 ? slot_new - 2 + RL::ROWS : slot_new - 2;   // row_a - 2
+#pragma unroll 1
+        for (int j = 0; j < R; ++j) {
+            const int sc_ = sd_ + 1 == RL::ROWS ? 0 : sd_ + 1;
+            const int su_ = sc_ + 1 == RL::ROWS ? 0 : sc_ + 1;
+            const int row = row_a - 1 + j;
+            if (row >= r0 && row < r1) {
+                const float2* const rc = ring + sc_ * RING_COLS + lane;
+                const float2* const rd = ring + sd_ * RING_COLS + lane + 1;
+                const float2* const ru = ring + su_ * RING_COLS + lane + 1;
+                const f2 cx = rc[1], cy = rc[RL::PLANE + 1], cz = rc[2 * RL::PLANE + 1];
+                // (right - left), (up - down): water-grid.vert:164-187
+                const f2 ux = sub2(rc[2], rc[0]), uy = sub2(rc[RL::PLANE + 2], rc[RL::PLANE]), uz = sub2(rc[2 * RL::PLANE + 2], rc[2 * RL::PLANE]);
+                const f2 vx = sub2(ru[0], rd[0]), vy = sub2(ru[RL::PLANE], rd[RL::PLANE]), vz = sub2(ru[2 * RL::PLANE], rd[2 * RL::PLANE]);
+                f2 nx = fma2(uy, vz, mul2(make_float2(-vy.x, -vy.y), uz));
+                f2 ny = fma2(uz, vx, mul2(make_float2(-vz.x, -vz.y), ux));
+                f2 nz = fma2(ux, vy, mul2(make_float2(-vx.x, -vx.y), uy));
+                const f2 n2 = fma2(nx, nx, fma2(ny, ny, mul2(nz, nz)));
+                f2 inv = make_float2(rsq_approx(n2.x), rsq_approx(n2.y));
+                const f2 wx = sub2(bc(a.camx), cx), wy = sub2(bc(a.camy), cy), wz = sub2(bc(a.camz), cz);   // viewVecRaw, :158
+                // :190 — the sign of dot(normal, normalize(viewVecRaw)) is the sign of the unnormalised dot
+                f2 facing = fma2(nx, wx, fma2(ny, wy, mul2(nz, wz)));
+                if (facing.x < 0.0f) inv.x = -inv.x;
+                if (facing.y < 0.0f) inv.y = -inv.y;
+                nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
+                f2 fres = bc(0.0f);
+                float4 sA = make_float4(0.f, 0.f, 0.f, 0.f), sB = sA;
+                if (SHADE) {
+                    const f2 w2 = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
+                    const f2 winv = make_float2(rsq_approx(w2.x), rsq_approx(w2.y));
+                    const f2 e_x = mul2(wx, winv), e_y = mul2(wy, winv), e_z = mul2(wz, winv);          // frag:71-73
+                    const f2 f = fma2(nx, e_x, fma2(ny, e_y, mul2(nz, e_z)));                            // dot(normal, viewVec) >= 0
+                    const f2 f2x = add2(f, f);
+                    // R = reflect(-viewVec, normal) = -viewVec + 2 dot(normal, viewVec) normal   (frag:95)
+                    const f2 rx = fma2(nx, f2x, make_float2(-e_x.x, -e_x.y)), ry = fma2(ny, f2x, make_float2(-e_y.x, -e_y.y)),
+                             rz = fma2(nz, f2x, make_float2(-e_z.x, -e_z.y));
+                    f2 sdot = fma2(rx, bc(a.sunx), fma2(ry, bc(a.suny), mul2(rz, bc(a.sunz))));
+                    sdot = make_float2(fminf(fmaxf(sdot.x, 0.0f), 1.0f), fminf(fmaxf(sdot.y, 0.0f), 1.0f));
+                    // pow(sd, shininess) (frag:100): 0^0 = 1, 0^y = 0
+                    f2 sp;
+                    if (a.sun_shininess == 0.0f) {
+                        sp = bc(1.0f);
+                    } else {
+                        const f2 lg = mul2(make_float2(lg2_approx(sdot.x), lg2_approx(sdot.y)), bc(a.sun_shininess));
+                        sp = make_float2(ex2_approx(lg.x), ex2_approx(lg.y));
+                    }
+                    sp = mul2(sp, bc(a.sun_strength));
+                    const f2 om = sub2(bc(1.0f), f);                                                     // frag:110-111
+                    const f2 om2 = mul2(om, om);
+                    fres = fma2(mul2(mul2(om2, om2), om), bc(1.0f - 0.02f), bc(0.02f));
+                    float3 skyA = make_float3(0.f, 0.f, 0.f), skyB = skyA;
+                    if (a.sky_quads) {                                                                   // frag:96
+                        skyA = sky_rgb_quads(a, rx.x, ry.x, rz.x);
+                        skyB = sky_rgb_quads(a, rx.y, ry.y, rz.y);
+                    }
+                    sA = make_float4(skyA.x, skyA.y, skyA.z, sp.x);
+                    sB = make_float4(skyB.x, skyB.y, skyB.z, sp.y);
+                }
+                const size_t o = (size_t)(row - a.row_begin) * a.L;
+                if (outA) {
+                    const float4 op = make_float4(cx.x, cy.x, cz.x, 1.0f), on = make_float4(nx.x, ny.x, nz.x, fres.x);
+                    __stcs(a.pos + o + colA, op);
+                    __stcs(a.nrm + o + colA, on);
+                    if (SHADE) __stcs(a.shade + o + colA, sA);
+                    if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(sA); }
+                }
+                if (outB) {
+                    const float4 op = make_float4(cx.y, cy.y, cz.y, 1.0f), on = make_float4(nx.y, ny.y, nz.y, fres.y);
+                    __stcs(a.pos + o + colB, op);
+                    __stcs(a.nrm + o + colB, on);
+                    if (SHADE) __stcs(a.shade + o + colB, sB);
+                    if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(sB); }
+                }
+            }
+            sd_ = sc_;
+        }
+        slot_new = slot_new + R >= RL::ROWS ? slot_new + R - RL::ROWS : slot_new + R;
     }
     if (a.cks) acc.flush(a.cks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Footprint tables (built on the device when a texture is set)
+// ------------------------------------------------------------------------------------------------
+// GL_MIRRORED_REPEAT unrolled: entry (i, j), i in [0, 2w), j in [0, 2h), holds the texels at
+// wrap(i), wrap(i+1) x wrap(j), wrap(j+1) — the GL_LINEAR footprint whose lower-left texel index is
+// congruent to (i, j) modulo (2w, 2h).
+__global__ void build_heightmap_quads_kernel(const float* r, int w, int h, float4* quads) {
+    const int w2 = 2 * w, h2 = 2 * h;
+    const long long n = (long long)w2 * h2;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(k % w2), j = (int)(k / w2);
+        const int i0 = wrap_mirror(i, w, 0), i1 = wrap_mirror(i + 1, w, 0), j0 = wrap_mirror(j, h, 0), j1 = wrap_mirror(j + 1, h, 0);
+        quads[k] = make_float4(r[(size_t)j0 * w + i0], r[(size_t)j0 * w + i1], r[(size_t)j1 * w + i0], r[(size_t)j1 * w + i1]);
+    }
+}
+// CLAMP_TO_EDGE per face: entry (iu + 1, iv + 1), iu, iv in [-1, n-1], holds texels clamp(iu), clamp(iu+1) x clamp(iv), clamp(iv+1)
+__global__ void build_sky_quads_kernel(const uchar4* sky, int n, uint4* quads) {
+    const int n1 = n + 1;
+    const long long total = 6LL * n1 * n1;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int iu = (int)(k % n1) - 1, iv = (int)((k / n1) % n1) - 1, face = (int)(k / ((long long)n1 * n1));
+        const int i0 = min(max(iu, 0), n - 1), i1 = min(max(iu + 1, 0), n - 1), j0 = min(max(iv, 0), n - 1), j1 = min(max(iv + 1, 0), n - 1);
+        const unsigned* f = (const unsigned*)(sky + (size_t)face * n * n);
+        quads[k] = make_uint4(f[(size_t)j0 * n + i0], f[(size_t)j0 * n + i1], f[(size_t)j1 * n + i0], f[(size_t)j1 * n + i1]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
