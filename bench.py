@@ -93,36 +93,44 @@ class ClockSampler:
 def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
     """The reference's own CPU implementation of the path on the host cores: the reference
     water-grid.vert shader text compiled as C++ (oracle/_ref, kind 'reference') when it was built,
-    else the oracle port (kind 'port').  Bounded sample: whole rows of the SAME frame until about
-    `seconds_target` seconds of wall time have been spent."""
+    else the oracle port (kind 'port').  Bounded sample: bands of whole rows of consecutive animation
+    frames of the SAME workload until about `seconds_target` seconds of wall time have been spent."""
     from oracle import oracle as orc                      # cpu_baseline leg: the one place bench.py may use oracle/
     from tests.common import Scene
     from wave_tool_b200 import scenes
     O = orc.Oracle()
     R = orc.Ref()
     hm = scenes.procedural_heightmap(512)
-    sc = Scene(scenes.seeded_waves(W, cfg=cfg), scenes.camera(), scenes.animation_params(75), L, hm)
-    st, u, wu = sc.oracle_uniforms(O)
+    waves = scenes.seeded_waves(W, cfg=cfg)
     use_ref = R.available and L <= 4096 and W <= R.max_waves()
-    rows_done, t_spent, chunk = 0, 0.0, 8
     cores = O.num_threads()
-    while t_spent < seconds_target and rows_done + chunk <= L:
+    rows_total, t_spent, chunk, frame, row = 0, 0.0, 8, 75, 0
+    sc = Scene(waves, scenes.camera(), scenes.animation_params(frame), L, hm)
+    st, u, wu = sc.oracle_uniforms(O)
+    while t_spent < seconds_target:
+        hi = min(row + chunk, L)
         t0 = time.perf_counter()
         if use_ref:
-            R.vert_run(u, wu, hm, id_range=(rows_done * L, (rows_done + chunk) * L))
+            R.vert_run(u, wu, hm, id_range=(row * L, hi * L))
         else:
-            O.eval(u, wu, hm, rows=(rows_done, rows_done + chunk))
+            O.eval(u, wu, hm, rows=(row, hi))
         dt = time.perf_counter() - t0
         t_spent += dt
-        rows_done += chunk
+        rows_total += hi - row
+        row = hi
+        if row >= L:                                      # next animation frame
+            frame, row = frame + 1, 0
+            sc = Scene(waves, scenes.camera(), scenes.animation_params(frame), L, hm)
+            st, u, wu = sc.oracle_uniforms(O)
         if t_spent + 2 * dt > max_seconds:
             break
         if dt < 1.0:
-            chunk = min(chunk * 2, 256)
-    vw = rows_done * L * W
+            chunk = min(chunk * 2, 512)
+    vw = rows_total * L * W
     return {"value": vw / t_spent, "unit": "vertex-waves/s", "cores": cores, "kind": "reference" if use_ref else "port",
-            "sample": f"rows [0,{rows_done}) of one {L}x{L} frame with {W} waves (vertex stage: positions + 4-neighbour normals), "
-                      f"{t_spent:.1f} s wall, OpenMP over vertices, g++ -O2 -ffp-contract=off",
+            "sample": f"{rows_total} rows ({rows_total / L:.2f} frames) of the {L}x{L} grid with {W} waves, vertex stage "
+                      f"(positions + 4-neighbour normals: 5 evaluations per vertex as the shader does), {t_spent:.1f} s wall, "
+                      f"OpenMP over vertices on {cores} threads, g++ -O2 -ffp-contract=off",
             "seconds": t_spent, "vertex_waves": vw}
 
 
@@ -172,7 +180,8 @@ def run_ours(args):
     L, W, cfg, shade, desc = WORKLOADS[args.workload]
     K, Wm = args.steps, max(3, args.warmup)
     flags = api.FLAG_SHADE if shade else 0
-    if args.fast_phase:
+    recurrence = not args.exact_phase
+    if recurrence:
         flags |= api.FLAG_FAST_PHASE
 
     # ---- setup (untimed): context, wave table, textures, output ring ----------------------------
@@ -198,6 +207,7 @@ def run_ours(args):
     # roofline denominators measured on this very device (untimed)
     mufu_pairs = ctx.measure_peak(0)
     fma_flops = ctx.measure_peak(1)
+    fma2_flops = ctx.measure_peak(3)
     store_bps = ctx.measure_peak(2)
 
     def barrier():
@@ -264,7 +274,7 @@ def run_ours(args):
 
     # full read-back variant: every output byte copied to pinned host memory each step (PCIe-bound)
     rb = None
-    if args.readback and rank == 0:
+    if not args.no_readback and rank == 0 and world == 1:
         hp = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         hn = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         hs = torch.empty((n, 4), dtype=torch.float32).pin_memory() if shade else None
@@ -279,59 +289,105 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         rb = {"value": reps * vw_per_frame / dt, "unit": "vertex-waves/s", "d2h_bytes_per_step": n * 16 * (3 if shade else 2), "n_gpus": 1}
 
-    # gather the per-frame digests of the timed frames (the only collective; after the timed region)
-    digests = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K]
-    if world > 1:
-        launch(Wm, Wm + K, with_cks=True)
+    # ---- the other phase mode on the same frames (untimed region of the bench; rank 0, N=1) + deviation ----
+    other = None
+    if rank == 0:
+        oflags = flags ^ api.FLAG_FAST_PHASE
+        f_last = frames[Wm + K - 1]
+        slot_main = (Wm + K - 1) % ring                       # where the timed run left its last frame
+        slot_other = 1 - slot_main
+        ctx.eval_frame(f_last, L, pos.data_ptr() + slot_main * n * 16, nrm.data_ptr() + slot_main * n * 16,
+                       (shd.data_ptr() + slot_main * n * 16) if shade else 0, flags=flags, stream=sp)
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(K, 10))
+        for w_ in range(2):
+            ctx.eval_frame(f_last, L, pos.data_ptr() + slot_other * n * 16, nrm.data_ptr() + slot_other * n * 16,
+                           (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, stream=sp)
+        o0.record(stream)
+        for r_ in range(reps):
+            ctx.eval_frame(f_last, L, pos.data_ptr() + slot_other * n * 16, nrm.data_ptr() + slot_other * n * 16,
+                           (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, stream=sp)
+        o1.record(stream)
         torch.cuda.synchronize()
-        allr = shard.all_gather_checksums(cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K], dev)
+        oms = o0.elapsed_time(o1) / reps
+        pa, pb = pos[slot_main * n:(slot_main + 1) * n, :3], pos[slot_other * n:(slot_other + 1) * n, :3]
+        na, nb = nrm[slot_main * n:(slot_main + 1) * n, :3], nrm[slot_other * n:(slot_other + 1) * n, :3]
+        dpos = float((pa - pb).abs().max().item())
+        dn = (na - nb).norm(dim=1)
+        dn = torch.minimum(dn, (na + nb).norm(dim=1))          # the view-facing flip is sign-ambiguous at grazing incidence
+        other = {"ms_per_frame": oms, "vertex_waves_per_sec": vw_per_frame / (oms * 1e-3),
+                 "phase": "bit-faithful fp32 phase, MUFU pair per vertex-wave" if recurrence else "rotation recurrence",
+                 "max_position_deviation_between_modes": dpos, "position_tolerance": 1e-4 * float(total_amp),
+                 "max_normal_deviation_rad_between_modes": float(dn.max().item()), "normal_tolerance_rad": 1e-3,
+                 "checked_on": "all %d vertices of the last timed frame, on the device" % n}
+
+    # gather the per-frame digests of the timed frames (the only collective; after the timed region)
+    launch(Wm, Wm + K, with_cks=True)
+    torch.cuda.synchronize()
+    local_digests = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K]
+    if world > 1:
+        allr = shard.all_gather_checksums(local_digests, dev)
         digest_of_digests = shard.combine_checksums(allr.ravel())
     else:
-        launch(Wm, Wm + K, with_cks=True)
-        torch.cuda.synchronize()
-        digest_of_digests = shard.combine_checksums(cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[Wm:Wm + K])
+        digest_of_digests = shard.combine_checksums(local_digests)
 
     if rank == 0:
         peaks = measured_peaks()
         kernel_ms = ms_local / K                                    # one evaluation kernel per step
-        trans_per_s = vw_per_frame * TRANSCENDENTALS_PER_VERTEX_WAVE / (kernel_ms * 1e-3)
-        sfu_peak = 2.0 * mufu_pairs                                  # measured MUFU-only micro-kernel, this device, this run
         out_bytes = n * 16 * (3 if shade else 2)
         hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + ("" if recurrence else "_exact"))
         except Exception:
             pass
-        compute_bound = (vw_per_frame * 2 / sfu_peak) >= (out_bytes / (hbm_peak * 1e9))
+        alg = {"vertex_waves": vw_per_frame, "transcendentals": vw_per_frame * TRANSCENDENTALS_PER_VERTEX_WAVE,
+               "flop": vw_per_frame * FLOP_PER_VERTEX_WAVE, "bytes_written": out_bytes}
+        trans_per_s = alg["transcendentals"] / (kernel_ms * 1e-3)
+        flop_per_s = alg["flop"] / (kernel_ms * 1e-3)
+        sfu_peak = 2.0 * mufu_pairs                                  # measured MUFU-only micro-kernel, this device, this run
         roof_sfu = {"bound": "sfu", "achieved": trans_per_s / 1e9, "peak": sfu_peak / 1e9, "unit": "Gtranscendental/s",
                     "frac": trans_per_s / sfu_peak, "traffic": traffic,
-                    "peak_source": "MUFU-only micro-kernel (sin+cos) measured on this device in this run (wt_measure_peak); "
-                                   "nominal 16/clk/SM x 148 SM x clocks.max.sm",
-                    "nominal_peak": 16 * 148 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6 / 1e9,
-                    "algorithmic_per_launch": {"vertex_waves": vw_per_frame, "transcendentals": vw_per_frame * 2,
-                                               "flop": vw_per_frame * FLOP_PER_VERTEX_WAVE, "bytes_written": out_bytes}}
+                    "peak_source": "of measured: MUFU-only micro-kernel (sin+cos) on this device in this run (wt_measure_peak 0); "
+                                   "nominal 16/clk/SM x 148 SM x clocks.max.sm = %.0f" % (16 * 148 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6 / 1e9),
+                    "algorithmic_per_launch": alg}
+        roof_fp32 = {"bound": "fp32", "achieved": flop_per_s / 1e12, "peak": fma_flops / 1e12, "unit": "TFLOP/s",
+                     "frac": flop_per_s / fma_flops, "traffic": traffic,
+                     "peak_source": "of measured: FFMA-only micro-kernel on this device in this run (wt_measure_peak 1; packed FFMA2: %.1f); "
+                                    "MEASURED_PEAKS.json has no FP32 figure; nominal 128 FMA/clk/SM = 74.4" % (fma2_flops / 1e12),
+                     "algorithmic_per_launch": alg,
+                     "note": "15 FLOP per vertex-wave (SURVEY 8d); the recurrence executes ~15.5 FLOP + 0.5 MUFU per vertex-wave"}
         roof_hbm = {"bound": "hbm", "achieved": out_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": out_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, of measured)" if peaks else "fallback 6650 GB/s",
-                    "store_stream_measured_gbs": store_bps / 1e9}
+                    "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "of fallback: 6650 GB/s",
+                    "store_stream_measured_gbs": store_bps / 1e9, "algorithmic_per_launch": alg}
+        t_sfu = alg["transcendentals"] / sfu_peak if not recurrence else 0.25 * alg["transcendentals"] / sfu_peak
+        t_fp32, t_hbm = alg["flop"] / fma_flops, out_bytes / (hbm_peak * 1e9)
+        if t_hbm >= max(t_sfu, t_fp32):
+            primary, secondary = roof_hbm, [roof_fp32 if recurrence else roof_sfu]
+        elif recurrence:
+            primary, secondary = roof_fp32, [roof_sfu, roof_hbm]
+        else:
+            primary, secondary = roof_sfu, [roof_fp32, roof_hbm]
         line = {
             "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": n_gpus, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "grid_len": L, "waves": W, "shade": shade, "frames_per_step_per_gpu": 1,
                        "parallelism": f"frame-sharded x{n_gpus} (frame f on rank f mod N), no data-path collective",
                        "l2": "each step writes %d MB of fresh output into a 2-deep ring (> 126 MB L2)" % (out_bytes // 2 ** 20),
-                       "phase": "fast (pre-folded FMA)" if args.fast_phase else "bit-faithful fp32 phase"},
+                       "phase": "rotation recurrence (WT_FLAG_FAST_PHASE): MUFU seed every 8 rows, complex rotation in between"
+                                if recurrence else "bit-faithful fp32 phase, MUFU sin/cos pair per vertex-wave"},
             "ms_per_frame": ms_per_step,
-            "roofline": roof_sfu if compute_bound else roof_hbm,
-            "roofline_secondary": roof_hbm if compute_bound else roof_sfu,
-            "fp32_fma_peak_measured_tflops": fma_flops / 1e12,
+            "roofline": primary,
+            "roofline_secondary": secondary,
             "e2e": {"value": e2e_value, "unit": "vertex-waves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host camera/params -> wt_build_frame -> wt_eval_frame(+digest) -> 40-byte digest read back to pinned host memory, synchronised every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "digest_of_timed_frames": {k: (int(v) if not isinstance(v, float) else v) for k, v in digest_of_digests.items()},
         }
+        if other:
+            line["other_phase_mode"] = other
         if rb:
             line["e2e_full_readback"] = rb
         if n_gpus == 1 and not args.no_cpu_baseline:
@@ -351,8 +407,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3")
-    ap.add_argument("--fast-phase", action="store_true", help="use the pre-folded (not bit-faithful) wave phase")
-    ap.add_argument("--readback", action="store_true", help="also time full output read-back to pinned host memory")
+    ap.add_argument("--exact-phase", action="store_true",
+                    help="time the bit-faithful-phase wave loop (one MUFU pair per vertex-wave) instead of the rotation recurrence")
+    ap.add_argument("--fast-phase", action="store_true", help="(default; kept for compatibility)")
+    ap.add_argument("--no-readback", action="store_true", help="skip the full output read-back (PCIe-bound) variant of e2e")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

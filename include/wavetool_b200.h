@@ -202,7 +202,8 @@ int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, un
 /* Number of kernels this ctx has launched so far (evaluation + helper kernels). */
 uint64_t wt_launch_count(const wt_ctx* ctx);
 /* Micro-benchmarks for the roofline denominators: kind 0 = MUFU (sin+cos pairs/s),
- * 1 = FP32 FMA (FLOP/s), 2 = HBM float4 store stream (bytes/s).  Synchronous; result in *per_second. */
+ * 1 = FP32 FMA (FLOP/s), 2 = HBM float4 store stream (bytes/s), 3 = packed FP32 FFMA2 (FLOP/s).
+ * Synchronous; result in *per_second. */
 int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second);
 
 #ifdef __cplusplus

@@ -13,6 +13,10 @@ from wave_tool_b200 import api, scenes
 
 pytestmark = pytest.mark.gpu
 
+# the two phase modes of the production kernel: bit-faithful fp32 phase + MUFU pair per vertex-wave, and
+# MUFU seed + rotation recurrence (WT_FLAG_FAST_PHASE).  Both must meet the same tolerances.
+MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE}
+
 
 def torch_mod():
     import torch
@@ -57,14 +61,15 @@ def hm():
 # --------------------------------------------------------------------------------------------------
 # configs[0]: the reference default scene (513^2 grid, the 4 hard-coded wave slots)
 # --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("t", [0.0, 1.5])
-def test_cfg1_default_scene_full_grid(oracle, hm, t):
+def test_cfg1_default_scene_full_grid(oracle, hm, t, mode):
     p = scenes.animation_params(int(round(t * 60)))
     sc = Scene(scenes.default_waves(), scenes.camera(), p, 513, hm)
     st, frame = sc.frame()
     assert st == api.WT_OK
     ctx = sc.make_context()
-    got = gpu_eval(ctx, frame, 513)
+    got = gpu_eval(ctx, frame, 513, flags=MODES[mode])
     want = sc.oracle_eval(oracle)
     stats = compare(got, want, sc, label=f"cfg1 t={t}")
     print("cfg1", t, stats)
@@ -112,8 +117,10 @@ def test_no_transcendentals_means_bit_exact(oracle, hm):
 # --------------------------------------------------------------------------------------------------
 # configs[1]: 1024^2 grid, 8 Gerstner waves + heightmap noise, animation
 # --------------------------------------------------------------------------------------------------
-def test_cfg2_animation_frames_and_batch(oracle, hm):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_cfg2_animation_frames_and_batch(oracle, hm, mode):
     torch = torch_mod()
+    fl = MODES[mode]
     L, waves, cam = 1024, scenes.seeded_waves(8, cfg=2), scenes.camera()
     frame_ids = [0, 1, 499, 999]
     frames = [api.build_frame(cam, scenes.animation_params(f), api.total_amplitude(waves))[1] for f in frame_ids]
@@ -122,9 +129,9 @@ def test_cfg2_animation_frames_and_batch(oracle, hm):
     singles = []
     for f, frame in zip(frame_ids, frames):
         sc.params = scenes.animation_params(f)
-        got = gpu_eval(ctx, frame, L, checksum=True)
+        got = gpu_eval(ctx, frame, L, flags=fl, checksum=True)
         want = sc.oracle_eval(oracle)
-        stats = compare(got, want, sc, label=f"cfg2 frame {f}")
+        stats = compare(got, want, sc, label=f"cfg2 frame {f} {mode}")
         print("cfg2 frame", f, stats)
         assert tuple(got["checksum"])[:3] == numpy_checksum(got["pos"], got["normal"], None)[:3]
         assert got["checksum"]["min_y"] == got["pos"][:, 1].min() and got["checksum"]["max_y"] == got["pos"][:, 1].max()
@@ -133,7 +140,7 @@ def test_cfg2_animation_frames_and_batch(oracle, hm):
     # the golden vectors of the reference's own shader for this configuration (t = 0.5 -> frame 30)
     z = np.load(os.path.join(GOLDEN, "vert_seeded8.npz"))
     sc.params = scenes.animation_params(30)
-    got = gpu_eval(ctx, sc.frame()[1], L)
+    got = gpu_eval(ctx, sc.frame()[1], L, flags=fl)
     gold = {"pos": z["world"], "normal": np.concatenate([z["out"]["normal"], np.zeros((len(z["ids"]), 1), np.float32)], 1)}
     compare({"pos": got["pos"][z["ids"]], "normal": got["normal"][z["ids"]]}, gold, sc, label="cfg2 golden")
     # wt_eval_batch: ring of 2 buffers + per-frame digests == the single-frame calls, bit for bit
@@ -141,7 +148,7 @@ def test_cfg2_animation_frames_and_batch(oracle, hm):
     ring_p = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
     ring_n = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
     cks = torch.zeros(40 * len(frames), dtype=torch.uint8, device="cuda")
-    ctx.eval_batch(frames, L, ring_p.data_ptr(), ring_n.data_ptr(), 0, 2, cks.data_ptr(), flags=api.FLAG_CHECKSUM,
+    ctx.eval_batch(frames, L, ring_p.data_ptr(), ring_n.data_ptr(), 0, 2, cks.data_ptr(), flags=api.FLAG_CHECKSUM | fl,
                    stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     digests = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
@@ -164,58 +171,62 @@ def cfg3(hm):
     return sc, frame, ctx
 
 
-def test_cfg3_shaded_vs_oracle_on_sampled_rows(oracle, cfg3):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_cfg3_shaded_vs_oracle_on_sampled_rows(oracle, cfg3, mode):
     sc, frame, ctx = cfg3
     L = sc.L
     rows = [0, 1, 2, 117, 118, 119, 120, 121, 1500, 2047, 2048, 3333, 4093, 4094, 4095]
-    got = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE, checksum=True)
+    got = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE | MODES[mode], checksum=True)
     want = sc.oracle_eval(oracle, shade=True, ids=rows_to_ids(rows, L))
     stats = compare(take_rows(got, rows, L), want, sc, shade=True, label="cfg3")
     print("cfg3", stats)
     assert tuple(got["checksum"])[:3] == numpy_checksum(got["pos"], got["normal"], got["shade"])[:3]
     # columns too: the strip seams of the tile kernel (every column of a few rows was covered above;
     # here a full-height slice of columns around likely seams)
-    cols = np.array([0, 1, 2, 155, 156, 157, 158, 159, 160, 161, 2046, 2047, 2048, 4093, 4094, 4095])
+    cols = np.array([0, 1, 2, 30, 31, 32, 60, 61, 62, 63, 64, 123, 124, 125, 2046, 2047, 2048, 4029, 4030, 4031, 4093, 4094, 4095])
     ids = (np.arange(L)[:, None] * L + cols[None, :]).ravel()
     want = sc.oracle_eval(oracle, shade=True, ids=ids)
     sub = {k: got[k][ids] for k in ("pos", "normal", "shade")}
     compare(sub, want, sc, shade=True, label="cfg3 columns")
 
 
-def test_cfg3_full_grid_vs_reference_order_kernel(cfg3):
-    """Full 4096^2 coverage: the tile kernel against the reference-order kernel (itself checked against
+@pytest.mark.parametrize("mode", list(MODES))
+def test_cfg3_full_grid_vs_reference_order_kernel(cfg3, mode):
+    """Full 4096^2 coverage: the production kernel against the reference-order kernel (itself checked against
     the oracle above and in cfg1) — every vertex, every strip/chunk seam."""
     sc, frame, ctx = cfg3
-    a = gpu_eval(ctx, frame, sc.L, flags=api.FLAG_SHADE)
+    a = gpu_eval(ctx, frame, sc.L, flags=api.FLAG_SHADE | MODES[mode])
     b = gpu_eval(ctx, frame, sc.L, flags=api.FLAG_SHADE | api.FLAG_REFERENCE_ORDER)
     stats = compare(a, b, sc, shade=True, label="cfg3 tile vs reference-order")
     print("cfg3 full", stats)
 
 
-def test_cfg3_fast_phase_variant_within_tolerance(oracle, cfg3):
-    sc, frame, ctx = cfg3
-    L = sc.L
-    rows = [0, 1, 2000, 4095]
-    got = gpu_eval(ctx, frame, L, flags=api.FLAG_FAST_PHASE)
-    want = sc.oracle_eval(oracle, ids=rows_to_ids(rows, L))
-    stats = compare(take_rows(got, rows, L), want, sc, label="cfg3 fast-phase")
-    print("cfg3 fast-phase", stats)
-
-
-def test_row_sharded_equals_unsharded_bit_exact(cfg3):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_row_sharded_equals_unsharded_bit_exact(cfg3, mode):
     """Row sharding: every vertex is a pure function of (col,row) — 8 row shards give
     the very same bits as one evaluation, and their digests fold into the unsharded digest."""
     from wave_tool_b200 import shard
     sc, frame, ctx = cfg3
     L = 1024     # same scene, smaller grid (memory/time)
-    full = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE, checksum=True)
+    fl = api.FLAG_SHADE | MODES[mode]
+    full = gpu_eval(ctx, frame, L, flags=fl, checksum=True)
     parts = []
     for r in range(8):
         b, e = shard.row_shard(L, r, 8)
-        part = gpu_eval(ctx, frame, L, flags=api.FLAG_SHADE, rows=(b, e), checksum=True)
-        for k in ("pos", "normal", "shade"):
-            assert np.array_equal(part[k].view(np.uint32), full[k][b * L:e * L].view(np.uint32)), (r, k)
+        part = gpu_eval(ctx, frame, L, flags=fl, rows=(b, e), checksum=True)
+        if mode == "exact":
+            # every vertex is a pure function of (col,row): the very same bits whatever the shard
+            for k in ("pos", "normal", "shade"):
+                assert np.array_equal(part[k].view(np.uint32), full[k][b * L:e * L].view(np.uint32)), (r, k)
+        else:
+            # the recurrence re-seeds every 8 rows counted from the shard's first row, so a vertex's rounding
+            # depends on where its shard starts: equal within the parity tolerance, not bit for bit
+            sub = {k: full[k][b * L:e * L] for k in ("pos", "normal", "shade")}
+            compare(part, sub, sc, pos_tol=5e-5 * sc.total_amplitude, normal_tol=5e-4, label=f"shard {r}")
+            assert tuple(part["checksum"])[:3] == numpy_checksum(part["pos"], part["normal"], part["shade"])[:3]
         parts.append(part["checksum"])
+    if mode != "exact":
+        return
     c = shard.combine_checksums(np.array(parts))
     f = full["checksum"]
     assert (c["position_bits"], c["normal_bits"], c["shade_bits"], c["vertices"]) == (f["position_bits"], f["normal_bits"], f["shade_bits"], f["vertices"])
@@ -225,13 +236,14 @@ def test_row_sharded_equals_unsharded_bit_exact(cfg3):
 # --------------------------------------------------------------------------------------------------
 # configs[3]: 8192^2 grid, 256 waves (row bands only — 2.15 GB per full frame)
 # --------------------------------------------------------------------------------------------------
-def test_cfg4_8192_grid_256_waves_row_bands(oracle, hm):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_cfg4_8192_grid_256_waves_row_bands(oracle, hm, mode):
     L = 8192
     sc = Scene(scenes.seeded_waves(256, cfg=4), scenes.camera(), scenes.animation_params(1023), L, hm)
     st, frame = sc.frame()
     ctx = sc.make_context()
     for band in [(0, 6), (4090, 4100), (8186, 8192)]:
-        got = gpu_eval(ctx, frame, L, rows=band)
+        got = gpu_eval(ctx, frame, L, rows=band, flags=MODES[mode])
         rows = [band[0], band[1] - 1]
         want = sc.oracle_eval(oracle, ids=rows_to_ids(rows, L))
         stats = compare(take_rows(got, rows, L, row_begin=band[0]), want, sc, label=f"cfg4 rows {band}")
@@ -241,8 +253,9 @@ def test_cfg4_8192_grid_256_waves_row_bands(oracle, hm):
 # --------------------------------------------------------------------------------------------------
 # configs[4]: 16384^2 grid, 32 waves, horizon-grazing / high-altitude projector edge cases
 # --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("name", list(scenes.EDGE_CAMERAS))
-def test_cfg5_edge_cameras_16384(oracle, hm, name):
+def test_cfg5_edge_cameras_16384(oracle, hm, name, mode):
     L = 16384
     sc = Scene(scenes.seeded_waves(32, cfg=5), scenes.camera(**scenes.EDGE_CAMERAS[name]), scenes.animation_params(11), L, hm)
     st, frame = sc.frame()
@@ -253,7 +266,7 @@ def test_cfg5_edge_cameras_16384(oracle, hm, name):
         return
     ctx = sc.make_context()
     for band in [(0, 4), (8190, 8194), (16380, 16384)]:
-        got = gpu_eval(ctx, frame, L, rows=band)
+        got = gpu_eval(ctx, frame, L, rows=band, flags=MODES[mode])
         rows = [band[0] + 1]
         ids = rows_to_ids(rows, L)
         want = sc.oracle_eval(oracle, ids=ids)
@@ -286,23 +299,25 @@ def test_cfg5_edge_cameras_16384(oracle, hm, name):
 # --------------------------------------------------------------------------------------------------
 # boundary behaviour
 # --------------------------------------------------------------------------------------------------
-def test_ragged_and_tiny_grids(oracle, hm):
-    for L in (2, 3, 5, 31, 64, 127, 130, 255, 257, 1000):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_ragged_and_tiny_grids(oracle, hm, mode):
+    for L in (2, 3, 5, 31, 61, 62, 63, 64, 65, 124, 125, 127, 130, 255, 257, 1000):
         sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), L, hm)
         st, frame = sc.frame()
         ctx = sc.make_context()
-        got = gpu_eval(ctx, frame, L)
+        got = gpu_eval(ctx, frame, L, flags=MODES[mode])
         want = sc.oracle_eval(oracle)
         compare(got, want, sc, label=f"L={L}")
 
 
-def test_wave_count_tiers(oracle, hm):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_wave_count_tiers(oracle, hm, mode):
     for W in (0, 1, 4, 16, 17, 64, 65, 256, 257, 1000):
         waves = scenes.seeded_waves(W, cfg=9) if W else np.zeros((0, 6), np.float32)
         sc = Scene(waves, scenes.camera(), scenes.animation_params(5), 96, hm)
         st, frame = sc.frame()
         ctx = sc.make_context()
-        got = gpu_eval(ctx, frame, 96)
+        got = gpu_eval(ctx, frame, 96, flags=MODES[mode])
         want = sc.oracle_eval(oracle)
         tol = None if W else 1e-12
         compare(got, want, sc, pos_tol=tol, label=f"W={W}")

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,7 +40,7 @@ struct wt_ctx {
     float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)
     int hm_w = 0, hm_h = 0;
     uchar4* d_sky = nullptr;        // 6 faces RGBA8 (reference-order kernel)
-    uint4* d_sky_quads = nullptr;   // clamp-to-edge footprint table (production kernel)
+    uchar4* d_sky_black = nullptr;  // 1x1 black cubemap: shading without a skybox reads sky = 0, no branch in the production kernel
     int sky_n = 0;
     // scratch for the *_host entry points
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
@@ -116,14 +117,16 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
 }
 
-template <int CAP, int MODE, bool SHADE>
-cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+template <int CAP, int MODE, bool SHADE, bool CKS>
+cudaError_t launch_warp_cks(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
     constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
-    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE>;
-    constexpr int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP;
+    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS>;
+    static const char* env_smem = std::getenv("WT_EXTRA_SMEM");   // experiment knob: cap the CTAs per SM
+    const int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP + (env_smem ? std::atoi(env_smem) : 0);
     static thread_local struct { int L = -1, rows = -1, dev = -1; Plan p; } cache;   // per instantiation
     const int rows = a.row_end - a.row_begin;
     if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * WARPS_PER_CTA, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         cache.p = make_plan(ctx->sm_count * per_sm * WARPS_PER_CTA, a.L, rows, R);
@@ -140,17 +143,15 @@ cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab,
         // MODE 1 adds the offset inside an FMA chain: hand it over reduced mod 2pi (in double) so it costs no precision
         table.w[i].phi = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
     }
-    if (MODE == 1) {
-        // largest per-row phase step over the grid: |w| * longest column edge * du
-        const float e0 = std::hypot(a.tlx - a.blx, a.tlz - a.blz), e1 = std::hypot(a.trx - a.brx, a.trz - a.brz);
-        float wmax = 0.f;
-        for (const WaveK& w : tab) wmax = std::max(wmax, std::hypot(w.Dx, w.Dz));
-        const float dmax = wmax * std::max(e0, e1) * a.du;
-        a.delta_reduce = !(dmax < 3.0f);
-    }
+    { static const char* e = std::getenv("WT_DBG"); a.dbg = e ? std::atoi(e) : 0; }
     kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
+}
+
+template <int CAP, int MODE, bool SHADE>
+cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    return a.cks ? launch_warp_cks<CAP, MODE, SHADE, true>(ctx, a, tab, stream) : launch_warp_cks<CAP, MODE, SHADE, false>(ctx, a, tab, stream);
 }
 
 template <int CAP, bool SHADE>
@@ -210,7 +211,8 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
     a.one = 1.0f;
     a.hm_r = ctx->d_hm_r; a.hm_quads = ctx->d_hm_quads; a.hm_w = ctx->hm_w; a.hm_h = ctx->hm_h;
     a.hm_pow2 = ((ctx->hm_w & (ctx->hm_w - 1)) == 0) && ((ctx->hm_h & (ctx->hm_h - 1)) == 0);
-    a.sky = ctx->d_sky; a.sky_quads = ctx->d_sky_quads; a.sky_n = ctx->sky_n;
+    a.sky = ctx->d_sky; a.sky_n = ctx->sky_n;
+    if (!a.sky) { a.sky = ctx->d_sky_black; a.sky_n = 1; }
     a.pos = (float4*)d_pos; a.nrm = (float4*)d_nrm; a.shade = (float4*)d_shade;
     a.cks = (flags & WT_FLAG_CHECKSUM) ? (wt_checksum*)d_cks : nullptr;
     a.L = (int)L; a.row_begin = (int)r0; a.row_end = (int)r1;
@@ -254,6 +256,8 @@ int wt_create(wt_ctx** out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     WT_CUDA(nullptr, cudaMalloc(&ctx->s_cks, sizeof(wt_checksum)));
+    WT_CUDA(nullptr, cudaMalloc(&ctx->d_sky_black, 6 * sizeof(uchar4)));
+    WT_CUDA(nullptr, cudaMemset(ctx->d_sky_black, 0, 6 * sizeof(uchar4)));
     *out = ctx;
     return WT_OK;
 }
@@ -262,7 +266,7 @@ void wt_destroy(wt_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_hm_r); cudaFree(ctx->d_hm_quads);
-    cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_quads);
+    cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     delete ctx;
 }
@@ -321,15 +325,11 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
     if (!faces || n <= 0 || n > 16384) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: bad cubemap");
     for (int f = 0; f < 6; ++f) if (!faces[f]) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: face pointer is NULL");
     DeviceGuard g(ctx->device);
-    cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_quads);
-    ctx->d_sky = nullptr; ctx->d_sky_quads = nullptr;
+    cudaFree(ctx->d_sky);
+    ctx->d_sky = nullptr;
     const size_t face_bytes = (size_t)n * n * 4;
     WT_CUDA(ctx, cudaMalloc(&ctx->d_sky, 6 * face_bytes));
     for (int f = 0; f < 6; ++f) WT_CUDA(ctx, cudaMemcpy((uint8_t*)ctx->d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice));
-    WT_CUDA(ctx, cudaMalloc(&ctx->d_sky_quads, 6 * (size_t)(n + 1) * (n + 1) * sizeof(uint4)));
-    build_sky_quads_kernel<<<ctx->sm_count * 8, 256>>>(ctx->d_sky, n, ctx->d_sky_quads);
-    ctx->launches++;
-    WT_CUDA(ctx, cudaDeviceSynchronize());
     ctx->sky_n = n;
     return WT_OK;
 }
@@ -408,19 +408,20 @@ int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second) {
     WT_CUDA(ctx, cudaMalloc(&sink, 256));
     double best = 0.0;
     const int blocks = ctx->sm_count * 8, threads = 256;
-    if (kind == 0 || kind == 1) {
+    if (kind == 0 || kind == 1 || kind == 3) {
         const int iters = 4096;
         for (int rep = 0; rep < 5; ++rep) {
             cudaEventRecord(e0);
             if (kind == 0) peak_mufu_kernel<<<blocks, threads>>>(sink, iters);
-            else peak_fma_kernel<<<blocks, threads>>>(sink, iters);
+            else if (kind == 1) peak_fma_kernel<<<blocks, threads>>>(sink, iters);
+            else peak_fma2_kernel<<<blocks, threads>>>(sink, iters);
             cudaEventRecord(e1);
             WT_CUDA(ctx, cudaEventSynchronize(e1));
             ctx->launches++;
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e0, e1);
             // kind 0: sin+cos PAIRS per second (2 MUFU ops each); kind 1: FLOP/s (2 per FMA)
-            double work = (double)blocks * threads * 8.0 * iters * (kind == 0 ? 1.0 : 2.0);
+            double work = (double)blocks * threads * 8.0 * iters * (kind == 0 ? 1.0 : kind == 1 ? 2.0 : 4.0);
             if (rep > 0) best = std::max(best, work / (ms * 1e-3));
         }
     } else if (kind == 2) {
@@ -440,7 +441,7 @@ int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second) {
         cudaFree(buf);
     } else {
         cudaFree(sink);
-        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_measure_peak: kind must be 0, 1 or 2");
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_measure_peak: kind must be 0, 1, 2 or 3");
     }
     cudaFree(sink);
     cudaEventDestroy(e0);
