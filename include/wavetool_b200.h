@@ -205,6 +205,14 @@ uint64_t wt_launch_count(const wt_ctx* ctx);
  * 1 = FP32 FMA (FLOP/s), 2 = HBM float4 store stream (bytes/s), 3 = packed FP32 FFMA2 (FLOP/s).
  * Synchronous; result in *per_second. */
 int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second);
+/* Diagnostic: with the environment variable WT_TRACE=1 the production kernel records, per work item
+ * (one warp's strip x row chunk), {SM id, CTA, start, end} in %globaltimer nanoseconds.  Copies the
+ * records of the most recent launch (4 x uint64 each) to `out`; returns the number of items copied
+ * (0 when tracing is off) or < 0.  Synchronises the device. */
+int wt_debug_read_trace(wt_ctx* ctx, uint64_t* out, unsigned max_items);
+/* Diagnostic: re-reads the WT_* development knobs (WT_DYN, WT_DYN_WARPS, WT_TRACE, WT_DBG, WT_EXTRA_SMEM) from
+ * the environment; they are otherwise read once when the library is loaded. */
+void wt_debug_reload_env(void);
 
 #ifdef __cplusplus
 }

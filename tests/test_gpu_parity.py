@@ -323,6 +323,31 @@ def test_wave_count_tiers(oracle, hm, mode):
         compare(got, want, sc, pos_tol=tol, label=f"W={W}")
 
 
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 61, 256])
+def test_sky_footprint_on_noise_cubemap(oracle, hm, n, mode):
+    """texture(skybox, R) with a maximal-contrast cubemap: the kernel's sky colour must equal the oracle's
+    GL sampler (face selection, per-face CLAMP_TO_EDGE, exact fp32 bilinear weights) evaluated on the kernel's
+    own position and normal.  A wrong texel order, tile origin or border of the gather atlas would be off by
+    O(1); the only legitimate outliers are vertices whose reflection vector sits on a cube edge (non-seamless
+    sampling: the face is decided by the last bit)."""
+    sky = scenes.noise_skybox(n, seed=100 + n)
+    sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(pos=(0.0, 9.0, 70.0), pitch=-20.0), scenes.animation_params(11), 320, hm, skybox=sky)
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    got = gpu_eval(ctx, frame, 320, flags=api.FLAG_SHADE | MODES[mode])
+    st, u, _ = sc.oracle_uniforms(oracle)
+    want_shade, _ = oracle.shade(u, sky, got["pos"], got["normal"])
+    err = np.abs(got["shade"][:, :3].astype(np.float64) - want_shade[:, :3]).max(axis=1)
+    # a 1e-7 relative difference of R moves the sample by ~1e-7 n texels; colour slope <= 1 per texel
+    tol = 1e-3
+    bad = err > tol
+    print("noise sky", n, mode, float(np.median(err)), float(err.max()), int(bad.sum()))
+    assert bad.sum() <= max(3, len(err) // 2000), f"n={n}: {int(bad.sum())} vertices off by more than {tol} (max {err.max():.3f})"
+    assert got["shade"][:, :3].std() > 0.05 or n == 1     # the cubemap really was sampled
+
+
 def test_non_power_of_two_heightmap(oracle):
     hm = scenes.procedural_heightmap(200)[:150]      # 200 x 150 texels
     sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), 300, hm)

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "wt_project_grid", "wt_build_frame",
     "wt_create", "wt_destroy", "wt_set_waves", "wt_set_heightmap_rgba8", "wt_set_skybox_rgba8",
     "wt_eval_frame", "wt_eval_batch", "wt_eval_frame_host", "wt_launch_count", "wt_measure_peak",
+    "wt_debug_read_trace", "wt_debug_reload_env",
 ]
 
 
@@ -86,7 +87,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
         _build.build()
     if not os.path.exists(_build.LIB_PATH):
         raise WaveToolError(WT_ERR_NO_DEVICE, f"{_build.LIB_PATH} is missing: the CUDA extension is required (no CPU fallback)")
-    L = C.CDLL(_build.LIB_PATH)
+    # development knob: WT_LIB points at a tuning variant built by tools/build_variant.py
+    L = C.CDLL(os.environ.get("WT_LIB") or _build.LIB_PATH)
     L.wt_version.restype = C.c_char_p
     L.wt_last_error.restype = C.c_char_p
     L.wt_last_error.argtypes = [C.c_void_p]
@@ -117,6 +119,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_launch_count.restype = C.c_uint64
     L.wt_launch_count.argtypes = [C.c_void_p]
     L.wt_measure_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.wt_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+    L.wt_debug_reload_env.restype = None
     _lib = L
     return L
 
@@ -248,6 +252,12 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.wt_launch_count(self._h))
+
+    def read_trace(self, max_items: int = 1 << 20) -> np.ndarray:
+        """WT_TRACE=1 diagnostic: (items, 4) uint64 rows {smid, cta, t_start_ns, t_end_ns} of the last launch."""
+        buf = np.zeros((max_items, 4), np.uint64)
+        n = _check(self._lib.wt_debug_read_trace(self._h, buf.ctypes.data, max_items), self._h)
+        return buf[:n].copy()
 
     def measure_peak(self, kind: int) -> float:
         v = C.c_double()

@@ -42,14 +42,41 @@ struct wt_ctx {
     uchar4* d_sky = nullptr;        // 6 faces RGBA8 (reference-order kernel)
     uchar4* d_sky_black = nullptr;  // 1x1 black cubemap: shading without a skybox reads sky = 0, no branch in the production kernel
     int sky_n = 0;
+    // production kernel: padded face atlas in a block-linear CUDA array + a gather-capable texture object
+    cudaArray_t sky_array = nullptr, sky_array_black = nullptr;
+    cudaTextureObject_t sky_tex = 0, sky_tex_black = 0;
     // scratch for the *_host entry points
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
     size_t s_elems = 0;
     wt_checksum* s_cks = nullptr;
     uint64_t launches = 0;
+    // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
+    int* d_queues = nullptr;
+    unsigned queue_next = 0;
+    // WT_TRACE diagnostic: per work item {smid, cta, t_start, t_end} of the most recent production launch
+    unsigned long long* d_trace = nullptr;
+    size_t trace_cap = 0, trace_items = 0;
 };
+constexpr unsigned N_QUEUES = 256;
 
 namespace {
+
+// Development knobs, read from the environment once (wt_debug_reload_env re-reads them):
+//   WT_DYN        rows per dynamically queued work item (0 = static plan; unset = built-in policy)
+//   WT_DYN_WARPS  cap on the resident warps per SM of the dynamic plan
+//   WT_TRACE      record per-work-item {SM, CTA, start, end} (wt_debug_read_trace)
+//   WT_DBG        bit 0: wave loop only (skips heightmap and output stage; outputs are NOT written)
+//   WT_EXTRA_SMEM extra dynamic shared memory per CTA (caps the CTAs per SM)
+struct Knobs {
+    int dyn = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0;
+    void load() {
+        auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
+        dyn = geti("WT_DYN", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
+        extra_smem = geti("WT_EXTRA_SMEM", 0);
+    }
+    Knobs() { load(); }
+};
+Knobs g_knobs;
 
 struct DeviceGuard {
     int prev = -1;
@@ -76,8 +103,15 @@ int fail(wt_ctx* ctx, int code, const std::string& msg) {
 // ------------------------------------------------------------------------------------------------
 // Launch planning for surface_warp_kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int R_EXACT = 4;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
-constexpr int R_RECUR = 8;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
+#ifndef WT_R_EXACT
+#define WT_R_EXACT 4
+#endif
+#ifndef WT_R_RECUR
+#define WT_R_RECUR 8
+#endif
+constexpr int R_EXACT = WT_R_EXACT;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
+constexpr int DYN_ROWS_RECUR = 22;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 3 marching steps)
+constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
 
 struct Plan {
     int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;
@@ -109,6 +143,42 @@ Plan make_plan(int slots, int L, int rows, int R) {
     return best;
 }
 
+// Builds the (3 (n+2)) x (2 (n+2)) RGBA8 atlas of a cubemap (tile column = face / 2, tile row = face % 2, every
+// face surrounded by a 1-texel border replicating its edge: per-face GL_CLAMP_TO_EDGE) in a CUDA array created
+// for texture gather, and a texture object over it (point access, unnormalised coordinates, unorm8 -> float).
+cudaError_t make_sky_atlas(const uint8_t* const faces[6], int n, cudaArray_t* arr_out, cudaTextureObject_t* tex_out) {
+    const int tile = n + 2, W = 3 * tile, H = 2 * tile;
+    std::vector<uchar4> atlas((size_t)W * H);
+    for (int f = 0; f < 6; ++f) {
+        const uchar4* src = reinterpret_cast<const uchar4*>(faces[f]);
+        const int x0 = (f / 2) * tile, y0 = (f % 2) * tile;
+        for (int y = 0; y < tile; ++y) {
+            const int sy = std::min(std::max(y - 1, 0), n - 1);
+            uchar4* dst = atlas.data() + (size_t)(y0 + y) * W + x0;
+            const uchar4* row = src + (size_t)sy * n;
+            dst[0] = row[0];
+            std::memcpy(dst + 1, row, (size_t)n * sizeof(uchar4));
+            dst[tile - 1] = row[n - 1];
+        }
+    }
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    cudaError_t e = cudaMallocArray(arr_out, &fmt, W, H, cudaArrayTextureGather);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy2DToArray(*arr_out, 0, 0, atlas.data(), (size_t)W * sizeof(uchar4), (size_t)W * sizeof(uchar4), H, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    cudaResourceDesc res;
+    std::memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = *arr_out;
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    return cudaCreateTextureObject(tex_out, &res, &td, nullptr);
+}
+
 int wave_capacity(unsigned n) { return n <= 16 ? 16 : n <= 64 ? 64 : n <= 256 ? 256 : 1000; }
 
 template <int CAP>
@@ -117,25 +187,59 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
 }
 
-template <int CAP, int MODE, bool SHADE, bool CKS>
-cudaError_t launch_warp_cks(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2>
+cudaError_t launch_warp_hm(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
     constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
-    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS>;
-    static const char* env_smem = std::getenv("WT_EXTRA_SMEM");   // experiment knob: cap the CTAs per SM
-    const int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP + (env_smem ? std::atoi(env_smem) : 0);
-    static thread_local struct { int L = -1, rows = -1, dev = -1; Plan p; } cache;   // per instantiation
+    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2>;
+    const int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP + g_knobs.extra_smem;
+    static thread_local struct { int L = -1, rows = -1, dev = -1, slots = 0; Plan p; } cache;   // per instantiation
     const int rows = a.row_end - a.row_begin;
     if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * WARPS_PER_CTA, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        cache.p = make_plan(ctx->sm_count * per_sm * WARPS_PER_CTA, a.L, rows, R);
+        cache.slots = ctx->sm_count * per_sm * WARPS_PER_CTA;
+        cache.p = make_plan(cache.slots, a.L, rows, R);
         cache.L = a.L; cache.rows = rows; cache.dev = ctx->device;
     }
-    const Plan& p = cache.p;
+    Plan p = cache.p;
+    // Dynamic work distribution (MODE 1): the warp schedulers favour some resident warps heavily, so equal static
+    // shares finish far apart (profiles/README.md); with small items handed out through an atomic queue every
+    // warp stays busy until the queue runs dry.  Used when there are enough items to go round several times;
+    // WT_DYN overrides the rows per item (0 = static plan).
+    const bool forced = g_knobs.dyn >= 0;
+    const int dyn_rows = forced ? g_knobs.dyn : (MODE == 1 ? DYN_ROWS_RECUR : 0);
+    a.queue = nullptr;
+    if (dyn_rows > 0) {
+        int rpc = ((dyn_rows + 2 + R - 1) / R) * R - 2;
+        if (rpc < 1) rpc = R;
+        const int n_chunks = (rows + rpc - 1) / rpc;
+        const long long items = (long long)p.n_strips * n_chunks;
+        int slots = cache.slots;
+        if (g_knobs.dyn_warps > 0) slots = std::min(slots, ctx->sm_count * g_knobs.dyn_warps);
+        if (forced || items >= 3LL * slots) {
+            p.rows_per_chunk = rpc;
+            p.n_chunks = n_chunks;
+            p.ctas = (int)std::min<long long>(items, slots);
+            a.queue = ctx->d_queues + 2 * (ctx->queue_next++ % N_QUEUES);
+        }
+    }
     a.n_strips = p.n_strips;
     a.rows_per_chunk = p.rows_per_chunk;
     a.n_chunks = p.n_chunks;
+    a.n_items = p.n_strips * p.n_chunks;
+    a.trace = nullptr;
+    {
+        if (g_knobs.trace) {
+            if (ctx->trace_cap < (size_t)a.n_items) {
+                cudaFree(ctx->d_trace);
+                ctx->d_trace = nullptr;
+                if (cudaMalloc(&ctx->d_trace, (size_t)a.n_items * 32) == cudaSuccess) ctx->trace_cap = a.n_items;
+            }
+            a.trace = ctx->d_trace;
+            ctx->trace_items = a.trace ? a.n_items : 0;
+        }
+    }
     static thread_local WaveTable<CAP> table;
     fill_table(table, tab);
     for (size_t i = 0; i < tab.size(); ++i) {
@@ -143,10 +247,16 @@ cudaError_t launch_warp_cks(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& 
         // MODE 1 adds the offset inside an FMA chain: hand it over reduced mod 2pi (in double) so it costs no precision
         table.w[i].phi = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
     }
-    { static const char* e = std::getenv("WT_DBG"); a.dbg = e ? std::atoi(e) : 0; }
+    a.dbg = g_knobs.dbg;
     kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
+}
+
+template <int CAP, int MODE, bool SHADE, bool CKS>
+cudaError_t launch_warp_cks(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    // non-power-of-two heightmaps take the instantiation with the out-of-line modulo
+    return a.hm_pow2 ? launch_warp_hm<CAP, MODE, SHADE, CKS, true>(ctx, a, tab, stream) : launch_warp_hm<CAP, MODE, SHADE, CKS, false>(ctx, a, tab, stream);
 }
 
 template <int CAP, int MODE, bool SHADE>
@@ -211,8 +321,8 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
     a.one = 1.0f;
     a.hm_r = ctx->d_hm_r; a.hm_quads = ctx->d_hm_quads; a.hm_w = ctx->hm_w; a.hm_h = ctx->hm_h;
     a.hm_pow2 = ((ctx->hm_w & (ctx->hm_w - 1)) == 0) && ((ctx->hm_h & (ctx->hm_h - 1)) == 0);
-    a.sky = ctx->d_sky; a.sky_n = ctx->sky_n;
-    if (!a.sky) { a.sky = ctx->d_sky_black; a.sky_n = 1; }
+    a.sky = ctx->d_sky; a.sky_n = ctx->sky_n; a.sky_tex = ctx->sky_tex;
+    if (!a.sky) { a.sky = ctx->d_sky_black; a.sky_n = 1; a.sky_tex = ctx->sky_tex_black; }
     a.pos = (float4*)d_pos; a.nrm = (float4*)d_nrm; a.shade = (float4*)d_shade;
     a.cks = (flags & WT_FLAG_CHECKSUM) ? (wt_checksum*)d_cks : nullptr;
     a.L = (int)L; a.row_begin = (int)r0; a.row_end = (int)r1;
@@ -258,6 +368,13 @@ int wt_create(wt_ctx** out, int device) {
     WT_CUDA(nullptr, cudaMalloc(&ctx->s_cks, sizeof(wt_checksum)));
     WT_CUDA(nullptr, cudaMalloc(&ctx->d_sky_black, 6 * sizeof(uchar4)));
     WT_CUDA(nullptr, cudaMemset(ctx->d_sky_black, 0, 6 * sizeof(uchar4)));
+    {
+        const uint8_t black[4] = {0, 0, 0, 0};
+        const uint8_t* const faces[6] = {black, black, black, black, black, black};
+        WT_CUDA(nullptr, make_sky_atlas(faces, 1, &ctx->sky_array_black, &ctx->sky_tex_black));
+    }
+    WT_CUDA(nullptr, cudaMalloc(&ctx->d_queues, 2 * N_QUEUES * sizeof(int)));
+    WT_CUDA(nullptr, cudaMemset(ctx->d_queues, 0, 2 * N_QUEUES * sizeof(int)));
     *out = ctx;
     return WT_OK;
 }
@@ -267,7 +384,12 @@ void wt_destroy(wt_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_hm_r); cudaFree(ctx->d_hm_quads);
     cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_black);
+    if (ctx->sky_tex) cudaDestroyTextureObject(ctx->sky_tex);
+    if (ctx->sky_tex_black) cudaDestroyTextureObject(ctx->sky_tex_black);
+    if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
+    if (ctx->sky_array_black) cudaFreeArray(ctx->sky_array_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
+    cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
     delete ctx;
 }
 
@@ -327,9 +449,12 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_sky);
     ctx->d_sky = nullptr;
+    if (ctx->sky_tex) { cudaDestroyTextureObject(ctx->sky_tex); ctx->sky_tex = 0; }
+    if (ctx->sky_array) { cudaFreeArray(ctx->sky_array); ctx->sky_array = nullptr; }
     const size_t face_bytes = (size_t)n * n * 4;
     WT_CUDA(ctx, cudaMalloc(&ctx->d_sky, 6 * face_bytes));
     for (int f = 0; f < 6; ++f) WT_CUDA(ctx, cudaMemcpy((uint8_t*)ctx->d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice));
+    WT_CUDA(ctx, make_sky_atlas(faces, n, &ctx->sky_array, &ctx->sky_tex));
     ctx->sky_n = n;
     return WT_OK;
 }
@@ -397,6 +522,17 @@ int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned 
 }
 
 uint64_t wt_launch_count(const wt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void wt_debug_reload_env(void) { g_knobs.load(); }
+
+int wt_debug_read_trace(wt_ctx* ctx, uint64_t* out, unsigned max_items) {
+    if (!ctx || !out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_debug_read_trace: NULL argument");
+    DeviceGuard g(ctx->device);
+    const size_t n = std::min<size_t>(ctx->trace_items, max_items);
+    WT_CUDA(ctx, cudaDeviceSynchronize());
+    if (n) WT_CUDA(ctx, cudaMemcpy(out, ctx->d_trace, n * 32, cudaMemcpyDeviceToHost));
+    return (int)n;
+}
 
 int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second) {
     if (!ctx || !per_second) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_measure_peak: NULL argument");

@@ -59,6 +59,10 @@ struct EvalArgs {
     // cubemap stands in when no skybox was set)
     const uchar4* sky;
     int sky_n;
+    // production kernel: the same texels as a 2-D texture atlas (block-linear CUDA array, point/gather access):
+    // face f occupies the (n+2)^2 tile at column f/2 (the major axis), row f%2 (its sign), its edge texels replicated into the 1-texel
+    // border, so a 2x2 gather anywhere inside a face IS the per-face CLAMP_TO_EDGE bilinear footprint
+    unsigned long long sky_tex;
     // outputs (element 0 = (row_begin, col 0))
     float4* pos;
     float4* nrm;
@@ -69,6 +73,10 @@ struct EvalArgs {
     int rows_per_chunk; // output rows per warp
     int n_chunks;
     int dbg;            // experiment knob (WT_DBG): bit 0 = skip heights/epilogue
+    // dynamic work distribution (NULL = static: item = blockIdx.x): queue[0] = next item, queue[1] = warps done
+    int* queue;
+    int n_items;
+    unsigned long long* trace;   // experiment knob (WT_TRACE): per work item {smid, item, t_start, t_end} in globaltimer ns
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -287,37 +295,60 @@ __device__ __forceinline__ void sincos2(f2 k, f2& s, f2& c) {
     const float MAGIC = 12582912.0f;
     const float TWO_PI_HI = 6.2831854820251465f;
     const float TWO_PI_LO = -1.7484556000744883e-07f;
+#ifdef WT_NO_CW
+    f2 r = k; (void)INV_2PI; (void)MAGIC; (void)TWO_PI_HI; (void)TWO_PI_LO;
+#else
     f2 n = add2(fma2(k, bc(INV_2PI), bc(MAGIC)), bc(-MAGIC));
     f2 r = fma2(n, bc(-TWO_PI_HI), k);
     r = fma2(n, bc(-TWO_PI_LO), r);
+#endif
     s = make_float2(__sinf(r.x), __sinf(r.y));
     c = make_float2(__cosf(r.x), __cosf(r.y));
 }
 
 // texture(heightmap, scale*(x,-z)).r for the two columns of a lane, from the footprint table; then
 // water-grid.vert:141-147.  Same fp32 operations in the same order as heightmap_r/finish_height.
-__device__ __forceinline__ int wrap_period(int i, int period, int pow2) {
-    if (pow2) return i & (period - 1);
+__device__ __forceinline__ int wrap_period_any(int i, int period) {
     int m = i % period;
     return m < 0 ? m + period : m;
 }
-__device__ __forceinline__ f2 finish_height2(const EvalArgs& a, f2 px, f2 py, f2 pz) {
+// non-power-of-two heightmaps: the four footprint coordinates modulo (2w, 2h); kept out of line so the
+// integer-division sequences stay out of the hot instruction stream of the usual power-of-two case
+__device__ __noinline__ int4 wrap_period4_any(int4 v, int w2, int h2) {
+    return make_int4(wrap_period_any(v.x, w2), wrap_period_any(v.y, w2), wrap_period_any(v.z, h2), wrap_period_any(v.w, h2));
+}
+// Split in two so that the table loads of several rows are in flight together: hm_fetch2 computes the
+// bilinear weights and issues the two 16-byte footprint loads, hm_finish2 blends and applies :141-147.
+struct HmTap { f2 al, be; float4 qa, qb; };
+template <bool POW2>
+__device__ __forceinline__ HmTap hm_fetch2(const EvalArgs& a, f2 px, f2 pz) {
     const float one = a.one;
     f2 s = mul2(bc(a.hm_scale), px);
     f2 t = mul2(bc(-a.hm_scale), pz);
     f2 um = sub2x(mul2(s, bc((float)a.hm_w)), bc(0.5f), one);
     f2 vm = sub2x(mul2(t, bc((float)a.hm_h)), bc(0.5f), one);
     f2 fu = make_float2(floorf(um.x), floorf(um.y)), fv = make_float2(floorf(vm.x), floorf(vm.y));
-    f2 al = sub2(um, fu), be = sub2(vm, fv);
+    HmTap h;
+    h.al = sub2(um, fu); h.be = sub2(vm, fv);
     const int w2 = 2 * a.hm_w, h2 = 2 * a.hm_h;
-    const float4 qa = __ldg(a.hm_quads + (size_t)wrap_period((int)fv.x, h2, a.hm_pow2) * w2 + wrap_period((int)fu.x, w2, a.hm_pow2));
-    const float4 qb = __ldg(a.hm_quads + (size_t)wrap_period((int)fv.y, h2, a.hm_pow2) * w2 + wrap_period((int)fu.y, w2, a.hm_pow2));
-    f2 oma = sub2(bc(1.0f), al), omb = sub2(bc(1.0f), be);
-    f2 w00 = mul2(oma, omb), w10 = mul2(al, omb), w01 = mul2(oma, be), w11 = mul2(al, be);
-    f2 acc = mul2(w00, make_float2(qa.x, qb.x));
-    acc = add2x(mul2(w10, make_float2(qa.y, qb.y)), acc, one);
-    acc = add2x(mul2(w01, make_float2(qa.z, qb.z)), acc, one);
-    acc = add2x(mul2(w11, make_float2(qa.w, qb.w)), acc, one);
+    int4 ij = make_int4((int)fu.x, (int)fu.y, (int)fv.x, (int)fv.y);
+    if (POW2) {
+        ij.x &= w2 - 1; ij.y &= w2 - 1; ij.z &= h2 - 1; ij.w &= h2 - 1;
+    } else {
+        ij = wrap_period4_any(ij, w2, h2);
+    }
+    h.qa = __ldg(a.hm_quads + (unsigned)(ij.z * w2 + ij.x));   // (2w)(2h) <= 2^30 entries (wt_set_heightmap_rgba8)
+    h.qb = __ldg(a.hm_quads + (unsigned)(ij.w * w2 + ij.y));
+    return h;
+}
+__device__ __forceinline__ f2 hm_finish2(const EvalArgs& a, const HmTap& h, f2 py) {
+    const float one = a.one;
+    f2 oma = sub2(bc(1.0f), h.al), omb = sub2(bc(1.0f), h.be);
+    f2 w00 = mul2(oma, omb), w10 = mul2(h.al, omb), w01 = mul2(oma, h.be), w11 = mul2(h.al, h.be);
+    f2 acc = mul2(w00, make_float2(h.qa.x, h.qb.x));
+    acc = add2x(mul2(w10, make_float2(h.qa.y, h.qb.y)), acc, one);
+    acc = add2x(mul2(w01, make_float2(h.qa.z, h.qb.z)), acc, one);
+    acc = add2x(mul2(w11, make_float2(h.qa.w, h.qb.w)), acc, one);
     f2 bump = mul2(bc(a.hm_disp), mul2(bc(2.0f), sub2(acc, bc(0.5f))));
     return add2(add2x(bump, py, one), bc(a.bounce));
 }
@@ -325,54 +356,74 @@ __device__ __forceinline__ f2 finish_height2(const EvalArgs& a, f2 px, f2 py, f2
 // texture(skybox, R).rgb for the production kernel: GL 4.1 cube map face selection, per-face
 // CLAMP_TO_EDGE bilinear.  (Reciprocal and weights are not bit-ordered like the oracle: the sky colour
 // has its own, absolute tolerance.)
-__device__ __forceinline__ float3 sky_rgb_fast(const EvalArgs& a, float rx, float ry, float rz) {
+// texture(skybox, R).rgb for the production kernel: GL 4.1 cube map face selection, per-face CLAMP_TO_EDGE
+// bilinear.  The three channels of the 2x2 footprint come from three texture-gather instructions (tld4.r/g/b)
+// on the padded face atlas; the bilinear weights are exact fp32, computed here (the texture unit's own filter
+// would quantise them to 8 bits).  (Reciprocal and weights are not bit-ordered like the oracle: the sky
+// colour has its own, absolute tolerance.)
+struct SkyTap { float4 r, g, b; float al, be; };   // per channel: texels (i0,j1), (i1,j1), (i1,j0), (i0,j0) as c/255
+__device__ __forceinline__ float4 tld4(unsigned long long tex, float x, float y, int comp) {
+    float4 v;
+    if (comp == 0) asm volatile("tld4.r.2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6}];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(tex), "f"(x), "f"(y));
+    else if (comp == 1) asm volatile("tld4.g.2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6}];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(tex), "f"(x), "f"(y));
+    else asm volatile("tld4.b.2d.v4.f32.f32 {%0,%1,%2,%3}, [%4, {%5,%6}];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(tex), "f"(x), "f"(y));
+    return v;
+}
+__device__ __forceinline__ SkyTap sky_fetch(const EvalArgs& a, float rx, float ry, float rz) {
+    // Face selection without branches.  ma = max(|rx|,|ry|,|rz|); ties resolve x before y before z like the
+    // GL 4.1 table the oracle follows.
     const float ax = fabsf(rx), ay = fabsf(ry), az = fabsf(rz);
-    int face;
-    float sc, tc, ma;
-    if (ax >= ay && ax >= az) {
-        ma = ax; tc = -ry;
-        if (rx >= 0.0f) { face = 0; sc = -rz; } else { face = 1; sc = rz; }
-    } else if (ay >= az) {
-        ma = ay; sc = rx;
-        if (ry >= 0.0f) { face = 2; tc = rz; } else { face = 3; tc = -rz; }
-    } else {
-        ma = az; tc = -ry;
-        if (rz >= 0.0f) { face = 4; sc = rx; } else { face = 5; sc = -rx; }
-    }
+    const bool isx = ax >= ay && ax >= az;
+    const bool isy = !isx && ay >= az;
+    const float ma = fmaxf(ax, fmaxf(ay, az));
+    const float major = isx ? rx : (isy ? ry : rz);
+    const bool pos = major >= 0.0f;
+    // sc: +x:-rz  -x:+rz  +-y:+rx  +z:+rx  -z:-rx        tc: +y:+rz  -y:-rz  else:-ry
+    const float sc_abs = isx ? rz : rx;
+    const bool sc_neg = isx ? pos : (isy ? false : !pos);
+    const float sc = sc_neg ? -sc_abs : sc_abs;
+    const float tc_abs = isy ? rz : ry;
+    const bool tc_neg = isy ? !pos : true;
+    const float tc = tc_neg ? -tc_abs : tc_abs;
     const int n = a.sky_n;
     const float hn = 0.5f * (float)n;
     const float inv = rcp_approx(ma);
-    // (0.5 (sc/|ma| + 1)) n - 0.5, then floor/frac without the XU pipe: adding 1.5*2^23 rounds to the nearest
-    // integer and leaves it in the low mantissa bits.  Rounding um - 0.5 instead of flooring um only differs on
-    // exact integers, where the neighbouring footprint with weight 1 yields the same sample.
+    // um = (0.5 (sc/|ma| + 1)) n - 0.5 in [-0.5, n - 0.5]; floor/frac without the XU pipe: adding 1.5*2^23 rounds
+    // to the nearest integer.  Rounding um - 0.5 instead of flooring um only differs on exact integers, where the
+    // neighbouring footprint with weight 1 yields the same sample.
     const float MAGIC = 12582912.0f;
     const float um = fmaf(sc * inv, hn, hn - 0.5f), vm = fmaf(tc * inv, hn, hn - 0.5f);
-    const float tu = (um - 0.5f) + MAGIC, tv = (vm - 0.5f) + MAGIC;
-    const float al = um - (tu - MAGIC), be = vm - (tv - MAGIC);
-    // CLAMP_TO_EDGE per face; the four texels of the footprint straight from the RGBA8 faces (the compact layout
-    // keeps the cubemap resident in the 126 MB L2; a pre-gathered footprint table four times the size is not)
-    const int iu = __float_as_int(tu) - 0x4B400000, iv = __float_as_int(tv) - 0x4B400000;
-    const int i0 = min(max(iu, 0), n - 1), i1 = min(max(iu + 1, 0), n - 1);
-    const int j0 = min(max(iv, 0), n - 1), j1 = min(max(iv + 1, 0), n - 1);
-    const unsigned* const fb = reinterpret_cast<const unsigned*>(a.sky) + (size_t)face * n * n;
-    const unsigned* const row0 = fb + (size_t)j0 * n;
-    const unsigned* const row1 = fb + (size_t)j1 * n;
-    uint4 q;
-    q.x = __ldg(row0 + i0); q.y = __ldg(row0 + i1); q.z = __ldg(row1 + i0); q.w = __ldg(row1 + i1);
-    const float oma = 1.0f - al, omb = 1.0f - be;
-    const f2 w0 = mul2(make_float2(oma, al), bc(omb)), w1 = mul2(make_float2(oma, al), bc(be));   // (w00, w10), (w01, w11)
-    // byte -> float on the ALU/FMA pipes: PRMT builds the bit pattern of 2^23 + c, one packed add removes the 2^23
-    const f2 M = bc(-8388608.0f);
-#define WT_B2F(word0, word1, k) add2(make_float2(__uint_as_float(__byte_perm(word0, 0x4B000000u, 0x7540 | (k))), \
-                                                 __uint_as_float(__byte_perm(word1, 0x4B000000u, 0x7540 | (k)))), M)
-    const f2 r0 = WT_B2F(q.x, q.y, 0), r1 = WT_B2F(q.z, q.w, 0);
-    const f2 g0 = WT_B2F(q.x, q.y, 1), g1 = WT_B2F(q.z, q.w, 1);
-    const f2 b0 = WT_B2F(q.x, q.y, 2), b1 = WT_B2F(q.z, q.w, 2);
-#undef WT_B2F
-    const f2 sr = fma2(w1, r1, mul2(w0, r0)), sg = fma2(w1, g1, mul2(w0, g0)), sb = fma2(w1, b1, mul2(w0, b0));
-    const float k = 1.0f / 255.0f;
-    return make_float3((sr.x + sr.y) * k, (sg.x + sg.y) * k, (sb.x + sb.y) * k);
+    const float fu = ((um - 0.5f) + MAGIC) - MAGIC, fv = ((vm - 0.5f) + MAGIC) - MAGIC;   // floor(um), floor(vm) in {-1 .. n-1}
+    SkyTap t;
+    t.al = um - fu; t.be = vm - fv;
+    // atlas tile origin of the face (+1 for the border) and the footprint's centre: texels (fu, fu+1) of the face
+    // are atlas texels X0+1+fu, X0+2+fu, whose shared edge is at X0 + fu + 2 — the gather coordinate
+    const float tile = (float)(n + 2);
+    const float X0 = isx ? 0.0f : (isy ? tile : tile + tile);   // tile column = major axis
+    const float Y0 = pos ? 0.0f : tile;                          // tile row = sign of the major component
+    const float gx = X0 + fu + 2.0f, gy = Y0 + fv + 2.0f;
+    t.r = tld4(a.sky_tex, gx, gy, 0);
+    t.g = tld4(a.sky_tex, gx, gy, 1);
+    t.b = tld4(a.sky_tex, gx, gy, 2);
+    return t;
 }
+__device__ __forceinline__ float3 sky_blend(const SkyTap& t) {
+    // gather order: x = (i0, j1), y = (i1, j1), z = (i1, j0), w = (i0, j0)
+    const float oma = 1.0f - t.al, omb = 1.0f - t.be;
+    const f2 wxy = mul2(make_float2(oma, t.al), bc(t.be));     // (w01, w11)
+    const f2 wzw = mul2(make_float2(t.al, oma), bc(omb));      // (w10, w00)
+    const f2 sr = fma2(wxy, make_float2(t.r.x, t.r.y), mul2(wzw, make_float2(t.r.z, t.r.w)));
+    const f2 sg = fma2(wxy, make_float2(t.g.x, t.g.y), mul2(wzw, make_float2(t.g.z, t.g.w)));
+    const f2 sb = fma2(wxy, make_float2(t.b.x, t.b.y), mul2(wzw, make_float2(t.b.z, t.b.w)));
+    return make_float3(sr.x + sr.y, sg.x + sg.y, sb.x + sb.y);
+}
+
+// One output row in flight between the two halves of the output stage (see surface_warp_kernel)
+struct EpiRow {
+    f2 nx, ny, nz, fres, sp;
+    SkyTap skyA, skyB;
+    int row, slot;   // slot: ring row of the vertex itself (its position is re-read when the row is stored)
+};
 
 // ------------------------------------------------------------------------------------------------
 // Production kernel.
@@ -385,6 +436,44 @@ __device__ __forceinline__ float3 sky_rgb_fast(const EvalArgs& a, float rx, floa
 //   columns) -> for the R rows whose up/down neighbours are now known: normal, flip, shading,
 //   coalesced float4 stores.  Only __syncwarp(); warps never wait for each other.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// dynamic work distribution: lane 0 takes the next item off the queue, the warp shares it
+__device__ __forceinline__ int next_item(int* queue, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(queue, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// build-time tuning knobs (tools/build_variant.py compiles alternative values side by side)
+#ifndef WT_WAVE_UNROLL
+#define WT_WAVE_UNROLL 1        // wave-loop unroll factor of MODE 1: independent rotation chains in flight per warp
+#endif
+#ifndef WT_WAVE_UNROLL_EXACT
+#define WT_WAVE_UNROLL_EXACT 1
+#endif
+#ifndef WT_LB_RECUR
+#define WT_LB_RECUR 16          // __launch_bounds__ min CTAs (= warps) per SM, MODE 1
+#endif
+#ifndef WT_LB_EXACT
+#define WT_LB_EXACT 24
+#endif
+#ifndef WT_HM_BATCH
+#define WT_HM_BATCH 4           // rows whose heightmap footprint loads are in flight together
+#endif
+#ifndef WT_EPI_UNROLL_EXACT
+#define WT_EPI_UNROLL_EXACT 1
+#endif
+#ifndef WT_EPI_UNROLL
+#define WT_EPI_UNROLL 2         // rows of the output stage in flight per warp (MODE 1)
+#endif
+#define WT_STR(x) #x
+#define WT_UNROLL(n) _Pragma(WT_STR(unroll n))
+#define WT_UNROLL_IF(c, a, b) _Pragma(WT_STR(unroll ((c) ? (a) : (b))))
+
 constexpr int WARPS_PER_CTA = 1;   // one warp per CTA: every loop bound derives from blockIdx alone, so ptxas keeps the wave constants in uniform registers
 constexpr int RING_COLS = 34;   // entries per ring row: [0] = (-, A of lane 31), [1 + l] = (A_l, B_l), [33] = (B of lane 0, -)
 
@@ -395,14 +484,20 @@ struct RingLayout {
     static constexpr int BYTES_PER_WARP = 3 * PLANE * (int)sizeof(float2);
 };
 
-template <int CAP, int R, int MODE, bool SHADE, bool CKS>
-__global__ void __launch_bounds__(32, MODE == 1 ? 16 : 24)
+template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2>
+__global__ void __launch_bounds__(32, MODE == 1 ? WT_LB_RECUR : WT_LB_EXACT)
 surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
     extern __shared__ float2 ring_all[];
     using RL = RingLayout<R>;
     const int lane = threadIdx.x;
-    const int item = blockIdx.x;
     float2* const ring = ring_all;
+    const bool dyn = a.queue != nullptr;
+    int item = blockIdx.x;
+    if (dyn) item = next_item(a.queue, lane);
+    ChecksumAcc acc;
+  while (item < a.n_items) {
+    unsigned long long t_start = 0;
+    if (a.trace) t_start = global_ns();
     const int strip = item % a.n_strips, chunk = item / a.n_strips;
     const int strip0 = strip * STRIP_COLS;
     const int r0 = a.row_begin + chunk * a.rows_per_chunk;
@@ -412,7 +507,6 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
     const bool outB = lane <= 30 && colB < a.L;
     const float one = a.one;
 
-    ChecksumAcc acc;
     int slot_new = 2;   // ring row that receives the first row of the next step; rows -2/-1 of the first step are never read
 
     for (int row_a = r0 - 1; row_a <= r1; row_a += R) {
@@ -442,7 +536,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             f2 gx[R], gz[R];
 #pragma unroll
             for (int j = 0; j < R; ++j) { gx[j] = px[j]; gz[j] = pz[j]; }
-#pragma unroll 1
+            WT_UNROLL(WT_WAVE_UNROLL_EXACT)
             for (int i = 0; i < a.n_waves; ++i) {
                 const WaveK wk = wt.w[i];   // phi holds fl(phaseConstant_phi * t) for this launch
 #pragma unroll
@@ -459,7 +553,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             }
         } else {
             const f2 gx0 = px[0], gz0 = pz[0];
-#pragma unroll 1
+            WT_UNROLL(WT_WAVE_UNROLL)
             for (int i = 0; i < a.n_waves; ++i) {
                 const WaveK wk = wt.w[i];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
                 f2 s, c;
@@ -499,21 +593,34 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         // ---- heightmap detail + bounce, final positions into the ring ----
         __syncwarp();   // the previous step's readers are done with the rows being overwritten
         {
+            // HM_BATCH rows at a time: all their footprint loads are issued before the first blend
+            constexpr int HM_BATCH = R < WT_HM_BATCH ? R : WT_HM_BATCH;
+            const bool seam = lane == 0 || lane == 31;
+            const int seam_col = lane ? 0 : 33;
             int slot = slot_new;
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                py[j] = finish_height2(a, px[j], py[j], pz[j]);
-                float2* const row = ring + slot * RING_COLS;
-                row[1 + lane] = px[j];
-                row[RL::PLANE + 1 + lane] = py[j];
-                row[2 * RL::PLANE + 1 + lane] = pz[j];
-                if (lane == 31) {
-                    row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
+            for (int j0 = 0; j0 < R; j0 += HM_BATCH) {
+                HmTap tap[HM_BATCH];
+#pragma unroll
+                for (int jj = 0; jj < HM_BATCH; ++jj)
+                    if (j0 + jj < R) tap[jj] = hm_fetch2<HMP2>(a, px[j0 + jj], pz[j0 + jj]);
+#pragma unroll
+                for (int jj = 0; jj < HM_BATCH; ++jj) {
+                    const int j = j0 + jj;
+                    if (j >= R) break;
+                    py[j] = hm_finish2(a, tap[jj], py[j]);
+                    float2* const row = ring + slot * RING_COLS;
+                    row[1 + lane] = px[j];
+                    row[RL::PLANE + 1 + lane] = py[j];
+                    row[2 * RL::PLANE + 1 + lane] = pz[j];
+                    if (lane == 31) {
+                        row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
+                    }
+                    if (lane == 0) {
+                        row[33] = make_float2(px[j].y, 0.f); row[RL::PLANE + 33] = make_float2(py[j].y, 0.f); row[2 * RL::PLANE + 33] = make_float2(pz[j].y, 0.f);
+                    }
+                    slot = slot + 1 == RL::ROWS ? 0 : slot + 1;
                 }
-                if (lane == 0) {
-                    row[33] = make_float2(px[j].y, 0.f); row[RL::PLANE + 33] = make_float2(py[j].y, 0.f); row[2 * RL::PLANE + 33] = make_float2(pz[j].y, 0.f);
-                }
-                slot = slot + 1 == RL::ROWS ? 0 : slot + 1;
             }
         }
         __syncwarp();
@@ -521,17 +628,19 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         // ---- outputs for rows row_a-1 .. row_a+R-2 (their up/down neighbours are in the ring now) ----
         // Straight-line code, only the stores are predicated: the R rows are independent, so their
         // shared-memory reads, MUFU chains and cubemap gathers overlap instead of queueing row by row.
+        // The rows are independent: with two of them per loop trip their ring reads, MUFU chains and cubemap
+        // gathers overlap.  Only the stores are predicated.
         int sd_ = slot_new - 2 < 0 ? slot_new - 2 + RL::ROWS : slot_new - 2;   // row_a - 2
-#pragma unroll 1
-        for (int j = 0; j < R; ++j) {
+        // front half of one output row: ring reads, normal, view-facing flip, shading terms, cubemap gathers ISSUED
+        auto front = [&](EpiRow& e, const int j) {
             const int sc_ = sd_ + 1 == RL::ROWS ? 0 : sd_ + 1;
             const int su_ = sc_ + 1 == RL::ROWS ? 0 : sc_ + 1;
-            const int row = row_a - 1 + j;
-            const bool valid = row >= r0 && row < r1;
             const float2* const rc = ring + sc_ * RING_COLS + lane;
             const float2* const rd = ring + sd_ * RING_COLS + lane + 1;
             const float2* const ru = ring + su_ * RING_COLS + lane + 1;
             sd_ = sc_;
+            e.row = row_a - 1 + j;
+            e.slot = sc_;
             const f2 cx = rc[1], cy = rc[RL::PLANE + 1], cz = rc[2 * RL::PLANE + 1];
             // (right - left), (up - down): water-grid.vert:164-187
             const f2 ux = sub2(rc[2], rc[0]), uy = sub2(rc[RL::PLANE + 2], rc[RL::PLANE]), uz = sub2(rc[2 * RL::PLANE + 2], rc[2 * RL::PLANE]);
@@ -547,8 +656,8 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             inv.x = facing.x < 0.0f ? -inv.x : inv.x;
             inv.y = facing.y < 0.0f ? -inv.y : inv.y;
             nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
-            f2 fres = bc(0.0f);
-            float4 sA = make_float4(0.f, 0.f, 0.f, 0.f), sB = sA;
+            e.nx = nx; e.ny = ny; e.nz = nz;
+            e.fres = bc(0.0f); e.sp = bc(0.0f);
             if (SHADE) {
                 const f2 w2 = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
                 const f2 winv = make_float2(rsq_approx(w2.x), rsq_approx(w2.y));
@@ -558,37 +667,77 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 // R = reflect(-viewVec, normal) = -viewVec + 2 dot(normal, viewVec) normal   (frag:95)
                 const f2 rx = fma2(nx, f2x, make_float2(-e_x.x, -e_x.y)), ry = fma2(ny, f2x, make_float2(-e_y.x, -e_y.y)),
                          rz = fma2(nz, f2x, make_float2(-e_z.x, -e_z.y));
-                const float3 skyA = sky_rgb_fast(a, rx.x, ry.x, rz.x), skyB = sky_rgb_fast(a, rx.y, ry.y, rz.y);   // frag:96
+                e.skyA = sky_fetch(a, rx.x, ry.x, rz.x);                                          // frag:96
+                e.skyB = sky_fetch(a, rx.y, ry.y, rz.y);
                 f2 sdot = fma2(rx, bc(a.sunx), fma2(ry, bc(a.suny), mul2(rz, bc(a.sunz))));
                 sdot = make_float2(fminf(fmaxf(sdot.x, 0.0f), 1.0f), fminf(fmaxf(sdot.y, 0.0f), 1.0f));
                 // pow(sd, shininess) (frag:100) = 2^(shininess log2 sd): 0^y = 0 for y > 0; 0^0 = 1 is patched below
                 const f2 lg = mul2(make_float2(lg2_approx(sdot.x), lg2_approx(sdot.y)), bc(a.sun_shininess));
                 f2 sp = make_float2(ex2_approx(lg.x), ex2_approx(lg.y));
                 if (a.sun_shininess == 0.0f) sp = bc(1.0f);
-                sp = mul2(sp, bc(a.sun_strength));
+                e.sp = mul2(sp, bc(a.sun_strength));
                 const f2 om = sub2(bc(1.0f), f);                                                     // frag:110-111
                 const f2 om2 = mul2(om, om);
-                fres = fma2(mul2(mul2(om2, om2), om), bc(1.0f - 0.02f), bc(0.02f));
-                sA = make_float4(skyA.x, skyA.y, skyA.z, sp.x);
-                sB = make_float4(skyB.x, skyB.y, skyB.z, sp.y);
+                e.fres = fma2(mul2(mul2(om2, om2), om), bc(1.0f - 0.02f), bc(0.02f));
             }
-            const size_t o = (size_t)(row - a.row_begin) * a.L;
-            if (outA && valid) {
-                const float4 op = make_float4(cx.x, cy.x, cz.x, 1.0f), on = make_float4(nx.x, ny.x, nz.x, fres.x);
-                __stcs(a.pos + o + colA, op);
-                __stcs(a.nrm + o + colA, on);
-                if (SHADE) __stcs(a.shade + o + colA, sA);
-                if (CKS) { acc.add(op, on); if (SHADE) acc.add_shade(sA); }
+        };
+        // back half: texels converted and blended, position re-read from the ring, the three float4 stores
+        auto back = [&](const EpiRow& e) {
+            const int row = e.row;
+            const bool valid = row >= r0 && row < r1;
+            const float2* const rc = ring + e.slot * RING_COLS + lane;
+            const f2 cx = rc[1], cy = rc[RL::PLANE + 1], cz = rc[2 * RL::PLANE + 1];
+            float4 sA = make_float4(0.f, 0.f, 0.f, 0.f), sB = sA;
+            if (SHADE) {
+                const float3 skyA = sky_blend(e.skyA), skyB = sky_blend(e.skyB);
+                sA = make_float4(skyA.x, skyA.y, skyA.z, e.sp.x);
+                sB = make_float4(skyB.x, skyB.y, skyB.z, e.sp.y);
             }
-            if (outB && valid) {
-                const float4 op = make_float4(cx.y, cy.y, cz.y, 1.0f), on = make_float4(nx.y, ny.y, nz.y, fres.y);
-                __stcs(a.pos + o + colB, op);
-                __stcs(a.nrm + o + colB, on);
-                if (SHADE) __stcs(a.shade + o + colB, sB);
-                if (CKS) { acc.add(op, on); if (SHADE) acc.add_shade(sB); }
+            // one element offset per row; the stores themselves are the only predicated instructions
+            const size_t o = (size_t)(row - a.row_begin) * a.L + colA;
+            const bool stA = outA && valid, stB = outB && valid;
+            const float4 opA = make_float4(cx.x, cy.x, cz.x, 1.0f), onA = make_float4(e.nx.x, e.ny.x, e.nz.x, e.fres.x);
+            const float4 opB = make_float4(cx.y, cy.y, cz.y, 1.0f), onB = make_float4(e.nx.y, e.ny.y, e.nz.y, e.fres.y);
+            float4* const pp = a.pos + o;
+            float4* const pn = a.nrm + o;
+            if (stA) __stcs(pp, opA);
+            if (stB) __stcs(pp + 32, opB);
+            if (stA) __stcs(pn, onA);
+            if (stB) __stcs(pn + 32, onB);
+            if (SHADE) {
+                float4* const ps = a.shade + o;
+                if (stA) __stcs(ps, sA);
+                if (stB) __stcs(ps + 32, sB);
+            }
+            if (CKS) {
+                if (stA) { acc.add(opA, onA); if (SHADE) acc.add_shade(sA); }
+                if (stB) { acc.add(opB, onB); if (SHADE) acc.add_shade(sB); }
+            }
+        };
+        {
+            // MODE 0 runs at 80 registers (24 warps per SM): one row at a time there, two rows in flight otherwise
+            WT_UNROLL_IF(MODE == 0, WT_EPI_UNROLL_EXACT, WT_EPI_UNROLL)
+            for (int j = 0; j < R; ++j) {
+                EpiRow e;
+                front(e, j);
+                back(e);
             }
         }
         slot_new = slot_new + R >= RL::ROWS ? slot_new + R - RL::ROWS : slot_new + R;
+    }
+    if (a.trace && lane == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* t = a.trace + 4 * (size_t)item;
+        t[0] = smid; t[1] = blockIdx.x; t[2] = t_start; t[3] = global_ns();
+    }
+    if (!dyn) break;
+    __syncwarp();   // every lane is done with the ring before the next item overwrites it
+    item = next_item(a.queue, lane);
+  }
+    if (dyn && lane == 0) {
+        // the last warp to run dry re-arms the queue for the next launch that uses it
+        if (atomicAdd(a.queue + 1, 1) == (int)gridDim.x - 1) { a.queue[1] = 0; __threadfence(); a.queue[0] = 0; }
     }
     if (CKS) acc.flush(a.cks);
 }

@@ -92,6 +92,12 @@ def procedural_skybox(n: int = 2048) -> np.ndarray:
     return faces
 
 
+def noise_skybox(n: int, seed: int = 1) -> np.ndarray:
+    """(6,n,n,4) uint8 cubemap of independent uniform random texels: maximal contrast between neighbouring
+    texels and across face edges, so any mix-up of the bilinear footprint (texel order, face, clamp) shows."""
+    return np.random.default_rng(seed).integers(0, 256, size=(6, n, n, 4), dtype=np.uint8)
+
+
 def camera(pos=(0.0, 4.0, 70.0), yaw=-90.0, pitch=0.0, fov=72.0, aspect=1.0, z_near=0.1, z_far=100.0) -> api.Camera:
     """Camera ctor arguments; defaults are the reference's (render-engine.cpp:52, camera.cpp:40-45)."""
     return api.Camera(fov, aspect, z_near, z_far, (C.c_float * 3)(*pos), yaw, pitch)
