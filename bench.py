@@ -100,6 +100,12 @@ def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
     from wave_tool_b200 import scenes
     O = orc.Oracle()
     R = orc.Ref()
+    # all the host threads this process may use — torchrun exports OMP_NUM_THREADS=1, which would otherwise
+    # pin the reference arm to one core (the oracle and oracle/_ref share one OpenMP runtime)
+    try:
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        O.set_num_threads(os.cpu_count() or 1)
     hm = scenes.procedural_heightmap(512)
     waves = scenes.seeded_waves(W, cfg=cfg)
     use_ref = R.available and L <= 4096 and W <= R.max_waves()
