@@ -10,11 +10,8 @@ name, defs = sys.argv[1], sys.argv[2:]
 out_dir = os.path.join(B.PKG_DIR, "variants")
 os.makedirs(out_dir, exist_ok=True)
 out = os.path.join(out_dir, f"libwt_{name}.so")
-cmd = [B._nvcc()] + B.NVCC_FLAGS + defs + ["-Xptxas", "-v", "-o", out] + [os.path.join(B.CSRC, s) for s in B.SOURCES] + ["-ccbin", "/usr/bin/g++"]
-r = subprocess.run(cmd, capture_output=True, text=True)
-if r.returncode:
-    sys.exit(r.stdout + r.stderr)
-lines = r.stderr.splitlines()
+log = B.compile_all(out, extra_flags=defs, verbose=True, obj_dir=os.path.join(out_dir, 'obj_' + name))
+lines = log.splitlines()
 for i, l in enumerate(lines):
     if "Compiling entry function" in l and "surface_warp_kernelILi64E" in l and "ELb1ELb0E" in l:
         print(l.split("'")[1][:60], "|", lines[i + 2].strip() if "spill" in lines[i + 2] else "", "|", lines[i + 3].strip() if i + 3 < len(lines) else "")

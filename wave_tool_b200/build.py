@@ -9,12 +9,15 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libwavetool_b200.so")
-SOURCES = ["wt_device.cu", "wt_host.cpp"]
-HEADERS = ["wt_kernels.cuh", "wt_internal.h", "wt_host_math.h", os.path.join("..", "..", "include", "wavetool_b200.h")]
+# the production kernel's instantiations are split over four translation units so that they compile in parallel
+SOURCES = ["wt_device.cu", "wt_launch_exact.cu", "wt_launch_exact_shade.cu", "wt_launch_recur.cu", "wt_launch_recur_shade.cu", "wt_host.cpp"]
+HEADERS = ["wt_kernels.cuh", "wt_aux_kernels.cuh", "wt_launch.cuh", "wt_ctx.h", "wt_internal.h", "wt_host_math.h",
+           os.path.join("..", "..", "include", "wavetool_b200.h")]
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17", "-shared",
+    "-lineinfo", "-O3", "-std=c++17",
     # host code: position independent, and NO fp contraction — the CPU prologue reproduces the
     # reference's fp32 operation order (wt_host_math.h)
     "-Xcompiler", "-fPIC,-ffp-contract=off",
@@ -36,18 +39,37 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def compile_all(out_path: str, extra_flags=(), verbose: bool = False, obj_dir: str = OBJ_DIR) -> str:
+    """nvcc -c every translation unit (in parallel), then link them into one shared library.  Returns ptxas' log."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); nvcc should use the distro g++
+    common = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++"]
+
+    def one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        res = subprocess.run(common + ["-c", "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        done = list(pool.map(one, SOURCES))
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", out_path] + [o for o, _ in done],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    return "".join(log for _, log in done)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA translation unit for sm_100a into wave_tool_b200/libwavetool_b200.so."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    # the image exports CXX=/opt/gcc/bin/g++ (a wrapper); nvcc should use the distro g++
-    res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"], capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    log = compile_all(LIB_PATH, verbose=verbose)
     if verbose:
-        print(res.stderr)
+        print(log)
     return LIB_PATH
 
 

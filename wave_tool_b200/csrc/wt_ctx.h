@@ -1,0 +1,93 @@
+// CUDA-side internals shared by wt_device.cu and the wt_launch_*.cu translation units: the context, the
+// development knobs and the launch planning of surface_warp_kernel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "wt_internal.h"
+#include "wt_kernels.cuh"
+
+struct wt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    // wave tables (host copies; handed to the kernels as __grid_constant__ parameters per launch)
+    unsigned n_waves = 0;
+    bool waves_set = false;
+    std::vector<wt::WaveK> tab_exact, tab_fast, tab_raw;
+    // textures
+    float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
+    float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)
+    int hm_w = 0, hm_h = 0;
+    uchar4* d_sky = nullptr;        // 6 faces RGBA8 (reference-order kernel)
+    uchar4* d_sky_black = nullptr;  // 1x1 black cubemap: shading without a skybox reads sky = 0, no branch in the production kernel
+    int sky_n = 0;
+    // production kernel: padded face atlas in a block-linear CUDA array + a gather-capable texture object
+    cudaArray_t sky_array = nullptr, sky_array_black = nullptr;
+    cudaTextureObject_t sky_tex = 0, sky_tex_black = 0;
+    // scratch for the *_host entry points
+    float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
+    size_t s_elems = 0;
+    wt_checksum* s_cks = nullptr;
+    uint64_t launches = 0;
+    // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
+    int* d_queues = nullptr;
+    unsigned queue_next = 0;
+    // WT_TRACE diagnostic: per work item {smid, cta, t_start, t_end} of the most recent production launch
+    unsigned long long* d_trace = nullptr;
+    size_t trace_cap = 0, trace_items = 0;
+};
+constexpr unsigned N_QUEUES = 256;
+
+namespace wt {
+
+// Development knobs, read from the environment once (wt_debug_reload_env re-reads them):
+//   WT_DYN        rows per dynamically queued work item (0 = static plan; unset = built-in policy)
+//   WT_DYN_WARPS  cap on the resident warps per SM of the dynamic plan
+//   WT_TRACE      record per-work-item {SM, CTA, start, end} (wt_debug_read_trace)
+//   WT_DBG        bit 0: wave loop only (skips heightmap and output stage; outputs are NOT written)
+//   WT_EXTRA_SMEM extra dynamic shared memory per CTA (caps the CTAs per SM)
+struct Knobs {
+    int dyn = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0;
+    void load() {
+        auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
+        dyn = geti("WT_DYN", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
+        extra_smem = geti("WT_EXTRA_SMEM", 0);
+    }
+    Knobs() { load(); }
+};
+extern Knobs g_knobs;
+
+// ------------------------------------------------------------------------------------------------
+// Launch planning for surface_warp_kernel
+// ------------------------------------------------------------------------------------------------
+#ifndef WT_R_EXACT
+#define WT_R_EXACT 4
+#endif
+#ifndef WT_R_RECUR
+#define WT_R_RECUR 8
+#endif
+constexpr int R_EXACT = WT_R_EXACT;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
+constexpr int DYN_ROWS_RECUR = 22;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 3 marching steps)
+constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
+
+struct Plan {
+    int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;
+};
+
+Plan make_plan(int slots, int L, int rows, int R);
+
+inline int wave_capacity(unsigned n) { return n <= 64 ? 64 : n <= 256 ? 256 : 1000; }
+
+// The production kernel's instantiations are spread over four translation units (MODE x SHADE) so that
+// they compile in parallel (wave_tool_b200/build.py); each defines one of these.
+cudaError_t launch_production_exact(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
+cudaError_t launch_production_exact_shade(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
+cudaError_t launch_production_recur(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
+cudaError_t launch_production_recur_shade(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
+
+}  // namespace wt

@@ -11,8 +11,8 @@
 #include <string>
 #include <vector>
 
-#include "wt_internal.h"
-#include "wt_kernels.cuh"
+#include "wt_ctx.h"
+#include "wt_aux_kernels.cuh"
 
 namespace wt {
 
@@ -27,95 +27,8 @@ int set_thread_error(int code, const char* msg) {
 
 using namespace wt;
 
-struct wt_ctx {
-    int device = 0;
-    int sm_count = 0;
-    std::string err;
-    // wave tables (host copies; handed to the kernels as __grid_constant__ parameters per launch)
-    unsigned n_waves = 0;
-    bool waves_set = false;
-    std::vector<WaveK> tab_exact, tab_fast, tab_raw;
-    // textures
-    float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
-    float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)
-    int hm_w = 0, hm_h = 0;
-    uchar4* d_sky = nullptr;        // 6 faces RGBA8 (reference-order kernel)
-    uchar4* d_sky_black = nullptr;  // 1x1 black cubemap: shading without a skybox reads sky = 0, no branch in the production kernel
-    int sky_n = 0;
-    // production kernel: padded face atlas in a block-linear CUDA array + a gather-capable texture object
-    cudaArray_t sky_array = nullptr, sky_array_black = nullptr;
-    cudaTextureObject_t sky_tex = 0, sky_tex_black = 0;
-    // scratch for the *_host entry points
-    float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
-    size_t s_elems = 0;
-    wt_checksum* s_cks = nullptr;
-    uint64_t launches = 0;
-    // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
-    int* d_queues = nullptr;
-    unsigned queue_next = 0;
-    // WT_TRACE diagnostic: per work item {smid, cta, t_start, t_end} of the most recent production launch
-    unsigned long long* d_trace = nullptr;
-    size_t trace_cap = 0, trace_items = 0;
-};
-constexpr unsigned N_QUEUES = 256;
-
-namespace {
-
-// Development knobs, read from the environment once (wt_debug_reload_env re-reads them):
-//   WT_DYN        rows per dynamically queued work item (0 = static plan; unset = built-in policy)
-//   WT_DYN_WARPS  cap on the resident warps per SM of the dynamic plan
-//   WT_TRACE      record per-work-item {SM, CTA, start, end} (wt_debug_read_trace)
-//   WT_DBG        bit 0: wave loop only (skips heightmap and output stage; outputs are NOT written)
-//   WT_EXTRA_SMEM extra dynamic shared memory per CTA (caps the CTAs per SM)
-struct Knobs {
-    int dyn = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0;
-    void load() {
-        auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
-        dyn = geti("WT_DYN", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
-        extra_smem = geti("WT_EXTRA_SMEM", 0);
-    }
-    Knobs() { load(); }
-};
+namespace wt {
 Knobs g_knobs;
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-int fail(wt_ctx* ctx, int code, const std::string& msg) {
-    if (ctx) ctx->err = msg;
-    set_thread_error(code, msg.c_str());
-    return code;
-}
-
-#define WT_CUDA(ctx, expr)                                                                              \
-    do {                                                                                                \
-        cudaError_t e_ = (expr);                                                                        \
-        if (e_ != cudaSuccess) return fail(ctx, WT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// Launch planning for surface_warp_kernel
-// ------------------------------------------------------------------------------------------------
-#ifndef WT_R_EXACT
-#define WT_R_EXACT 4
-#endif
-#ifndef WT_R_RECUR
-#define WT_R_RECUR 8
-#endif
-constexpr int R_EXACT = WT_R_EXACT;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
-constexpr int DYN_ROWS_RECUR = 22;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 3 marching steps)
-constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
-
-struct Plan {
-    int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;
-};
 
 // Work items are warps: n_strips strips of STRIP_COLS columns x n_chunks chunks of rows.  Every item
 // marches rows_per_chunk + 2 rows (the +-1-row stencil halo is recomputed, never exchanged), in steps
@@ -142,6 +55,36 @@ Plan make_plan(int slots, int L, int rows, int R) {
     }
     return best;
 }
+
+}  // namespace wt
+
+
+
+namespace {
+
+
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(wt_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    set_thread_error(code, msg.c_str());
+    return code;
+}
+
+#define WT_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                \
+        cudaError_t e_ = (expr);                                                                        \
+        if (e_ != cudaSuccess) return fail(ctx, WT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
 
 // Builds the (3 (n+2)) x (2 (n+2)) RGBA8 atlas of a cubemap (tile column = face / 2, tile row = face % 2, every
 // face surrounded by a 1-texel border replicating its edge: per-face GL_CLAMP_TO_EDGE) in a CUDA array created
@@ -179,89 +122,10 @@ cudaError_t make_sky_atlas(const uint8_t* const faces[6], int n, cudaArray_t* ar
     return cudaCreateTextureObject(tex_out, &res, &td, nullptr);
 }
 
-int wave_capacity(unsigned n) { return n <= 16 ? 16 : n <= 64 ? 64 : n <= 256 ? 256 : 1000; }
-
 template <int CAP>
 void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memset(&t, 0, sizeof(t));
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
-}
-
-template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2>
-cudaError_t launch_warp_hm(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
-    constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
-    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2>;
-    const int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP + g_knobs.extra_smem;
-    static thread_local struct { int L = -1, rows = -1, dev = -1, slots = 0; Plan p; } cache;   // per instantiation
-    const int rows = a.row_end - a.row_begin;
-    if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * WARPS_PER_CTA, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        cache.slots = ctx->sm_count * per_sm * WARPS_PER_CTA;
-        cache.p = make_plan(cache.slots, a.L, rows, R);
-        cache.L = a.L; cache.rows = rows; cache.dev = ctx->device;
-    }
-    Plan p = cache.p;
-    // Dynamic work distribution (MODE 1): the warp schedulers favour some resident warps heavily, so equal static
-    // shares finish far apart (profiles/README.md); with small items handed out through an atomic queue every
-    // warp stays busy until the queue runs dry.  Used when there are enough items to go round several times;
-    // WT_DYN overrides the rows per item (0 = static plan).
-    const bool forced = g_knobs.dyn >= 0;
-    const int dyn_rows = forced ? g_knobs.dyn : (MODE == 1 ? DYN_ROWS_RECUR : 0);
-    a.queue = nullptr;
-    if (dyn_rows > 0) {
-        int rpc = ((dyn_rows + 2 + R - 1) / R) * R - 2;
-        if (rpc < 1) rpc = R;
-        const int n_chunks = (rows + rpc - 1) / rpc;
-        const long long items = (long long)p.n_strips * n_chunks;
-        int slots = cache.slots;
-        if (g_knobs.dyn_warps > 0) slots = std::min(slots, ctx->sm_count * g_knobs.dyn_warps);
-        if (forced || items >= 3LL * slots) {
-            p.rows_per_chunk = rpc;
-            p.n_chunks = n_chunks;
-            p.ctas = (int)std::min<long long>(items, slots);
-            a.queue = ctx->d_queues + 2 * (ctx->queue_next++ % N_QUEUES);
-        }
-    }
-    a.n_strips = p.n_strips;
-    a.rows_per_chunk = p.rows_per_chunk;
-    a.n_chunks = p.n_chunks;
-    a.n_items = p.n_strips * p.n_chunks;
-    a.trace = nullptr;
-    {
-        if (g_knobs.trace) {
-            if (ctx->trace_cap < (size_t)a.n_items) {
-                cudaFree(ctx->d_trace);
-                ctx->d_trace = nullptr;
-                if (cudaMalloc(&ctx->d_trace, (size_t)a.n_items * 32) == cudaSuccess) ctx->trace_cap = a.n_items;
-            }
-            a.trace = ctx->d_trace;
-            ctx->trace_items = a.trace ? a.n_items : 0;
-        }
-    }
-    static thread_local WaveTable<CAP> table;
-    fill_table(table, tab);
-    for (size_t i = 0; i < tab.size(); ++i) {
-        const float c = tab[i].phi * a.t;   // fl(phi * t), water-grid.vert:78
-        // MODE 1 adds the offset inside an FMA chain: hand it over reduced mod 2pi (in double) so it costs no precision
-        table.w[i].phi = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
-    }
-    a.dbg = g_knobs.dbg;
-    kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
-    ctx->launches++;
-    return cudaGetLastError();
-}
-
-template <int CAP, int MODE, bool SHADE, bool CKS>
-cudaError_t launch_warp_cks(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
-    // non-power-of-two heightmaps take the instantiation with the out-of-line modulo
-    return a.hm_pow2 ? launch_warp_hm<CAP, MODE, SHADE, CKS, true>(ctx, a, tab, stream) : launch_warp_hm<CAP, MODE, SHADE, CKS, false>(ctx, a, tab, stream);
-}
-
-template <int CAP, int MODE, bool SHADE>
-cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
-    return a.cks ? launch_warp_cks<CAP, MODE, SHADE, true>(ctx, a, tab, stream) : launch_warp_cks<CAP, MODE, SHADE, false>(ctx, a, tab, stream);
 }
 
 template <int CAP, bool SHADE>
@@ -273,16 +137,6 @@ cudaError_t launch_reference_order(wt_ctx* ctx, EvalArgs& a, const std::vector<W
     surface_reference_order_kernel<CAP, SHADE><<<std::max(blocks, 1), 256, 0, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
-}
-
-template <int CAP>
-cudaError_t dispatch_cap(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
-    const bool shade = flags & WT_FLAG_SHADE;
-    if (flags & WT_FLAG_REFERENCE_ORDER)
-        return shade ? launch_reference_order<CAP, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<CAP, false>(ctx, a, ctx->tab_raw, stream);
-    if (flags & WT_FLAG_FAST_PHASE)
-        return shade ? launch_warp<CAP, 1, true>(ctx, a, ctx->tab_fast, stream) : launch_warp<CAP, 1, false>(ctx, a, ctx->tab_fast, stream);
-    return shade ? launch_warp<CAP, 0, true>(ctx, a, ctx->tab_exact, stream) : launch_warp<CAP, 0, false>(ctx, a, ctx->tab_exact, stream);
 }
 
 int validate_eval(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
@@ -330,12 +184,17 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
 }
 
 cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
-    switch (wave_capacity(ctx->n_waves)) {
-        case 16: return dispatch_cap<16>(ctx, a, flags, stream);
-        case 64: return dispatch_cap<64>(ctx, a, flags, stream);
-        case 256: return dispatch_cap<256>(ctx, a, flags, stream);
-        default: return dispatch_cap<1000>(ctx, a, flags, stream);
+    const bool shade = flags & WT_FLAG_SHADE;
+    if (flags & WT_FLAG_REFERENCE_ORDER) {
+        switch (wave_capacity(ctx->n_waves)) {
+            case 64: return shade ? launch_reference_order<64, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<64, false>(ctx, a, ctx->tab_raw, stream);
+            case 256: return shade ? launch_reference_order<256, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<256, false>(ctx, a, ctx->tab_raw, stream);
+            default: return shade ? launch_reference_order<1000, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<1000, false>(ctx, a, ctx->tab_raw, stream);
+        }
     }
+    if (flags & WT_FLAG_FAST_PHASE)
+        return shade ? launch_production_recur_shade(ctx, a, flags, stream) : launch_production_recur(ctx, a, flags, stream);
+    return shade ? launch_production_exact_shade(ctx, a, flags, stream) : launch_production_exact(ctx, a, flags, stream);
 }
 
 }  // namespace

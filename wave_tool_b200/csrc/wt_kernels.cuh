@@ -251,23 +251,6 @@ struct ChecksumAcc {
     }
 };
 
-__global__ void checksum_init_kernel(wt_checksum* c, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        c[i].position_bits = 0; c[i].normal_bits = 0; c[i].shade_bits = 0; c[i].vertices = 0;
-        ((unsigned*)&c[i].min_y)[0] = 0xffffffffu;
-        ((unsigned*)&c[i].max_y)[0] = 0u;
-    }
-}
-__global__ void checksum_finalize_kernel(wt_checksum* c, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        unsigned kmin = ((unsigned*)&c[i].min_y)[0], kmax = ((unsigned*)&c[i].max_y)[0];
-        c[i].min_y = key_float(kmin);
-        c[i].max_y = key_float(kmax);
-    }
-}
-
 // single-instruction MUFU approximations (flush-to-zero forms: no denormal fix-up code around them)
 __device__ __forceinline__ float rsq_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -314,7 +297,7 @@ __device__ __forceinline__ int wrap_period_any(int i, int period) {
 }
 // non-power-of-two heightmaps: the four footprint coordinates modulo (2w, 2h); kept out of line so the
 // integer-division sequences stay out of the hot instruction stream of the usual power-of-two case
-__device__ __noinline__ int4 wrap_period4_any(int4 v, int w2, int h2) {
+static __device__ __noinline__ int4 wrap_period4_any(int4 v, int w2, int h2) {
     return make_int4(wrap_period_any(v.x, w2), wrap_period_any(v.y, w2), wrap_period_any(v.z, h2), wrap_period_any(v.w, h2));
 }
 // Split in two so that the table loads of several rows are in flight together: hm_fetch2 computes the
@@ -740,148 +723,6 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         if (atomicAdd(a.queue + 1, 1) == (int)gridDim.x - 1) { a.queue[1] = 0; __threadfence(); a.queue[0] = 0; }
     }
     if (CKS) acc.flush(a.cks);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Footprint tables (built on the device when a texture is set)
-// ------------------------------------------------------------------------------------------------
-// GL_MIRRORED_REPEAT unrolled: entry (i, j), i in [0, 2w), j in [0, 2h), holds the texels at
-// wrap(i), wrap(i+1) x wrap(j), wrap(j+1) — the GL_LINEAR footprint whose lower-left texel index is
-// congruent to (i, j) modulo (2w, 2h).
-__global__ void build_heightmap_quads_kernel(const float* r, int w, int h, float4* quads) {
-    const int w2 = 2 * w, h2 = 2 * h;
-    const long long n = (long long)w2 * h2;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k % w2), j = (int)(k / w2);
-        const int i0 = wrap_mirror(i, w, 0), i1 = wrap_mirror(i + 1, w, 0), j0 = wrap_mirror(j, h, 0), j1 = wrap_mirror(j + 1, h, 0);
-        quads[k] = make_float4(r[(size_t)j0 * w + i0], r[(size_t)j0 * w + i1], r[(size_t)j1 * w + i0], r[(size_t)j1 * w + i1]);
-    }
-}
-// ------------------------------------------------------------------------------------------------
-// Reference-order kernel: one thread per vertex, the shader's own structure (water-grid.vert:114-194)
-// ------------------------------------------------------------------------------------------------
-template <int CAP>
-__device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const WaveTable<CAP>& wt, float u, float v) {
-    // :87-91
-    float x = mix_rn(mix_rn(a.blx, a.brx, u), mix_rn(a.tlx, a.trx, u), v);
-    float z = mix_rn(mix_rn(a.blz, a.brz, u), mix_rn(a.tlz, a.trz, u), v);
-    P3 p = {x, 0.0f, z};
-    for (int i = 0; i < a.n_waves; ++i) {   // :76-82, table holds the raw uniforms: cX = Q_i here
-        const WaveK wk = wt.w[i];
-        float k = add_rn(mul_rn(wk.w, add_rn(mul_rn(wk.Dx, x), mul_rn(wk.Dz, z))), mul_rn(wk.phi, a.t));
-        float s, c;
-        sincosf(k, &s, &c);
-        float qc = mul_rn(wk.cX, c);
-        p.x = add_rn(p.x, mul_rn(wk.A, mul_rn(wk.Dx, qc)));
-        p.y = add_rn(p.y, mul_rn(wk.A, s));
-        p.z = add_rn(p.z, mul_rn(wk.A, mul_rn(wk.Dz, qc)));
-    }
-    p.y = finish_height(a, p.x, p.y, p.z);
-    return p;
-}
-
-template <int CAP, bool SHADE>
-__global__ void __launch_bounds__(256) surface_reference_order_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
-    const long long n = (long long)(a.row_end - a.row_begin) * a.L;
-    ChecksumAcc acc;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const int row = a.row_begin + (int)(k / a.L), col = (int)(k % a.L);
-        const float du = a.du;
-        const float u = mul_rn((float)col, du), v = mul_rn((float)row, du);   // :123-125
-        P3 c = displaced_reference_order<CAP>(a, wt, u, v);
-        P3 left = displaced_reference_order<CAP>(a, wt, sub_rn(u, du), v);    // :164-167: uv -/+ du
-        P3 right = displaced_reference_order<CAP>(a, wt, add_rn(u, du), v);
-        P3 down = displaced_reference_order<CAP>(a, wt, u, sub_rn(v, du));
-        P3 up = displaced_reference_order<CAP>(a, wt, u, add_rn(v, du));
-        // :187-190 with IEEE sqrt/div like the CPU reference
-        float ux = sub_rn(right.x, left.x), uy = sub_rn(right.y, left.y), uz = sub_rn(right.z, left.z);
-        float vx = sub_rn(up.x, down.x), vy = sub_rn(up.y, down.y), vz = sub_rn(up.z, down.z);
-        float nx = sub_rn(mul_rn(uy, vz), mul_rn(vy, uz));
-        float ny = sub_rn(mul_rn(uz, vx), mul_rn(vz, ux));
-        float nz = sub_rn(mul_rn(ux, vy), mul_rn(vx, uy));
-        float inv = __fdiv_rn(1.0f, __fsqrt_rn(add_rn(add_rn(mul_rn(nx, nx), mul_rn(ny, ny)), mul_rn(nz, nz))));
-        nx = mul_rn(nx, inv); ny = mul_rn(ny, inv); nz = mul_rn(nz, inv);
-        float wx = sub_rn(a.camx, c.x), wy = sub_rn(a.camy, c.y), wz = sub_rn(a.camz, c.z);
-        float ww = add_rn(add_rn(mul_rn(wx, wx), mul_rn(wy, wy)), mul_rn(wz, wz));
-        float winv = __fdiv_rn(1.0f, __fsqrt_rn(ww));
-        float ex = mul_rn(wx, winv), ey = mul_rn(wy, winv), ez = mul_rn(wz, winv);
-        float facing = add_rn(add_rn(mul_rn(nx, ex), mul_rn(ny, ey)), mul_rn(nz, ez));
-        if (facing < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
-        float4 on = make_float4(nx, ny, nz, 0.0f), os = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (SHADE) {
-            // frag:71-73 viewVec = viewVecRaw / length
-            float len = __fsqrt_rn(ww);
-            float fx = __fdiv_rn(wx, len), fy = __fdiv_rn(wy, len), fz = __fdiv_rn(wz, len);
-            // frag:95 reflect(-viewVec, normal) = I - N * dot(N, I) * 2
-            float ix = -fx, iy = -fy, iz = -fz;
-            float d = add_rn(add_rn(mul_rn(nx, ix), mul_rn(ny, iy)), mul_rn(nz, iz));
-            float rx = sub_rn(ix, mul_rn(mul_rn(nx, d), 2.0f)), ry = sub_rn(iy, mul_rn(mul_rn(ny, d), 2.0f)), rz = sub_rn(iz, mul_rn(mul_rn(nz, d), 2.0f));
-            float3 sky = make_float3(0.f, 0.f, 0.f);
-            if (a.sky) sky = sky_rgb(a, rx, ry, rz);
-            float sd = add_rn(add_rn(mul_rn(rx, a.sunx), mul_rn(ry, a.suny)), mul_rn(rz, a.sunz));
-            sd = fminf(fmaxf(sd, 0.0f), 1.0f);
-            float sun = mul_rn(a.sun_strength, powf(sd, a.sun_shininess));
-            float ct = add_rn(add_rn(mul_rn(nx, fx), mul_rn(ny, fy)), mul_rn(nz, fz));
-            on.w = add_rn(0.02f, mul_rn(sub_rn(1.0f, 0.02f), powf(sub_rn(1.0f, ct), 5.0f)));
-            os = make_float4(sky.x, sky.y, sky.z, sun);
-        }
-        float4 op = make_float4(c.x, c.y, c.z, 1.0f);
-        a.pos[k] = op;
-        a.nrm[k] = on;
-        if (SHADE) a.shade[k] = os;
-        if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(os); }
-    }
-    if (a.cks) acc.flush(a.cks);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Roofline denominators measured on the device itself (wt_measure_peak)
-// ------------------------------------------------------------------------------------------------
-__global__ void peak_mufu_kernel(float* sink, int iters) {
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = 0.001f * (threadIdx.x + 1) + 0.1f * j;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __sinf(x[j]) + __cosf(x[j]);   // 1 sin + 1 cos per element-iteration
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += x[j];
-    if (s == 123.456f) sink[0] = s;
-}
-__global__ void peak_fma_kernel(float* sink, int iters) {
-    float x[8];
-    const float a = 1.0000001f, b = 1e-9f * threadIdx.x;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = 0.001f * (threadIdx.x + 1) + 0.1f * j;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __fmaf_rn(x[j], a, b);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += x[j];
-    if (s == 123.456f) sink[0] = s;
-}
-// packed fp32: FFMA2 (two FMAs per lane per instruction)
-__global__ void peak_fma2_kernel(float* sink, int iters) {
-    float2 x[8];
-    const float2 a = make_float2(1.0000001f, 0.9999999f), b = make_float2(1e-9f * threadIdx.x, 1e-9f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = make_float2(0.001f * (threadIdx.x + 1) + 0.1f * j, 0.5f + 0.1f * j);
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __ffma2_rn(x[j], a, b);
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += x[j].x + x[j].y;
-    if (s == 123.456f) sink[0] = s;
-}
-__global__ void peak_store_kernel(float4* dst, size_t n) {
-    const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) __stcs(dst + i, v);
 }
 
 }  // namespace wt
