@@ -45,6 +45,8 @@ extern "C" {
 #define WT_FLAG_CHECKSUM 0x2u         /* fold the outputs into the wt_checksum record passed to the call */
 #define WT_FLAG_FAST_PHASE 0x4u       /* pre-folded 2-FMA wave phase (not bit-faithful to the reference's fp32 phase) */
 #define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
+#define WT_FLAG_VARYINGS 0x10u        /* also write the vertex stage's other outputs (wt_eval_frame_ex): gl_Position,
+                                         xyPositionNDCSpaceHeight0, heightmap_colour.r, normalVecInViewSpaceOnlyYaw */
 
 typedef struct wt_ctx wt_ctx;
 
@@ -183,6 +185,33 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n);
  * ------------------------------------------------------------------------------------------- */
 int wt_eval_frame(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsigned row_begin, unsigned row_end,
                   void* d_position, void* d_normal, void* d_shade, void* d_checksum, unsigned flags, void* cuda_stream);
+
+/* Every output stream of the vertex stage.  position/normal are mandatory; shade with WT_FLAG_SHADE; the three
+ * varyings buffers with WT_FLAG_VARYINGS; checksum with WT_FLAG_CHECKSUM.  All device pointers, one float4 per
+ * vertex, element k = (row - row_begin) * grid_len + col:
+ *     clip_position  gl_Position = viewProjection * position                         (water-grid.vert:150)
+ *     varyings_a     (xyPositionNDCSpaceHeight0.x, .y, heightmap_colour.r, 0)         (:153-154, :141)
+ *     varyings_b     (normalVecInViewSpaceOnlyYaw.xyz, 0)                             (:193)
+ * viewVecRaw (:158) is cameraPosition - position and is not stored.  heightmap_colour is a debug varying of
+ * which the shader consumes .r only (:110); g, b, a are not produced. */
+typedef struct wt_outputs {
+    void* position;
+    void* normal;
+    void* shade;
+    void* clip_position;
+    void* varyings_a;
+    void* varyings_b;
+    void* checksum;
+} wt_outputs;
+
+/* wt_eval_frame with the full set of output streams. */
+int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsigned row_begin, unsigned row_end,
+                     const wt_outputs* outputs, unsigned flags, void* cuda_stream);
+
+/* The index buffer glDrawElements consumes — replaces the tessellation loop of src/program.cpp:686-717: two
+ * counter-clockwise triangles per grid cell, (bl, tr, tl) and (bl, br, tr), cells row-major from the bottom-left.
+ * Writes 6 (grid_len-1)^2 indices to `out` (HOST memory; may be NULL to query) and the count to *count. */
+int wt_grid_indices(unsigned grid_len, uint32_t* out, uint64_t capacity, uint64_t* count);
 
 /* A batch of n_frames independent frames (animation; frame sharding takes a subset per GPU).
  * Frame f writes slot (f % ring_depth) of each ring buffer (slot stride = (row_end-row_begin)*grid_len

@@ -348,6 +348,69 @@ def test_sky_footprint_on_noise_cubemap(oracle, hm, n, mode):
     assert got["shade"][:, :3].std() > 0.05 or n == 1     # the cubemap really was sampled
 
 
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("shade", [False, True])
+def test_varyings_clip_ndc_yaw_normal(oracle, hm, mode, shade):
+    """WT_FLAG_VARYINGS (wt_eval_frame_ex): gl_Position, xyPositionNDCSpaceHeight0, heightmap_colour.r and
+    normalVecInViewSpaceOnlyYaw (water-grid.vert:141,150-154,193) against the oracle's copies of the same
+    varyings, on a camera that is neither axis-aligned nor level so that every matrix entry matters."""
+    torch = torch_mod()
+    L = 384
+    sky = scenes.procedural_skybox(64) if shade else None
+    sc = Scene(scenes.seeded_waves(16, cfg=7), scenes.camera(pos=(3.0, 11.0, 60.0), yaw=-75.0, pitch=-17.0, aspect=1.6),
+               scenes.animation_params(23), L, hm, skybox=sky)
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    n = L * L
+    bufs = {k: torch.empty((n, 4), dtype=torch.float32, device="cuda") for k in ("pos", "normal", "shade", "clip", "va", "vb")}
+    out = api.Outputs(bufs["pos"].data_ptr(), bufs["normal"].data_ptr(), bufs["shade"].data_ptr() if shade else None,
+                      bufs["clip"].data_ptr(), bufs["va"].data_ptr(), bufs["vb"].data_ptr(), None)
+    flags = api.FLAG_VARYINGS | MODES[mode] | (api.FLAG_SHADE if shade else 0)
+    assert ctx.eval_frame_ex(frame, L, out, flags=flags, stream=torch.cuda.current_stream().cuda_stream) == api.WT_OK
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in bufs.items()}
+    want = sc.oracle_eval(oracle, shade=shade, extra=True)
+    stats = compare({"pos": got["pos"], "normal": got["normal"], "shade": got["shade"]}, want, sc, shade=shade, label="varyings scene")
+    # the same launch without the flag writes the very same position / normal bits
+    plain = gpu_eval(ctx, frame, L, flags=flags & ~api.FLAG_VARYINGS)
+    assert np.array_equal(plain["pos"].view(np.uint32), got["pos"].view(np.uint32))
+    assert np.array_equal(plain["normal"].view(np.uint32), got["normal"].view(np.uint32))
+    ex = want["extra"].astype(np.float64)
+    clip_w, ndc_w, yaw_w, hm_w = ex[:, 0:4], ex[:, 4:6], ex[:, 9:12], ex[:, 12]
+    perr = np.abs(got["pos"][:, :3].astype(np.float64) - want["pos"][:, :3]).max(axis=1)
+    vp = np.array(frame.viewProjection[:], np.float64).reshape(4, 4).T            # row r = vp[r, :]
+    gain = np.abs(vp[:, :3]).sum(axis=1)                                           # |d clip_r / d position|_1
+    clip_err = np.abs(got["clip"].astype(np.float64) - clip_w)
+    assert np.all(clip_err <= perr[:, None] * gain[None, :] + 4e-6 * (np.abs(clip_w) + np.abs(vp[:, 3])[None, :] + 1.0)), clip_err.max()
+    # ndc0 = clip0.xy / clip0.w: first-order error bound from the position error, plus a few ulp
+    w0 = clip_w[:, 3] - vp[3, 1] * want["pos"][:, 1].astype(np.float64)            # w of the height-0 point
+    ndc_err = np.abs(got["va"][:, :2].astype(np.float64) - ndc_w)
+    bound = (perr[:, None] * (gain[None, :2] + np.abs(ndc_w) * gain[3]) / np.abs(w0)[:, None]) + 8e-6 * (1.0 + np.abs(ndc_w))
+    assert np.all(ndc_err <= bound), float((ndc_err - bound).max())
+    hm_err = np.abs(got["va"][:, 2].astype(np.float64) - hm_w)
+    assert np.all(hm_err <= 5.0 * perr + 1e-6), hm_err.max()
+    assert np.all(got["va"][:, 3] == 0.0) and np.all(got["vb"][:, 3] == 0.0)
+    ang = np.minimum(angle_between(got["vb"][:, :3], yaw_w), angle_between(got["vb"][:, :3], -yaw_w))
+    nang = np.minimum(angle_between(got["normal"][:, :3], want["normal"][:, :3]), angle_between(got["normal"][:, :3], -want["normal"][:, :3]))
+    assert np.all(ang <= nang + 2e-6), float((ang - nang).max())                   # a rotation: no angle is amplified
+    assert np.abs(np.linalg.norm(got["vb"][:, :3].astype(np.float64), axis=1) - 1.0).max() < 1e-6
+    print("varyings", mode, shade, stats, float(clip_err.max()), float(ndc_err.max()), float(hm_err.max()))
+
+
+def test_varyings_argument_checks(hm):
+    torch = torch_mod()
+    sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    b = torch.empty((64 * 64, 4), dtype=torch.float32, device="cuda")
+    with pytest.raises(api.WaveToolError):
+        ctx.eval_frame_ex(frame, 64, api.Outputs(b.data_ptr(), b.data_ptr(), None, None, None, None, None), flags=api.FLAG_VARYINGS)
+    with pytest.raises(api.WaveToolError):
+        ctx.eval_frame_ex(frame, 64, api.Outputs(b.data_ptr(), b.data_ptr(), None, b.data_ptr(), b.data_ptr(), b.data_ptr(), None),
+                          flags=api.FLAG_VARYINGS | api.FLAG_REFERENCE_ORDER)
+
+
 def test_non_power_of_two_heightmap(oracle):
     hm = scenes.procedural_heightmap(200)[:150]      # 200 x 150 texels
     sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), 300, hm)

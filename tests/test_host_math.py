@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 from tests.common import GOLDEN, Scene
 from wave_tool_b200 import api, scenes
@@ -97,3 +98,19 @@ def test_unorm8_reciprocal_trick_is_exact():
     rem = (c.astype(np.float64) - q.astype(np.float64) * 255.0).astype(np.float32)
     q2 = (q.astype(np.float64) + rem.astype(np.float64) * np.float64(r)).astype(np.float32)
     assert np.array_equal(q2, c / np.float32(255))
+
+
+def test_grid_indices_match_reference_tessellation():
+    """wt_grid_indices against a literal restatement of the tessellation loop of src/program.cpp:686-717."""
+    for L in (2, 3, 5, 17, 513):
+        grid = np.arange(L * L, dtype=np.uint32).reshape(L, L)      # gridIndices[row][col] = counterIndex (:695-700)
+        want = []
+        for row in range(L - 1):                                      # :704-716
+            for col in range(L - 1):
+                want += [grid[row, col], grid[row + 1, col + 1], grid[row + 1, col],
+                         grid[row, col], grid[row, col + 1], grid[row + 1, col + 1]]
+        got = api.grid_indices(L)
+        assert got.dtype == np.uint32 and len(got) == 6 * (L - 1) ** 2
+        assert np.array_equal(got, np.array(want, np.uint32))
+    with pytest.raises(api.WaveToolError):
+        api.grid_indices(1)

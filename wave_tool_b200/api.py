@@ -16,7 +16,7 @@ from . import build as _build
 WT_OK, WT_NO_GRID = 0, 1
 WT_ERR_INVALID_ARGUMENT, WT_ERR_CUDA, WT_ERR_NO_DEVICE, WT_ERR_NOT_READY, WT_ERR_DEGENERATE = -1, -2, -3, -4, -5
 WT_MAX_WAVES = 1000
-FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER = 0x1, 0x2, 0x4, 0x8
+FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER, FLAG_VARYINGS = 0x1, 0x2, 0x4, 0x8, 0x10
 
 # every symbol include/wavetool_b200.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTED_SYMBOLS = [
@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "wt_project_grid", "wt_build_frame",
     "wt_create", "wt_destroy", "wt_set_waves", "wt_set_heightmap_rgba8", "wt_set_skybox_rgba8",
     "wt_eval_frame", "wt_eval_batch", "wt_eval_frame_host", "wt_launch_count", "wt_measure_peak",
-    "wt_debug_read_trace", "wt_debug_reload_env",
+    "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
 ]
 
 
@@ -63,6 +63,11 @@ class Checksum(C.Structure):
 
     def as_tuple(self):
         return (self.position_bits, self.normal_bits, self.shade_bits, self.min_y, self.max_y, self.vertices)
+
+
+class Outputs(C.Structure):
+    _fields_ = [("position", C.c_void_p), ("normal", C.c_void_p), ("shade", C.c_void_p), ("clip_position", C.c_void_p),
+                ("varyings_a", C.c_void_p), ("varyings_b", C.c_void_p), ("checksum", C.c_void_p)]
 
 
 CHECKSUM_DTYPE = np.dtype([("position_bits", "u8"), ("normal_bits", "u8"), ("shade_bits", "u8"),
@@ -121,6 +126,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_measure_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.wt_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
     L.wt_debug_reload_env.restype = None
+    L.wt_eval_frame_ex.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs), C.c_uint, C.c_void_p]
+    L.wt_grid_indices.argtypes = [C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -175,6 +182,15 @@ def project_grid(cam: Camera, displaceable_amplitude: float):
     return st, corners
 
 
+def grid_indices(grid_len: int) -> np.ndarray:
+    """The water mesh index buffer (program.cpp:686-717) as a (6 (L-1)^2,) uint32 array."""
+    n = C.c_uint64()
+    _check(lib().wt_grid_indices(grid_len, None, 0, C.byref(n)))
+    out = np.empty(n.value, np.uint32)
+    _check(lib().wt_grid_indices(grid_len, out.ctypes.data, n.value, C.byref(n)))
+    return out
+
+
 def build_frame(cam: Camera, params: Params, total_wave_amplitude: float):
     f = Frame()
     st = _check(lib().wt_build_frame(C.byref(cam), C.byref(params), C.c_float(total_wave_amplitude), C.byref(f)))
@@ -227,6 +243,11 @@ class Context:
         r0, r1 = rows if rows is not None else (0, grid_len)
         return _check(self._lib.wt_eval_frame(self._h, C.byref(frame), grid_len, r0, r1, d_pos, d_normal, d_shade or None,
                                               d_checksum or None, flags, stream or None), self._h)
+
+    def eval_frame_ex(self, frame: Frame, grid_len: int, outputs: "Outputs", flags: int = 0, rows=None, stream: int = 0):
+        """wt_eval_frame_ex: every output stream of the vertex stage (Outputs holds raw device addresses)."""
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        return _check(self._lib.wt_eval_frame_ex(self._h, C.byref(frame), grid_len, r0, r1, C.byref(outputs), flags, stream or None), self._h)
 
     def eval_batch(self, frames, grid_len: int, d_pos_ring: int, d_normal_ring: int, d_shade_ring: int = 0, ring_depth: int = 2,
                    d_checksums: int = 0, flags: int = 0, rows=None, stream: int = 0):

@@ -179,6 +179,8 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
     if (!a.sky) { a.sky = ctx->d_sky_black; a.sky_n = 1; a.sky_tex = ctx->sky_tex_black; }
     a.pos = (float4*)d_pos; a.nrm = (float4*)d_nrm; a.shade = (float4*)d_shade;
     a.cks = (flags & WT_FLAG_CHECKSUM) ? (wt_checksum*)d_cks : nullptr;
+    std::memcpy(a.vp, f.viewProjection, sizeof(a.vp));
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) a.vy[3 * c + r] = f.viewMatOnlyYaw[4 * c + r];
     a.L = (int)L; a.row_begin = (int)r0; a.row_end = (int)r1;
     return a;
 }
@@ -329,6 +331,45 @@ int wt_eval_frame(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, u
     WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
     if (a.cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
+    return WT_OK;
+}
+
+int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, const wt_outputs* out, unsigned flags, void* stream_) {
+    if (!out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_eval_frame_ex: outputs is NULL");
+    int st = validate_eval(ctx, frame, L, r0, r1, out->position, out->normal, out->shade, out->checksum, flags);
+    if (st != WT_OK) return st;
+    const bool vary = flags & WT_FLAG_VARYINGS;
+    if (vary && (!out->clip_position || !out->varyings_a || !out->varyings_b))
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS needs the clip_position, varyings_a and varyings_b buffers");
+    if (vary && (flags & WT_FLAG_REFERENCE_ORDER))
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS is not available with WT_FLAG_REFERENCE_ORDER");
+    DeviceGuard g(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    EvalArgs a = make_args(ctx, *frame, L, r0, r1, out->position, out->normal, out->shade, out->checksum, flags);
+    if (vary) { a.clip = (float4*)out->clip_position; a.vary_a = (float4*)out->varyings_a; a.vary_b = (float4*)out->varyings_b; }
+    if (a.cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
+    if (a.cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    WT_CUDA(ctx, cudaGetLastError());
+    return WT_OK;
+}
+
+// water mesh tessellation, src/program.cpp:686-717: two counter-clockwise triangles per grid cell, cells in row-major
+// order from the bottom-left, vertex id = row * grid_len + col
+int wt_grid_indices(unsigned L, uint32_t* out, uint64_t capacity, uint64_t* count) {
+    if (L < 2 || L > 32768) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_grid_indices: grid_len must be in [2, 32768]");
+    const uint64_t n = 6ull * (L - 1) * (L - 1);
+    if (count) *count = n;
+    if (!out) return WT_OK;
+    if (capacity < n) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_grid_indices: capacity too small");
+    uint64_t k = 0;
+    for (unsigned row = 0; row + 1 < L; ++row) {
+        for (unsigned col = 0; col + 1 < L; ++col) {
+            const uint32_t bl = row * L + col, br = bl + 1, tl = bl + L, tr = tl + 1;
+            out[k++] = bl; out[k++] = tr; out[k++] = tl;
+            out[k++] = bl; out[k++] = br; out[k++] = tr;
+        }
+    }
     return WT_OK;
 }
 

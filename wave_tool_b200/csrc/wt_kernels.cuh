@@ -68,6 +68,12 @@ struct EvalArgs {
     float4* nrm;
     float4* shade;
     wt_checksum* cks;   // NULL unless WT_FLAG_CHECKSUM
+    // WT_FLAG_VARYINGS: the remaining vertex-stage outputs of water-grid.vert (:150-154, :141, :193)
+    float4* clip;       // gl_Position = viewProjection * position
+    float4* vary_a;     // (xyPositionNDCSpaceHeight0.x, .y, heightmap_colour.r, 0)
+    float4* vary_b;     // (normalVecInViewSpaceOnlyYaw.xyz, 0)
+    float vp[16];       // viewProjection, column-major
+    float vy[12];       // upper-left 3 rows of viewMatOnlyYaw's first three columns: vy[3*c + r]
     int L, row_begin, row_end;
     int n_strips;       // warps across a row
     int rows_per_chunk; // output rows per warp
@@ -324,7 +330,7 @@ __device__ __forceinline__ HmTap hm_fetch2(const EvalArgs& a, f2 px, f2 pz) {
     h.qb = __ldg(a.hm_quads + (unsigned)(ij.w * w2 + ij.y));
     return h;
 }
-__device__ __forceinline__ f2 hm_finish2(const EvalArgs& a, const HmTap& h, f2 py) {
+__device__ __forceinline__ f2 hm_finish2(const EvalArgs& a, const HmTap& h, f2 py, f2& texel_r) {
     const float one = a.one;
     f2 oma = sub2(bc(1.0f), h.al), omb = sub2(bc(1.0f), h.be);
     f2 w00 = mul2(oma, omb), w10 = mul2(h.al, omb), w01 = mul2(oma, h.be), w11 = mul2(h.al, h.be);
@@ -332,6 +338,7 @@ __device__ __forceinline__ f2 hm_finish2(const EvalArgs& a, const HmTap& h, f2 p
     acc = add2x(mul2(w10, make_float2(h.qa.y, h.qb.y)), acc, one);
     acc = add2x(mul2(w01, make_float2(h.qa.z, h.qb.z)), acc, one);
     acc = add2x(mul2(w11, make_float2(h.qa.w, h.qb.w)), acc, one);
+    texel_r = acc;   // heightmap_colour.r (:141)
     f2 bump = mul2(bc(a.hm_disp), mul2(bc(2.0f), sub2(acc, bc(0.5f))));
     return add2(add2x(bump, py, one), bc(a.bounce));
 }
@@ -460,18 +467,19 @@ __device__ __forceinline__ int next_item(int* queue, int lane) {
 constexpr int WARPS_PER_CTA = 1;   // one warp per CTA: every loop bound derives from blockIdx alone, so ptxas keeps the wave constants in uniform registers
 constexpr int RING_COLS = 34;   // entries per ring row: [0] = (-, A of lane 31), [1 + l] = (A_l, B_l), [33] = (B of lane 0, -)
 
-template <int R>
+template <int R, bool VARY = false>
 struct RingLayout {
     static constexpr int ROWS = R + 2;
     static constexpr int PLANE = ROWS * RING_COLS;                   // float2 entries per component
-    static constexpr int BYTES_PER_WARP = 3 * PLANE * (int)sizeof(float2);
+    static constexpr int PLANES = VARY ? 4 : 3;                      // x, y, z (+ the heightmap sample with WT_FLAG_VARYINGS)
+    static constexpr int BYTES_PER_WARP = PLANES * PLANE * (int)sizeof(float2);
 };
 
-template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2>
+template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY>
 __global__ void __launch_bounds__(32, MODE == 1 ? WT_LB_RECUR : WT_LB_EXACT)
 surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
     extern __shared__ float2 ring_all[];
-    using RL = RingLayout<R>;
+    using RL = RingLayout<R, VARY>;
     const int lane = threadIdx.x;
     float2* const ring = ring_all;
     const bool dyn = a.queue != nullptr;
@@ -591,8 +599,10 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 for (int jj = 0; jj < HM_BATCH; ++jj) {
                     const int j = j0 + jj;
                     if (j >= R) break;
-                    py[j] = hm_finish2(a, tap[jj], py[j]);
+                    f2 texel_r;
+                    py[j] = hm_finish2(a, tap[jj], py[j], texel_r);
                     float2* const row = ring + slot * RING_COLS;
+                    if (VARY) row[3 * RL::PLANE + 1 + lane] = texel_r;
                     row[1 + lane] = px[j];
                     row[RL::PLANE + 1 + lane] = py[j];
                     row[2 * RL::PLANE + 1 + lane] = pz[j];
@@ -691,6 +701,35 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 float4* const ps = a.shade + o;
                 if (stA) __stcs(ps, sA);
                 if (stB) __stcs(ps + 32, sB);
+            }
+            if (VARY) {
+                // gl_Position = viewProjection * position (:150); the same with y = 0, .xy / .w (:153-154)
+                const float* const m = a.vp;
+                f2 cl[4], c0[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    c0[r] = fma2(bc(m[8 + r]), cz, fma2(bc(m[r]), cx, bc(m[12 + r])));
+                    cl[r] = fma2(bc(m[4 + r]), cy, c0[r]);
+                }
+                const f2 iw = make_float2(__fdividef(1.0f, c0[3].x), __fdividef(1.0f, c0[3].y));
+                const f2 ndx = mul2(c0[0], iw), ndy = mul2(c0[1], iw);
+                // normalVecInViewSpaceOnlyYaw = normalize((viewMatOnlyYaw * vec4(normal, 0)).xyz) (:193)
+                const float* const y = a.vy;
+                f2 yn[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) yn[r] = fma2(bc(y[6 + r]), e.nz, fma2(bc(y[3 + r]), e.ny, mul2(bc(y[r]), e.nx)));
+                const f2 y2 = fma2(yn[0], yn[0], fma2(yn[1], yn[1], mul2(yn[2], yn[2])));
+                const f2 yi = make_float2(rsq_approx(y2.x), rsq_approx(y2.y));
+                const f2 hr = rc[3 * RL::PLANE + 1];
+                float4* const pc = a.clip + o;
+                float4* const pa = a.vary_a + o;
+                float4* const pb = a.vary_b + o;
+                if (stA) __stcs(pc, make_float4(cl[0].x, cl[1].x, cl[2].x, cl[3].x));
+                if (stB) __stcs(pc + 32, make_float4(cl[0].y, cl[1].y, cl[2].y, cl[3].y));
+                if (stA) __stcs(pa, make_float4(ndx.x, ndy.x, hr.x, 0.0f));
+                if (stB) __stcs(pa + 32, make_float4(ndx.y, ndy.y, hr.y, 0.0f));
+                if (stA) __stcs(pb, make_float4(yn[0].x * yi.x, yn[1].x * yi.x, yn[2].x * yi.x, 0.0f));
+                if (stB) __stcs(pb + 32, make_float4(yn[0].y * yi.y, yn[1].y * yi.y, yn[2].y * yi.y, 0.0f));
             }
             if (CKS) {
                 if (stA) { acc.add(opA, onA); if (SHADE) acc.add_shade(sA); }

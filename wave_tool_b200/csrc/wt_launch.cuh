@@ -13,11 +13,11 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
 }
 
-template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2>
-cudaError_t launch_warp_hm(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY>
+cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
     constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
-    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2>;
-    const int smem = WARPS_PER_CTA * RingLayout<R>::BYTES_PER_WARP + g_knobs.extra_smem;
+    auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2, VARY>;
+    const int smem = WARPS_PER_CTA * RingLayout<R, VARY>::BYTES_PER_WARP + g_knobs.extra_smem;
     static thread_local struct { int L = -1, rows = -1, dev = -1, slots = 0; Plan p; } cache;   // per instantiation
     const int rows = a.row_end - a.row_begin;
     if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
@@ -77,6 +77,11 @@ cudaError_t launch_warp_hm(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& t
     kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
+}
+
+template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2>
+cudaError_t launch_warp_hm(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    return a.clip ? launch_warp_vary<CAP, MODE, SHADE, CKS, HMP2, true>(ctx, a, tab, stream) : launch_warp_vary<CAP, MODE, SHADE, CKS, HMP2, false>(ctx, a, tab, stream);
 }
 
 template <int CAP, int MODE, bool SHADE, bool CKS>
