@@ -79,6 +79,14 @@ typedef struct wt_params {
     float sunStrength;                  /* default 1.0  */
 } wt_params;
 
+/* The animation controls of the RenderEngine — reference src/render-engine.h:218-219,226-227. */
+typedef struct wt_animation {
+    float animationSpeedTimeOfDayInSecondsPerHour;                /* default 1.0, >= 0 */
+    float animationSpeedVerticalBounceWavePhasePeriodInSeconds;   /* default 3.0, >= 0 */
+    int isAnimatingTimeOfDay;                                     /* default 0 */
+    int isAnimatingWaves;                                         /* default 1 */
+} wt_animation;
+
 /* One draw call's uniform set, as uploaded at render-engine.cpp:1057-1110 (in-scope subset;
  * names follow the GLSL uniforms of water-grid.vert:37-64 / water-grid.frag:39-47).
  * Matrices are column-major like glm::value_ptr. */
@@ -139,6 +147,12 @@ float wt_steepness_Q_i(const wt_wave* wave, unsigned count);
 void wt_sun_position(float time_of_day_hours, float out[3]);
 /* verticalBounceWaveDisplacement of render-engine.cpp:299-300. */
 float wt_bounce_displacement(float amplitude, float phase);
+
+/* The reference's per-UI-frame animation step: time of day (program.cpp:220-225), wave time and bounce phase
+ * (program.cpp:452-464), advanced by delta_time_s (the reference passes 1 / ImGui framerate).  Accumulates in
+ * fp32 exactly like the reference (so frame f is NOT f * dt rounded once). */
+void wt_default_animation(wt_animation* out);
+int wt_animation_advance(wt_params* params, const wt_animation* anim, float delta_time_s);
 
 /* Projected-grid builder, render-engine.cpp:797-1042.  displaceable_amplitude is
  * TotalAmplitude() + heightmapDisplacementScale + verticalBounceWaveAmplitude (:803).
@@ -219,6 +233,17 @@ int wt_grid_indices(unsigned grid_len, uint32_t* out, uint64_t capacity, uint64_
 int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsigned grid_len, unsigned row_begin,
                   unsigned row_end, void* d_position_ring, void* d_normal_ring, void* d_shade_ring, unsigned ring_depth,
                   void* d_checksums, unsigned flags, void* cuda_stream);
+
+/* Headless animation runner — the loop Program::start() drives (program.cpp:94: advance the animation state, render):
+ * starting from *params (updated in place), for k = 0 .. n_frames-1 it evaluates the frame with the CURRENT state
+ * into ring slot (k % ring_depth) / d_checksums[k], then advances the state `frame_stride` times by delta_time_s.
+ * Frame sharding over G GPUs: rank r first advances its own copy of the state r times, then runs with
+ * frame_stride = G.  A frame whose frustum misses the water (WT_NO_GRID) launches nothing and leaves a zero
+ * checksum; *n_evaluated (may be NULL) counts the frames that were drawn.  Stream-ordered, no synchronisation. */
+int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const wt_animation* anim, float total_wave_amplitude,
+                     float delta_time_s, unsigned frame_stride, unsigned n_frames, unsigned grid_len, unsigned row_begin,
+                     unsigned row_end, void* d_position_ring, void* d_normal_ring, void* d_shade_ring, unsigned ring_depth,
+                     void* d_checksums, unsigned flags, void* cuda_stream, unsigned* n_evaluated);
 
 /* Host-buffer convenience (synchronous): evaluates into ctx-owned device scratch and copies the
  * requested outputs to HOST memory.  Any of h_position/h_normal/h_shade/h_checksum may be NULL. */

@@ -411,6 +411,52 @@ def test_varyings_argument_checks(hm):
                           flags=api.FLAG_VARYINGS | api.FLAG_REFERENCE_ORDER)
 
 
+def test_run_animation_is_the_frame_by_frame_loop(hm):
+    """wt_run_animation (native driver: advance state, build frame, launch) must produce, frame for frame, the
+    digests of the same loop driven from Python through wt_animation_advance / wt_build_frame / wt_eval_frame —
+    unsharded and frame-sharded (stride 2, two start offsets)."""
+    torch = torch_mod()
+    L, n_frames, dt = 200, 9, 1.0 / 60.0
+    waves = scenes.seeded_waves(8, cfg=2)
+    sc = Scene(waves, scenes.camera(), api.default_params(), L, hm)
+    ctx = sc.make_context()
+    anim = api.default_animation()
+    anim.isAnimatingTimeOfDay = 1
+    total = sc.total_amplitude
+    n = L * L
+    ring = [torch.empty((2 * n, 4), dtype=torch.float32, device="cuda") for _ in range(3)]
+    sky = scenes.procedural_skybox(32)
+    ctx.set_skybox(sky)
+    flags = api.FLAG_SHADE | api.FLAG_CHECKSUM
+    # reference loop
+    p = api.default_params()
+    want = []
+    for k in range(2 * n_frames):
+        st, fr = api.build_frame(scenes.camera(), p, total)
+        assert st == api.WT_OK
+        want.append(tuple(gpu_eval(ctx, fr, L, flags=api.FLAG_SHADE, checksum=True)["checksum"]))
+        api.animation_advance(p, anim, dt)
+    for first, stride, count in ((0, 1, 2 * n_frames), (0, 2, n_frames), (1, 2, n_frames)):
+        p = api.default_params()
+        for _ in range(first):
+            api.animation_advance(p, anim, dt)
+        cks = torch.zeros(40 * count, dtype=torch.uint8, device="cuda")
+        drawn = ctx.run_animation(scenes.camera(), p, anim, total, dt, count, L, ring[0].data_ptr(), ring[1].data_ptr(), ring[2].data_ptr(), 2,
+                                  cks.data_ptr(), flags=flags, frame_stride=stride, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert drawn == count
+        got = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
+        for k in range(count):
+            assert tuple(got[k]) == want[first + k * stride], (first, stride, k)
+    # a camera that looks away from the water draws nothing and leaves zero digests (render-engine.cpp:894)
+    p = api.default_params()
+    cks = torch.full((40 * 3,), 7, dtype=torch.uint8, device="cuda")
+    up = scenes.camera(**scenes.EDGE_CAMERAS["looking_up_no_grid"])
+    drawn = ctx.run_animation(up, p, anim, total, dt, 3, L, ring[0].data_ptr(), ring[1].data_ptr(), ring[2].data_ptr(), 2, cks.data_ptr(), flags=flags)
+    torch.cuda.synchronize()
+    assert drawn == 0 and int(cks.cpu().numpy().view(api.CHECKSUM_DTYPE)["vertices"].sum()) == 0
+
+
 def test_non_power_of_two_heightmap(oracle):
     hm = scenes.procedural_heightmap(200)[:150]      # 200 x 150 texels
     sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), 300, hm)

@@ -114,3 +114,30 @@ def test_grid_indices_match_reference_tessellation():
         assert np.array_equal(got, np.array(want, np.uint32))
     with pytest.raises(api.WaveToolError):
         api.grid_indices(1)
+
+
+def test_animation_advance_matches_reference_state_machine():
+    """wt_animation_advance against a literal fp32 restatement of program.cpp:220-225 and :452-464."""
+    f = np.float32
+    for tod_on, period, sph in ((0, 3.0, 1.0), (1, 0.7, 2.5), (1, 0.0, 0.0)):
+        p = api.default_params()
+        anim = api.default_animation()
+        anim.isAnimatingTimeOfDay = tod_on
+        anim.animationSpeedVerticalBounceWavePhasePeriodInSeconds = period
+        anim.animationSpeedTimeOfDayInSecondsPerHour = sph
+        t, ph, tod = f(p.waveAnimationTimeInSeconds), f(p.verticalBounceWavePhase), f(p.timeOfDayInHours)
+        for k in range(2000):
+            dt = f(1.0) / f(60.0 if k % 3 else 144.0)              # deltaTimeInSeconds = 1 / Framerate (:453)
+            api.animation_advance(p, anim, float(dt))
+            if tod_on and f(sph) > 0:                               # :220-225
+                tod = f(tod + f(f(f(1.0) / f(sph)) * dt))
+                tod = f(tod - f(f(24.0) * np.floor(f(tod / f(24.0)))))
+            t = f(t + dt)                                           # :455-457
+            if t < 0:
+                t = f(0)
+            if f(period) > 0:                                       # :459-463
+                ph = f(ph + f(f(f(1.0) / f(period)) * dt))
+                ph = f(ph - f(f(1.0) * np.floor(f(ph / f(1.0)))))
+            assert f(p.waveAnimationTimeInSeconds) == t and f(p.verticalBounceWavePhase) == ph and f(p.timeOfDayInHours) == tod, k
+    d = api.default_animation()
+    assert (d.animationSpeedTimeOfDayInSecondsPerHour, d.animationSpeedVerticalBounceWavePhasePeriodInSeconds, d.isAnimatingTimeOfDay, d.isAnimatingWaves) == (1.0, 3.0, 0, 1)

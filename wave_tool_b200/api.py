@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "wt_create", "wt_destroy", "wt_set_waves", "wt_set_heightmap_rgba8", "wt_set_skybox_rgba8",
     "wt_eval_frame", "wt_eval_batch", "wt_eval_frame_host", "wt_launch_count", "wt_measure_peak",
     "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
+    "wt_default_animation", "wt_animation_advance", "wt_run_animation",
 ]
 
 
@@ -63,6 +64,11 @@ class Checksum(C.Structure):
 
     def as_tuple(self):
         return (self.position_bits, self.normal_bits, self.shade_bits, self.min_y, self.max_y, self.vertices)
+
+
+class Animation(C.Structure):
+    _fields_ = [("animationSpeedTimeOfDayInSecondsPerHour", C.c_float), ("animationSpeedVerticalBounceWavePhasePeriodInSeconds", C.c_float),
+                ("isAnimatingTimeOfDay", C.c_int), ("isAnimatingWaves", C.c_int)]
 
 
 class Outputs(C.Structure):
@@ -128,6 +134,12 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_debug_reload_env.restype = None
     L.wt_eval_frame_ex.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs), C.c_uint, C.c_void_p]
     L.wt_grid_indices.argtypes = [C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.wt_default_animation.argtypes = [C.POINTER(Animation)]
+    L.wt_default_animation.restype = None
+    L.wt_animation_advance.argtypes = [C.POINTER(Params), C.POINTER(Animation), C.c_float]
+    L.wt_run_animation.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Params), C.POINTER(Animation), C.c_float, C.c_float, C.c_uint, C.c_uint,
+                                   C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p,
+                                   C.POINTER(C.c_uint)]
     _lib = L
     return L
 
@@ -180,6 +192,17 @@ def project_grid(cam: Camera, displaceable_amplitude: float):
     corners = np.zeros((4, 4), np.float32)
     st = _check(lib().wt_project_grid(C.byref(cam), C.c_float(displaceable_amplitude), corners.ctypes.data))
     return st, corners
+
+
+def default_animation() -> Animation:
+    a = Animation()
+    lib().wt_default_animation(C.byref(a))
+    return a
+
+
+def animation_advance(params: Params, anim: Animation, dt: float) -> None:
+    """In place: one UI frame of the reference's animation state machine (program.cpp:220-225, 452-464)."""
+    _check(lib().wt_animation_advance(C.byref(params), C.byref(anim), C.c_float(dt)))
 
 
 def grid_indices(grid_len: int) -> np.ndarray:
@@ -248,6 +271,17 @@ class Context:
         """wt_eval_frame_ex: every output stream of the vertex stage (Outputs holds raw device addresses)."""
         r0, r1 = rows if rows is not None else (0, grid_len)
         return _check(self._lib.wt_eval_frame_ex(self._h, C.byref(frame), grid_len, r0, r1, C.byref(outputs), flags, stream or None), self._h)
+
+    def run_animation(self, cam: Camera, params: Params, anim: Animation, total_wave_amplitude: float, dt: float, n_frames: int, grid_len: int,
+                      d_pos_ring: int, d_normal_ring: int, d_shade_ring: int = 0, ring_depth: int = 2, d_checksums: int = 0, flags: int = 0,
+                      frame_stride: int = 1, rows=None, stream: int = 0) -> int:
+        """wt_run_animation: params is advanced in place; returns the number of frames that were drawn."""
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        n = C.c_uint()
+        _check(self._lib.wt_run_animation(self._h, C.byref(cam), C.byref(params), C.byref(anim), C.c_float(total_wave_amplitude), C.c_float(dt),
+                                          frame_stride, n_frames, grid_len, r0, r1, d_pos_ring, d_normal_ring, d_shade_ring or None, ring_depth,
+                                          d_checksums or None, flags, stream or None, C.byref(n)), self._h)
+        return n.value
 
     def eval_batch(self, frames, grid_len: int, d_pos_ring: int, d_normal_ring: int, d_shade_ring: int = 0, ring_depth: int = 2,
                    d_checksums: int = 0, flags: int = 0, rows=None, stream: int = 0):

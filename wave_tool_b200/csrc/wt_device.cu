@@ -395,6 +395,43 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
     return WT_OK;
 }
 
+int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const wt_animation* anim, float total_amp, float dt,
+                     unsigned stride, unsigned n_frames, unsigned L, unsigned r0, unsigned r1, void* d_pos_ring, void* d_nrm_ring,
+                     void* d_shade_ring, unsigned ring_depth, void* d_checksums, unsigned flags, void* stream_, unsigned* n_evaluated) {
+    if (n_evaluated) *n_evaluated = 0;
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_run_animation: ctx is NULL");
+    if (!cam || !params || !anim) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_run_animation: NULL argument");
+    if (ring_depth == 0 || stride == 0) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_run_animation: ring_depth and frame_stride must be >= 1");
+    if (n_frames == 0) return WT_OK;
+    wt_frame probe;
+    std::memset(&probe, 0, sizeof(probe));
+    int st = validate_eval(ctx, &probe, L, r0, r1, d_pos_ring, d_nrm_ring, d_shade_ring, d_checksums, flags);
+    if (st != WT_OK) return st;
+    DeviceGuard g(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool cks = flags & WT_FLAG_CHECKSUM;
+    if (cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    const size_t slot = (size_t)(r1 - r0) * L;
+    unsigned drawn = 0;
+    for (unsigned k = 0; k < n_frames; ++k) {
+        wt_frame frame;
+        st = wt_build_frame(cam, params, total_amp, &frame);
+        if (st < 0) return fail(ctx, st, std::string("wt_run_animation: ") + wt_last_error(nullptr));
+        if (st == WT_OK) {
+            const size_t off = (size_t)(k % ring_depth) * slot;
+            EvalArgs a = make_args(ctx, frame, L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
+                                   d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
+            WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
+            ++drawn;
+        }
+        for (unsigned s_ = 0; s_ < stride; ++s_) wt_animation_advance(params, anim, dt);
+    }
+    if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    WT_CUDA(ctx, cudaGetLastError());
+    if (n_evaluated) *n_evaluated = drawn;
+    return WT_OK;
+}
+
 int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, float* h_pos, float* h_nrm, float* h_shade,
                        wt_checksum* h_cks, unsigned flags) {
     if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "ctx is NULL");

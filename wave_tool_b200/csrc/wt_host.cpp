@@ -232,6 +232,35 @@ int wt_project_grid(const wt_camera* cam, float displaceable_amplitude, float co
     return st;
 }
 
+void wt_default_animation(wt_animation* out) {   // render-engine.h:218-219,226-227
+    if (!out) return;
+    out->animationSpeedTimeOfDayInSecondsPerHour = 1.0f;
+    out->animationSpeedVerticalBounceWavePhasePeriodInSeconds = 3.0f;
+    out->isAnimatingTimeOfDay = 0;
+    out->isAnimatingWaves = 1;
+}
+
+// One UI frame of the reference's animation state machine: program.cpp:220-225 (time of day) and :452-464
+// (wave time, bounce phase).  fp32, incremental accumulation exactly as the reference does it.
+int wt_animation_advance(wt_params* p, const wt_animation* anim, float delta_time_s) {
+    if (!p || !anim) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_animation_advance: NULL argument");
+    if (anim->isAnimatingTimeOfDay && anim->animationSpeedTimeOfDayInSecondsPerHour > 0.0f) {
+        const float dh = (1.0f / anim->animationSpeedTimeOfDayInSecondsPerHour) * delta_time_s;
+        p->timeOfDayInHours += dh;
+        p->timeOfDayInHours = floor_mod(p->timeOfDayInHours, 24.0f);
+    }
+    if (anim->isAnimatingWaves) {
+        p->waveAnimationTimeInSeconds += delta_time_s;
+        if (p->waveAnimationTimeInSeconds < 0.0f) p->waveAnimationTimeInSeconds = 0.0f;
+        if (anim->animationSpeedVerticalBounceWavePhasePeriodInSeconds > 0.0f) {
+            const float dp = (1.0f / anim->animationSpeedVerticalBounceWavePhasePeriodInSeconds) * delta_time_s;
+            p->verticalBounceWavePhase += dp;
+            p->verticalBounceWavePhase = floor_mod(p->verticalBounceWavePhase, 1.0f);
+        }
+    }
+    return WT_OK;
+}
+
 int wt_build_frame(const wt_camera* cam, const wt_params* p, float total_wave_amplitude, wt_frame* out) {
     if (!cam || !p || !out) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_build_frame: NULL argument");
     std::memset(out, 0, sizeof(*out));

@@ -544,9 +544,12 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             }
         } else {
             const f2 gx0 = px[0], gz0 = pz[0];
+            WaveK wk_next = wt.w[0];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
             WT_UNROLL(WT_WAVE_UNROLL)
             for (int i = 0; i < a.n_waves; ++i) {
-                const WaveK wk = wt.w[i];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
+                // the next wave's constants are fetched from the constant bank one trip ahead
+                const WaveK wk = wk_next;
+                wk_next = wt.w[i + 1 < a.n_waves ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gx0, fma2(bc(wk.Dz), gz0, bc(wk.phi))), s, c);
                 // per-row phase step: small unless the wave is undersampled by the grid; MUFU's own range
