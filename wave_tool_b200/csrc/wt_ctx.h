@@ -37,6 +37,9 @@ struct wt_ctx {
     // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
     int* d_queues = nullptr;
     unsigned queue_next = 0;
+    // small frames: internal streams on which consecutive frames of a batch overlap (created on first use)
+    cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     // WT_TRACE diagnostic: per work item {smid, cta, t_start, t_end} of the most recent production launch
     unsigned long long* d_trace = nullptr;
     size_t trace_cap = 0, trace_items = 0;
@@ -51,12 +54,13 @@ namespace wt {
 //   WT_TRACE      record per-work-item {SM, CTA, start, end} (wt_debug_read_trace)
 //   WT_DBG        bit 0: wave loop only (skips heightmap and output stage; outputs are NOT written)
 //   WT_EXTRA_SMEM extra dynamic shared memory per CTA (caps the CTAs per SM)
+//   WT_FANOUT     internal streams used for batches of small frames (1 = none; unset = built-in policy)
 struct Knobs {
-    int dyn = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0;
+    int dyn = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0, fanout = -1;
     void load() {
         auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
         dyn = geti("WT_DYN", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
-        extra_smem = geti("WT_EXTRA_SMEM", 0);
+        extra_smem = geti("WT_EXTRA_SMEM", 0); fanout = geti("WT_FANOUT", -1);
     }
     Knobs() { load(); }
 };

@@ -251,6 +251,11 @@ void wt_destroy(wt_ctx* ctx) {
     if (ctx->sky_array_black) cudaFreeArray(ctx->sky_array_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -373,6 +378,51 @@ int wt_grid_indices(unsigned L, uint32_t* out, uint64_t capacity, uint64_t* coun
     return WT_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Batches of SMALL frames (a 1024^2 frame is ~1300 warp items: half the machine, a few microseconds): consecutive
+// frames go to alternating internal streams so that their kernels overlap and one frame's tail is filled by the
+// next frame's head.  Frames that share a ring slot stay on one stream (k divides ring_depth), so every slot is
+// still written in frame order.  Fork/join with events: the caller's stream ordering is preserved.
+struct FanOut {
+    wt_ctx* ctx;
+    cudaStream_t user;
+    int k = 1;
+    FanOut(wt_ctx* c, cudaStream_t u, unsigned ring_depth, unsigned n_frames, unsigned L, unsigned rows) : ctx(c), user(u) {
+        const unsigned long long verts = (unsigned long long)L * rows;
+        int want = verts <= (1ull << 20) ? 4 : verts <= (1ull << 22) ? 2 : 1;
+        if (g_knobs.fanout >= 1) want = std::min(g_knobs.fanout, 4);
+        while (want > 1 && (ring_depth % want != 0 || n_frames < (unsigned)want)) --want;
+        k = want;
+    }
+    cudaError_t begin() {
+        if (k == 1) return cudaSuccess;
+        cudaError_t e;
+        if (!ctx->ev_fork && (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (int i = 0; i < k; ++i) {
+            if (!ctx->aux_stream[i] && (e = cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if (!ctx->ev_join[i] && (e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        if ((e = cudaEventRecord(ctx->ev_fork, user)) != cudaSuccess) return e;
+        for (int i = 0; i < k; ++i) if ((e = cudaStreamWaitEvent(ctx->aux_stream[i], ctx->ev_fork, 0)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    cudaStream_t stream_for(unsigned frame) const { return k == 1 ? user : ctx->aux_stream[frame % k]; }
+    cudaError_t end() {
+        if (k == 1) return cudaSuccess;
+        cudaError_t e;
+        for (int i = 0; i < k; ++i) {
+            if ((e = cudaEventRecord(ctx->ev_join[i], ctx->aux_stream[i])) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(user, ctx->ev_join[i], 0)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+};
+}  // namespace
+
+extern "C" {
+
 int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsigned L, unsigned r0, unsigned r1, void* d_pos_ring,
                   void* d_nrm_ring, void* d_shade_ring, unsigned ring_depth, void* d_checksums, unsigned flags, void* stream_) {
     if (n_frames == 0) return WT_OK;
@@ -384,12 +434,15 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
     const bool cks = flags & WT_FLAG_CHECKSUM;
     if (cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     const size_t slot = (size_t)(r1 - r0) * L;
+    FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
+    WT_CUDA(ctx, fan.begin());
     for (unsigned f = 0; f < n_frames; ++f) {
         const size_t off = (size_t)(f % ring_depth) * slot;
         EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
-        WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
+        WT_CUDA(ctx, launch_eval(ctx, a, flags, fan.stream_for(f)));
     }
+    WT_CUDA(ctx, fan.end());
     if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     return WT_OK;
@@ -413,6 +466,8 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     if (cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     const size_t slot = (size_t)(r1 - r0) * L;
     unsigned drawn = 0;
+    FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
+    WT_CUDA(ctx, fan.begin());
     for (unsigned k = 0; k < n_frames; ++k) {
         wt_frame frame;
         st = wt_build_frame(cam, params, total_amp, &frame);
@@ -421,11 +476,12 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
             const size_t off = (size_t)(k % ring_depth) * slot;
             EvalArgs a = make_args(ctx, frame, L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
-            WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
+            WT_CUDA(ctx, launch_eval(ctx, a, flags, fan.stream_for(k)));
             ++drawn;
         }
         for (unsigned s_ = 0; s_ < stride; ++s_) wt_animation_advance(params, anim, dt);
     }
+    WT_CUDA(ctx, fan.end());
     if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     if (n_evaluated) *n_evaluated = drawn;
