@@ -37,9 +37,12 @@ WORKLOADS = {
     "cfg3": (4096, 64, 3, True, "configs[2]: 4096x4096 grid, 64 waves, normals + Fresnel/sky-cubemap/sun-specular terms"),
     "cfg2": (1024, 8, 2, False, "configs[1]: 1024x1024 projected grid, 8 Gerstner waves + heightmap noise, animation frames"),
     "cfg4": (8192, 256, 4, False, "configs[3]: 8192x8192 grid, 256 waves, frame batch sharded by frame"),
+    "cfg5": (16384, 32, 5, False, "configs[4]: 16384x16384 grid, 32 waves, sharded by grid rows (strong scaling)"),
 }
+ROW_SHARDED = {"cfg5"}
 TRANSCENDENTALS_PER_VERTEX_WAVE = 2      # 1 sin + 1 cos (water-grid.vert:78-81), SURVEY.md §8d
 FLOP_PER_VERTEX_WAVE = 15
+_REAL_STDOUT = sys.stdout
 SKYBOX_N = 2048                           # reference: 2048^2 faces (render-engine.h:191)
 
 
@@ -164,7 +167,7 @@ def run_reference(args):
             "config": {"workload": desc, "grid_len": L, "waves": W, "note": "each step is a bounded row sample of one frame on the host cores"},
             "cpu_baseline": cb, "e2e": {"value": value, "unit": "vertex-waves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "ms_per_frame_extrapolated": 1e3 * (L * L * W) / value}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -198,14 +201,22 @@ def run_ours(args):
     ctx.set_heightmap(scenes.procedural_heightmap(512))
     if shade:
         ctx.set_skybox(scenes.procedural_skybox(SKYBOX_N))
-    n = L * L
+    # frame sharding (weak scaling): every rank evaluates whole frames, frame f on rank f mod N;
+    # row sharding (cfg5, strong scaling): every rank evaluates its band of rows of the SAME frames
+    row_sharded = args.workload in ROW_SHARDED
+    rows = shard.row_shard(L, rank, n_gpus) if row_sharded else (0, L)
+    n = (rows[1] - rows[0]) * L                                         # vertices this rank evaluates per frame
     ring = 2
     pos = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
     nrm = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
     shd = torch.empty((ring * n, 4), dtype=torch.float32, device=dev) if shade else None
-    total_frames = (Wm + K) * n_gpus
-    my_frames = shard.frame_shard(total_frames, rank, n_gpus)          # global frame indices of this rank
-    frames = scenes.frames_for_animation(cam, waves, first=rank, count=Wm + K, stride=n_gpus)
+    if row_sharded:
+        my_frames = list(range(Wm + K))
+        frames = scenes.frames_for_animation(cam, waves, first=0, count=Wm + K, stride=1)
+    else:
+        total_frames = (Wm + K) * n_gpus
+        my_frames = shard.frame_shard(total_frames, rank, n_gpus)      # global frame indices of this rank
+        frames = scenes.frames_for_animation(cam, waves, first=rank, count=Wm + K, stride=n_gpus)
     cks = torch.zeros((Wm + K) * 40, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
@@ -225,7 +236,7 @@ def run_ours(args):
     def launch(lo, hi, with_cks=False):
         arr = (api.Frame * (hi - lo))(*frames[lo:hi])
         ctx.eval_batch(arr, L, pos.data_ptr(), nrm.data_ptr(), shd.data_ptr() if shade else 0, ring,
-                       cks.data_ptr() + 40 * lo if with_cks else 0, flags=flags | (api.FLAG_CHECKSUM if with_cks else 0), stream=sp)
+                       cks.data_ptr() + 40 * lo if with_cks else 0, flags=flags | (api.FLAG_CHECKSUM if with_cks else 0), rows=rows, stream=sp)
 
     # ---- device-timed region: W warm-up steps, then exactly K steps ------------------------------
     launch(0, Wm)
@@ -246,8 +257,9 @@ def run_ours(args):
     ms = shard.max_over_ranks(ms_local, dev) if world > 1 else ms_local
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
 
-    vw_per_frame = n * W
-    value = n_gpus * K * vw_per_frame / (ms * 1e-3)
+    vw_per_frame = n * W                                               # this rank's share of one step
+    frames_total = K if row_sharded else n_gpus * K                    # whole frames the job evaluated in the timed region
+    value = frames_total * L * L * W / (ms * 1e-3)
     ms_per_step = ms / K
 
     # ---- end-to-end through the C ABI with HOST inputs/outputs -----------------------------------
@@ -263,7 +275,7 @@ def run_ours(args):
         st, fr = api.build_frame(cam, scenes.animation_params(f), total_amp)
         slot = k % ring
         ctx.eval_frame(fr, L, pos.data_ptr() + slot * n * 16, nrm.data_ptr() + slot * n * 16, (shd.data_ptr() + slot * n * 16) if shade else 0,
-                       cks.data_ptr(), flags=flags | api.FLAG_CHECKSUM, stream=sp)
+                       cks.data_ptr(), flags=flags | api.FLAG_CHECKSUM, rows=rows, stream=sp)
         pinned.copy_(cks[:40], non_blocking=True)
         stream.synchronize()
 
@@ -276,11 +288,11 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_s = shard.max_over_ranks(e2e_s, dev) if world > 1 else e2e_s
-    e2e_value = n_gpus * K * vw_per_frame / e2e_s
+    e2e_value = frames_total * L * L * W / e2e_s
 
     # full read-back variant: every output byte copied to pinned host memory each step (PCIe-bound)
     rb = None
-    if not args.no_readback and rank == 0 and world == 1:
+    if not args.no_readback and rank == 0 and world == 1 and n <= (1 << 25):
         hp = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         hn = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         hs = torch.empty((n, 4), dtype=torch.float32).pin_memory() if shade else None
@@ -303,16 +315,16 @@ def run_ours(args):
         slot_main = (Wm + K - 1) % ring                       # where the timed run left its last frame
         slot_other = 1 - slot_main
         ctx.eval_frame(f_last, L, pos.data_ptr() + slot_main * n * 16, nrm.data_ptr() + slot_main * n * 16,
-                       (shd.data_ptr() + slot_main * n * 16) if shade else 0, flags=flags, stream=sp)
+                       (shd.data_ptr() + slot_main * n * 16) if shade else 0, flags=flags, rows=rows, stream=sp)
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(3, min(K, 10))
         for w_ in range(2):
             ctx.eval_frame(f_last, L, pos.data_ptr() + slot_other * n * 16, nrm.data_ptr() + slot_other * n * 16,
-                           (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, stream=sp)
+                           (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, rows=rows, stream=sp)
         o0.record(stream)
         for r_ in range(reps):
             ctx.eval_frame(f_last, L, pos.data_ptr() + slot_other * n * 16, nrm.data_ptr() + slot_other * n * 16,
-                           (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, stream=sp)
+                           (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, rows=rows, stream=sp)
         o1.record(stream)
         torch.cuda.synchronize()
         oms = o0.elapsed_time(o1) / reps
@@ -377,9 +389,11 @@ def run_ours(args):
             primary, secondary = roof_sfu, [roof_fp32, roof_hbm]
         line = {
             "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": n_gpus, "steps": K, "warmup": Wm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if row_sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "grid_len": L, "waves": W, "shade": shade, "frames_per_step_per_gpu": 1,
-                       "parallelism": f"frame-sharded x{n_gpus} (frame f on rank f mod N), no data-path collective",
+                       "parallelism": (f"row-sharded x{n_gpus} (rank g evaluates rows [g L/N, (g+1) L/N) of every frame; the +-1-row stencil halo is recomputed), "
+                                       "no data-path collective") if row_sharded else
+                                      f"frame-sharded x{n_gpus} (frame f on rank f mod N), no data-path collective",
                        "l2": "each step writes %d MB of fresh output into a 2-deep ring (> 126 MB L2)" % (out_bytes // 2 ** 20),
                        "phase": "rotation recurrence (WT_FLAG_FAST_PHASE): MUFU seed every 8 rows, complex rotation in between"
                                 if recurrence else "bit-faithful fp32 phase, MUFU sin/cos pair per vertex-wave"},
@@ -400,19 +414,30 @@ def run_ours(args):
             cb = cpu_reference_rate(L, W, cfg)
             cb.pop("seconds", None); cb.pop("vertex_waves", None)
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the real stdout."""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner, ...) goes to stderr
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3")
+    ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3",
+                    help="cfg3 is the bench line (BASELINE.json's metric is quoted on it); the others are extra measurements")
     ap.add_argument("--exact-phase", action="store_true",
                     help="time the bit-faithful-phase wave loop (one MUFU pair per vertex-wave) instead of the rotation recurrence")
     ap.add_argument("--fast-phase", action="store_true", help="(default; kept for compatibility)")
