@@ -1,14 +1,10 @@
 mkdir -p gpurun_out
-T=r1v4
-python tools/explore_sched.py --tag base --mode fast --configs=-1:0,14:0,22:0,30:0,38:0,46:0,62:0 2>&1 | grep '"tag"' | cut -c1-120
-timeout 600 python bench.py --workload cfg4 --steps 5 --no-cpu-baseline --no-readback > gpurun_out/${T}_bench_cfg4.json 2> gpurun_out/${T}_bench.err; tail -c 300 gpurun_out/${T}_bench.err
-timeout 600 python bench.py --workload cfg5 --steps 5 --no-cpu-baseline --no-readback > gpurun_out/${T}_bench_cfg5.json 2>> gpurun_out/${T}_bench.err; tail -c 300 gpurun_out/${T}_bench.err
-timeout 600 python bench.py --workload cfg2 --steps 200 --no-cpu-baseline > gpurun_out/${T}_bench_cfg2.json 2>> gpurun_out/${T}_bench.err
+T=r1v5
+timeout 600 python bench.py --exact-phase --no-cpu-baseline > gpurun_out/${T}_bench_cfg3_exact.json 2>> gpurun_out/${T}_bench_cfg3.err
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:surface_warp -s 3 -c 2 -f -o gpurun_out/${T}_prof_exact python bench.py --exact-phase --steps 3 --warmup 3 --no-cpu-baseline --no-readback > gpurun_out/${T}_ncu_full2.log 2>&1
+timeout 300 python -m pytest tests -m gpu -x -q -k "cfg3 or shard or ragged" 2>&1 | tail -2
 python - <<'PY'
 import json
-for f in ["cfg4","cfg5","cfg2"]:
-    try:
-        d=json.load(open(f"gpurun_out/r1v4_bench_{f}.json"))
-        print(f, "ms/step %.4f value %.3e e2e %.3e"%(d["ms_per_step"], d["value"], d["e2e"]["value"]), d["roofline"]["bound"], round(d["roofline"]["frac"],3), d["scaling"])
-    except Exception as e: print(f, "failed", e)
+d=json.load(open("gpurun_out/r1v5_bench_cfg3_exact.json"))
+print("exact ms/step %.4f value %.3e"%(d["ms_per_step"], d["value"]), d["roofline"]["bound"], round(d["roofline"]["frac"],3))
 PY

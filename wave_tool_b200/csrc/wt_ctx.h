@@ -50,16 +50,17 @@ namespace wt {
 
 // Development knobs, read from the environment once (wt_debug_reload_env re-reads them):
 //   WT_DYN        rows per dynamically queued work item (0 = static plan; unset = built-in policy)
+//   WT_DYN_SMALL  rows per item of the tail of the dynamic plan (0 = single level), WT_DYN_TAIL = percent of the rows it covers
 //   WT_DYN_WARPS  cap on the resident warps per SM of the dynamic plan
 //   WT_TRACE      record per-work-item {SM, CTA, start, end} (wt_debug_read_trace)
 //   WT_DBG        bit 0: wave loop only (skips heightmap and output stage; outputs are NOT written)
 //   WT_EXTRA_SMEM extra dynamic shared memory per CTA (caps the CTAs per SM)
 //   WT_FANOUT     internal streams used for batches of small frames (1 = none; unset = built-in policy)
 struct Knobs {
-    int dyn = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0, fanout = -1;
+    int dyn = -1, dyn_small = -1, dyn_tail = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0, fanout = -1;
     void load() {
         auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
-        dyn = geti("WT_DYN", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
+        dyn = geti("WT_DYN", -1); dyn_small = geti("WT_DYN_SMALL", -1); dyn_tail = geti("WT_DYN_TAIL", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
         extra_smem = geti("WT_EXTRA_SMEM", 0); fanout = geti("WT_FANOUT", -1);
     }
     Knobs() { load(); }
@@ -76,11 +77,15 @@ extern Knobs g_knobs;
 #define WT_R_RECUR 8
 #endif
 constexpr int R_EXACT = WT_R_EXACT;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
-constexpr int DYN_ROWS_RECUR = 22;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 3 marching steps)
+constexpr int DYN_ROWS_RECUR = 38;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 5 marching steps)
+constexpr int DYN_ROWS_EXACT = 30;   // ... MODE 0 (8 marching steps)
+constexpr int DYN_SMALL_RECUR = 14, DYN_SMALL_EXACT = 0;   // rows per item of the tail of the launch (0 = single level)
+constexpr int DYN_TAIL_PERCENT = 25;
 constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
 
 struct Plan {
     int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;
+    int n_big = -1, rows_small = 0;   // two-level dynamic plan (n_big < 0: every chunk has rows_per_chunk rows)
 };
 
 Plan make_plan(int slots, int L, int rows, int R);

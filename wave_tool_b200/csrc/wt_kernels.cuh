@@ -76,8 +76,11 @@ struct EvalArgs {
     float vy[12];       // upper-left 3 rows of viewMatOnlyYaw's first three columns: vy[3*c + r]
     int L, row_begin, row_end;
     int n_strips;       // warps across a row
-    int rows_per_chunk; // output rows per warp
+    int rows_per_chunk; // output rows per work item
     int n_chunks;
+    // two-level dynamic plan: chunks [0, n_big) hold rows_per_chunk rows, the rest rows_small rows (they are handed
+    // out last and fill the tail of the launch); static / single-level plans have n_big == n_chunks
+    int n_big, rows_small;
     int dbg;            // experiment knob (WT_DBG): bit 0 = skip heights/epilogue
     // dynamic work distribution (NULL = static: item = blockIdx.x): queue[0] = next item, queue[1] = warps done
     int* queue;
@@ -491,8 +494,9 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
     if (a.trace) t_start = global_ns();
     const int strip = item % a.n_strips, chunk = item / a.n_strips;
     const int strip0 = strip * STRIP_COLS;
-    const int r0 = a.row_begin + chunk * a.rows_per_chunk;
-    const int r1 = min(r0 + a.rows_per_chunk, a.row_end);
+    const bool big = chunk < a.n_big;
+    const int r0 = a.row_begin + (big ? chunk * a.rows_per_chunk : a.n_big * a.rows_per_chunk + (chunk - a.n_big) * a.rows_small);
+    const int r1 = min(r0 + (big ? a.rows_per_chunk : a.rows_small), a.row_end);
     const int colA = strip0 - 1 + lane, colB = colA + 32;
     const bool outA = lane >= 1 && colA < a.L;
     const bool outB = lane <= 30 && colB < a.L;

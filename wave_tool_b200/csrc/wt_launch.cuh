@@ -29,23 +29,32 @@ cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>&
         cache.L = a.L; cache.rows = rows; cache.dev = ctx->device;
     }
     Plan p = cache.p;
-    // Dynamic work distribution (MODE 1): the warp schedulers favour some resident warps heavily, so equal static
+    // Dynamic work distribution: the warp schedulers favour some resident warps heavily, so equal static
     // shares finish far apart (profiles/README.md); with small items handed out through an atomic queue every
     // warp stays busy until the queue runs dry.  Used when there are enough items to go round several times;
     // WT_DYN overrides the rows per item (0 = static plan).
     const bool forced = g_knobs.dyn >= 0;
-    const int dyn_rows = forced ? g_knobs.dyn : (MODE == 1 ? DYN_ROWS_RECUR : 0);
+    const int dyn_rows = forced ? g_knobs.dyn : (MODE == 1 ? DYN_ROWS_RECUR : DYN_ROWS_EXACT);
     a.queue = nullptr;
     if (dyn_rows > 0) {
-        int rpc = ((dyn_rows + 2 + R - 1) / R) * R - 2;
-        if (rpc < 1) rpc = R;
-        const int n_chunks = (rows + rpc - 1) / rpc;
-        const long long items = (long long)p.n_strips * n_chunks;
+        auto round_rows = [](int want) { int r = ((want + 2 + R - 1) / R) * R - 2; return r < 1 ? R : r; };   // rows + 2 a multiple of R
+        const int rpc = round_rows(dyn_rows);
+        // two levels: the last `tail` percent of the rows go out in small items, after all the big ones
+        const int small_want = g_knobs.dyn_small >= 0 ? g_knobs.dyn_small : (MODE == 1 ? DYN_SMALL_RECUR : DYN_SMALL_EXACT);
+        const int tail_pct = g_knobs.dyn_tail >= 0 ? g_knobs.dyn_tail : DYN_TAIL_PERCENT;
+        int n_big = (rows + rpc - 1) / rpc, n_small = 0, rps = 0;
+        if (small_want > 0 && small_want < dyn_rows && tail_pct > 0) {
+            rps = round_rows(small_want);
+            n_big = (int)((long long)rows * (100 - tail_pct) / 100 / rpc);
+            n_small = (rows - n_big * rpc + rps - 1) / rps;
+        }
+        const long long items = (long long)p.n_strips * (n_big + n_small);
         int slots = cache.slots;
         if (g_knobs.dyn_warps > 0) slots = std::min(slots, ctx->sm_count * g_knobs.dyn_warps);
-        if (forced || items >= 3LL * slots) {
+        if (forced || items >= 2LL * slots) {
             p.rows_per_chunk = rpc;
-            p.n_chunks = n_chunks;
+            p.n_chunks = n_big + n_small;
+            p.n_big = n_big; p.rows_small = rps;
             p.ctas = (int)std::min<long long>(items, slots);
             a.queue = ctx->d_queues + 2 * (ctx->queue_next++ % N_QUEUES);
         }
@@ -53,6 +62,8 @@ cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>&
     a.n_strips = p.n_strips;
     a.rows_per_chunk = p.rows_per_chunk;
     a.n_chunks = p.n_chunks;
+    a.n_big = p.n_big < 0 ? p.n_chunks : p.n_big;
+    a.rows_small = p.rows_small > 0 ? p.rows_small : p.rows_per_chunk;
     a.n_items = p.n_strips * p.n_chunks;
     a.trace = nullptr;
     {
