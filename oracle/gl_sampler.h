@@ -9,6 +9,9 @@
 //       /root/reference/src/render-engine.cpp:1308-1322
 //   * sky cubemap: RGBA8, GL_LINEAR, GL_CLAMP_TO_EDGE, seamless filtering never enabled
 //       /root/reference/src/render-engine.cpp:90-110
+//   * screen-space inputs of the water fragment shader: depth texture GL_DEPTH_COMPONENT/GL_FLOAT,
+//     GL_NEAREST, GL_CLAMP_TO_EDGE (/root/reference/src/render-engine.cpp:128-136); local reflection /
+//     refraction colour textures RGBA8, GL_LINEAR, GL_CLAMP_TO_EDGE (:143-151, :172-180)
 // Algorithm restated from the OpenGL 4.1 core specification, section 3.8 ("Texturing"):
 //   - "Texture Minification", LINEAR:  i0 = wrap(floor(u - 1/2)), i1 = wrap(floor(u - 1/2) + 1),
 //     alpha = frac(u - 1/2); tau = (1-a)(1-b) t00 + a(1-b) t10 + (1-a) b t01 + a b t11
@@ -83,6 +86,19 @@ inline void sample_linear_rgba(const uint8_t* rgba, int w, int h, T s, T t, T ou
 template <typename T>
 inline void texture2d_mirrored_linear(const Image2D& img, T s, T t, T out[4]) {
     sample_linear_rgba<T, wrap_mirrored_repeat>(img.rgba, img.w, img.h, s, t, out);
+}
+
+// texture(sampler2D, st) with the sampler state of the local reflection / refraction textures.
+template <typename T>
+inline void texture2d_clamp_linear(const Image2D& img, T s, T t, T out[4]) {
+    sample_linear_rgba<T, wrap_clamp_to_edge>(img.rgba, img.w, img.h, s, t, out);
+}
+
+// texture(depthTexture2D, st).x: GL_NEAREST ("Texture Minification", NEAREST: i = wrap(floor(u))), CLAMP_TO_EDGE.
+template <typename T>
+inline T texture2d_clamp_nearest_r32f(const float* texels, int w, int h, T s, T t) {
+    long long i = (long long)std::floor(s * (T)w), j = (long long)std::floor(t * (T)h);
+    return (T)texels[(size_t)wrap_clamp_to_edge(j, h) * w + wrap_clamp_to_edge(i, w)];
 }
 
 // texture(samplerCube, r) with the reference's sky cubemap sampler state (non-seamless).

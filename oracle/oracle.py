@@ -62,6 +62,29 @@ class RefVertUniforms(C.Structure):
                 ("waveAnimationTimeInSeconds", C.c_float)]
 
 
+class ComposeUniforms(C.Structure):
+    """Uniforms of the screen-space layers + fog of water-grid.frag (:34-55)."""
+    _fields_ = [("fogColourFarAtCurrentTime", C.c_float * 4), ("fogDepthRadiusFar", C.c_float), ("fogDepthRadiusNear", C.c_float),
+                ("softEdgesDeltaDepthThreshold", C.c_float), ("tintDeltaDepthThreshold", C.c_float), ("waterClarity", C.c_float),
+                ("zNear", C.c_float), ("zFar", C.c_float), ("viewportWidthHeight", C.c_float * 2),
+                ("cameraPosition", C.c_float * 3), ("sunPosition", C.c_float * 3)]
+
+
+class ScreenTextures(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("reflections", C.c_void_p), ("refractions", C.c_void_p), ("w", C.c_int), ("h", C.c_int)]
+
+
+class RefFragUniforms(C.Structure):
+    _fields_ = [("fogColourFarAtCurrentTime", C.c_float * 4), ("fogDepthRadiusFar", C.c_float), ("fogDepthRadiusNear", C.c_float),
+                ("softEdgesDeltaDepthThreshold", C.c_float), ("sunPosition", C.c_float * 3), ("sunShininess", C.c_float),
+                ("sunStrength", C.c_float), ("tintDeltaDepthThreshold", C.c_float), ("viewportWidthHeight", C.c_float * 2),
+                ("waterClarity", C.c_float), ("zFar", C.c_float), ("zNear", C.c_float)]
+
+
+REF_FRAG_IN_DTYPE = np.dtype([("gl_FragCoord", "f4", 4), ("heightmap_colour", "f4", 4), ("normal", "f4", 3),
+                              ("normalVecInViewSpaceOnlyYaw", "f4", 3), ("viewVecRaw", "f4", 3), ("xyPositionNDCSpaceHeight0", "f4", 2)])
+
+
 class Textures(C.Structure):
     _fields_ = [("heightmap_rgba", C.c_void_p), ("hm_w", C.c_int), ("hm_h", C.c_int),
                 ("sky_faces", C.c_void_p * 6), ("sky_n", C.c_int)]
@@ -106,6 +129,7 @@ class Oracle:
         L.wto_eval_f32.argtypes = common + [C.c_void_p] * 4
         L.wto_eval_f64.argtypes = common + [C.c_void_p] * 4
         L.wto_shade_f32.argtypes = [C.POINTER(Uniforms), C.POINTER(Textures), C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.wto_compose_f32.argtypes = [C.POINTER(ComposeUniforms), C.POINTER(ScreenTextures), C.c_longlong] + [C.c_void_p] * 7
 
     # --- host-side scalar rules -------------------------------------------------------------
     def num_threads(self) -> int:
@@ -190,6 +214,20 @@ class Oracle:
         return {"pos": pos, "normal": nrm, "shade": shd, "extra": ext}
 
 
+    def compose(self, cu: ComposeUniforms, depth: np.ndarray, reflections: np.ndarray, refractions: np.ndarray,
+                pos4, nrm4, shade4, clip4, vary_a, vary_b) -> np.ndarray:
+        """water-grid.frag:66-69,76-89,113-162 at caller-supplied vertices -> colour (n,4).  nrm4.w carries
+        fresnel_f_theta, shade4 = (sky.rgb, sun), vary_a = (ndc0.xy, ., .), vary_b = (yaw normal, .)."""
+        d = np.ascontiguousarray(depth, np.float32)
+        rl = np.ascontiguousarray(reflections, np.uint8)
+        rr = np.ascontiguousarray(refractions, np.uint8)
+        assert d.ndim == 2 and rl.shape == d.shape + (4,) and rr.shape == rl.shape
+        st = ScreenTextures(d.ctypes.data, rl.ctypes.data, rr.ctypes.data, d.shape[1], d.shape[0])
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (pos4, nrm4, shade4, clip4, vary_a, vary_b)]
+        out = np.empty((len(arrs[0]), 4), np.float32)
+        self.lib.wto_compose_f32(C.byref(cu), C.byref(st), len(out), *[a.ctypes.data for a in arrs], out.ctypes.data)
+        return out
+
     def shade(self, u: Uniforms, sky_faces, pos4: np.ndarray, nrm4: np.ndarray):
         """water-grid.frag:71-73,95-111 at caller-supplied vertices -> (shade (n,4), fresnel (n,))."""
         tx = Textures()
@@ -222,6 +260,11 @@ class Ref:
             P.wtref_bounce_displacement.argtypes = [C.c_float, C.c_float]
             P.wtref_sun_position.argtypes = [C.c_float, c_float_p]
             P.wtref_project_grid.argtypes = [C.POINTER(Camera), C.c_float, C.POINTER(GridF32)]
+        self.frag = _load(os.path.join(HERE, "_ref", "libwt_ref_frag.so"))
+        if self.frag is not None:
+            self.frag.wtref_frag_set_uniforms.argtypes = [C.POINTER(RefFragUniforms), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                          C.POINTER(C.c_void_p), C.c_int]
+            self.frag.wtref_frag_run.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
         if self.vert is not None:
             V = self.vert
             V.wtref_vert_set_uniforms.argtypes = [C.POINTER(RefVertUniforms), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -253,6 +296,20 @@ class Ref:
         g = GridF32()
         st = self.proj.wtref_project_grid(C.byref(cam), C.c_float(float(displaceable_amplitude)), C.byref(g))
         return st, g
+
+    def frag_run(self, fu: RefFragUniforms, depth, reflections, refractions, sky_faces, frag_in: np.ndarray) -> np.ndarray:
+        """Runs the compiled water-grid.frag main() on REF_FRAG_IN_DTYPE records -> colour (n,4)."""
+        d = np.ascontiguousarray(depth, np.float32)
+        rl = np.ascontiguousarray(reflections, np.uint8)
+        rr = np.ascontiguousarray(refractions, np.uint8)
+        sky = np.ascontiguousarray(sky_faces, np.uint8)
+        ptrs = (C.c_void_p * 6)(*[sky[f].ctypes.data for f in range(6)])
+        self.frag.wtref_frag_set_uniforms(C.byref(fu), d.ctypes.data, rl.ctypes.data, rr.ctypes.data, d.shape[1], d.shape[0], ptrs, sky.shape[1])
+        fi = np.ascontiguousarray(frag_in)
+        assert fi.dtype == REF_FRAG_IN_DTYPE
+        out = np.empty((len(fi), 4), np.float32)
+        self.frag.wtref_frag_run(fi.ctypes.data, len(fi), out.ctypes.data)
+        return out
 
     def vert_run(self, u: Uniforms, wave_uniforms: np.ndarray, heightmap_rgba: np.ndarray, ids=None, id_range=None):
         """Runs the compiled shader main() and returns the REF_VERT_OUT_DTYPE records.  World-space

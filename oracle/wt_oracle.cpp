@@ -357,6 +357,24 @@ struct wto_textures {
     const uint8_t* sky_faces[6]; int sky_n;           // may be all-NULL when shading is not requested
 };
 
+// Uniforms of the screen-space layers of water-grid.frag (:34-55) and its fog block; upload sites
+// src/render-engine.cpp:1060-1063,1087-1088,1096,1100,1107,1109-1110.
+struct wto_compose_uniforms {
+    float fogColourFarAtCurrentTime[4];
+    float fogDepthRadiusFar, fogDepthRadiusNear;
+    float softEdgesDeltaDepthThreshold, tintDeltaDepthThreshold, waterClarity;
+    float zNear, zFar;
+    float viewportWidthHeight[2];
+    float cameraPosition[3];
+    float sunPosition[3];
+};
+struct wto_screen_textures {
+    const float* depth;            // w x h, GL row order, window-space depth in [0,1]
+    const uint8_t* reflections;    // w x h RGBA8
+    const uint8_t* refractions;    // w x h RGBA8
+    int w, h;
+};
+
 }  // extern "C"
 
 namespace {
@@ -425,6 +443,58 @@ void shade_vertex(const wto_uniforms& u, const wt_gl::CubeRGBA8* sky, V3<T> view
     T cos_theta = dot(n, vv3);                                          // frag:110
     *fresnel = (T)0.02f + ((T)1 - (T)0.02f) * std::pow((T)1 - cos_theta, (T)5);   // frag:107-111
     shade4[0] = sky_c[0]; shade4[1] = sky_c[1]; shade4[2] = sky_c[2]; shade4[3] = sun_term;
+}
+
+// water-grid.frag:66-69,76-89,113-162 evaluated at a vertex: everything of main() that is not the three terms
+// shade_vertex covers.  The fragment inputs a rasteriser would interpolate are taken un-interpolated at the
+// vertex: gl_FragCoord from gl_Position through the viewport transform (GL 4.1 §2.14.1: xw = (xd + 1) w/2,
+// zw = (zd + 1)/2 with the default depth range), the varyings as written by the vertex stage.
+template <typename T>
+void compose_vertex(const wto_compose_uniforms& u, const wto_screen_textures& st, V3<T> P, T fresnel_f_theta, const T shade4[4], V4<T> clip,
+                    T ndc0x, T ndc0y, V3<T> yawn, T colour[4]) {
+    auto mixT = [](T x, T y, T a) { return x * ((T)1 - a) + y * a; };
+    auto linearize = [&](T depth) { return ((T)u.zNear * depth) / ((T)u.zFar - depth * ((T)u.zFar - (T)u.zNear)); };   // :66-69
+    const T vw = (T)u.viewportWidthHeight[0], vh = (T)u.viewportWidthHeight[1];
+    V3<T> cam{(T)u.cameraPosition[0], (T)u.cameraPosition[1], (T)u.cameraPosition[2]};
+    V3<T> view_raw = cam - P;
+    T len = std::sqrt(dot(view_raw, view_raw));                          // :71
+    T vdc = clampT(len / (T)u.zFar, (T)0, (T)1);                         // :72
+    // gl_FragCoord
+    T ndx = clip.x / clip.w, ndy = clip.y / clip.w, ndz = clip.z / clip.w;
+    T fx = (ndx + (T)1) * (vw / (T)2), fy = (ndy + (T)1) * (vh / (T)2), fz = (ndz + (T)1) / (T)2;
+    T uvx = fx / vw, uvy = fy / vh;                                       // :79
+    T h0x = (ndc0x + (T)1) / (T)2, h0y = (ndc0y + (T)1) / (T)2;           // :81
+    T back = linearize(wt_gl::texture2d_clamp_nearest_r32f<T>(st.depth, st.w, st.h, uvx, uvy));   // :84
+    T hack = back > (T)0.999f ? (T)0 : (T)1;                              // :86
+    T frag = linearize(fz);                                               // :87
+    T dclamped = clampT(back - frag, (T)0, (T)1);                         // :89-91
+    // :118-133 local reflections / refractions
+    T ds = (T)0.1f * ((T)1 - vdc);
+    T rlx = clampT(mixT(uvx, h0x, ds) + ds * yawn.x, (T)0, (T)1), rly = clampT(mixT(uvy, h0y, ds) + ds * (-yawn.z), (T)0, (T)1);
+    T rrx = clampT(mixT(uvx, h0x, ds) + ds * (-yawn.x), (T)0, (T)1), rry = clampT(mixT(uvy, h0y, ds) + ds * yawn.z, (T)0, (T)1);
+    T refl[4], refr[4];
+    wt_gl::texture2d_clamp_linear<T>(wt_gl::Image2D{st.reflections, st.w, st.h}, rlx, rly, refl);
+    wt_gl::texture2d_clamp_linear<T>(wt_gl::Image2D{st.refractions, st.w, st.h}, rrx, rry, refr);
+    // :136-141 tint
+    const T DEEP[3] = {(T)0.0f, (T)0.341f, (T)0.482f}, SHALLOW[3] = {(T)0.3f, (T)0.941f, (T)0.903f};
+    T tint_f = (T)u.tintDeltaDepthThreshold == (T)0 ? (T)0 : hack * ((T)1 - clampT(dclamped / (T)u.tintDeltaDepthThreshold, (T)0, (T)1));
+    T sun_y = clampT((T)u.sunPosition[1], (T)0, (T)1);
+    T out[3];
+    for (int c = 0; c < 3; ++c) {
+        T tint = sun_y * mixT(DEEP[c], SHALLOW[c], tint_f);
+        T transmission = mixT(tint, refr[c], (T)u.waterClarity * refr[3] * ((T)1 - dclamped));   // :143
+        T reflection = mixT(shade4[c] + shade4[3], refl[c], refl[3]);                             // :145 (SUN_BASE_COLOUR = 1)
+        out[c] = mixT(transmission, reflection, fresnel_f_theta);                                  // :151
+    }
+    // :154-156 soft edges
+    T hardness = (T)u.softEdgesDeltaDepthThreshold == (T)0 ? (T)1
+                 : (T)1 - (hack * ((T)1 - clampT(dclamped / (T)u.softEdgesDeltaDepthThreshold, (T)0, (T)1)));
+    // :160-162 fog
+    T fa = (T)u.fogColourFarAtCurrentTime[3];
+    T fog_a = vdc >= (T)u.fogDepthRadiusFar ? fa : vdc <= (T)u.fogDepthRadiusNear ? (T)0
+              : fa * ((vdc - (T)u.fogDepthRadiusNear) / ((T)u.fogDepthRadiusFar - (T)u.fogDepthRadiusNear));
+    for (int c = 0; c < 3; ++c) colour[c] = mixT(out[c], (T)u.fogColourFarAtCurrentTime[c], fog_a);
+    colour[3] = hardness;
 }
 
 // Per-vertex outputs.  pos4 = (x,y,z,1) world position (water-grid.vert `position`),
@@ -551,6 +621,19 @@ int wto_eval_f64(const wto_uniforms* u, const wto_wave* waves, const wto_texture
 // The in-scope fragment terms alone, evaluated at caller-supplied vertices: pos4/nrm4 are (n,4) arrays
 // (e.g. a kernel's own outputs); writes shade4 (n,4) and fresnel (n).  Lets a test check the shading
 // FUNCTION tightly, independent of how errors of the normal propagate through pow(., shininess).
+// The screen-space layers + fog of water-grid.frag at caller-supplied vertices (all (n,4) arrays: pos4, nrm4 =
+// (normal, fresnel_f_theta), shade4 = (sky.rgb, sun), clip4 = gl_Position, vary_a = (ndc0.xy, ., .), vary_b = (yaw normal, .)).
+int wto_compose_f32(const wto_compose_uniforms* u, const wto_screen_textures* st, long long n, const float* pos4, const float* nrm4,
+                    const float* shade4, const float* clip4, const float* vary_a, const float* vary_b, float* colour4) {
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < n; ++k) {
+        compose_vertex<float>(*u, *st, V3<float>{pos4[4 * k], pos4[4 * k + 1], pos4[4 * k + 2]}, nrm4[4 * k + 3], shade4 + 4 * k,
+                              V4<float>{clip4[4 * k], clip4[4 * k + 1], clip4[4 * k + 2], clip4[4 * k + 3]}, vary_a[4 * k], vary_a[4 * k + 1],
+                              V3<float>{vary_b[4 * k], vary_b[4 * k + 1], vary_b[4 * k + 2]}, colour4 + 4 * k);
+    }
+    return 0;
+}
+
 int wto_shade_f32(const wto_uniforms* u, const wto_textures* tx, long long n, const float* pos4, const float* nrm4, float* shade4, float* fresnel) {
     wt_gl::CubeRGBA8 cube{{tx->sky_faces[0], tx->sky_faces[1], tx->sky_faces[2], tx->sky_faces[3], tx->sky_faces[4], tx->sky_faces[5]}, tx->sky_n};
 #pragma omp parallel for schedule(static)

@@ -13,6 +13,8 @@ Outputs (tests/golden/):
   scalars.npz               Q_i / sun / bounce / total-amplitude rules
   vert_default.npz          water-grid.vert outputs, default scene (513^2, 4 wave slots), t in {0, 1.5}
   vert_seeded8.npz          water-grid.vert outputs, 1024^2 grid, 8 seeded waves, t = 0.5
+  frag_default.npz          water-grid.frag outputs (final colour) for vertices of the default scene at t = 1.5, fed the
+                            vertex stage's own varyings + synthetic screen-space inputs (stored alongside)
 """
 import os
 import sys
@@ -129,6 +131,39 @@ def main():
     u, wu = ref_uniforms(R, cam, waves8, params, 1024)
     out, world = run_vert(R, u, wu, hm4, ids8)
     np.savez_compressed(os.path.join(HERE, "vert_seeded8.npz"), ids=ids8, out=out, world=world, waves=waves8)
+    # ---- fragment shader on the default scene's vertex outputs (t = 1.5) -----------------------------
+    rng = np.random.default_rng(2024)
+    w, h = 96, 64
+    depth = rng.uniform(0.90, 1.0, size=(h, w)).astype(np.float32)
+    depth[rng.uniform(size=(h, w)) < 0.33] = 1.0
+    refl = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    refr = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+    refl[..., 3][rng.uniform(size=(h, w)) < 0.4] = 0
+    sky = rng.integers(0, 256, size=(6, 16, 16, 4), dtype=np.uint8)
+    sel = np.arange(0, len(ids), 7)
+    vo, world = rec["out_t1.5"][sel], rec["world_t1.5"][sel]
+    f = np.float32
+    fu = orc.RefFragUniforms()
+    sun = R.sun_position(9.0)
+    sy = f(min(max(float(sun[1]), 0.0), 1.0))
+    fu.fogColourFarAtCurrentTime[:] = [float(sy)] * 3 + [0.1]          # render-engine.cpp:295 with fogColourFarAtNoon (1,1,1,0.1)
+    fu.fogDepthRadiusFar, fu.fogDepthRadiusNear, fu.softEdgesDeltaDepthThreshold = 1.0, 0.0, 0.05
+    fu.sunPosition[:] = sun
+    fu.sunShininess, fu.sunStrength, fu.tintDeltaDepthThreshold, fu.waterClarity = 50.0, 1.0, 0.1, 0.3
+    fu.viewportWidthHeight[:] = [float(w), float(h)]
+    fu.zFar, fu.zNear = 100.0, 0.1
+    fi = np.zeros(len(sel), orc.REF_FRAG_IN_DTYPE)
+    clip = vo["gl_Position"]
+    nd = (clip[:, :3] / clip[:, 3:4]).astype(f)
+    fi["gl_FragCoord"][:, 0] = (nd[:, 0] + f(1)) * (f(w) / f(2))        # viewport transform, GL 4.1 section 2.14.1
+    fi["gl_FragCoord"][:, 1] = (nd[:, 1] + f(1)) * (f(h) / f(2))
+    fi["gl_FragCoord"][:, 2] = (nd[:, 2] + f(1)) / f(2)
+    fi["gl_FragCoord"][:, 3] = f(1) / clip[:, 3]
+    for k in ("heightmap_colour", "normal", "normalVecInViewSpaceOnlyYaw", "viewVecRaw", "xyPositionNDCSpaceHeight0"):
+        fi[k] = vo[k]
+    colour = R.frag_run(fu, depth, refl, refr, sky, fi)
+    np.savez_compressed(os.path.join(HERE, "frag_default.npz"), depth=depth, reflections=refl, refractions=refr, sky=sky, frag_in=fi, world=world,
+                        uniforms=np.frombuffer(bytes(fu), np.uint8).copy(), colour=colour)
     print("golden fixtures written to", HERE)
 
 

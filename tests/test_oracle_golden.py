@@ -115,3 +115,39 @@ def test_fp64_twin_close_to_fp32(oracle, heightmap):
     b = oracle.eval(u, wu, heightmap, ids=ids, f64=True)
     err = np.abs(a["pos"][:, :3] - b["pos"][:, :3]).max()
     assert err < 1e-4, err          # within the parity tolerance for sum(A) = 1
+
+
+def test_fragment_shader_golden(oracle):
+    """The oracle's fragment restatement (shade + screen-space layers + fog) against colours the reference's
+    own water-grid.frag text produced (tests/golden/make_golden.py), bit for bit."""
+    z = np.load(os.path.join(GOLDEN, "frag_default.npz"))
+    fu = orc.RefFragUniforms.from_buffer_copy(z["uniforms"].tobytes())
+    fi = z["frag_in"]
+    n = len(fi)
+    cam = np.array(scenes.camera().pos[:], np.float32)
+    u = orc.Uniforms()
+    u.cameraPosition[:] = cam
+    u.sunPosition[:] = fu.sunPosition[:]
+    u.sunShininess, u.sunStrength = fu.sunShininess, fu.sunStrength
+    pos4 = np.concatenate([(cam[None, :] - fi["viewVecRaw"]).astype(np.float32), np.ones((n, 1), np.float32)], 1)
+    # position = cameraPosition - viewVecRaw is exact here only if the subtraction round-trips; use the stored world position
+    pos4[:, :3] = z["world"][:, :3]
+    nrm4 = np.concatenate([fi["normal"], np.zeros((n, 1), np.float32)], 1)
+    shade, fres = oracle.shade(u, z["sky"], pos4, nrm4)
+    nrm4[:, 3] = fres
+    cu = orc.ComposeUniforms()
+    for k in ("fogColourFarAtCurrentTime", "viewportWidthHeight", "sunPosition"):
+        getattr(cu, k)[:] = getattr(fu, k)[:]
+    for k in ("fogDepthRadiusFar", "fogDepthRadiusNear", "softEdgesDeltaDepthThreshold", "tintDeltaDepthThreshold", "waterClarity", "zFar", "zNear"):
+        setattr(cu, k, getattr(fu, k))
+    cu.cameraPosition[:] = cam
+    # gl_Position back from gl_FragCoord is not exact; the golden run stored the varyings, so feed clip through
+    # the same viewport transform the generator used: recover clip from the stored world position instead
+    g = oracle.project_grid(orc.Camera.from_buffer_copy(bytes(scenes.camera())), np.float32(1.26))[1]
+    vp = np.array(g.view_proj, np.float32).reshape(4, 4).T
+    p = pos4
+    clip = np.stack([(vp[r, 0] * p[:, 0] + vp[r, 1] * p[:, 1]) + (vp[r, 2] * p[:, 2] + vp[r, 3] * p[:, 3]) for r in range(4)], 1).astype(np.float32)
+    va = np.concatenate([fi["xyPositionNDCSpaceHeight0"], np.zeros((n, 2), np.float32)], 1)
+    vb = np.concatenate([fi["normalVecInViewSpaceOnlyYaw"], np.zeros((n, 1), np.float32)], 1)
+    colour = oracle.compose(cu, z["depth"], z["reflections"], z["refractions"], pos4, nrm4, shade, clip, va, vb)
+    assert np.array_equal(bits(colour), bits(z["colour"])), float(np.abs(colour - z["colour"]).max())

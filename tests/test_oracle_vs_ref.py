@@ -68,3 +68,57 @@ def test_integer_vertex_id_semantics_match_shader_up_to_4096(oracle, ref, height
     o = oracle.eval(u, wu, heightmap, ids=ids)
     r = ref.vert_run(u, wu, heightmap, ids=ids)
     assert np.array_equal(bits(o["pos"]), bits(r["gl_Position"]))
+
+
+def test_fragment_shader_bit_exact(oracle, ref, heightmap):
+    """The oracle's fragment restatement — shade_vertex (water-grid.frag:71-73,95-111) + compose_vertex
+    (:66-69,76-89,113-162) — against the reference's own water-grid.frag text compiled as C++
+    (oracle/_ref/libwt_ref_frag.so), fed the same un-interpolated varyings and the same gl_FragCoord."""
+    from tests.common import compose_uniforms, screen_inputs
+    assert ref.frag is not None
+    f = np.float32
+    rng = np.random.default_rng(3)
+    for case, (name, kw) in enumerate(list(scenes.EDGE_CAMERAS.items())[:5] + [("tilted", dict(pos=(3.0, 11.0, 60.0), yaw=-75.0, pitch=-17.0, aspect=1.6))]):
+        p = api.default_params()
+        p.waveAnimationTimeInSeconds = float(rng.uniform(0, 20))
+        p.timeOfDayInHours = float([9.0, 12.0, 17.5, 5.0, 20.0, 13.0][case])
+        p.sunShininess = float([50.0, 1.0, 200.0, 0.0, 8.0, 50.0][case])
+        sky = scenes.noise_skybox(16, seed=case)
+        L = 192
+        sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(**kw), p, L, heightmap, skybox=sky)
+        st, u, wu = sc.oracle_uniforms(oracle)
+        if st != 0:
+            continue
+        w, h = [(96, 64), (33, 17), (128, 128), (7, 5), (64, 96), (96, 64)][case]
+        depth, refl, refr = screen_inputs(w, h, seed=case)
+        over = [dict(), dict(tintDeltaDepthThreshold=0.0), dict(softEdgesDeltaDepthThreshold=0.0), dict(fogDepthRadiusNear=0.2, fogDepthRadiusFar=0.6),
+                dict(waterClarity=1.0), dict()][case]
+        cu = compose_uniforms(sc, oracle, w, h, **over)
+        ids = np.unique(rng.integers(0, L * L, 3000))
+        o = oracle.eval(u, wu, heightmap, sky, ids=ids, shade=True, extra=True)
+        ex = o["extra"]
+        colour_o = oracle.compose(cu, depth, refl, refr, o["pos"], o["normal"], o["shade"], ex[:, 0:4], ex[:, 4:8], np.concatenate([ex[:, 9:12], ex[:, :1]], 1))
+        # the fragment inputs a rasteriser would hand over, un-interpolated; gl_FragCoord by the viewport transform
+        fi = np.zeros(len(ids), orc.REF_FRAG_IN_DTYPE)
+        clip = ex[:, 0:4]
+        nd = (clip[:, :3] / clip[:, 3:4]).astype(f)
+        fi["gl_FragCoord"][:, 0] = (nd[:, 0] + f(1)) * (f(w) / f(2))
+        fi["gl_FragCoord"][:, 1] = (nd[:, 1] + f(1)) * (f(h) / f(2))
+        fi["gl_FragCoord"][:, 2] = (nd[:, 2] + f(1)) / f(2)
+        fi["gl_FragCoord"][:, 3] = f(1) / clip[:, 3]
+        fi["heightmap_colour"] = ex[:, 12:16]
+        fi["normal"] = o["normal"][:, :3]
+        fi["normalVecInViewSpaceOnlyYaw"] = ex[:, 9:12]
+        fi["viewVecRaw"] = ex[:, 6:9]
+        fi["xyPositionNDCSpaceHeight0"] = ex[:, 4:6]
+        fu = orc.RefFragUniforms()
+        for k_ in ("fogColourFarAtCurrentTime", "viewportWidthHeight", "sunPosition"):
+            getattr(fu, k_)[:] = getattr(cu, k_)[:]
+        for k_ in ("fogDepthRadiusFar", "fogDepthRadiusNear", "softEdgesDeltaDepthThreshold", "tintDeltaDepthThreshold", "waterClarity", "zFar", "zNear"):
+            setattr(fu, k_, getattr(cu, k_))
+        fu.sunShininess, fu.sunStrength = u.sunShininess, u.sunStrength
+        colour_r = ref.frag_run(fu, depth, refl, refr, sky, fi)
+        ok = np.isfinite(colour_r).all(axis=1)
+        assert ok.mean() > 0.99
+        same = bits(colour_o[ok]) == bits(colour_r[ok])
+        assert same.all(), (name, int((~same).sum()), float(np.abs(colour_o[ok] - colour_r[ok]).max()))
