@@ -227,6 +227,36 @@ int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsi
  * Writes 6 (grid_len-1)^2 indices to `out` (HOST memory; may be NULL to query) and the count to *count. */
 int wt_grid_indices(unsigned grid_len, uint32_t* out, uint64_t capacity, uint64_t* count);
 
+/* ---------------------------------------------------------------------------------------------
+ * Compose pass — the screen-space layers of water-grid.frag evaluated per vertex (:66-69,76-89,113-162: depth
+ * delta, local reflection / refraction lookups, tint, Fresnel mix, soft edges, fog) on the outputs of an evaluation
+ * with WT_FLAG_SHADE | WT_FLAG_VARYINGS.  The fragment inputs a rasteriser would interpolate are taken at the vertex.
+ * ------------------------------------------------------------------------------------------- */
+/* The RenderEngine fields / uniforms the layers read — reference src/render-engine.h:221-223,229,234-235 and the
+ * uniform uploads src/render-engine.cpp:1096,1100,1107,1109-1110. */
+typedef struct wt_compose_params {
+    float fogColourFarAtNoon[4];          /* default (1,1,1,0.1); darkened by clamp(sunPosition.y,0,1) per frame (render-engine.cpp:295) */
+    float fogDepthRadiusFar;              /* default 1.0 */
+    float fogDepthRadiusNear;             /* default 0.0 */
+    float softEdgesDeltaDepthThreshold;   /* default 0.05 */
+    float tintDeltaDepthThreshold;        /* default 0.1 */
+    float waterClarity;                   /* default 0.3 */
+    float zNear, zFar;                    /* the camera's clip distances */
+    float viewportWidth, viewportHeight;
+} wt_compose_params;
+void wt_default_compose_params(wt_compose_params* out, const wt_camera* cam, unsigned viewport_width, unsigned viewport_height);
+
+/* Replaces the three FBO attachments the water program samples (render-engine.cpp:128-188, bound at :1060,:1087-1088):
+ * depth (float, window-space, GL_NEAREST), local reflections and refractions (RGBA8, GL_LINEAR), all CLAMP_TO_EDGE,
+ * w x h texels, rows in GL order.  HOST pointers, copied during the call. */
+int wt_set_screen_textures(wt_ctx* ctx, const float* depth, const uint8_t* reflections_rgba, const uint8_t* refractions_rgba,
+                           int width, int height);
+
+/* colour (float4 per vertex: rgb after fog, a = edge hardness) from the vertex stage's outputs in `vertex_stage`
+ * (position, normal, shade, clip_position, varyings_a, varyings_b must be set).  Stream-ordered. */
+int wt_compose_frame(wt_ctx* ctx, const wt_frame* frame, const wt_compose_params* params, unsigned grid_len, unsigned row_begin,
+                     unsigned row_end, const wt_outputs* vertex_stage, void* d_colour, void* cuda_stream);
+
 /* A batch of n_frames independent frames (animation; frame sharding takes a subset per GPU).
  * Frame f writes slot (f % ring_depth) of each ring buffer (slot stride = (row_end-row_begin)*grid_len
  * float4) and, with WT_FLAG_CHECKSUM, d_checksums[f].  Stream-ordered, returns without synchronising. */

@@ -457,6 +457,67 @@ def test_run_animation_is_the_frame_by_frame_loop(hm):
     assert drawn == 0 and int(cks.cpu().numpy().view(api.CHECKSUM_DTYPE)["vertices"].sum()) == 0
 
 
+@pytest.mark.parametrize("mode", list(MODES))
+def test_compose_screen_space_layers(oracle, hm, mode):
+    """wt_compose_frame (water-grid.frag:66-69,76-89,113-162 per vertex) against the oracle's compose_vertex — itself
+    bit-exact with the reference's fragment shader text (tests/test_oracle_vs_ref.py) — fed the kernel's own
+    vertex-stage outputs: the same fp32 operations in the same order, so the colours agree to the last bit
+    except where a discontinuity (nearest-texel depth fetch, the 0.999 skybox test) sits within rounding."""
+    from tests.common import compose_uniforms, screen_inputs
+    torch = torch_mod()
+    L, w, h = 320, 96, 64
+    sky = scenes.noise_skybox(32, seed=9)
+    p = api.default_params()
+    p.timeOfDayInHours = 10.5
+    sc = Scene(scenes.seeded_waves(16, cfg=7), scenes.camera(pos=(3.0, 11.0, 60.0), yaw=-75.0, pitch=-17.0, aspect=1.5), p, L, hm, skybox=sky)
+    p.waveAnimationTimeInSeconds = 2.25
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    depth, refl, refr = screen_inputs(w, h, seed=21)
+    ctx.set_screen_textures(depth, refl, refr)
+    n = L * L
+    bufs = {k: torch.empty((n, 4), dtype=torch.float32, device="cuda") for k in ("pos", "normal", "shade", "clip", "va", "vb", "colour")}
+    out = api.Outputs(bufs["pos"].data_ptr(), bufs["normal"].data_ptr(), bufs["shade"].data_ptr(), bufs["clip"].data_ptr(), bufs["va"].data_ptr(),
+                      bufs["vb"].data_ptr(), None)
+    sp = torch.cuda.current_stream().cuda_stream
+    ctx.eval_frame_ex(frame, L, out, flags=api.FLAG_SHADE | api.FLAG_VARYINGS | MODES[mode], stream=sp)
+    for over in (dict(), dict(tintDeltaDepthThreshold=0.0, softEdgesDeltaDepthThreshold=0.0), dict(fogDepthRadiusNear=0.1, fogDepthRadiusFar=0.5, waterClarity=1.0)):
+        cp = api.default_compose_params(sc.cam, w, h)
+        for k, v in over.items():
+            setattr(cp, k, v)
+        ctx.compose_frame(frame, cp, L, out, bufs["colour"].data_ptr(), stream=sp)
+        torch.cuda.synchronize()
+        got = {k: v.cpu().numpy() for k, v in bufs.items()}
+        cu = compose_uniforms(sc, oracle, w, h, **over)
+        want = oracle.compose(cu, depth, refl, refr, got["pos"], got["normal"], got["shade"], got["clip"], got["va"], got["vb"])
+        ok = np.isfinite(want).all(axis=1) & np.isfinite(got["colour"]).all(axis=1)
+        assert ok.mean() > 0.999
+        same = (got["colour"][ok].view(np.uint32) == want[ok].view(np.uint32)).all(axis=1)
+        err = np.abs(got["colour"][ok].astype(np.float64) - want[ok]).max(axis=1)
+        print("compose", mode, over, "bit-equal %.5f" % same.mean(), "max err %.2e" % err.max())
+        assert same.mean() > 0.999
+        assert np.sort(err)[int(0.9999 * len(err))] <= 1e-6
+        assert 0.0 <= got["colour"][ok].min() and got["colour"][ok].max() <= 2.0 and got["colour"][ok][:, :3].std() > 0.02
+
+
+def test_compose_argument_checks(hm):
+    torch = torch_mod()
+    sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    b = torch.empty((64 * 64, 4), dtype=torch.float32, device="cuda")
+    full = api.Outputs(*([b.data_ptr()] * 6), None)
+    cp = api.default_compose_params(sc.cam, 8, 8)
+    with pytest.raises(api.WaveToolError) as e:
+        ctx.compose_frame(frame, cp, 64, full, b.data_ptr())
+    assert e.value.status == api.WT_ERR_NOT_READY
+    ctx.set_screen_textures(np.ones((8, 8), np.float32), np.zeros((8, 8, 4), np.uint8), np.zeros((8, 8, 4), np.uint8))
+    with pytest.raises(api.WaveToolError):
+        ctx.compose_frame(frame, cp, 64, api.Outputs(b.data_ptr(), b.data_ptr(), None, None, None, None, None), b.data_ptr())
+    assert ctx.compose_frame(frame, cp, 64, full, b.data_ptr()) == api.WT_OK
+
+
 def test_non_power_of_two_heightmap(oracle):
     hm = scenes.procedural_heightmap(200)[:150]      # 200 x 150 texels
     sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), 300, hm)

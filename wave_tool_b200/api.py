@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = [
     "wt_eval_frame", "wt_eval_batch", "wt_eval_frame_host", "wt_launch_count", "wt_measure_peak",
     "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
     "wt_default_animation", "wt_animation_advance", "wt_run_animation",
+    "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
 ]
 
 
@@ -69,6 +70,12 @@ class Checksum(C.Structure):
 class Animation(C.Structure):
     _fields_ = [("animationSpeedTimeOfDayInSecondsPerHour", C.c_float), ("animationSpeedVerticalBounceWavePhasePeriodInSeconds", C.c_float),
                 ("isAnimatingTimeOfDay", C.c_int), ("isAnimatingWaves", C.c_int)]
+
+
+class ComposeParams(C.Structure):
+    _fields_ = [("fogColourFarAtNoon", C.c_float * 4), ("fogDepthRadiusFar", C.c_float), ("fogDepthRadiusNear", C.c_float),
+                ("softEdgesDeltaDepthThreshold", C.c_float), ("tintDeltaDepthThreshold", C.c_float), ("waterClarity", C.c_float),
+                ("zNear", C.c_float), ("zFar", C.c_float), ("viewportWidth", C.c_float), ("viewportHeight", C.c_float)]
 
 
 class Outputs(C.Structure):
@@ -134,6 +141,11 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_debug_reload_env.restype = None
     L.wt_eval_frame_ex.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs), C.c_uint, C.c_void_p]
     L.wt_grid_indices.argtypes = [C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.wt_default_compose_params.argtypes = [C.POINTER(ComposeParams), C.POINTER(Camera), C.c_uint, C.c_uint]
+    L.wt_default_compose_params.restype = None
+    L.wt_set_screen_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.wt_compose_frame.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(ComposeParams), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs),
+                                   C.c_void_p, C.c_void_p]
     L.wt_default_animation.argtypes = [C.POINTER(Animation)]
     L.wt_default_animation.restype = None
     L.wt_animation_advance.argtypes = [C.POINTER(Params), C.POINTER(Animation), C.c_float]
@@ -192,6 +204,12 @@ def project_grid(cam: Camera, displaceable_amplitude: float):
     corners = np.zeros((4, 4), np.float32)
     st = _check(lib().wt_project_grid(C.byref(cam), C.c_float(displaceable_amplitude), corners.ctypes.data))
     return st, corners
+
+
+def default_compose_params(cam: Camera, viewport_w: int, viewport_h: int) -> ComposeParams:
+    p = ComposeParams()
+    lib().wt_default_compose_params(C.byref(p), C.byref(cam), viewport_w, viewport_h)
+    return p
 
 
 def default_animation() -> Animation:
@@ -271,6 +289,18 @@ class Context:
         """wt_eval_frame_ex: every output stream of the vertex stage (Outputs holds raw device addresses)."""
         r0, r1 = rows if rows is not None else (0, grid_len)
         return _check(self._lib.wt_eval_frame_ex(self._h, C.byref(frame), grid_len, r0, r1, C.byref(outputs), flags, stream or None), self._h)
+
+    def set_screen_textures(self, depth: np.ndarray, reflections: np.ndarray, refractions: np.ndarray):
+        d = np.ascontiguousarray(depth, np.float32)
+        rl = np.ascontiguousarray(reflections, np.uint8)
+        rr = np.ascontiguousarray(refractions, np.uint8)
+        assert d.ndim == 2 and rl.shape == d.shape + (4,) and rr.shape == rl.shape
+        _check(self._lib.wt_set_screen_textures(self._h, d.ctypes.data, rl.ctypes.data, rr.ctypes.data, d.shape[1], d.shape[0]), self._h)
+
+    def compose_frame(self, frame: Frame, params: "ComposeParams", grid_len: int, vertex_stage: "Outputs", d_colour: int, rows=None, stream: int = 0):
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        return _check(self._lib.wt_compose_frame(self._h, C.byref(frame), C.byref(params), grid_len, r0, r1, C.byref(vertex_stage), d_colour,
+                                                 stream or None), self._h)
 
     def run_animation(self, cam: Camera, params: Params, anim: Animation, total_wave_amplitude: float, dt: float, n_frames: int, grid_len: int,
                       d_pos_ring: int, d_normal_ring: int, d_shade_ring: int = 0, ring_depth: int = 2, d_checksums: int = 0, flags: int = 0,

@@ -29,6 +29,10 @@ struct wt_ctx {
     // production kernel: padded face atlas in a block-linear CUDA array + a gather-capable texture object
     cudaArray_t sky_array = nullptr, sky_array_black = nullptr;
     cudaTextureObject_t sky_tex = 0, sky_tex_black = 0;
+    // screen-space inputs of the compose pass (wt_set_screen_textures)
+    float* d_depth = nullptr;
+    uchar4 *d_refl = nullptr, *d_refr = nullptr;
+    int screen_w = 0, screen_h = 0;
     // scratch for the *_host entry points
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
     size_t s_elems = 0;

@@ -251,6 +251,7 @@ void wt_destroy(wt_ctx* ctx) {
     if (ctx->sky_array_black) cudaFreeArray(ctx->sky_array_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
     for (int i = 0; i < 4; ++i) {
         if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
