@@ -9,8 +9,8 @@
 //
 // PINNING: the reference ships no tests or golden vectors for this path.  This
 // restatement is pinned instead against the reference ITSELF run in the build container:
-// oracle/_ref/libwt_ref_{proj,vert}.so, compiled by oracle/Makefile from the reference's own
-// camera.cpp, render-engine.h, GLM and the water-grid.vert shader TEXT (as C++), see
+// oracle/_ref/libwt_ref_{proj,vert,frag}.so, compiled by oracle/Makefile from the reference's own
+// camera.cpp, render-engine.h, GLM and the water-grid.vert / water-grid.frag shader TEXTS (as C++), see
 // tests/test_oracle_vs_ref.py (bit-exact) and the committed vectors under tests/golden/.
 //
 // Each function cites the reference lines it follows (paths relative to /root/reference).
