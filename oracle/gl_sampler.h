@@ -88,6 +88,18 @@ inline void texture2d_mirrored_linear(const Image2D& img, T s, T t, T out[4]) {
     sample_linear_rgba<T, wrap_mirrored_repeat>(img.rgba, img.w, img.h, s, t, out);
 }
 
+// texture(sampler1D, s): RGBA8, GL_LINEAR, GL_CLAMP_TO_EDGE, LOD 0 — the sky-gradient texture
+// (/root/reference/src/texture.cpp:40-49).  Same LINEAR rule as the 2-D case, one dimension.
+template <typename T>
+inline void texture1d_clamp_linear(const uint8_t* rgba, int length, T s, T out[4]) {
+    T um = s * (T)length - (T)0.5;
+    T fu = std::floor(um);
+    T a = um - fu;
+    long long iu = (long long)fu;
+    int i0 = wrap_clamp_to_edge(iu, length), i1 = wrap_clamp_to_edge(iu + 1, length);
+    for (int c = 0; c < 4; ++c) out[c] = ((T)1 - a) * unorm8<T>(rgba[4 * i0 + c]) + a * unorm8<T>(rgba[4 * i1 + c]);
+}
+
 // texture(sampler2D, st) with the sampler state of the local reflection / refraction textures.
 template <typename T>
 inline void texture2d_clamp_linear(const Image2D& img, T s, T t, T out[4]) {

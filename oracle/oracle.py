@@ -70,6 +70,34 @@ class ComposeUniforms(C.Structure):
                 ("cameraPosition", C.c_float * 3), ("sunPosition", C.c_float * 3)]
 
 
+class SkyUniforms(C.Structure):
+    """Inputs of the skybox synthesis (render-engine.cpp:289-297, 333-424)."""
+    _fields_ = [("sunPosition", C.c_float * 3), ("sunHorizonDarkness", C.c_float), ("sunShininess", C.c_float), ("sunStrength", C.c_float),
+                ("oneMinusCloudProportion", C.c_float), ("overcastStrength", C.c_float), ("fogColourFarAtCurrentTime", C.c_float * 4),
+                ("draw_stars", C.c_int), ("draw_skysphere", C.c_int), ("draw_clouds", C.c_int)]
+
+
+class SkyTextures(C.Structure):
+    _fields_ = [("gradient_rgba", C.c_void_p), ("gradient_len", C.c_int), ("stars", C.c_void_p * 6), ("stars_n", C.c_int),
+                ("clouds", C.c_void_p * 6), ("clouds_n", C.c_int)]
+
+
+def sky_textures(gradient, stars, clouds):
+    """(SkyTextures, keep-alive list) from a (G,4) gradient and optional (6,n,n,4) star / cloud cubemaps."""
+    g = np.ascontiguousarray(gradient, np.uint8).reshape(-1, 4)
+    tx = SkyTextures()
+    tx.gradient_rgba, tx.gradient_len = g.ctypes.data, len(g)
+    keep = [g]
+    for name, faces in (("stars", stars), ("clouds", clouds)):
+        if faces is not None:
+            a = np.ascontiguousarray(faces, np.uint8)
+            keep.append(a)
+            for f in range(6):
+                getattr(tx, name)[f] = a[f].ctypes.data
+            setattr(tx, name + "_n", a.shape[1])
+    return tx, keep
+
+
 class ScreenTextures(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("reflections", C.c_void_p), ("refractions", C.c_void_p), ("w", C.c_int), ("h", C.c_int)]
 
@@ -130,6 +158,9 @@ class Oracle:
         L.wto_eval_f64.argtypes = common + [C.c_void_p] * 4
         L.wto_shade_f32.argtypes = [C.POINTER(Uniforms), C.POINTER(Textures), C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.wto_compose_f32.argtypes = [C.POINTER(ComposeUniforms), C.POINTER(ScreenTextures), C.c_longlong] + [C.c_void_p] * 7
+        L.wto_sky_synthesize.argtypes = [C.POINTER(SkyUniforms), C.POINTER(SkyTextures), C.c_int, C.c_void_p]
+        L.wto_skysphere_colour_f32.argtypes = [C.POINTER(SkyUniforms), C.POINTER(SkyTextures), C.c_longlong, C.c_void_p, C.c_void_p]
+        L.wto_clouds_colour_f32.argtypes = [C.POINTER(SkyUniforms), C.POINTER(SkyTextures), C.c_longlong, C.c_void_p, C.c_void_p]
 
     # --- host-side scalar rules -------------------------------------------------------------
     def num_threads(self) -> int:
@@ -214,6 +245,21 @@ class Oracle:
         return {"pos": pos, "normal": nrm, "shade": shd, "extra": ext}
 
 
+    def sky_synthesize(self, su: SkyUniforms, gradient, stars, clouds, n: int) -> np.ndarray:
+        """The skybox cubemap of render-engine.cpp:306-442 -> (6,n,n,4) uint8."""
+        tx, keep = sky_textures(gradient, stars, clouds)
+        out = np.empty((6, n, n, 4), np.uint8)
+        self.lib.wto_sky_synthesize(C.byref(su), C.byref(tx), n, out.ctypes.data)
+        return out
+
+    def sky_layer(self, which: str, su: SkyUniforms, gradient, stars, clouds, dirs: np.ndarray) -> np.ndarray:
+        tx, keep = sky_textures(gradient, stars, clouds)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        out = np.empty((len(d), 4), np.float32)
+        fn = self.lib.wto_skysphere_colour_f32 if which == "skysphere" else self.lib.wto_clouds_colour_f32
+        fn(C.byref(su), C.byref(tx), len(d), d.ctypes.data, out.ctypes.data)
+        return out
+
     def compose(self, cu: ComposeUniforms, depth: np.ndarray, reflections: np.ndarray, refractions: np.ndarray,
                 pos4, nrm4, shade4, clip4, vary_a, vary_b) -> np.ndarray:
         """water-grid.frag:66-69,76-89,113-162 at caller-supplied vertices -> colour (n,4).  nrm4.w carries
@@ -265,6 +311,11 @@ class Ref:
             self.frag.wtref_frag_set_uniforms.argtypes = [C.POINTER(RefFragUniforms), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                           C.POINTER(C.c_void_p), C.c_int]
             self.frag.wtref_frag_run.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
+        self.sky = _load(os.path.join(HERE, "_ref", "libwt_ref_sky.so"))
+        if self.sky is not None:
+            self.sky.wtref_skysphere_run.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_longlong, C.c_void_p]
+            self.sky.wtref_clouds_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+            self.sky.wtref_stars_run.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
         if self.vert is not None:
             V = self.vert
             V.wtref_vert_set_uniforms.argtypes = [C.POINTER(RefVertUniforms), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -296,6 +347,24 @@ class Ref:
         g = GridF32()
         st = self.proj.wtref_project_grid(C.byref(cam), C.c_float(float(displaceable_amplitude)), C.byref(g))
         return st, g
+
+    def sky_layer_run(self, which: str, su: SkyUniforms, gradient, stars, clouds, dirs: np.ndarray) -> np.ndarray:
+        """Runs the compiled skysphere.frag / skybox-clouds.frag / skybox-stars.frag main() on directions -> colour (n,4)."""
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        out = np.empty((len(d), 4), np.float32)
+        sun = np.array(su.sunPosition[:], np.float32)
+        if which == "skysphere":
+            g = np.ascontiguousarray(gradient, np.uint8).reshape(-1, 4)
+            self.sky.wtref_skysphere_run(g.ctypes.data, len(g), su.sunHorizonDarkness, sun.ctypes.data, su.sunShininess, su.sunStrength,
+                                         d.ctypes.data, len(d), out.ctypes.data)
+        else:
+            a = np.ascontiguousarray(clouds if which == "clouds" else stars, np.uint8)
+            ptrs = (C.c_void_p * 6)(*[a[f].ctypes.data for f in range(6)])
+            if which == "clouds":
+                self.sky.wtref_clouds_run(ptrs, a.shape[1], su.oneMinusCloudProportion, su.overcastStrength, sun.ctypes.data, d.ctypes.data, len(d), out.ctypes.data)
+            else:
+                self.sky.wtref_stars_run(ptrs, a.shape[1], d.ctypes.data, len(d), out.ctypes.data)
+        return out
 
     def frag_run(self, fu: RefFragUniforms, depth, reflections, refractions, sky_faces, frag_in: np.ndarray) -> np.ndarray:
         """Runs the compiled water-grid.frag main() on REF_FRAG_IN_DTYPE records -> colour (n,4)."""

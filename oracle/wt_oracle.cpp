@@ -368,6 +368,21 @@ struct wto_compose_uniforms {
     float cameraPosition[3];
     float sunPosition[3];
 };
+// Inputs of the skybox synthesis (render-engine.cpp:306-442): the RenderEngine fields and per-frame values the
+// three sky programs and the fog quad receive, and the three source textures.
+struct wto_sky_uniforms {
+    float sunPosition[3];            // render-engine.cpp:289-291
+    float sunHorizonDarkness, sunShininess, sunStrength;      // :368-371
+    float oneMinusCloudProportion, overcastStrength;          // :386-387, :297
+    float fogColourFarAtCurrentTime[4];                       // :295, :424
+    int draw_stars, draw_skysphere, draw_clouds;              // the m_isVisible / nullptr tests of :333,:352,:381
+};
+struct wto_sky_textures {
+    const uint8_t* gradient_rgba; int gradient_len;           // 1-D sky gradient (program.cpp:644)
+    const uint8_t* stars[6]; int stars_n;
+    const uint8_t* clouds[6]; int clouds_n;
+};
+
 struct wto_screen_textures {
     const float* depth;            // w x h, GL row order, window-space depth in [0,1]
     const uint8_t* reflections;    // w x h RGBA8
@@ -443,6 +458,99 @@ void shade_vertex(const wto_uniforms& u, const wt_gl::CubeRGBA8* sky, V3<T> view
     T cos_theta = dot(n, vv3);                                          // frag:110
     *fresnel = (T)0.02f + ((T)1 - (T)0.02f) * std::pow((T)1 - cos_theta, (T)5);   // frag:107-111
     shade4[0] = sky_c[0]; shade4[1] = sky_c[1]; shade4[2] = sky_c[2]; shade4[3] = sun_term;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Skybox synthesis: the colour each texel of the 6 x n x n RGBA8 skybox cubemap receives from
+// render-engine.cpp:306-442 — clear, then stars, sky sphere, clouds and the fog quad blended in this order with
+// glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) (:303) into an RGBA8 colour attachment.
+// ----------------------------------------------------------------------------------------------
+// skysphere.frag:48-76
+template <typename T>
+void skysphere_colour(const wto_sky_uniforms& u, const wto_sky_textures& tx, V3<T> normalVec, T out[4]) {
+    auto mixT = [](T x, T y, T a) { return x * ((T)1 - a) + y * a; };
+    V3<T> L = normalize(V3<T>{(T)u.sunPosition[0], (T)u.sunPosition[1], (T)u.sunPosition[2]});
+    V3<T> N = normalize(normalVec);
+    T a1 = (T)0.25f * (L.y + (T)1), a2 = (T)1 - a1;
+    T peak[4], hor[4];
+    wt_gl::texture1d_clamp_linear<T>(tx.gradient_rgba, tx.gradient_len, a1, peak);
+    wt_gl::texture1d_clamp_linear<T>(tx.gradient_rgba, tx.gradient_len, a2, hor);
+    T a3 = dot(N, L);
+    T spec = a3 > (T)0 ? (T)u.sunStrength * (T)1 * std::pow(a3, (T)u.sunShininess) : (T)0;
+    for (int c = 0; c < 3; ++c) {
+        T horizon = mixT(hor[c], (T)0, (T)u.sunHorizonDarkness);
+        T diffuse = a3 >= (T)0 ? mixT(horizon, peak[c], a3) : mixT(horizon, (T)0, std::fabs(a3) * ((T)1 - std::fabs(L.y)));
+        out[c] = diffuse + spec;
+    }
+    const T THRESHOLD = (T)0.1f;
+    T alpha1 = L.y < THRESHOLD ? (L.y + (T)1) / (THRESHOLD + (T)1) : (T)1;
+    T alpha2 = (a3 + (T)1) / (T)2;
+    out[3] = std::max(alpha1, alpha2);
+}
+// skybox-clouds.frag:46-67
+template <typename T>
+void clouds_colour(const wto_sky_uniforms& u, const wto_sky_textures& tx, V3<T> str, T out[4]) {
+    auto mixT = [](T x, T y, T a) { return x * ((T)1 - a) + y * a; };
+    wt_gl::CubeRGBA8 cube{{tx.clouds[0], tx.clouds[1], tx.clouds[2], tx.clouds[3], tx.clouds[4], tx.clouds[5]}, tx.clouds_n};
+    T raw[4];
+    wt_gl::texture_cube_clamp_linear<T>(cube, str.x, str.y, str.z, raw);
+    T lin = (T)0.2126f * raw[0] + (T)0.7152f * raw[1] + (T)0.0722f * raw[2];
+    T srgb = lin <= (T)0.0031308f ? (T)12.92f * lin : (T)1.055f * std::pow(lin, (T)1 / (T)2.4f) - (T)0.055f;
+    T intensity = clampT((T)u.sunPosition[1], (T)0.2f, (T)1);
+    T omp = (T)u.oneMinusCloudProportion;
+    T col[4] = {intensity, intensity, intensity, srgb > omp ? (srgb - omp) / ((T)1 - omp) : (T)0};
+    T a = clampT((T)u.sunPosition[1], (T)0, (T)1) * (T)u.overcastStrength;
+    if (srgb > omp) {
+        for (int c = 0; c < 3; ++c) out[c] = mixT(col[c], srgb, a);
+        out[3] = mixT(col[3], (T)1, a);
+    } else {
+        out[0] = out[1] = out[2] = (T)0.5f;
+        out[3] = a;
+    }
+}
+// One layer blended into an RGBA8 destination: GL 4.1 section 4.1.7 — source, destination and factors clamped to [0,1]
+// (fixed-point colour buffer), Cd' = Cs * As + Cd * (1 - As) on all four channels, result converted to unorm8
+// (section 2.1.5: round to nearest).
+template <typename T>
+void blend_rgba8(uint8_t dst[4], const T src_in[4]) {
+    T src[4];
+    for (int c = 0; c < 4; ++c) src[c] = clampT(src_in[c], (T)0, (T)1);
+    for (int c = 0; c < 4; ++c) {
+        T d = (T)dst[c] / (T)255;
+        T v = clampT(src[c] * src[3] + d * ((T)1 - src[3]), (T)0, (T)1);
+        dst[c] = (uint8_t)std::floor(v * (T)255 + (T)0.5);
+    }
+}
+// The direction the rasteriser hands the fragment at the centre of texel (i, j) of face f: the faces are drawn with a
+// 90-degree frustum and the look-at bases of render-engine.h:198-203, which make the framebuffer pixel (i, j) the
+// cube-map texel (s, t) = ((i + 1/2)/n, (j + 1/2)/n) of that face (GL 4.1 cube-map face table, inverted).
+template <typename T>
+V3<T> sky_texel_direction(int face, int i, int j, int n) {
+    T sc = ((T)2 * ((T)i + (T)0.5)) / (T)n - (T)1, tc = ((T)2 * ((T)j + (T)0.5)) / (T)n - (T)1;
+    switch (face) {
+        case 0: return V3<T>{(T)1, -tc, -sc};
+        case 1: return V3<T>{(T)-1, -tc, sc};
+        case 2: return V3<T>{sc, (T)1, tc};
+        case 3: return V3<T>{sc, (T)-1, -tc};
+        case 4: return V3<T>{sc, -tc, (T)1};
+        default: return V3<T>{-sc, -tc, (T)-1};
+    }
+}
+template <typename T>
+void sky_texel(const wto_sky_uniforms& u, const wto_sky_textures& tx, int face, int i, int j, int n, uint8_t out[4]) {
+    V3<T> d = sky_texel_direction<T>(face, i, j, n);
+    out[0] = out[1] = out[2] = out[3] = 255;                      // glClearColor(1,1,1,1) (render-engine.cpp:694), glClear :330
+    T src[4];
+    if (u.draw_stars) {                                            // skybox-stars.frag:41
+        wt_gl::CubeRGBA8 cube{{tx.stars[0], tx.stars[1], tx.stars[2], tx.stars[3], tx.stars[4], tx.stars[5]}, tx.stars_n};
+        wt_gl::texture_cube_clamp_linear<T>(cube, d.x, d.y, d.z, src);
+        src[3] = (T)1;
+        blend_rgba8<T>(out, src);
+    }
+    if (u.draw_skysphere) { skysphere_colour<T>(u, tx, d, src); blend_rgba8<T>(out, src); }
+    if (u.draw_clouds) { clouds_colour<T>(u, tx, d, src); blend_rgba8<T>(out, src); }
+    for (int c = 0; c < 4; ++c) src[c] = (T)u.fogColourFarAtCurrentTime[c];   // screen-space-quad.frag:45, solidColour
+    blend_rgba8<T>(out, src);
 }
 
 // water-grid.frag:66-69,76-89,113-162 evaluated at a vertex: everything of main() that is not the three terms
@@ -621,6 +729,25 @@ int wto_eval_f64(const wto_uniforms* u, const wto_wave* waves, const wto_texture
 // The in-scope fragment terms alone, evaluated at caller-supplied vertices: pos4/nrm4 are (n,4) arrays
 // (e.g. a kernel's own outputs); writes shade4 (n,4) and fresnel (n).  Lets a test check the shading
 // FUNCTION tightly, independent of how errors of the normal propagate through pow(., shininess).
+// Skybox synthesis: faces_out = 6 * n * n RGBA8 texels, GL face order.
+int wto_sky_synthesize(const wto_sky_uniforms* u, const wto_sky_textures* tx, int n, uint8_t* faces_out) {
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < 6LL * n * n; ++k) {
+        const int face = (int)(k / ((long long)n * n)), j = (int)((k / n) % n), i = (int)(k % n);
+        sky_texel<float>(*u, *tx, face, i, j, n, faces_out + 4 * k);
+    }
+    return 0;
+}
+// the layer functions alone, on caller-supplied directions (pinned against the compiled shader texts)
+int wto_skysphere_colour_f32(const wto_sky_uniforms* u, const wto_sky_textures* tx, long long n, const float* dir3, float* colour4) {
+    for (long long k = 0; k < n; ++k) skysphere_colour<float>(*u, *tx, V3<float>{dir3[3 * k], dir3[3 * k + 1], dir3[3 * k + 2]}, colour4 + 4 * k);
+    return 0;
+}
+int wto_clouds_colour_f32(const wto_sky_uniforms* u, const wto_sky_textures* tx, long long n, const float* dir3, float* colour4) {
+    for (long long k = 0; k < n; ++k) clouds_colour<float>(*u, *tx, V3<float>{dir3[3 * k], dir3[3 * k + 1], dir3[3 * k + 2]}, colour4 + 4 * k);
+    return 0;
+}
+
 // The screen-space layers + fog of water-grid.frag at caller-supplied vertices (all (n,4) arrays: pos4, nrm4 =
 // (normal, fresnel_f_theta), shade4 = (sky.rgb, sun), clip4 = gl_Position, vary_a = (ndc0.xy, ., .), vary_b = (yaw normal, .)).
 int wto_compose_f32(const wto_compose_uniforms* u, const wto_screen_textures* st, long long n, const float* pos4, const float* nrm4,

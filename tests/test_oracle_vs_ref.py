@@ -122,3 +122,23 @@ def test_fragment_shader_bit_exact(oracle, ref, heightmap):
         assert ok.mean() > 0.99
         same = bits(colour_o[ok]) == bits(colour_r[ok])
         assert same.all(), (name, int((~same).sum()), float(np.abs(colour_o[ok] - colour_r[ok]).max()))
+
+
+def test_sky_layer_shaders_bit_exact(oracle, ref):
+    """The oracle's restatement of skysphere.frag / skybox-clouds.frag / skybox-stars.frag against the reference's own
+    shader texts compiled as C++ (oracle/_ref/libwt_ref_sky.so), on random directions and times of day."""
+    from tests.common import sky_sources, sky_uniforms
+    assert ref.sky is not None
+    rng = np.random.default_rng(17)
+    gradient, stars, clouds = sky_sources(seed=3)
+    dirs = rng.normal(size=(4000, 3)).astype(np.float32) * rng.uniform(0.2, 3.0, size=(4000, 1)).astype(np.float32)
+    for hours, cp, oc, dark, shin in ((9.0, 0.6, 0.0, 0.25, 50.0), (12.0, 0.9, 0.7, 0.0, 1.0), (18.5, 0.3, 1.0, 1.0, 200.0), (2.0, 0.0, 0.3, 0.5, 0.0), (6.0, 1.0, 0.5, 0.25, 8.0)):
+        su = sky_uniforms(oracle, hours, cloud_proportion=cp, overcast=oc, darkness=dark, shininess=shin)
+        for which in ("skysphere", "clouds"):
+            o = oracle.sky_layer(which, su, gradient, stars, clouds, dirs)
+            r = ref.sky_layer_run(which, su, gradient, stars, clouds, dirs)
+            ok = np.isfinite(r).all(axis=1)
+            assert ok.mean() > 0.99
+            assert np.array_equal(bits(o[ok]), bits(r[ok])), (which, hours, float(np.abs(o[ok] - r[ok]).max()))
+        r = ref.sky_layer_run("stars", su, gradient, stars, clouds, dirs)
+        assert np.all(r[:, 3] == 1.0) and r[:, :3].std() > 0.01
