@@ -257,6 +257,32 @@ int wt_set_screen_textures(wt_ctx* ctx, const float* depth, const uint8_t* refle
 int wt_compose_frame(wt_ctx* ctx, const wt_frame* frame, const wt_compose_params* params, unsigned grid_len, unsigned row_begin,
                      unsigned row_end, const wt_outputs* vertex_stage, void* d_colour, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Skybox synthesis — replaces the cubemap render pass of src/render-engine.cpp:306-442 that produces the `skybox`
+ * the water samples: per texel the clear colour, then stars (skybox-stars.frag), the sky sphere (skysphere.frag), clouds
+ * (skybox-clouds.frag) and the fog quad, blended in that order with GL_SRC_ALPHA / GL_ONE_MINUS_SRC_ALPHA into RGBA8.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct wt_sky_params {          /* RenderEngine fields, src/render-engine.h:220-221,228,230-233 */
+    float timeOfDayInHours;             /* default 9.0 */
+    float cloudProportion;              /* default 0.6 */
+    float overcastStrength;             /* default 0.0 */
+    float sunHorizonDarkness;           /* default 0.25 */
+    float sunShininess, sunStrength;    /* defaults 50.0, 1.0 */
+    float fogColourFarAtNoon[4];        /* default (1,1,1,0.1) */
+    int drawStars, drawSkysphere, drawClouds;   /* the m_isVisible switches of the three sky objects; default 1 */
+} wt_sky_params;
+void wt_default_sky_params(wt_sky_params* out);
+
+/* The three source textures: the 1-D sky gradient (program.cpp:644; RGBA8, GL_LINEAR, CLAMP_TO_EDGE) and the star and
+ * cloud cubemaps (six n x n RGBA8 faces in GL order, rows as loaded — cubemaps are not flipped, render-engine.cpp:1332).
+ * stars / clouds may be NULL (layer not drawn).  HOST pointers, copied during the call. */
+int wt_set_sky_layers(wt_ctx* ctx, const uint8_t* gradient_rgba, int gradient_len, const uint8_t* const stars[6], int stars_n,
+                      const uint8_t* const clouds[6], int clouds_n);
+/* Synthesizes the 6 x n x n skybox into the context (exactly as if wt_set_skybox_rgba8 had been called with the result). */
+int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* params, int n, void* cuda_stream);
+/* Copies the context's current skybox faces (6 * n * n RGBA8) to HOST memory; out may be NULL to query n.  Synchronises. */
+int wt_get_skybox_rgba8(wt_ctx* ctx, uint8_t* out, int* n_out);
+
 /* A batch of n_frames independent frames (animation; frame sharding takes a subset per GPU).
  * Frame f writes slot (f % ring_depth) of each ring buffer (slot stride = (row_end-row_begin)*grid_len
  * float4) and, with WT_FLAG_CHECKSUM, d_checksums[f].  Stream-ordered, returns without synchronising. */

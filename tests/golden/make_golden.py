@@ -13,6 +13,7 @@ Outputs (tests/golden/):
   scalars.npz               Q_i / sun / bounce / total-amplitude rules
   vert_default.npz          water-grid.vert outputs, default scene (513^2, 4 wave slots), t in {0, 1.5}
   vert_seeded8.npz          water-grid.vert outputs, 1024^2 grid, 8 seeded waves, t = 0.5
+  sky_layers.npz            skysphere.frag / skybox-clouds.frag outputs on random directions, four times of day
   frag_default.npz          water-grid.frag outputs (final colour) for vertices of the default scene at t = 1.5, fed the
                             vertex stage's own varyings + synthetic screen-space inputs (stored alongside)
 """
@@ -164,6 +165,25 @@ def main():
     colour = R.frag_run(fu, depth, refl, refr, sky, fi)
     np.savez_compressed(os.path.join(HERE, "frag_default.npz"), depth=depth, reflections=refl, refractions=refr, sky=sky, frag_in=fi, world=world,
                         uniforms=np.frombuffer(bytes(fu), np.uint8).copy(), colour=colour)
+    # ---- sky layer shaders (skysphere.frag, skybox-clouds.frag) on random directions ------------------
+    rng = np.random.default_rng(77)
+    G = 64
+    tt = np.linspace(0.0, 1.0, G)
+    gradient = np.stack([40 + 200 * tt, 90 + 120 * np.sin(3 * tt) ** 2, 255 - 180 * tt, np.full_like(tt, 255)], 1).round().astype(np.uint8)
+    clouds = rng.integers(0, 256, size=(6, 12, 12, 4), dtype=np.uint8)
+    dirs = (rng.normal(size=(1500, 3)) * rng.uniform(0.2, 3.0, size=(1500, 1))).astype(np.float32)
+    cases, sphere_out, cloud_out = [], [], []
+    for hours, cp, oc, dark, shin in ((9.0, 0.6, 0.0, 0.25, 50.0), (12.0, 0.9, 0.7, 0.0, 1.0), (18.5, 0.3, 1.0, 1.0, 200.0), (2.0, 0.0, 0.3, 0.5, 0.0)):
+        su = orc.SkyUniforms()
+        su.sunPosition[:] = R.sun_position(hours)
+        su.sunHorizonDarkness, su.sunShininess, su.sunStrength = dark, shin, 1.0
+        su.oneMinusCloudProportion = float(np.float32(1.0) - np.float32(cp))
+        su.overcastStrength = oc
+        cases.append((hours, cp, oc, dark, shin))
+        sphere_out.append(R.sky_layer_run("skysphere", su, gradient, None, clouds, dirs))
+        cloud_out.append(R.sky_layer_run("clouds", su, gradient, None, clouds, dirs))
+    np.savez_compressed(os.path.join(HERE, "sky_layers.npz"), gradient=gradient, clouds=clouds, dirs=dirs, cases=np.array(cases, np.float32),
+                        skysphere=np.array(sphere_out), cloud_layer=np.array(cloud_out))
     print("golden fixtures written to", HERE)
 
 

@@ -151,3 +151,18 @@ def test_fragment_shader_golden(oracle):
     vb = np.concatenate([fi["normalVecInViewSpaceOnlyYaw"], np.zeros((n, 1), np.float32)], 1)
     colour = oracle.compose(cu, z["depth"], z["reflections"], z["refractions"], pos4, nrm4, shade, clip, va, vb)
     assert np.array_equal(bits(colour), bits(z["colour"])), float(np.abs(colour - z["colour"]).max())
+
+
+def test_sky_layer_shaders_golden(oracle):
+    """The oracle's sky-sphere and cloud layer functions against colours the reference's own shader texts produced."""
+    z = np.load(os.path.join(GOLDEN, "sky_layers.npz"))
+    for k, (hours, cp, oc, dark, shin) in enumerate(z["cases"]):
+        su = orc.SkyUniforms()
+        su.sunPosition[:] = oracle.sun_position(hours)
+        su.sunHorizonDarkness, su.sunShininess, su.sunStrength = float(dark), float(shin), 1.0
+        su.oneMinusCloudProportion = float(np.float32(1.0) - np.float32(cp))
+        su.overcastStrength = float(oc)
+        for which, key in (("skysphere", "skysphere"), ("clouds", "cloud_layer")):
+            got = oracle.sky_layer(which, su, z["gradient"], None, z["clouds"], z["dirs"])
+            ok = np.isfinite(z[key][k]).all(axis=1)
+            assert np.array_equal(bits(got[ok]), bits(z[key][k][ok])), (which, float(hours))

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
     "wt_default_animation", "wt_animation_advance", "wt_run_animation",
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
+    "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
 ]
 
 
@@ -76,6 +77,12 @@ class ComposeParams(C.Structure):
     _fields_ = [("fogColourFarAtNoon", C.c_float * 4), ("fogDepthRadiusFar", C.c_float), ("fogDepthRadiusNear", C.c_float),
                 ("softEdgesDeltaDepthThreshold", C.c_float), ("tintDeltaDepthThreshold", C.c_float), ("waterClarity", C.c_float),
                 ("zNear", C.c_float), ("zFar", C.c_float), ("viewportWidth", C.c_float), ("viewportHeight", C.c_float)]
+
+
+class SkyParams(C.Structure):
+    _fields_ = [("timeOfDayInHours", C.c_float), ("cloudProportion", C.c_float), ("overcastStrength", C.c_float), ("sunHorizonDarkness", C.c_float),
+                ("sunShininess", C.c_float), ("sunStrength", C.c_float), ("fogColourFarAtNoon", C.c_float * 4),
+                ("drawStars", C.c_int), ("drawSkysphere", C.c_int), ("drawClouds", C.c_int)]
 
 
 class Outputs(C.Structure):
@@ -146,6 +153,11 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_set_screen_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.wt_compose_frame.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(ComposeParams), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs),
                                    C.c_void_p, C.c_void_p]
+    L.wt_default_sky_params.argtypes = [C.POINTER(SkyParams)]
+    L.wt_default_sky_params.restype = None
+    L.wt_set_sky_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.wt_synthesize_skybox.argtypes = [C.c_void_p, C.POINTER(SkyParams), C.c_int, C.c_void_p]
+    L.wt_get_skybox_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
     L.wt_default_animation.argtypes = [C.POINTER(Animation)]
     L.wt_default_animation.restype = None
     L.wt_animation_advance.argtypes = [C.POINTER(Params), C.POINTER(Animation), C.c_float]
@@ -209,6 +221,12 @@ def project_grid(cam: Camera, displaceable_amplitude: float):
 def default_compose_params(cam: Camera, viewport_w: int, viewport_h: int) -> ComposeParams:
     p = ComposeParams()
     lib().wt_default_compose_params(C.byref(p), C.byref(cam), viewport_w, viewport_h)
+    return p
+
+
+def default_sky_params() -> SkyParams:
+    p = SkyParams()
+    lib().wt_default_sky_params(C.byref(p))
     return p
 
 
@@ -289,6 +307,30 @@ class Context:
         """wt_eval_frame_ex: every output stream of the vertex stage (Outputs holds raw device addresses)."""
         r0, r1 = rows if rows is not None else (0, grid_len)
         return _check(self._lib.wt_eval_frame_ex(self._h, C.byref(frame), grid_len, r0, r1, C.byref(outputs), flags, stream or None), self._h)
+
+    def set_sky_layers(self, gradient: np.ndarray, stars=None, clouds=None):
+        g = np.ascontiguousarray(gradient, np.uint8).reshape(-1, 4)
+        keep, ptrs, sizes = [g], [], []
+        for faces in (stars, clouds):
+            if faces is None:
+                ptrs.append(None); sizes.append(0)
+            else:
+                a = np.ascontiguousarray(faces, np.uint8)
+                keep.append(a)
+                arr = (C.c_void_p * 6)(*[a[f].ctypes.data for f in range(6)])
+                keep.append(arr)
+                ptrs.append(C.cast(arr, C.c_void_p)); sizes.append(a.shape[1])
+        _check(self._lib.wt_set_sky_layers(self._h, g.ctypes.data, len(g), ptrs[0], sizes[0], ptrs[1], sizes[1]), self._h)
+
+    def synthesize_skybox(self, params: "SkyParams", n: int, stream: int = 0):
+        return _check(self._lib.wt_synthesize_skybox(self._h, C.byref(params), n, stream or None), self._h)
+
+    def get_skybox(self) -> np.ndarray:
+        n = C.c_int()
+        _check(self._lib.wt_get_skybox_rgba8(self._h, None, C.byref(n)), self._h)
+        out = np.empty((6, n.value, n.value, 4), np.uint8)
+        _check(self._lib.wt_get_skybox_rgba8(self._h, out.ctypes.data, C.byref(n)), self._h)
+        return out
 
     def set_screen_textures(self, depth: np.ndarray, reflections: np.ndarray, refractions: np.ndarray):
         d = np.ascontiguousarray(depth, np.float32)

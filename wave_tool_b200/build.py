@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libwavetool_b200.so")
 # the production kernel's instantiations are split over four translation units so that they compile in parallel
-SOURCES = ["wt_device.cu", "wt_launch_exact.cu", "wt_launch_exact_shade.cu", "wt_launch_recur.cu", "wt_launch_recur_shade.cu", "wt_compose.cu", "wt_host.cpp"]
+SOURCES = ["wt_device.cu", "wt_launch_exact.cu", "wt_launch_exact_shade.cu", "wt_launch_recur.cu", "wt_launch_recur_shade.cu", "wt_compose.cu", "wt_sky.cu", "wt_host.cpp"]
 HEADERS = ["wt_kernels.cuh", "wt_aux_kernels.cuh", "wt_launch.cuh", "wt_ctx.h", "wt_internal.h", "wt_host_math.h",
            os.path.join("..", "..", "include", "wavetool_b200.h")]
 OBJ_DIR = os.path.join(PKG_DIR, "build")

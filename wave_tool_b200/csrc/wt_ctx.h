@@ -29,6 +29,11 @@ struct wt_ctx {
     // production kernel: padded face atlas in a block-linear CUDA array + a gather-capable texture object
     cudaArray_t sky_array = nullptr, sky_array_black = nullptr;
     cudaTextureObject_t sky_tex = 0, sky_tex_black = 0;
+    // sources of the skybox synthesis (wt_set_sky_layers); sky_surface_ok: sky_array was created for surface writes
+    std::vector<uint8_t> sky_gradient;
+    uchar4 *d_stars = nullptr, *d_clouds = nullptr;
+    int stars_n = 0, clouds_n = 0;
+    bool sky_surface_ok = false;
     // screen-space inputs of the compose pass (wt_set_screen_textures)
     float* d_depth = nullptr;
     uchar4 *d_refl = nullptr, *d_refr = nullptr;

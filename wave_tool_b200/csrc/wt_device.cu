@@ -252,6 +252,7 @@ void wt_destroy(wt_ctx* ctx) {
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
+    cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
     for (int i = 0; i < 4; ++i) {
         if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -323,6 +324,7 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
     for (int f = 0; f < 6; ++f) WT_CUDA(ctx, cudaMemcpy((uint8_t*)ctx->d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice));
     WT_CUDA(ctx, make_sky_atlas(faces, n, &ctx->sky_array, &ctx->sky_tex));
     ctx->sky_n = n;
+    ctx->sky_surface_ok = false;   // this array was not created for surface writes: a later synthesis re-creates it
     return WT_OK;
 }
 

@@ -1,0 +1,300 @@
+// Skybox synthesis — replaces the cubemap render pass of src/render-engine.cpp:306-442: for each
+// of the 6 x n x n texels the clear colour, then the star cubemap (skybox-stars.frag), the sky sphere
+// (skysphere.frag), the cloud cubemap (skybox-clouds.frag) and the fog quad (screen-space-quad.frag) blended in that
+// order with glBlendFunc(GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA) into RGBA8.  One thread per texel; the result is
+// written straight into the context's skybox (linear faces + the padded gather atlas the surface kernel samples).
+// HBM-bound: 4 B written per texel, the two source cubemaps are read with 2-D locality.
+#include <cmath>
+#include <string>
+
+#include "wt_ctx.h"
+
+namespace wt {
+
+struct SkyArgs {
+    uchar4* out;                 // 6 * n * n texels, GL face order
+    int n;
+    const uchar4* stars; int stars_n;     // NULL: layer not drawn
+    const uchar4* clouds; int clouds_n;
+    int draw_sphere;
+    float Lx, Ly, Lz;            // normalize(sunPosition)
+    float sun_y;                 // sunPosition.y (un-normalised, clouds shader)
+    float peak[3], horizon[3];   // the two gradient samples of skysphere.frag:55-56 (per-frame constants, host)
+    float shininess, strength, alpha1;
+    float omp, overcast;         // oneMinusCloudProportion, overcastStrength
+    float fog[4];
+};
+
+__device__ __forceinline__ float mixs(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
+__device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// texture(samplerCube, r): GL 4.1 face selection, per-face CLAMP_TO_EDGE, GL_LINEAR with exact fp32 weights (oracle order)
+__device__ __forceinline__ float4 cube_rgba8(const uchar4* faces, int n, float rx, float ry, float rz) {
+    const float ax = fabsf(rx), ay = fabsf(ry), az = fabsf(rz);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { ma = ax; if (rx >= 0.0f) { face = 0; sc = -rz; tc = -ry; } else { face = 1; sc = rz; tc = -ry; } }
+    else if (ay >= az) { ma = ay; if (ry >= 0.0f) { face = 2; sc = rx; tc = rz; } else { face = 3; sc = rx; tc = -rz; } }
+    else { ma = az; if (rz >= 0.0f) { face = 4; sc = rx; tc = -ry; } else { face = 5; sc = -rx; tc = -ry; } }
+    const float s = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(sc, ma), 1.0f)), t = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(tc, ma), 1.0f));
+    const float um = __fsub_rn(__fmul_rn(s, (float)n), 0.5f), vm = __fsub_rn(__fmul_rn(t, (float)n), 0.5f);
+    const float fu = floorf(um), fv = floorf(vm);
+    const float al = __fsub_rn(um, fu), be = __fsub_rn(vm, fv);
+    const int iu = (int)fu, iv = (int)fv;
+    const int i0 = min(max(iu, 0), n - 1), i1 = min(max(iu + 1, 0), n - 1), j0 = min(max(iv, 0), n - 1), j1 = min(max(iv + 1, 0), n - 1);
+    const uchar4* f = faces + (size_t)face * n * n;
+    const uchar4 t00 = __ldg(f + (size_t)j0 * n + i0), t10 = __ldg(f + (size_t)j0 * n + i1), t01 = __ldg(f + (size_t)j1 * n + i0), t11 = __ldg(f + (size_t)j1 * n + i1);
+    const float oma = __fsub_rn(1.0f, al), omb = __fsub_rn(1.0f, be);
+    const float w00 = __fmul_rn(oma, omb), w10 = __fmul_rn(al, omb), w01 = __fmul_rn(oma, be), w11 = __fmul_rn(al, be);
+    auto ch = [&](unsigned c00, unsigned c10, unsigned c01, unsigned c11) {
+        float acc = __fmul_rn(w00, unorm8(c00));
+        acc = __fadd_rn(acc, __fmul_rn(w10, unorm8(c10)));
+        acc = __fadd_rn(acc, __fmul_rn(w01, unorm8(c01)));
+        return __fadd_rn(acc, __fmul_rn(w11, unorm8(c11)));
+    };
+    return make_float4(ch(t00.x, t10.x, t01.x, t11.x), ch(t00.y, t10.y, t01.y, t11.y), ch(t00.z, t10.z, t01.z, t11.z), 1.0f);
+}
+
+// one layer into the RGBA8 destination: operands clamped to [0,1], Cd' = Cs As + Cd (1 - As) on all four channels,
+// converted back to unorm8 with round-to-nearest (GL 4.1 sections 4.1.7, 2.1.5)
+__device__ __forceinline__ void blend(unsigned dst[4], float r, float g, float b, float a) {
+    const float src[4] = {sat(r), sat(g), sat(b), sat(a)};
+    const float oma = __fsub_rn(1.0f, src[3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float d = unorm8(dst[c]);   // what the blender reads back from the RGBA8 attachment: c / 255
+        const float v = sat(__fadd_rn(__fmul_rn(src[c], src[3]), __fmul_rn(d, oma)));
+        dst[c] = (unsigned)floorf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f));
+    }
+}
+
+__global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
+    const long long total = 6LL * a.n * a.n;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int face = (int)(k / ((long long)a.n * a.n)), j = (int)((k / a.n) % a.n), i = (int)(k % a.n);
+        // direction through the centre of texel (i, j) of the face (inverse of the GL cube-map face table)
+        const float sc = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)i, 0.5f)), (float)a.n), 1.0f);
+        const float tc = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)j, 0.5f)), (float)a.n), 1.0f);
+        float dx, dy, dz;
+        switch (face) {
+            case 0: dx = 1.0f; dy = -tc; dz = -sc; break;
+            case 1: dx = -1.0f; dy = -tc; dz = sc; break;
+            case 2: dx = sc; dy = 1.0f; dz = tc; break;
+            case 3: dx = sc; dy = -1.0f; dz = -tc; break;
+            case 4: dx = sc; dy = -tc; dz = 1.0f; break;
+            default: dx = -sc; dy = -tc; dz = -1.0f; break;
+        }
+        unsigned dst[4] = {255u, 255u, 255u, 255u};                      // glClearColor(1,1,1,1), render-engine.cpp:694,330
+        if (a.stars) {                                                   // skybox-stars.frag:41
+            const float4 s = cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
+            blend(dst, s.x, s.y, s.z, 1.0f);
+        }
+        if (a.draw_sphere) {                                             // skysphere.frag:48-76
+            const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+            const float nx = __fmul_rn(dx, inv), ny = __fmul_rn(dy, inv), nz = __fmul_rn(dz, inv);
+            const float a3 = __fadd_rn(__fadd_rn(__fmul_rn(nx, a.Lx), __fmul_rn(ny, a.Ly)), __fmul_rn(nz, a.Lz));
+            const float spec = a3 > 0.0f ? __fmul_rn(__fmul_rn(a.strength, 1.0f), powf(a3, a.shininess)) : 0.0f;
+            const float night = __fmul_rn(fabsf(a3), __fsub_rn(1.0f, fabsf(a.Ly)));
+            float col[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float diffuse = a3 >= 0.0f ? mixs(a.horizon[c], a.peak[c], a3) : mixs(a.horizon[c], 0.0f, night);
+                col[c] = __fadd_rn(diffuse, spec);
+            }
+            const float alpha = fmaxf(a.alpha1, __fdiv_rn(__fadd_rn(a3, 1.0f), 2.0f));
+            blend(dst, col[0], col[1], col[2], alpha);
+        }
+        if (a.clouds) {                                                  // skybox-clouds.frag:46-67
+            const float4 raw = cube_rgba8(a.clouds, a.clouds_n, dx, dy, dz);
+            const float lin = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, raw.x), __fmul_rn(0.7152f, raw.y)), __fmul_rn(0.0722f, raw.z));
+            const float srgb = lin <= 0.0031308f ? __fmul_rn(12.92f, lin) : __fsub_rn(__fmul_rn(1.055f, powf(lin, __fdiv_rn(1.0f, 2.4f))), 0.055f);
+            const float intensity = fminf(fmaxf(a.sun_y, 0.2f), 1.0f);
+            const float oc = __fmul_rn(sat(a.sun_y), a.overcast);
+            if (srgb > a.omp) {
+                const float ca = __fdiv_rn(__fsub_rn(srgb, a.omp), __fsub_rn(1.0f, a.omp));
+                const float v = mixs(intensity, srgb, oc);
+                blend(dst, v, v, v, mixs(ca, 1.0f, oc));
+            } else {
+                blend(dst, 0.5f, 0.5f, 0.5f, oc);
+            }
+        }
+        blend(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3]);             // screen-space-quad.frag:45
+        a.out[k] = make_uchar4((unsigned char)dst[0], (unsigned char)dst[1], (unsigned char)dst[2], (unsigned char)dst[3]);
+    }
+}
+
+// linear faces -> the padded gather atlas (tile column = face / 2, tile row = face % 2, 1-texel border replicating the edge)
+__global__ void __launch_bounds__(256) sky_atlas_kernel(const uchar4* faces, int n, cudaSurfaceObject_t surf) {
+    const int tile = n + 2, W = 3 * tile, H = 2 * tile;
+    const long long total = (long long)W * H;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(k % W), Y = (int)(k / W);
+        const int face = 2 * (X / tile) + (Y / tile);
+        const int i = min(max(X % tile - 1, 0), n - 1), j = min(max(Y % tile - 1, 0), n - 1);
+        surf2Dwrite(faces[((size_t)face * n + j) * n + i], surf, X * (int)sizeof(uchar4), Y);
+    }
+}
+
+cudaError_t rebuild_sky_atlas(wt_ctx* ctx, const uchar4* d_faces, int n, cudaArray_t* arr, cudaTextureObject_t* tex, bool allocate, cudaStream_t stream) {
+    cudaError_t e;
+    const int tile = n + 2, W = 3 * tile, H = 2 * tile;
+    if (allocate) {
+        if (*tex) { cudaDestroyTextureObject(*tex); *tex = 0; }
+        if (*arr) { cudaFreeArray(*arr); *arr = nullptr; }
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        if ((e = cudaMallocArray(arr, &fmt, W, H, cudaArrayTextureGather | cudaArraySurfaceLoadStore)) != cudaSuccess) return e;
+        cudaResourceDesc res;
+        std::memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = *arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        if ((e = cudaCreateTextureObject(tex, &res, &td, nullptr)) != cudaSuccess) return e;
+    }
+    cudaResourceDesc res;
+    std::memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = *arr;
+    cudaSurfaceObject_t surf = 0;
+    if ((e = cudaCreateSurfaceObject(&surf, &res)) != cudaSuccess) return e;
+    const long long total = (long long)W * H;
+    sky_atlas_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16), 256, 0, stream>>>(d_faces, n, surf);
+    ctx->launches++;
+    e = cudaGetLastError();
+    // the surface object is only a handle: destroying it after the launch is enqueued is safe once the stream has run the kernel
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaDestroySurfaceObject(surf);
+    return e;
+}
+
+// texture(sampler1D, s).rgb of the sky gradient on the host (two samples per frame): GL_LINEAR, CLAMP_TO_EDGE, fp32
+static void gradient_sample(const std::vector<uint8_t>& g, float s, float out[3]) {
+    const int len = (int)(g.size() / 4);
+    const float um = s * (float)len - 0.5f;
+    const float fu = std::floor(um);
+    const float a = um - fu;
+    const long long iu = (long long)fu;
+    const int i0 = (int)std::min<long long>(std::max<long long>(iu, 0), len - 1), i1 = (int)std::min<long long>(std::max<long long>(iu + 1, 0), len - 1);
+    for (int c = 0; c < 3; ++c) out[c] = (1.0f - a) * ((float)g[4 * i0 + c] / 255.0f) + a * ((float)g[4 * i1 + c] / 255.0f);
+}
+
+}  // namespace wt
+
+using namespace wt;
+
+extern "C" {
+
+void wt_default_sky_params(wt_sky_params* out) {   // render-engine.h:220-221,228,230-233
+    if (!out) return;
+    out->timeOfDayInHours = 9.0f;
+    out->cloudProportion = 0.6f;
+    out->overcastStrength = 0.0f;
+    out->sunHorizonDarkness = 0.25f;
+    out->sunShininess = 50.0f;
+    out->sunStrength = 1.0f;
+    out->fogColourFarAtNoon[0] = out->fogColourFarAtNoon[1] = out->fogColourFarAtNoon[2] = 1.0f;
+    out->fogColourFarAtNoon[3] = 0.1f;
+    out->drawStars = out->drawSkysphere = out->drawClouds = 1;
+}
+
+int wt_set_sky_layers(wt_ctx* ctx, const uint8_t* gradient_rgba, int gradient_len, const uint8_t* const stars[6], int stars_n,
+                      const uint8_t* const clouds[6], int clouds_n) {
+    if (!ctx) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_set_sky_layers: ctx is NULL");
+    auto fail = [&](int code, const char* msg) { ctx->err = msg; set_thread_error(code, msg); return code; };
+    if (!gradient_rgba || gradient_len <= 0) return fail(WT_ERR_INVALID_ARGUMENT, "wt_set_sky_layers: the sky gradient is required");
+    if ((stars && (stars_n <= 0 || stars_n > 16384)) || (clouds && (clouds_n <= 0 || clouds_n > 16384))) return fail(WT_ERR_INVALID_ARGUMENT, "wt_set_sky_layers: bad cubemap size");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    ctx->sky_gradient.assign(gradient_rgba, gradient_rgba + 4 * (size_t)gradient_len);
+    cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
+    ctx->d_stars = ctx->d_clouds = nullptr;
+    ctx->stars_n = ctx->clouds_n = 0;
+    cudaError_t e = cudaSuccess;
+    auto upload = [&](const uint8_t* const faces[6], int n, uchar4** dst) {
+        const size_t fb = (size_t)n * n * 4;
+        if ((e = cudaMalloc(dst, 6 * fb)) != cudaSuccess) return;
+        for (int f = 0; f < 6 && e == cudaSuccess; ++f) {
+            if (!faces[f]) { e = cudaErrorInvalidValue; return; }
+            e = cudaMemcpy((uint8_t*)*dst + f * fb, faces[f], fb, cudaMemcpyHostToDevice);
+        }
+    };
+    if (stars) { upload(stars, stars_n, &ctx->d_stars); if (e == cudaSuccess) ctx->stars_n = stars_n; }
+    if (e == cudaSuccess && clouds) { upload(clouds, clouds_n, &ctx->d_clouds); if (e == cudaSuccess) ctx->clouds_n = clouds_n; }
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(WT_ERR_CUDA, cudaGetErrorString(e));
+    return WT_OK;
+}
+
+int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* stream_) {
+    if (!ctx) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_synthesize_skybox: ctx is NULL");
+    auto fail = [&](int code, const std::string& msg) { ctx->err = msg; set_thread_error(code, msg.c_str()); return code; };
+    if (!p || n <= 0 || n > 16384) return fail(WT_ERR_INVALID_ARGUMENT, "wt_synthesize_skybox: bad argument");
+    if (ctx->sky_gradient.empty()) return fail(WT_ERR_NOT_READY, "wt_set_sky_layers has not been called");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaSuccess;
+    const bool fresh = ctx->sky_n != n || !ctx->d_sky || !ctx->sky_surface_ok;
+    if (fresh) {
+        cudaFree(ctx->d_sky);
+        ctx->d_sky = nullptr;
+        e = cudaMalloc(&ctx->d_sky, 6 * (size_t)n * n * sizeof(uchar4));
+    }
+    SkyArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (e == cudaSuccess) {
+        a.out = ctx->d_sky; a.n = n;
+        a.stars = p->drawStars ? ctx->d_stars : nullptr; a.stars_n = ctx->stars_n;
+        a.clouds = p->drawClouds ? ctx->d_clouds : nullptr; a.clouds_n = ctx->clouds_n;
+        a.draw_sphere = p->drawSkysphere;
+        float sun[3];
+        wt_sun_position(p->timeOfDayInHours, sun);                       // render-engine.cpp:289-291
+        const float inv = 1.0f / std::sqrt(sun[0] * sun[0] + sun[1] * sun[1] + sun[2] * sun[2]);   // glm::normalize = v * inversesqrt(dot)
+        a.Lx = sun[0] * inv; a.Ly = sun[1] * inv; a.Lz = sun[2] * inv;
+        a.sun_y = sun[1];
+        const float a1 = 0.25f * (a.Ly + 1.0f), a2 = 1.0f - a1;         // skysphere.frag:53-54
+        float hor[3];
+        gradient_sample(ctx->sky_gradient, a1, a.peak);
+        gradient_sample(ctx->sky_gradient, a2, hor);
+        for (int c = 0; c < 3; ++c) a.horizon[c] = hor[c] * (1.0f - p->sunHorizonDarkness) + 0.0f * p->sunHorizonDarkness;   // :56
+        a.shininess = p->sunShininess; a.strength = p->sunStrength;
+        a.alpha1 = a.Ly < 0.1f ? (a.Ly + 1.0f) / (0.1f + 1.0f) : 1.0f;    // :70
+        a.omp = 1.0f - p->cloudProportion;                               // render-engine.cpp:297
+        a.overcast = p->overcastStrength;
+        const float sy = std::fmin(std::fmax(sun[1], 0.0f), 1.0f);
+        for (int c = 0; c < 3; ++c) a.fog[c] = sy * p->fogColourFarAtNoon[c];   // :295
+        a.fog[3] = p->fogColourFarAtNoon[3];
+        const long long total = 6LL * n * n;
+        sky_synth_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16), 256, 0, stream>>>(a);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = rebuild_sky_atlas(ctx, ctx->d_sky, n, &ctx->sky_array, &ctx->sky_tex, fresh, stream);
+    if (e == cudaSuccess) { ctx->sky_n = n; ctx->sky_surface_ok = true; }
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return fail(WT_ERR_CUDA, cudaGetErrorString(e));
+    return WT_OK;
+}
+
+int wt_get_skybox_rgba8(wt_ctx* ctx, uint8_t* out, int* n_out) {
+    if (!ctx) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_get_skybox_rgba8: ctx is NULL");
+    if (n_out) *n_out = ctx->sky_n;
+    if (!out) return WT_OK;
+    if (!ctx->d_sky) { ctx->err = "no skybox has been set or synthesized"; return set_thread_error(WT_ERR_NOT_READY, ctx->err.c_str()); }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, ctx->d_sky, 6 * (size_t)ctx->sky_n * ctx->sky_n * 4, cudaMemcpyDeviceToHost);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return set_thread_error(WT_ERR_CUDA, ctx->err.c_str()); }
+    return WT_OK;
+}
+
+}  // extern "C"
