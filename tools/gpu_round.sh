@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s -k "skybox_synth" 2>&1 | tail -25
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sky_ -s 6 -c 2 -f -o gpurun_out/s6_sky python tools/time_sky.py 2048 2048 > gpurun_out/s6_sky.log 2>&1
+tail -3 gpurun_out/s6_sky.log

@@ -34,6 +34,7 @@ struct wt_ctx {
     uchar4 *d_stars = nullptr, *d_clouds = nullptr;
     int stars_n = 0, clouds_n = 0;
     bool sky_surface_ok = false;
+    cudaSurfaceObject_t sky_surf = 0;
     // screen-space inputs of the compose pass (wt_set_screen_textures)
     float* d_depth = nullptr;
     uchar4 *d_refl = nullptr, *d_refr = nullptr;

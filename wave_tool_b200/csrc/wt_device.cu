@@ -245,6 +245,7 @@ void wt_destroy(wt_ctx* ctx) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_hm_r); cudaFree(ctx->d_hm_quads);
     cudaFree(ctx->d_sky); cudaFree(ctx->d_sky_black);
+    if (ctx->sky_surf) cudaDestroySurfaceObject(ctx->sky_surf);
     if (ctx->sky_tex) cudaDestroyTextureObject(ctx->sky_tex);
     if (ctx->sky_tex_black) cudaDestroyTextureObject(ctx->sky_tex_black);
     if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
@@ -317,6 +318,7 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
     DeviceGuard g(ctx->device);
     cudaFree(ctx->d_sky);
     ctx->d_sky = nullptr;
+    if (ctx->sky_surf) { cudaDestroySurfaceObject(ctx->sky_surf); ctx->sky_surf = 0; }
     if (ctx->sky_tex) { cudaDestroyTextureObject(ctx->sky_tex); ctx->sky_tex = 0; }
     if (ctx->sky_array) { cudaFreeArray(ctx->sky_array); ctx->sky_array = nullptr; }
     const size_t face_bytes = (size_t)n * n * 4;

@@ -25,6 +25,25 @@ struct SkyArgs {
     float fog[4];
 };
 
+// Byte and floor conversions kept off the XU pipe (I2F / F2I / FRND issue at a quarter of the FP32 rate):
+//  * byte k of a word -> float: PRMT builds the bit pattern of 2^23 + c, one add removes the 2^23 (exact);
+//  * floor(x) for |x| < 2^22: round to nearest by adding 1.5 * 2^23, step down where that rounded up (exact).
+__device__ __forceinline__ float byte_f(unsigned word, unsigned k) { return __fadd_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | k)), -8388608.0f); }
+__device__ __forceinline__ float unorm8f(float f) {   // exact c / 255.0f for integer-valued f in [0,255] (see unorm8)
+    const float R = 1.0f / 255.0f;
+    const float q = __fmul_rn(f, R);
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, f), R, q);
+}
+__device__ __forceinline__ float floor_small(float x, int& as_int) {
+    const float MAGIC = 12582912.0f;
+    const float t = __fadd_rn(x, MAGIC);
+    float r = __fsub_rn(t, MAGIC);
+    int i = __float_as_int(t) - 0x4B400000;
+    if (r > x) { r = __fsub_rn(r, 1.0f); i -= 1; }
+    as_int = i;
+    return r;
+}
+
 __device__ __forceinline__ float mixs(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
 __device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 
@@ -38,40 +57,44 @@ __device__ __forceinline__ float4 cube_rgba8(const uchar4* faces, int n, float r
     else { ma = az; if (rz >= 0.0f) { face = 4; sc = rx; tc = -ry; } else { face = 5; sc = -rx; tc = -ry; } }
     const float s = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(sc, ma), 1.0f)), t = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(tc, ma), 1.0f));
     const float um = __fsub_rn(__fmul_rn(s, (float)n), 0.5f), vm = __fsub_rn(__fmul_rn(t, (float)n), 0.5f);
-    const float fu = floorf(um), fv = floorf(vm);
+    int iu, iv;
+    const float fu = floor_small(um, iu), fv = floor_small(vm, iv);
     const float al = __fsub_rn(um, fu), be = __fsub_rn(vm, fv);
-    const int iu = (int)fu, iv = (int)fv;
     const int i0 = min(max(iu, 0), n - 1), i1 = min(max(iu + 1, 0), n - 1), j0 = min(max(iv, 0), n - 1), j1 = min(max(iv + 1, 0), n - 1);
-    const uchar4* f = faces + (size_t)face * n * n;
-    const uchar4 t00 = __ldg(f + (size_t)j0 * n + i0), t10 = __ldg(f + (size_t)j0 * n + i1), t01 = __ldg(f + (size_t)j1 * n + i0), t11 = __ldg(f + (size_t)j1 * n + i1);
+    const unsigned* f = reinterpret_cast<const unsigned*>(faces) + (size_t)face * n * n;
+    const unsigned t00 = __ldg(f + (size_t)j0 * n + i0), t10 = __ldg(f + (size_t)j0 * n + i1), t01 = __ldg(f + (size_t)j1 * n + i0), t11 = __ldg(f + (size_t)j1 * n + i1);
     const float oma = __fsub_rn(1.0f, al), omb = __fsub_rn(1.0f, be);
     const float w00 = __fmul_rn(oma, omb), w10 = __fmul_rn(al, omb), w01 = __fmul_rn(oma, be), w11 = __fmul_rn(al, be);
-    auto ch = [&](unsigned c00, unsigned c10, unsigned c01, unsigned c11) {
-        float acc = __fmul_rn(w00, unorm8(c00));
-        acc = __fadd_rn(acc, __fmul_rn(w10, unorm8(c10)));
-        acc = __fadd_rn(acc, __fmul_rn(w01, unorm8(c01)));
-        return __fadd_rn(acc, __fmul_rn(w11, unorm8(c11)));
+    auto ch = [&](unsigned k) {
+        float acc = __fmul_rn(w00, unorm8f(byte_f(t00, k)));
+        acc = __fadd_rn(acc, __fmul_rn(w10, unorm8f(byte_f(t10, k))));
+        acc = __fadd_rn(acc, __fmul_rn(w01, unorm8f(byte_f(t01, k))));
+        return __fadd_rn(acc, __fmul_rn(w11, unorm8f(byte_f(t11, k))));
     };
-    return make_float4(ch(t00.x, t10.x, t01.x, t11.x), ch(t00.y, t10.y, t01.y, t11.y), ch(t00.z, t10.z, t01.z, t11.z), 1.0f);
+    return make_float4(ch(0), ch(1), ch(2), 1.0f);
 }
 
 // one layer into the RGBA8 destination: operands clamped to [0,1], Cd' = Cs As + Cd (1 - As) on all four channels,
 // converted back to unorm8 with round-to-nearest (GL 4.1 sections 4.1.7, 2.1.5)
-__device__ __forceinline__ void blend(unsigned dst[4], float r, float g, float b, float a) {
+// dst holds the attachment's bytes as integer-valued floats
+__device__ __forceinline__ void blend(float dst[4], float r, float g, float b, float a) {
     const float src[4] = {sat(r), sat(g), sat(b), sat(a)};
     const float oma = __fsub_rn(1.0f, src[3]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float d = unorm8(dst[c]);   // what the blender reads back from the RGBA8 attachment: c / 255
+        const float d = unorm8f(dst[c]);   // what the blender reads back from the RGBA8 attachment: c / 255
         const float v = sat(__fadd_rn(__fmul_rn(src[c], src[3]), __fmul_rn(d, oma)));
-        dst[c] = (unsigned)floorf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f));
+        int unused;
+        dst[c] = floor_small(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f), unused);
     }
 }
 
 __global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
-    const long long total = 6LL * a.n * a.n;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-        const int face = (int)(k / ((long long)a.n * a.n)), j = (int)((k / a.n) % a.n), i = (int)(k % a.n);
+    // grid = (ceil(n / 256), n, 6): the face and the row come from the block index (no integer divisions, and the face
+    // switch below is uniform per block)
+    const int face = blockIdx.z, j = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n) {
+        const size_t k = ((size_t)face * a.n + j) * a.n + i;
         // direction through the centre of texel (i, j) of the face (inverse of the GL cube-map face table)
         const float sc = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)i, 0.5f)), (float)a.n), 1.0f);
         const float tc = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)j, 0.5f)), (float)a.n), 1.0f);
@@ -84,7 +107,7 @@ __global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
             case 4: dx = sc; dy = -tc; dz = 1.0f; break;
             default: dx = -sc; dy = -tc; dz = -1.0f; break;
         }
-        unsigned dst[4] = {255u, 255u, 255u, 255u};                      // glClearColor(1,1,1,1), render-engine.cpp:694,330
+        float dst[4] = {255.0f, 255.0f, 255.0f, 255.0f};                 // glClearColor(1,1,1,1), render-engine.cpp:694,330
         if (a.stars) {                                                   // skybox-stars.frag:41
             const float4 s = cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
             blend(dst, s.x, s.y, s.z, 1.0f);
@@ -119,19 +142,21 @@ __global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
             }
         }
         blend(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3]);             // screen-space-quad.frag:45
-        a.out[k] = make_uchar4((unsigned char)dst[0], (unsigned char)dst[1], (unsigned char)dst[2], (unsigned char)dst[3]);
+        // pack the four integer-valued floats (0..255) into RGBA8: 2^23 + c has c in its low mantissa byte
+        const unsigned b0 = __float_as_uint(__fadd_rn(dst[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rn(dst[1], 8388608.0f));
+        const unsigned b2 = __float_as_uint(__fadd_rn(dst[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rn(dst[3], 8388608.0f));
+        reinterpret_cast<unsigned*>(a.out)[k] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
     }
 }
 
 // linear faces -> the padded gather atlas (tile column = face / 2, tile row = face % 2, 1-texel border replicating the edge)
 __global__ void __launch_bounds__(256) sky_atlas_kernel(const uchar4* faces, int n, cudaSurfaceObject_t surf) {
-    const int tile = n + 2, W = 3 * tile, H = 2 * tile;
-    const long long total = (long long)W * H;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-        const int X = (int)(k % W), Y = (int)(k / W);
-        const int face = 2 * (X / tile) + (Y / tile);
-        const int i = min(max(X % tile - 1, 0), n - 1), j = min(max(Y % tile - 1, 0), n - 1);
-        surf2Dwrite(faces[((size_t)face * n + j) * n + i], surf, X * (int)sizeof(uchar4), Y);
+    // grid = (ceil(tile / 256), tile, 6): one block row per atlas row of one face tile
+    const int tile = n + 2;
+    const int face = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < tile) {
+        const int i = min(max(x - 1, 0), n - 1), j = min(max(y - 1, 0), n - 1);
+        surf2Dwrite(faces[((size_t)face * n + j) * n + i], surf, ((face / 2) * tile + x) * (int)sizeof(uchar4), (face % 2) * tile + y);
     }
 }
 
@@ -154,21 +179,12 @@ cudaError_t rebuild_sky_atlas(wt_ctx* ctx, const uchar4* d_faces, int n, cudaArr
         td.readMode = cudaReadModeNormalizedFloat;
         td.normalizedCoords = 0;
         if ((e = cudaCreateTextureObject(tex, &res, &td, nullptr)) != cudaSuccess) return e;
+        if (ctx->sky_surf) { cudaDestroySurfaceObject(ctx->sky_surf); ctx->sky_surf = 0; }
+        if ((e = cudaCreateSurfaceObject(&ctx->sky_surf, &res)) != cudaSuccess) return e;   // kept for the life of the array
     }
-    cudaResourceDesc res;
-    std::memset(&res, 0, sizeof(res));
-    res.resType = cudaResourceTypeArray;
-    res.res.array.array = *arr;
-    cudaSurfaceObject_t surf = 0;
-    if ((e = cudaCreateSurfaceObject(&surf, &res)) != cudaSuccess) return e;
-    const long long total = (long long)W * H;
-    sky_atlas_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16), 256, 0, stream>>>(d_faces, n, surf);
+    sky_atlas_kernel<<<dim3((tile + 255) / 256, tile, 6), 256, 0, stream>>>(d_faces, n, ctx->sky_surf);
     ctx->launches++;
-    e = cudaGetLastError();
-    // the surface object is only a handle: destroying it after the launch is enqueued is safe once the stream has run the kernel
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaDestroySurfaceObject(surf);
-    return e;
+    return cudaGetLastError();
 }
 
 // texture(sampler1D, s).rgb of the sky gradient on the host (two samples per frame): GL_LINEAR, CLAMP_TO_EDGE, fp32
@@ -270,8 +286,7 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* strea
         const float sy = std::fmin(std::fmax(sun[1], 0.0f), 1.0f);
         for (int c = 0; c < 3; ++c) a.fog[c] = sy * p->fogColourFarAtNoon[c];   // :295
         a.fog[3] = p->fogColourFarAtNoon[3];
-        const long long total = 6LL * n * n;
-        sky_synth_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16), 256, 0, stream>>>(a);
+        sky_synth_kernel<<<dim3((n + 255) / 256, n, 6), 256, 0, stream>>>(a);
         ctx->launches++;
         e = cudaGetLastError();
     }
