@@ -338,6 +338,10 @@ def run_ours(args):
                  "max_position_deviation_between_modes": dpos, "position_tolerance": 1e-4 * float(total_amp),
                  "max_normal_deviation_rad_between_modes": float(dn.max().item()), "normal_tolerance_rad": 1e-3,
                  "checked_on": "all %d vertices of the last timed frame, on the device" % n}
+        if L > 8192:
+            other["note"] = ("on a 16384^2 grid the near-field vertex spacing is ~100 ulp of the fp32 coordinates: the reference's own fp32 "
+                             "evaluation sits up to ~3e-3 rad from its fp64 twin there, and the two phase modes round differently; "
+                             "tests/test_gpu_parity.py::test_cfg5_edge_cameras_16384 gates each mode against that measured noise floor")
 
     # gather the per-frame digests of the timed frames (the only collective; after the timed region)
     launch(Wm, Wm + K, with_cks=True)

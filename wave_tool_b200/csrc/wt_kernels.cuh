@@ -12,9 +12,13 @@
 //                             MODE 0  bit-faithful fp32 phase + one MUFU sin/cos pair per vertex-wave
 //                             MODE 1  one MUFU seed per wave per R rows, the other rows by complex
 //                                     rotation (the phase is affine in the row index along a column)
-//   surface_reference_order_kernel — straight transliteration of the shader (5 full evaluations per
-//                           vertex, libdevice sincosf, IEEE sqrt/div); used to cross-check the
-//                           production kernel at full grid sizes and as the "naive GPU port" timing.
+//                           With VARY also gl_Position, the height-0 NDC position, the heightmap sample and
+//                           the yaw-only view-space normal (water-grid.vert:141,150-154,193).
+//                           Work items (strip x row chunk) are static (one per CTA) or pulled from an
+//                           atomic queue by a persistent grid (wt_launch.cuh).
+//   surface_reference_order_kernel (wt_aux_kernels.cuh) — straight transliteration of the shader (5 full
+//                           evaluations per vertex, libdevice sincosf, IEEE sqrt/div); used to cross-check
+//                           the production kernel at full grid sizes and as the "naive GPU port" timing.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -567,13 +571,8 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
 #pragma unroll
                 for (int j = 1; j < R; ++j) {
                     // e^{i(k + dk)} = e^{ik} e^{i dk}
-#ifdef WT_SCALAR_ROT
-                    const f2 c2 = make_float2(fmaf(c.x, cd.x, -s.x * sd.x), fmaf(c.y, cd.y, -s.y * sd.y));
-                    s = make_float2(fmaf(s.x, cd.x, c.x * sd.x), fmaf(s.y, cd.y, c.y * sd.y));
-#else
                     const f2 c2 = fma2(c, cd, mul2(make_float2(-s.x, -s.y), sd));
                     s = fma2(s, cd, mul2(c, sd));
-#endif
                     c = c2;
                     px[j] = fma2(bc(wk.cX), c, px[j]);
                     py[j] = fma2(bc(wk.A), s, py[j]);

@@ -27,7 +27,7 @@ struct SkyArgs {
 
 // Byte and floor conversions kept off the XU pipe (I2F / F2I / FRND issue at a quarter of the FP32 rate):
 //  * byte k of a word -> float: PRMT builds the bit pattern of 2^23 + c, one add removes the 2^23 (exact);
-//  * floor(x) for |x| < 2^22: round to nearest by adding 1.5 * 2^23, step down where that rounded up (exact).
+//  * floor(x) for |x| < 2^22: x + 1.5 * 2^23 is positive, so adding with round-toward-zero floors it (exact).
 __device__ __forceinline__ float byte_f(unsigned word, unsigned k) { return __fadd_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | k)), -8388608.0f); }
 __device__ __forceinline__ float unorm8f(float f) {   // exact c / 255.0f for integer-valued f in [0,255] (see unorm8)
     const float R = 1.0f / 255.0f;
@@ -36,12 +36,9 @@ __device__ __forceinline__ float unorm8f(float f) {   // exact c / 255.0f for in
 }
 __device__ __forceinline__ float floor_small(float x, int& as_int) {
     const float MAGIC = 12582912.0f;
-    const float t = __fadd_rn(x, MAGIC);
-    float r = __fsub_rn(t, MAGIC);
-    int i = __float_as_int(t) - 0x4B400000;
-    if (r > x) { r = __fsub_rn(r, 1.0f); i -= 1; }
-    as_int = i;
-    return r;
+    const float t = __fadd_rz(x, MAGIC);
+    as_int = __float_as_int(t) - 0x4B400000;
+    return __fsub_rn(t, MAGIC);
 }
 
 __device__ __forceinline__ float mixs(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
