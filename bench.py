@@ -263,21 +263,20 @@ def run_ours(args):
     ms_per_step = ms / K
 
     # ---- end-to-end through the C ABI with HOST inputs/outputs -----------------------------------
-    # per step: camera+params (host structs) -> wt_build_frame (host prologue) -> wt_eval_frame with the
-    # digest -> device->host read of the 40-byte result into pinned memory, synchronised every step.
-    pinned = torch.empty(40, dtype=torch.uint8).pin_memory()
+    # per step ONE call, wt_step_host: camera + params (host structs) -> wt_build_frame (host prologue) -> fused kernel
+    # with the digest -> the 40-byte result copied to pinned host memory, stream synchronised every step.
     total_amp = api.total_amplitude(waves)
-    h2d = C.sizeof(api.Frame) + 32 * W            # the uniforms + wave table every launch carries to the device
+    h2d = C.sizeof(api.Frame) + 32 * W            # the uniforms + wave table every launch carries to the device (kernel parameters)
     d2h = 40
 
+    e2e_params = [scenes.animation_params(my_frames[min(Wm + k, len(my_frames) - 1)]) for k in range(K)]   # host inputs of the timed steps
+    e2e_out = api.Checksum()
+
     def e2e_step(k):
-        f = my_frames[Wm + k] if Wm + k < len(my_frames) else my_frames[-1]
-        st, fr = api.build_frame(cam, scenes.animation_params(f), total_amp)
+        # ONE C-ABI call per step: host camera + parameters in, the frame's digest (host) out
         slot = k % ring
-        ctx.eval_frame(fr, L, pos.data_ptr() + slot * n * 16, nrm.data_ptr() + slot * n * 16, (shd.data_ptr() + slot * n * 16) if shade else 0,
-                       cks.data_ptr(), flags=flags | api.FLAG_CHECKSUM, rows=rows, stream=sp)
-        pinned.copy_(cks[:40], non_blocking=True)
-        stream.synchronize()
+        ctx.step_host(cam, e2e_params[k % K], total_amp, L, pos.data_ptr() + slot * n * 16, nrm.data_ptr() + slot * n * 16,
+                      (shd.data_ptr() + slot * n * 16) if shade else 0, flags=flags, rows=rows, stream=sp, out=e2e_out)
 
     for k in range(3):
         e2e_step(k)
@@ -405,7 +404,7 @@ def run_ours(args):
             "roofline": primary,
             "roofline_secondary": secondary,
             "e2e": {"value": e2e_value, "unit": "vertex-waves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "host camera/params -> wt_build_frame -> wt_eval_frame(+digest) -> 40-byte digest read back to pinned host memory, synchronised every step"},
+                    "what": "one wt_step_host call per step: host camera/params -> wt_build_frame -> fused kernel (+digest) -> 40-byte digest copied to pinned host memory, stream synchronised"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "digest_of_timed_frames": {k: (int(v) if not isinstance(v, float) else v) for k, v in digest_of_digests.items()},

@@ -301,6 +301,14 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
                      unsigned row_end, void* d_position_ring, void* d_normal_ring, void* d_shade_ring, unsigned ring_depth,
                      void* d_checksums, unsigned flags, void* cuda_stream, unsigned* n_evaluated);
 
+/* One frame from HOST inputs to a HOST result (synchronous on `cuda_stream`): wt_build_frame (camera + parameters ->
+ * uniforms, projected grid), the evaluation into the caller's device buffers, and the frame's digest copied back to
+ * *h_checksum through pinned memory.  Returns WT_NO_GRID (zero digest, nothing launched) when the frustum misses the
+ * water.  The per-frame round trip of an application that keeps the vertex data on the GPU, as the reference does. */
+int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_wave_amplitude, unsigned grid_len,
+                 unsigned row_begin, unsigned row_end, void* d_position, void* d_normal, void* d_shade, unsigned flags,
+                 wt_checksum* h_checksum, void* cuda_stream);
+
 /* Host-buffer convenience (synchronous): evaluates into ctx-owned device scratch and copies the
  * requested outputs to HOST memory.  Any of h_position/h_normal/h_shade/h_checksum may be NULL. */
 int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsigned row_begin, unsigned row_end,

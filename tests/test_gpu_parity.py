@@ -553,6 +553,25 @@ def test_skybox_synthesis_matches_oracle(oracle, hm, hours, cp, oc, layers):
     assert np.array_equal(a["shade"].view(np.uint32), b["shade"].view(np.uint32))
 
 
+def test_step_host_round_trip(oracle, hm):
+    """wt_step_host = wt_build_frame + wt_eval_frame(+digest) + read-back in one call: same digest as the separate calls,
+    and WT_NO_GRID with a zero digest when the camera looks away from the water."""
+    torch = torch_mod()
+    L = 300
+    sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(13), L, hm, skybox=scenes.procedural_skybox(32))
+    ctx = sc.make_context()
+    st, frame = sc.frame()
+    n = L * L
+    b = [torch.empty((n, 4), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for flags in (api.FLAG_SHADE, api.FLAG_SHADE | api.FLAG_FAST_PHASE, 0):
+        want = gpu_eval(ctx, frame, L, flags=flags, checksum=True)["checksum"]
+        st, got = ctx.step_host(sc.cam, sc.params, sc.total_amplitude, L, b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr() if flags & 1 else 0,
+                                flags=flags, stream=torch.cuda.current_stream().cuda_stream)
+        assert st == api.WT_OK and got.as_tuple() == tuple(want)
+    st, got = ctx.step_host(scenes.camera(**scenes.EDGE_CAMERAS["looking_up_no_grid"]), sc.params, sc.total_amplitude, L, b[0].data_ptr(), b[1].data_ptr())
+    assert st == api.WT_NO_GRID and got.vertices == 0
+
+
 def test_skybox_synthesis_argument_checks(hm):
     sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)
     ctx = sc.make_context()

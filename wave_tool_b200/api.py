@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
     "wt_default_animation", "wt_animation_advance", "wt_run_animation",
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
-    "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
+    "wt_step_host", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
 ]
 
 
@@ -153,6 +153,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_set_screen_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.wt_compose_frame.argtypes = [C.c_void_p, C.POINTER(Frame), C.POINTER(ComposeParams), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs),
                                    C.c_void_p, C.c_void_p]
+    L.wt_step_host.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Params), C.c_float, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_uint, C.POINTER(Checksum), C.c_void_p]
     L.wt_default_sky_params.argtypes = [C.POINTER(SkyParams)]
     L.wt_default_sky_params.restype = None
     L.wt_set_sky_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -307,6 +309,15 @@ class Context:
         """wt_eval_frame_ex: every output stream of the vertex stage (Outputs holds raw device addresses)."""
         r0, r1 = rows if rows is not None else (0, grid_len)
         return _check(self._lib.wt_eval_frame_ex(self._h, C.byref(frame), grid_len, r0, r1, C.byref(outputs), flags, stream or None), self._h)
+
+    def step_host(self, cam: Camera, params: Params, total_wave_amplitude: float, grid_len: int, d_pos: int, d_normal: int, d_shade: int = 0,
+                  flags: int = 0, rows=None, stream: int = 0, out: "Checksum | None" = None):
+        """wt_step_host: host camera/params in, the frame's digest (host) out; returns (status, Checksum)."""
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        cks = out if out is not None else Checksum()
+        st = _check(self._lib.wt_step_host(self._h, C.byref(cam), C.byref(params), C.c_float(total_wave_amplitude), grid_len, r0, r1,
+                                           d_pos, d_normal, d_shade or None, flags, C.byref(cks), stream or None), self._h)
+        return st, cks
 
     def set_sky_layers(self, gradient: np.ndarray, stars=None, clouds=None):
         g = np.ascontiguousarray(gradient, np.uint8).reshape(-1, 4)

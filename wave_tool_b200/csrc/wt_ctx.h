@@ -43,6 +43,7 @@ struct wt_ctx {
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
     size_t s_elems = 0;
     wt_checksum* s_cks = nullptr;
+    wt_checksum* h_cks_pinned = nullptr;   // pinned staging record of wt_step_host
     uint64_t launches = 0;
     // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
     int* d_queues = nullptr;

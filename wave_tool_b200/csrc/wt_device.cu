@@ -254,6 +254,7 @@ void wt_destroy(wt_ctx* ctx) {
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
     cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
+    if (ctx->h_cks_pinned) cudaFreeHost(ctx->h_cks_pinned);
     for (int i = 0; i < 4; ++i) {
         if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -490,6 +491,30 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     if (n_evaluated) *n_evaluated = drawn;
+    return WT_OK;
+}
+
+// One whole frame from HOST inputs to a HOST result in a single call: camera + parameters -> wt_build_frame (the
+// reference's CPU prologue) -> fused kernel into the caller's device buffers -> the frame's digest copied back through
+// a pinned staging record -> stream synchronised.  This is the per-frame round trip of a host application that keeps
+// the vertex data on the GPU (as the reference does) and reads back a scalar result.
+int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_amp, unsigned L, unsigned r0, unsigned r1,
+                 void* d_pos, void* d_nrm, void* d_shade, unsigned flags, wt_checksum* h_out, void* stream_) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_step_host: ctx is NULL");
+    if (!cam || !params || !h_out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_host: NULL argument");
+    wt_frame frame;
+    int st = wt_build_frame(cam, params, total_amp, &frame);
+    if (st < 0) return fail(ctx, st, std::string("wt_step_host: ") + wt_last_error(nullptr));
+    std::memset(h_out, 0, sizeof(*h_out));
+    if (st == WT_NO_GRID) return WT_NO_GRID;
+    DeviceGuard g(ctx->device);
+    if (!ctx->h_cks_pinned) WT_CUDA(ctx, cudaMallocHost(&ctx->h_cks_pinned, sizeof(wt_checksum)));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->s_cks, flags | WT_FLAG_CHECKSUM, stream_);
+    if (st != WT_OK) return st;
+    WT_CUDA(ctx, cudaMemcpyAsync(ctx->h_cks_pinned, ctx->s_cks, sizeof(wt_checksum), cudaMemcpyDeviceToHost, stream));
+    WT_CUDA(ctx, cudaStreamSynchronize(stream));
+    *h_out = *ctx->h_cks_pinned;
     return WT_OK;
 }
 
