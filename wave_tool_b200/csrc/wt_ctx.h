@@ -51,6 +51,10 @@ struct wt_ctx {
     // small frames: internal streams on which consecutive frames of a batch overlap (created on first use)
     cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    // digests: a ring of pre-armed accumulator records + finished-warp counters, one per production launch in flight
+    wt_checksum* d_cks_acc = nullptr;
+    int* d_cks_done = nullptr;
+    unsigned cks_next = 0;
     // WT_TRACE diagnostic: per work item {smid, cta, t_start, t_end} of the most recent production launch
     unsigned long long* d_trace = nullptr;
     size_t trace_cap = 0, trace_items = 0;

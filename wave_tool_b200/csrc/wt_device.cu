@@ -234,6 +234,11 @@ int wt_create(wt_ctx** out, int device) {
         const uint8_t* const faces[6] = {black, black, black, black, black, black};
         WT_CUDA(nullptr, make_sky_atlas(faces, 1, &ctx->sky_array_black, &ctx->sky_tex_black));
     }
+    WT_CUDA(nullptr, cudaMalloc(&ctx->d_cks_acc, N_QUEUES * sizeof(wt_checksum)));
+    WT_CUDA(nullptr, cudaMalloc(&ctx->d_cks_done, N_QUEUES * sizeof(int)));
+    WT_CUDA(nullptr, cudaMemset(ctx->d_cks_done, 0, N_QUEUES * sizeof(int)));
+    checksum_init_kernel<<<(N_QUEUES + 127) / 128, 128>>>(ctx->d_cks_acc, (int)N_QUEUES);   // armed: zero sums, min/max keys at their identities
+    WT_CUDA(nullptr, cudaDeviceSynchronize());
     WT_CUDA(nullptr, cudaMalloc(&ctx->d_queues, 2 * N_QUEUES * sizeof(int)));
     WT_CUDA(nullptr, cudaMemset(ctx->d_queues, 0, 2 * N_QUEUES * sizeof(int)));
     *out = ctx;
@@ -252,6 +257,7 @@ void wt_destroy(wt_ctx* ctx) {
     if (ctx->sky_array_black) cudaFreeArray(ctx->sky_array_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done);
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
     cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
     if (ctx->h_cks_pinned) cudaFreeHost(ctx->h_cks_pinned);
@@ -338,9 +344,10 @@ int wt_eval_frame(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, u
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalArgs a = make_args(ctx, *frame, L, r0, r1, d_pos, d_nrm, d_shade, d_cks, flags);
-    if (a.cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    const bool ref_cks = a.cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digest itself
+    if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
-    if (a.cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    if (ref_cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     return WT_OK;
 }
@@ -358,9 +365,10 @@ int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalArgs a = make_args(ctx, *frame, L, r0, r1, out->position, out->normal, out->shade, out->checksum, flags);
     if (vary) { a.clip = (float4*)out->clip_position; a.vary_a = (float4*)out->varyings_a; a.vary_b = (float4*)out->varyings_b; }
-    if (a.cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    const bool ref_cks = a.cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digest itself
+    if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
-    if (a.cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    if (ref_cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     return WT_OK;
 }
@@ -438,7 +446,8 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool cks = flags & WT_FLAG_CHECKSUM;
-    if (cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    const bool ref_cks = cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digests itself
+    if (ref_cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     const size_t slot = (size_t)(r1 - r0) * L;
     FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
     WT_CUDA(ctx, fan.begin());
@@ -449,7 +458,7 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
         WT_CUDA(ctx, launch_eval(ctx, a, flags, fan.stream_for(f)));
     }
     WT_CUDA(ctx, fan.end());
-    if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    if (ref_cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     return WT_OK;
 }
@@ -469,7 +478,8 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool cks = flags & WT_FLAG_CHECKSUM;
-    if (cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    const bool ref_cks = cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digests itself
+    if (ref_cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     const size_t slot = (size_t)(r1 - r0) * L;
     unsigned drawn = 0;
     FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
@@ -484,11 +494,13 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
             WT_CUDA(ctx, launch_eval(ctx, a, flags, fan.stream_for(k)));
             ++drawn;
+        } else if (cks && !ref_cks) {
+            WT_CUDA(ctx, cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), fan.stream_for(k)));   // nothing drawn: zero digest
         }
         for (unsigned s_ = 0; s_ < stride; ++s_) wt_animation_advance(params, anim, dt);
     }
     WT_CUDA(ctx, fan.end());
-    if (cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    if (ref_cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     if (n_evaluated) *n_evaluated = drawn;
     return WT_OK;
@@ -508,11 +520,17 @@ int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, flo
     std::memset(h_out, 0, sizeof(*h_out));
     if (st == WT_NO_GRID) return WT_NO_GRID;
     DeviceGuard g(ctx->device);
-    if (!ctx->h_cks_pinned) WT_CUDA(ctx, cudaMallocHost(&ctx->h_cks_pinned, sizeof(wt_checksum)));
+    if (!ctx->h_cks_pinned) WT_CUDA(ctx, cudaHostAlloc(&ctx->h_cks_pinned, sizeof(wt_checksum), cudaHostAllocMapped));
     cudaStream_t stream = (cudaStream_t)stream_;
-    st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->s_cks, flags | WT_FLAG_CHECKSUM, stream_);
-    if (st != WT_OK) return st;
-    WT_CUDA(ctx, cudaMemcpyAsync(ctx->h_cks_pinned, ctx->s_cks, sizeof(wt_checksum), cudaMemcpyDeviceToHost, stream));
+    if (flags & WT_FLAG_REFERENCE_ORDER) {
+        st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->s_cks, flags | WT_FLAG_CHECKSUM, stream_);
+        if (st != WT_OK) return st;
+        WT_CUDA(ctx, cudaMemcpyAsync(ctx->h_cks_pinned, ctx->s_cks, sizeof(wt_checksum), cudaMemcpyDeviceToHost, stream));
+    } else {
+        // the kernel's last warp writes the finished digest straight into the mapped host record: no copy to enqueue
+        st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned, flags | WT_FLAG_CHECKSUM, stream_);
+        if (st != WT_OK) return st;
+    }
     WT_CUDA(ctx, cudaStreamSynchronize(stream));
     *h_out = *ctx->h_cks_pinned;
     return WT_OK;

@@ -71,7 +71,11 @@ struct EvalArgs {
     float4* pos;
     float4* nrm;
     float4* shade;
-    wt_checksum* cks;   // NULL unless WT_FLAG_CHECKSUM
+    wt_checksum* cks;   // NULL unless WT_FLAG_CHECKSUM: where the finished digest goes (device memory or mapped host memory)
+    // production kernel: a pre-armed accumulator record + a count of finished warps (wt_ctx ring); the last warp to
+    // finish decodes the record into *cks and re-arms both, so a digest costs no extra launch
+    wt_checksum* cks_acc;
+    int* cks_done;
     // WT_FLAG_VARYINGS: the remaining vertex-stage outputs of water-grid.vert (:150-154, :141, :193)
     float4* clip;       // gl_Position = viewProjection * position
     float4* vary_a;     // (xyPositionNDCSpaceHeight0.x, .y, heightmap_colour.r, 0)
@@ -767,7 +771,31 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         // the last warp to run dry re-arms the queue for the next launch that uses it
         if (atomicAdd(a.queue + 1, 1) == (int)gridDim.x - 1) { a.queue[1] = 0; __threadfence(); a.queue[0] = 0; }
     }
-    if (CKS) acc.flush(a.cks);
+    if (CKS) {
+        acc.flush(a.cks_acc);
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(a.cks_done, 1) == (int)gridDim.x - 1) {
+                __threadfence();
+                wt_checksum* const r = a.cks_acc;
+                wt_checksum out;
+                out.position_bits = atomicAdd((unsigned long long*)&r->position_bits, 0ULL);
+                out.normal_bits = atomicAdd((unsigned long long*)&r->normal_bits, 0ULL);
+                out.shade_bits = atomicAdd((unsigned long long*)&r->shade_bits, 0ULL);
+                out.vertices = atomicAdd((unsigned long long*)&r->vertices, 0ULL);
+                out.min_y = key_float(atomicAdd((unsigned*)&r->min_y, 0u));
+                out.max_y = key_float(atomicAdd((unsigned*)&r->max_y, 0u));
+                *a.cks = out;
+                // re-arm for the next launch that is handed this record
+                r->position_bits = 0; r->normal_bits = 0; r->shade_bits = 0; r->vertices = 0;
+                *(unsigned*)&r->min_y = 0xffffffffu;
+                *(unsigned*)&r->max_y = 0u;
+                __threadfence();
+                *a.cks_done = 0;
+                __threadfence_system();   // *cks may live in mapped host memory (wt_step_host)
+            }
+        }
+    }
 }
 
 }  // namespace wt

@@ -85,6 +85,11 @@ cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>&
         table.w[i].phi = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
     }
     a.dbg = g_knobs.dbg;
+    if (CKS) {
+        const unsigned slot = ctx->cks_next++ % N_QUEUES;
+        a.cks_acc = ctx->d_cks_acc + slot;
+        a.cks_done = ctx->d_cks_done + slot;
+    }
     kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
