@@ -311,6 +311,38 @@ def test_ragged_and_tiny_grids(oracle, hm, mode):
 
 
 @pytest.mark.parametrize("mode", list(MODES))
+def test_maximum_grid_length_row_bands(oracle, hm, mode):
+    """grid_len = 32768, the largest the ABI accepts (1 G vertices, 34 GB per full frame): row bands at the bottom, the
+    middle and the top against the oracle, with the same fp32-noise-aware gate as cfg5 (the vertex spacing is half of
+    cfg5's); grid_len = 32769 is refused."""
+    torch = torch_mod()
+    L = 32768
+    sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(pos=(0.0, 30.0, 70.0), pitch=-25.0), scenes.animation_params(4), L, hm)
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    for band in [(0, 3), (16383, 16386), (32765, 32768)]:
+        got = gpu_eval(ctx, frame, L, rows=band, flags=MODES[mode])
+        rows = [band[0] + 1]
+        ids = rows_to_ids(rows, L)
+        want = sc.oracle_eval(oracle, ids=ids)
+        truth = sc.oracle_eval(oracle, ids=ids, f64=True)
+        sub = take_rows(got, rows, L, row_begin=band[0])
+        tol = 1e-4 * sc.total_amplitude
+        o_err = np.abs(want["pos"][:, :3].astype(np.float64) - truth["pos"][:, :3]).max(axis=1)
+        g_err = np.abs(sub["pos"][:, :3].astype(np.float64) - want["pos"][:, :3]).max(axis=1)
+        assert g_err.max() <= max(tol, 2.0 * o_err.max()), (band, g_err.max(), o_err.max())
+        ang = np.minimum(angle_between(sub["normal"][:, :3], want["normal"][:, :3]), angle_between(sub["normal"][:, :3], -want["normal"][:, :3]))
+        o_ang = np.minimum(angle_between(want["normal"][:, :3], truth["normal"][:, :3].astype(np.float32)),
+                           angle_between(want["normal"][:, :3], -truth["normal"][:, :3].astype(np.float32)))
+        for q in (0.5, 0.999, 1.0):
+            assert np.quantile(ang, q) <= max(1e-3 if q > 0.9 else 1e-4, 2.0 * np.quantile(o_ang, q)), (band, q, np.quantile(ang, q), np.quantile(o_ang, q))
+    b = torch.empty((8, 4), dtype=torch.float32, device="cuda")
+    with pytest.raises(api.WaveToolError):
+        ctx.eval_frame(frame, 32769, b.data_ptr(), b.data_ptr(), rows=(0, 1))
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 def test_wave_count_tiers(oracle, hm, mode):
     for W in (0, 1, 4, 16, 17, 64, 65, 256, 257, 1000):
         waves = scenes.seeded_waves(W, cfg=9) if W else np.zeros((0, 6), np.float32)
