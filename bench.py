@@ -362,6 +362,11 @@ def run_ours(args):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + ("" if recurrence else "_exact"))
         except Exception:
             pass
+        pipes = None
+        try:
+            pipes = json.load(open(os.path.join(ROOT, "profiles", "pipes.json"))).get(args.workload + ("" if recurrence else "_exact"))
+        except Exception:
+            pass
         alg = {"vertex_waves": vw_per_frame, "transcendentals": vw_per_frame * TRANSCENDENTALS_PER_VERTEX_WAVE,
                "flop": vw_per_frame * FLOP_PER_VERTEX_WAVE, "bytes_written": out_bytes}
         trans_per_s = alg["transcendentals"] / (kernel_ms * 1e-3)
@@ -390,6 +395,9 @@ def run_ours(args):
             primary, secondary = roof_fp32, [roof_sfu, roof_hbm]
         else:
             primary, secondary = roof_sfu, [roof_fp32, roof_hbm]
+        if pipes:
+            primary = dict(primary)
+            primary["pipes_ncu"] = pipes          # what the binding pipe was actually doing (ncu capture of the same kernel, profiles/)
         line = {
             "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": n_gpus, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if row_sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
