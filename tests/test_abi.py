@@ -45,3 +45,24 @@ def test_no_cpu_fallback_without_gpu():
         api.Context(0)
     assert e.value.status == api.WT_ERR_NO_DEVICE
     assert "no CPU fallback" in str(e.value)
+
+
+def build_example(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "wt_headless")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+           os.path.join(ROOT, "examples", "wt_headless.cpp"), "-L" + os.path.dirname(build.LIB_PATH), "-lwavetool_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.dirname(build.LIB_PATH), "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+@pytest.mark.skipif(api.lib().wt_device_count() > 0, reason="a GPU is visible")
+def test_cpp_host_program_builds_against_the_c_abi_and_fails_loudly_without_gpu(tmp_path):
+    """examples/wt_headless.cpp is plain C++ on include/wavetool_b200.h (no CUDA compiler needed for the host side)."""
+    import subprocess
+    build.build()
+    exe = build_example(tmp_path)
+    res = subprocess.run([exe, "64", "2"], capture_output=True, text=True)
+    assert res.returncode == 2 and "no CPU fallback" in res.stderr

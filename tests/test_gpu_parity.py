@@ -604,6 +604,39 @@ def test_step_host_round_trip(oracle, hm):
     assert st == api.WT_NO_GRID and got.vertices == 0
 
 
+def test_cpp_host_program_matches_python_driver(tmp_path):
+    """examples/wt_headless.cpp (C++ host code on the C ABI, wt_run_animation) prints the same per-frame digests as
+    the same animation driven through the ctypes harness."""
+    import subprocess
+    from tests.test_abi import build_example
+    torch = torch_mod()
+    exe = build_example(tmp_path)
+    L, frames = 200, 5
+    res = subprocess.run([exe, str(L), str(frames)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    lines = [ln.split() for ln in res.stdout.splitlines() if ln.startswith("frame ")]
+    assert len(lines) == frames
+    hw = 64
+    yy, xx = np.meshgrid(np.arange(hw), np.arange(hw), indexing="ij")
+    v = (96 + ((xx * 7 + yy * 13) % 64)).astype(np.uint8)
+    hm = np.stack([v, v, v, np.full_like(v, 255)], -1)
+    waves = scenes.default_waves()
+    ctx = api.Context(0)
+    ctx.set_waves(waves)
+    ctx.set_heightmap(hm)
+    n = L * L
+    pos = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
+    nrm = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
+    cks = torch.zeros(40 * frames, dtype=torch.uint8, device="cuda")
+    p = api.default_params()
+    ctx.run_animation(api.default_camera(1.0), p, api.default_animation(), api.total_amplitude(waves), 1.0 / 60.0, frames, L,
+                      pos.data_ptr(), nrm.data_ptr(), 0, 2, cks.data_ptr(), flags=api.FLAG_CHECKSUM)
+    torch.cuda.synchronize()
+    want = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
+    for f, ln in enumerate(lines):
+        assert int(ln[3]) == int(want[f]["position_bits"]) and int(ln[5]) == int(want[f]["normal_bits"]) and int(ln[11]) == n
+
+
 def test_skybox_synthesis_argument_checks(hm):
     sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)
     ctx = sc.make_context()
