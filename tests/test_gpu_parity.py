@@ -637,6 +637,41 @@ def test_cpp_host_program_matches_python_driver(tmp_path):
         assert int(ln[3]) == int(want[f]["position_bits"]) and int(ln[5]) == int(want[f]["normal_bits"]) and int(ln[11]) == n
 
 
+def test_stream_ordering_on_a_non_default_stream(hm):
+    """Every entry point is stream-ordered on the caller's stream: a batch of small frames (fanned out over internal
+    streams, joined back with events) followed by work on the SAME user stream sees the finished results, with no
+    device-wide synchronisation in between; two contexts on two streams do not disturb each other."""
+    torch = torch_mod()
+    L, frames = 128, 12
+    waves = scenes.seeded_waves(8, cfg=2)
+    sc = Scene(waves, scenes.camera(), api.default_params(), L, hm)
+    ctxs = [sc.make_context(), sc.make_context()]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    n = L * L
+    fr = scenes.frames_for_animation(scenes.camera(), waves, first=0, count=frames)
+    results = []
+    for ctx, st in zip(ctxs, streams):
+        with torch.cuda.stream(st):
+            pos = torch.empty((4 * n, 4), dtype=torch.float32, device="cuda")
+            nrm = torch.empty((4 * n, 4), dtype=torch.float32, device="cuda")
+            cks = torch.zeros(40 * frames, dtype=torch.uint8, device="cuda")
+            ctx.eval_batch(fr, L, pos.data_ptr(), nrm.data_ptr(), 0, 4, cks.data_ptr(), flags=api.FLAG_CHECKSUM, stream=st.cuda_stream)
+            snap = pos.clone()                      # ordered after the batch on the same stream
+            results.append((pos, snap, cks))
+    for st in streams:
+        st.synchronize()
+    ref_ctx = sc.make_context()
+    for pos, snap, cks in results:
+        assert torch.equal(pos, snap)
+        got = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
+        for f in range(frames):
+            want = gpu_eval(ref_ctx, fr[f], L, checksum=True)
+            assert tuple(got[f]) == tuple(want["checksum"]), f
+            if f >= frames - 4:                      # the ring holds the last four frames
+                slot = f % 4
+                assert np.array_equal(pos[slot * n:(slot + 1) * n].cpu().numpy().view(np.uint32), want["pos"].view(np.uint32))
+
+
 def test_skybox_synthesis_argument_checks(hm):
     sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)
     ctx = sc.make_context()
