@@ -252,8 +252,10 @@ void wt_default_compose_params(wt_compose_params* out, const wt_camera* cam, uns
 int wt_set_screen_textures(wt_ctx* ctx, const float* depth, const uint8_t* reflections_rgba, const uint8_t* refractions_rgba,
                            int width, int height);
 
-/* colour (float4 per vertex: rgb after fog, a = edge hardness) from the vertex stage's outputs in `vertex_stage`
- * (position, normal, shade, clip_position, varyings_a, varyings_b must be set).  Stream-ordered. */
+/* colour (float4 per vertex: rgb after fog, a = edge hardness) from the vertex stage's outputs in `vertex_stage`:
+ * position, normal and shade (an evaluation with WT_FLAG_SHADE) are required; clip_position, varyings_a and varyings_b
+ * (WT_FLAG_VARYINGS) are read when all three are given, else recomputed from position and normal — 64 instead of
+ * 112 bytes of traffic per vertex.  Stream-ordered. */
 int wt_compose_frame(wt_ctx* ctx, const wt_frame* frame, const wt_compose_params* params, unsigned grid_len, unsigned row_begin,
                      unsigned row_end, const wt_outputs* vertex_stage, void* d_colour, void* cuda_stream);
 

@@ -531,6 +531,14 @@ def test_compose_screen_space_layers(oracle, hm, mode):
         assert same.mean() > 0.999
         assert np.sort(err)[int(0.9999 * len(err))] <= 1e-6
         assert 0.0 <= got["colour"][ok].min() and got["colour"][ok].max() <= 2.0 and got["colour"][ok][:, :3].std() > 0.02
+        # without the varyings buffers the pass recomputes gl_Position / NDC / yaw normal from position and normal: the same
+        # colours except where a last-bit difference of a screen coordinate crosses a depth texel or the 0.999 test
+        lean = api.Outputs(bufs["pos"].data_ptr(), bufs["normal"].data_ptr(), bufs["shade"].data_ptr(), None, None, None, None)
+        col2 = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+        ctx.compose_frame(frame, cp, L, lean, col2.data_ptr(), stream=sp)
+        torch.cuda.synchronize()
+        d2 = np.abs(col2.cpu().numpy()[ok].astype(np.float64) - got["colour"][ok]).max(axis=1)
+        assert np.sort(d2)[int(0.999 * len(d2))] <= 2e-5 and np.median(d2) <= 1e-6, (np.median(d2), np.sort(d2)[int(0.999 * len(d2))])
 
 
 def test_compose_argument_checks(hm):
@@ -546,8 +554,11 @@ def test_compose_argument_checks(hm):
     assert e.value.status == api.WT_ERR_NOT_READY
     ctx.set_screen_textures(np.ones((8, 8), np.float32), np.zeros((8, 8, 4), np.uint8), np.zeros((8, 8, 4), np.uint8))
     with pytest.raises(api.WaveToolError):
-        ctx.compose_frame(frame, cp, 64, api.Outputs(b.data_ptr(), b.data_ptr(), None, None, None, None, None), b.data_ptr())
+        ctx.compose_frame(frame, cp, 64, api.Outputs(b.data_ptr(), b.data_ptr(), None, None, None, None, None), b.data_ptr())      # no shade
+    with pytest.raises(api.WaveToolError):
+        ctx.compose_frame(frame, cp, 64, api.Outputs(b.data_ptr(), b.data_ptr(), b.data_ptr(), b.data_ptr(), None, None, None), b.data_ptr())   # 1 of 3 varyings
     assert ctx.compose_frame(frame, cp, 64, full, b.data_ptr()) == api.WT_OK
+    assert ctx.compose_frame(frame, cp, 64, api.Outputs(b.data_ptr(), b.data_ptr(), b.data_ptr(), None, None, None, None), b.data_ptr()) == api.WT_OK
 
 
 @pytest.mark.parametrize("hours,cp,oc,layers", [(9.0, 0.6, 0.0, (1, 1, 1)), (12.0, 0.9, 0.7, (1, 1, 1)), (18.5, 0.3, 1.0, (0, 1, 1)),

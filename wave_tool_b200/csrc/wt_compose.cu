@@ -21,6 +21,9 @@ struct ComposeArgs {
     long long n;
     float fog[4], fog_far, fog_near, soft_edges, tint_threshold, clarity, z_near, z_far, vw, vh;
     float camx, camy, camz, sun_y;
+    // clip == NULL: gl_Position, the height-0 NDC position and the yaw-only view-space normal are recomputed here from
+    // position and normal (the same FMA chains as the surface kernel's WT_FLAG_VARYINGS) instead of being read back
+    float vp[16], vy[12];
 };
 
 __device__ __forceinline__ float mix_f(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
@@ -48,7 +51,28 @@ __device__ __forceinline__ float4 sample_rgba8_clamp_linear(const uchar4* tex, i
 
 __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.n; k += (long long)gridDim.x * blockDim.x) {
-        const float4 P = __ldcs(a.pos + k), N = __ldcs(a.nrm + k), S = __ldcs(a.shade + k), C = __ldcs(a.clip + k), A = __ldcs(a.va + k), B = __ldcs(a.vb + k);
+        const float4 P = __ldcs(a.pos + k), N = __ldcs(a.nrm + k), S = __ldcs(a.shade + k);
+        float4 C, A, B;
+        if (a.clip) {
+            C = __ldcs(a.clip + k); A = __ldcs(a.va + k); B = __ldcs(a.vb + k);
+        } else {
+            const float* const m = a.vp;
+            float c0[4], cl[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                c0[r] = fmaf(m[8 + r], P.z, fmaf(m[r], P.x, m[12 + r]));
+                cl[r] = fmaf(m[4 + r], P.y, c0[r]);
+            }
+            C = make_float4(cl[0], cl[1], cl[2], cl[3]);
+            const float iw = __fdividef(1.0f, c0[3]);
+            A = make_float4(c0[0] * iw, c0[1] * iw, 0.0f, 0.0f);
+            const float* const y = a.vy;
+            float yn[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) yn[r] = fmaf(y[6 + r], N.z, fmaf(y[3 + r], N.y, y[r] * N.x));
+            const float yi = rsqrtf(fmaf(yn[0], yn[0], fmaf(yn[1], yn[1], yn[2] * yn[2])));
+            B = make_float4(yn[0] * yi, yn[1] * yi, yn[2] * yi, 0.0f);
+        }
         auto linearize = [&](float d) { return __fdiv_rn(__fmul_rn(a.z_near, d), __fsub_rn(a.z_far, __fmul_rn(d, __fsub_rn(a.z_far, a.z_near)))); };   // frag:66-69
         const float wx = __fsub_rn(a.camx, P.x), wy = __fsub_rn(a.camy, P.y), wz = __fsub_rn(a.camz, P.z);
         const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz)));   // frag:71
@@ -139,12 +163,18 @@ int wt_compose_frame(wt_ctx* ctx, const wt_frame* frame, const wt_compose_params
     auto fail = [&](int code, const std::string& msg) { ctx->err = msg; set_thread_error(code, msg.c_str()); return code; };
     if (!frame || !p || !in || !d_colour) return fail(WT_ERR_INVALID_ARGUMENT, "wt_compose_frame: NULL argument");
     if (L < 2 || r0 >= r1 || r1 > L) return fail(WT_ERR_INVALID_ARGUMENT, "need grid_len >= 2 and 0 <= row_begin < row_end <= grid_len");
-    if (!in->position || !in->normal || !in->shade || !in->clip_position || !in->varyings_a || !in->varyings_b)
-        return fail(WT_ERR_INVALID_ARGUMENT, "wt_compose_frame needs the outputs of an evaluation with WT_FLAG_SHADE | WT_FLAG_VARYINGS");
+    if (!in->position || !in->normal || !in->shade)
+        return fail(WT_ERR_INVALID_ARGUMENT, "wt_compose_frame needs the position, normal and shade outputs of an evaluation with WT_FLAG_SHADE");
+    const bool have_varyings = in->clip_position && in->varyings_a && in->varyings_b;
+    if (!have_varyings && (in->clip_position || in->varyings_a || in->varyings_b))
+        return fail(WT_ERR_INVALID_ARGUMENT, "wt_compose_frame: pass all three varyings buffers (WT_FLAG_VARYINGS) or none (they are then recomputed)");
     if (!ctx->d_depth) return fail(WT_ERR_NOT_READY, "wt_set_screen_textures has not been called");
     ComposeArgs a;
     a.pos = (const float4*)in->position; a.nrm = (const float4*)in->normal; a.shade = (const float4*)in->shade;
-    a.clip = (const float4*)in->clip_position; a.va = (const float4*)in->varyings_a; a.vb = (const float4*)in->varyings_b;
+    a.clip = have_varyings ? (const float4*)in->clip_position : nullptr;
+    a.va = (const float4*)in->varyings_a; a.vb = (const float4*)in->varyings_b;
+    std::memcpy(a.vp, frame->viewProjection, sizeof(a.vp));
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) a.vy[3 * c + r] = frame->viewMatOnlyYaw[4 * c + r];
     a.colour = (float4*)d_colour;
     a.depth = ctx->d_depth; a.refl = ctx->d_refl; a.refr = ctx->d_refr; a.w = ctx->screen_w; a.h = ctx->screen_h;
     a.n = (long long)(r1 - r0) * L;
