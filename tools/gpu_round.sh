@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "compose" 2>&1 | tail -6
-python tools/time_compose.py
+timeout 900 python -m pytest tests -m gpu -x -q -k "skybox" 2>&1 | tail -3
+python tools/time_sky.py 2048 2048

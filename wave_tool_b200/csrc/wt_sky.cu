@@ -14,6 +14,7 @@ namespace wt {
 struct SkyArgs {
     uchar4* out;                 // 6 * n * n texels, GL face order
     int n;
+    float inv_n_exact;           // 1 / n when n is a power of two (then x / n == x * (1 / n) exactly), else 0
     const uchar4* stars; int stars_n;     // NULL: layer not drawn
     const uchar4* clouds; int clouds_n;
     int draw_sphere;
@@ -52,7 +53,9 @@ __device__ __forceinline__ float4 cube_rgba8(const uchar4* faces, int n, float r
     if (ax >= ay && ax >= az) { ma = ax; if (rx >= 0.0f) { face = 0; sc = -rz; tc = -ry; } else { face = 1; sc = rz; tc = -ry; } }
     else if (ay >= az) { ma = ay; if (ry >= 0.0f) { face = 2; sc = rx; tc = rz; } else { face = 3; sc = rx; tc = -rz; } }
     else { ma = az; if (rz >= 0.0f) { face = 4; sc = rx; tc = -ry; } else { face = 5; sc = -rx; tc = -ry; } }
-    const float s = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(sc, ma), 1.0f)), t = __fmul_rn(0.5f, __fadd_rn(__fdiv_rn(tc, ma), 1.0f));
+    // the directions of texel centres have a major component of exactly +-1: x / 1 == x, no division needed
+    const float qs = ma == 1.0f ? sc : __fdiv_rn(sc, ma), qt = ma == 1.0f ? tc : __fdiv_rn(tc, ma);
+    const float s = __fmul_rn(0.5f, __fadd_rn(qs, 1.0f)), t = __fmul_rn(0.5f, __fadd_rn(qt, 1.0f));
     const float um = __fsub_rn(__fmul_rn(s, (float)n), 0.5f), vm = __fsub_rn(__fmul_rn(t, (float)n), 0.5f);
     int iu, iv;
     const float fu = floor_small(um, iu), fv = floor_small(vm, iv);
@@ -76,6 +79,8 @@ __device__ __forceinline__ float4 cube_rgba8(const uchar4* faces, int n, float r
 // dst holds the attachment's bytes as integer-valued floats
 __device__ __forceinline__ void blend(float dst[4], float r, float g, float b, float a) {
     const float src[4] = {sat(r), sat(g), sat(b), sat(a)};
+    // As == 0: Cs * 0 + Cd * 1 = Cd = c / 255, which converts back to the same byte c: nothing to do
+    if (src[3] == 0.0f) return;
     const float oma = __fsub_rn(1.0f, src[3]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -93,8 +98,10 @@ __global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
     if (i < a.n) {
         const size_t k = ((size_t)face * a.n + j) * a.n + i;
         // direction through the centre of texel (i, j) of the face (inverse of the GL cube-map face table)
-        const float sc = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)i, 0.5f)), (float)a.n), 1.0f);
-        const float tc = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fadd_rn((float)j, 0.5f)), (float)a.n), 1.0f);
+        // (2 (i + 1/2)) / n - 1; for a power-of-two n the division is a multiplication by the exact reciprocal
+        const float ni = __fmul_rn(2.0f, __fadd_rn((float)i, 0.5f)), nj = __fmul_rn(2.0f, __fadd_rn((float)j, 0.5f));
+        const float sc = __fsub_rn(a.inv_n_exact != 0.0f ? __fmul_rn(ni, a.inv_n_exact) : __fdiv_rn(ni, (float)a.n), 1.0f);
+        const float tc = __fsub_rn(a.inv_n_exact != 0.0f ? __fmul_rn(nj, a.inv_n_exact) : __fdiv_rn(nj, (float)a.n), 1.0f);
         float dx, dy, dz;
         switch (face) {
             case 0: dx = 1.0f; dy = -tc; dz = -sc; break;
@@ -263,6 +270,7 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* strea
     std::memset(&a, 0, sizeof(a));
     if (e == cudaSuccess) {
         a.out = ctx->d_sky; a.n = n;
+        a.inv_n_exact = (n & (n - 1)) == 0 ? 1.0f / (float)n : 0.0f;
         a.stars = p->drawStars ? ctx->d_stars : nullptr; a.stars_n = ctx->stars_n;
         a.clouds = p->drawClouds ? ctx->d_clouds : nullptr; a.clouds_n = ctx->clouds_n;
         a.draw_sphere = p->drawSkysphere;
