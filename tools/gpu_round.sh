@@ -1,2 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "skybox" 2>&1 | tail -3
-python tools/time_sky.py 2048 2048
+for k in 20 200 2000; do
+timeout 600 python bench.py --steps $k --no-cpu-baseline --no-readback 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print(d['steps'], 'ms/step %.4f value %.3e e2e %.3e'%(d['ms_per_step'], d['value'], d['e2e']['value']), d['clocks'])"
+done
