@@ -683,6 +683,38 @@ def test_stream_ordering_on_a_non_default_stream(hm):
                 assert np.array_equal(pos[slot * n:(slot + 1) * n].cpu().numpy().view(np.uint32), want["pos"].view(np.uint32))
 
 
+def test_large_grid_digest_is_shard_invariant(hm):
+    """Size-independent property at a BASELINE-size grid (8192^2, the two-level dynamic work queue in play): in the exact
+    mode every vertex is a pure function of (col, row), so the digest of the whole frame equals the fold of the digests
+    of an uneven set of row shards, and min/max of y fold the same way."""
+    from wave_tool_b200 import shard
+    torch = torch_mod()
+    L = 8192
+    sc = Scene(scenes.seeded_waves(8, cfg=4), scenes.camera(), scenes.animation_params(21), L, hm)
+    st, frame = sc.frame()
+    ctx = sc.make_context()
+    pos = torch.empty((L * L, 4), dtype=torch.float32, device="cuda")
+    nrm = torch.empty((L * L, 4), dtype=torch.float32, device="cuda")
+    cks = torch.zeros(40, dtype=torch.uint8, device="cuda")
+    sp = torch.cuda.current_stream().cuda_stream
+
+    def digest(rows):
+        ctx.eval_frame(frame, L, pos.data_ptr(), nrm.data_ptr(), 0, cks.data_ptr(), flags=api.FLAG_CHECKSUM, rows=rows, stream=sp)
+        torch.cuda.synchronize()
+        return cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[0].copy()
+
+    full = digest((0, L))
+    assert int(full["vertices"]) == L * L
+    cuts = [0, 1, 700, 701, 4096, 8000, 8191, L]
+    parts = np.array([digest((a, b)) for a, b in zip(cuts[:-1], cuts[1:])])
+    c = shard.combine_checksums(parts)
+    assert (c["position_bits"], c["normal_bits"], c["vertices"]) == (full["position_bits"], full["normal_bits"], full["vertices"])
+    assert c["min_y"] == full["min_y"] and c["max_y"] == full["max_y"]
+    # and the frame itself is sane: y within the displaceable amplitude around the base plane
+    amp = sc.total_amplitude + 1.0 + 0.1
+    assert -amp <= full["min_y"] < full["max_y"] <= amp
+
+
 def test_skybox_synthesis_argument_checks(hm):
     sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)
     ctx = sc.make_context()
