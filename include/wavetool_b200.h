@@ -311,6 +311,15 @@ int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, flo
                  unsigned row_begin, unsigned row_end, void* d_position, void* d_normal, void* d_shade, unsigned flags,
                  wt_checksum* h_checksum, void* cuda_stream);
 
+/* The same round trip split in two so that frames overlap: wt_step_submit builds and enqueues a frame and returns a
+ * ticket; wt_step_wait blocks until that frame's digest has arrived in host memory (WT_NO_GRID: zero digest).  Up to 4
+ * frames may be in flight — the host prepares frame k+1 while the GPU evaluates frame k, as a render loop does.  Not
+ * available with WT_FLAG_REFERENCE_ORDER. */
+int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_wave_amplitude, unsigned grid_len,
+                   unsigned row_begin, unsigned row_end, void* d_position, void* d_normal, void* d_shade, unsigned flags,
+                   void* cuda_stream, unsigned* ticket);
+int wt_step_wait(wt_ctx* ctx, unsigned ticket, wt_checksum* h_checksum);
+
 /* Host-buffer convenience (synchronous): evaluates into ctx-owned device scratch and copies the
  * requested outputs to HOST memory.  Any of h_position/h_normal/h_shade/h_checksum may be NULL. */
 int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, unsigned row_begin, unsigned row_end,

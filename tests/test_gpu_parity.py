@@ -613,6 +613,26 @@ def test_step_host_round_trip(oracle, hm):
         assert st == api.WT_OK and got.as_tuple() == tuple(want)
     st, got = ctx.step_host(scenes.camera(**scenes.EDGE_CAMERAS["looking_up_no_grid"]), sc.params, sc.total_amplitude, L, b[0].data_ptr(), b[1].data_ptr())
     assert st == api.WT_NO_GRID and got.vertices == 0
+    # pipelined: four frames in flight, digests come back per ticket in any order; a fifth unwaited ticket is refused later
+    ring = [torch.empty((4 * n, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+    params = [scenes.animation_params(20 + k) for k in range(6)]
+    want = []
+    for p_ in params:
+        st, fr = api.build_frame(sc.cam, p_, sc.total_amplitude)
+        want.append(tuple(gpu_eval(ctx, fr, L, flags=api.FLAG_FAST_PHASE, checksum=True)["checksum"]))
+    tickets = [ctx.step_submit(sc.cam, params[k], sc.total_amplitude, L, ring[0].data_ptr() + (k % 4) * n * 16, ring[1].data_ptr() + (k % 4) * n * 16,
+                               flags=api.FLAG_FAST_PHASE) for k in range(4)]
+    for k in (2, 0, 3, 1):
+        st, got = ctx.step_wait(tickets[k])
+        assert st == api.WT_OK and got.as_tuple() == want[k], k
+    for k in (4, 5):
+        tickets.append(ctx.step_submit(sc.cam, params[k], sc.total_amplitude, L, ring[0].data_ptr() + (k % 4) * n * 16, ring[1].data_ptr() + (k % 4) * n * 16,
+                                       flags=api.FLAG_FAST_PHASE))
+    assert ctx.step_wait(tickets[5])[1].as_tuple() == want[5] and ctx.step_wait(tickets[4])[1].as_tuple() == want[4]
+    with pytest.raises(api.WaveToolError):
+        ctx.step_wait(tickets[0])            # that record has been reused since
+    with pytest.raises(api.WaveToolError):
+        ctx.step_wait(999)
 
 
 def test_cpp_host_program_matches_python_driver(tmp_path):

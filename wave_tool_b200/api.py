@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
     "wt_default_animation", "wt_animation_advance", "wt_run_animation",
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
-    "wt_step_host", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
+    "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
 ]
 
 
@@ -155,6 +155,9 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
                                    C.c_void_p, C.c_void_p]
     L.wt_step_host.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Params), C.c_float, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_uint, C.POINTER(Checksum), C.c_void_p]
+    L.wt_step_submit.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Params), C.c_float, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_uint)]
+    L.wt_step_wait.argtypes = [C.c_void_p, C.c_uint, C.POINTER(Checksum)]
     L.wt_default_sky_params.argtypes = [C.POINTER(SkyParams)]
     L.wt_default_sky_params.restype = None
     L.wt_set_sky_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -317,6 +320,20 @@ class Context:
         cks = out if out is not None else Checksum()
         st = _check(self._lib.wt_step_host(self._h, C.byref(cam), C.byref(params), C.c_float(total_wave_amplitude), grid_len, r0, r1,
                                            d_pos, d_normal, d_shade or None, flags, C.byref(cks), stream or None), self._h)
+        return st, cks
+
+    def step_submit(self, cam: Camera, params: Params, total_wave_amplitude: float, grid_len: int, d_pos: int, d_normal: int, d_shade: int = 0,
+                    flags: int = 0, rows=None, stream: int = 0) -> int:
+        """wt_step_submit: enqueue one frame from host camera/params; returns the ticket for step_wait."""
+        r0, r1 = rows if rows is not None else (0, grid_len)
+        t = C.c_uint()
+        _check(self._lib.wt_step_submit(self._h, C.byref(cam), C.byref(params), C.c_float(total_wave_amplitude), grid_len, r0, r1,
+                                        d_pos, d_normal, d_shade or None, flags, stream or None, C.byref(t)), self._h)
+        return t.value
+
+    def step_wait(self, ticket: int, out: "Checksum | None" = None):
+        cks = out if out is not None else Checksum()
+        st = _check(self._lib.wt_step_wait(self._h, ticket, C.byref(cks)), self._h)
         return st, cks
 
     def set_sky_layers(self, gradient: np.ndarray, stars=None, clouds=None):

@@ -43,7 +43,10 @@ struct wt_ctx {
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
     size_t s_elems = 0;
     wt_checksum* s_cks = nullptr;
-    wt_checksum* h_cks_pinned = nullptr;   // pinned staging record of wt_step_host
+    wt_checksum* h_cks_pinned = nullptr;   // mapped host records of wt_step_host / wt_step_submit (STEP_RING + 1 of them)
+    cudaEvent_t step_event[4] = {nullptr, nullptr, nullptr, nullptr};
+    int step_status[4] = {0, 0, 0, 0};
+    unsigned step_next = 0;
     uint64_t launches = 0;
     // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
     int* d_queues = nullptr;
@@ -60,6 +63,7 @@ struct wt_ctx {
     size_t trace_cap = 0, trace_items = 0;
 };
 constexpr unsigned N_QUEUES = 256;
+constexpr unsigned STEP_RING = 4;   // frames in flight between wt_step_submit and wt_step_wait
 
 namespace wt {
 

@@ -261,6 +261,7 @@ void wt_destroy(wt_ctx* ctx) {
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
     cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
     if (ctx->h_cks_pinned) cudaFreeHost(ctx->h_cks_pinned);
+    for (unsigned i = 0; i < STEP_RING; ++i) if (ctx->step_event[i]) cudaEventDestroy(ctx->step_event[i]);
     for (int i = 0; i < 4; ++i) {
         if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -506,34 +507,58 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     return WT_OK;
 }
 
-// One whole frame from HOST inputs to a HOST result in a single call: camera + parameters -> wt_build_frame (the
-// reference's CPU prologue) -> fused kernel into the caller's device buffers -> the frame's digest copied back through
-// a pinned staging record -> stream synchronised.  This is the per-frame round trip of a host application that keeps
-// the vertex data on the GPU (as the reference does) and reads back a scalar result.
+// One whole frame from HOST inputs to a HOST result: camera + parameters -> wt_build_frame (the reference's CPU
+// prologue) -> fused kernel into the caller's device buffers, whose last warp writes the frame's digest straight into
+// a mapped host record.  wt_step_submit enqueues a frame and returns a ticket, wt_step_wait blocks until that frame's
+// digest has arrived: with up to STEP_RING frames in flight the host prepares frame k+1 while the GPU evaluates
+// frame k, as a render loop does.  wt_step_host = submit + wait.
+int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_amp, unsigned L, unsigned r0, unsigned r1,
+                   void* d_pos, void* d_nrm, void* d_shade, unsigned flags, void* stream_, unsigned* ticket) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_step_submit: ctx is NULL");
+    if (!cam || !params || !ticket) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_submit: NULL argument");
+    if (flags & WT_FLAG_REFERENCE_ORDER) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_submit: not available with WT_FLAG_REFERENCE_ORDER");
+    wt_frame frame;
+    int st = wt_build_frame(cam, params, total_amp, &frame);
+    if (st < 0) return fail(ctx, st, std::string("wt_step_submit: ") + wt_last_error(nullptr));
+    DeviceGuard g(ctx->device);
+    if (!ctx->h_cks_pinned) {
+        WT_CUDA(ctx, cudaHostAlloc(&ctx->h_cks_pinned, STEP_RING * sizeof(wt_checksum), cudaHostAllocMapped));
+        for (unsigned i = 0; i < STEP_RING; ++i) WT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->step_event[i], cudaEventDisableTiming));
+    }
+    const unsigned t = ctx->step_next++;
+    const unsigned slot = t % STEP_RING;
+    *ticket = t;
+    ctx->step_status[slot] = st;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (st == WT_OK) {
+        // the kernel's last warp writes the finished digest straight into the mapped host record: no copy to enqueue
+        st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned + slot, flags | WT_FLAG_CHECKSUM, stream_);
+        if (st != WT_OK) return st;
+    }
+    WT_CUDA(ctx, cudaEventRecord(ctx->step_event[slot], stream));
+    return ctx->step_status[slot];
+}
+
+int wt_step_wait(wt_ctx* ctx, unsigned ticket, wt_checksum* h_out) {
+    if (!ctx || !h_out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_wait: NULL argument");
+    if (!ctx->h_cks_pinned || ticket >= ctx->step_next || ctx->step_next - ticket > STEP_RING)
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_wait: unknown ticket (at most 4 frames may be in flight)");
+    const unsigned slot = ticket % STEP_RING;
+    DeviceGuard g(ctx->device);
+    WT_CUDA(ctx, cudaEventSynchronize(ctx->step_event[slot]));
+    if (ctx->step_status[slot] == WT_NO_GRID) { std::memset(h_out, 0, sizeof(*h_out)); return WT_NO_GRID; }
+    *h_out = ctx->h_cks_pinned[slot];
+    return WT_OK;
+}
+
 int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_amp, unsigned L, unsigned r0, unsigned r1,
                  void* d_pos, void* d_nrm, void* d_shade, unsigned flags, wt_checksum* h_out, void* stream_) {
     if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_step_host: ctx is NULL");
-    if (!cam || !params || !h_out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_host: NULL argument");
-    wt_frame frame;
-    int st = wt_build_frame(cam, params, total_amp, &frame);
-    if (st < 0) return fail(ctx, st, std::string("wt_step_host: ") + wt_last_error(nullptr));
-    std::memset(h_out, 0, sizeof(*h_out));
-    if (st == WT_NO_GRID) return WT_NO_GRID;
-    DeviceGuard g(ctx->device);
-    if (!ctx->h_cks_pinned) WT_CUDA(ctx, cudaHostAlloc(&ctx->h_cks_pinned, sizeof(wt_checksum), cudaHostAllocMapped));
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (flags & WT_FLAG_REFERENCE_ORDER) {
-        st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->s_cks, flags | WT_FLAG_CHECKSUM, stream_);
-        if (st != WT_OK) return st;
-        WT_CUDA(ctx, cudaMemcpyAsync(ctx->h_cks_pinned, ctx->s_cks, sizeof(wt_checksum), cudaMemcpyDeviceToHost, stream));
-    } else {
-        // the kernel's last warp writes the finished digest straight into the mapped host record: no copy to enqueue
-        st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned, flags | WT_FLAG_CHECKSUM, stream_);
-        if (st != WT_OK) return st;
-    }
-    WT_CUDA(ctx, cudaStreamSynchronize(stream));
-    *h_out = *ctx->h_cks_pinned;
-    return WT_OK;
+    if (!h_out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_host: NULL argument");
+    unsigned ticket = 0;
+    int st = wt_step_submit(ctx, cam, params, total_amp, L, r0, r1, d_pos, d_nrm, d_shade, flags, stream_, &ticket);
+    if (st < 0) return st;
+    return wt_step_wait(ctx, ticket, h_out);
 }
 
 int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, float* h_pos, float* h_nrm, float* h_shade,
