@@ -454,7 +454,7 @@ __device__ __forceinline__ int next_item(int* queue, int lane) {
 #define WT_WAVE_UNROLL 8        // wave-loop unroll factor of MODE 1 (measured: 1 -> 0.447 ms, 4 -> 0.443, 8 -> 0.438, 16 -> 0.506 at cfg3)
 #endif
 #ifndef WT_WAVE_UNROLL_EXACT
-#define WT_WAVE_UNROLL_EXACT 1
+#define WT_WAVE_UNROLL_EXACT 2   // MODE 0 runs at its 80-register cap: 2 -> -0.6 %, 4 and 8 slower
 #endif
 #ifndef WT_LB_RECUR
 #define WT_LB_RECUR 16          // __launch_bounds__ min CTAs (= warps) per SM, MODE 1
