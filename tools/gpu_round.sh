@@ -1,7 +1,14 @@
+# One GPU-box round: parity suite, smoke, the bench line (both phase modes), launch list and ncu captures.
+#   gpurun --timeout 2400 -- 'bash tools/gpu_round.sh'        (outputs under gpurun_out/, summaries via tools/ncu_summary.py)
+set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --exact-phase --no-cpu-baseline > gpurun_out/r1v9_bench_cfg3_exact.json 2>gpurun_out/r1v9_bench.err
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:surface_warp -s 3 -c 2 -f -o gpurun_out/r1v9_prof_exact python bench.py --exact-phase --steps 3 --warmup 3 --no-cpu-baseline --no-readback > gpurun_out/r1v9_ncu_full2.log 2>&1
-python -c "
-import json
-d=json.load(open('gpurun_out/r1v9_bench_cfg3_exact.json')); print('exact ms/step %.4f value %.3e e2e %.3e'%(d['ms_per_step'], d['value'], d['e2e']['value']), round(d['roofline']['frac'],3))"
+T=${TAG:-round}
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
+tail -3 gpurun_out/${T}_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | cut -c1-100
+timeout 600 python bench.py > gpurun_out/${T}_bench_cfg3.json 2> gpurun_out/${T}_bench.err; tail -2 gpurun_out/${T}_bench.err
+timeout 600 python bench.py --exact-phase --no-cpu-baseline > gpurun_out/${T}_bench_cfg3_exact.json 2>> gpurun_out/${T}_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches_cfg3.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-readback > gpurun_out/${T}_ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:surface_warp -s 3 -c 2 -f -o gpurun_out/${T}_prof_fast python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-readback > gpurun_out/${T}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:surface_warp -s 3 -c 2 -f -o gpurun_out/${T}_prof_exact python bench.py --exact-phase --steps 3 --warmup 3 --no-cpu-baseline --no-readback > gpurun_out/${T}_ncu_full2.log 2>&1
+ls -la gpurun_out | tail -12
