@@ -100,7 +100,12 @@ constexpr int DYN_ROWS_RECUR = 38;   // rows per dynamically queued work item, M
 constexpr int DYN_ROWS_EXACT = 30;   // ... MODE 0 (8 marching steps)
 constexpr int DYN_SMALL_RECUR = 14, DYN_SMALL_EXACT = 0;   // rows per item of the tail of the launch (0 = single level)
 constexpr int DYN_TAIL_PERCENT = 25;
-constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed + 7 rotations per wave)
+constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed per wave, row 1 by rotation, rows 2.. by the three-term recurrence)
+#ifndef WT_R_RECUR_BIG
+#define WT_R_RECUR_BIG 12
+#endif
+constexpr int R_RECUR_BIG = WT_R_RECUR_BIG;   // ... for the wave-table tiers above 64 waves: the wave loop dominates there, and 12 rows per seed at
+                                              // 12 warps per SM beat 8 rows at 16 (cfg4: 3.83 vs 4.27 ms; at 64 waves 0.412 vs 0.405 ms)
 
 struct Plan {
     int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;

@@ -459,6 +459,9 @@ __device__ __forceinline__ int next_item(int* queue, int lane) {
 #ifndef WT_LB_RECUR
 #define WT_LB_RECUR 16          // __launch_bounds__ min CTAs (= warps) per SM, MODE 1
 #endif
+#ifndef WT_LB_RECUR_BIG
+#define WT_LB_RECUR_BIG 12      // ... MODE 1 with more than 8 rows per step (the > 64-wave tiers): 168 registers, 3 warps per scheduler
+#endif
 #ifndef WT_LB_EXACT
 #define WT_LB_EXACT 24
 #endif
@@ -470,6 +473,14 @@ __device__ __forceinline__ int next_item(int* queue, int lane) {
 #endif
 #ifndef WT_EPI_UNROLL
 #define WT_EPI_UNROLL 2         // rows of the output stage in flight per warp (MODE 1)
+#endif
+#ifndef WT_CHEB
+#define WT_CHEB 1               // 1: rows 2.. of a MODE 1 step by the three-term recurrence, 0: by complex rotations (cfg3: 0.405 vs 0.438 ms)
+#endif
+#ifndef WT_SYM
+#define WT_SYM 0                // 1: symmetric-pair form of the MODE 1 wave loop (needs an odd WT_R_RECUR).  EXPERIMENT ONLY: 0.396 ms at
+                                // cfg3, closer to the fp64 evaluation than the reference is, but it cannot follow the reference's own
+                                // fp32 accumulation order and misses the parity bar where that noise exceeds it (profiles/README.md)
 #endif
 #define WT_STR(x) #x
 #define WT_UNROLL(n) _Pragma(WT_STR(unroll n))
@@ -487,7 +498,7 @@ struct RingLayout {
 };
 
 template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY>
-__global__ void __launch_bounds__(32, MODE == 1 ? WT_LB_RECUR : WT_LB_EXACT)
+__global__ void __launch_bounds__(32, MODE == 1 ? (R > 8 ? WT_LB_RECUR_BIG : WT_LB_RECUR) : WT_LB_EXACT)
 surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
     extern __shared__ float2 ring_all[];
     using RL = RingLayout<R, VARY>;
@@ -554,6 +565,60 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                     pz[j] = fma2(bc(wk.cZ), c, pz[j]);
                 }
             }
+        } else if (WT_SYM && (R & 1)) {
+            // Symmetric-pair form of the recurrence mode.  The R = 2H+1 rows of a step sit at phases
+            // k_c + j*dk, j = -H..H, around the centre row, and
+            //   cos(k_c +- j dk) = cos k_c cos(j dk) -+ sin k_c sin(j dk),   sin(k_c +- j dk) = sin k_c cos(j dk) +- cos k_c sin(j dk)
+            // so the SUM and the DIFFERENCE of the two rows of a pair each take one FMA per component per wave:
+            //   a_j += (c cos k_c) C_j,  b_j += (c sin k_c) S_j,   P[c+j] = a_j - b_j,  P[c-j] = a_j + b_j   (x, z; y with +-)
+            // 6 FMAs per wave per row PAIR instead of 2 x (4 rotation + 3 accumulation).  C_j, S_j = cos / sin(j dk) come from
+            // one MUFU pair, angle doubling (j even) and one rotation (j odd): depth <= 3 instead of a chain of R-1 rotations.
+            constexpr int H = R / 2;
+            const f2 gxc = px[H], gzc = pz[H];
+            f2 ax[H], bx[H], ay[H], by[H], az[H], bz[H];
+#pragma unroll
+            for (int j = 0; j < H; ++j) { ax[j] = bx[j] = ay[j] = by[j] = az[j] = bz[j] = bc(0.0f); }
+            f2 ccx = bc(0.0f), ccy = bc(0.0f), ccz = bc(0.0f);
+            WaveK wk_next = wt.w[0];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
+            WT_UNROLL(WT_WAVE_UNROLL)
+            for (int i = 0; i < a.n_waves; ++i) {
+                const WaveK wk = wk_next;
+                wk_next = wt.w[i + 1 < a.n_waves ? i + 1 : i];
+                f2 s, c;
+                sincos2(fma2(bc(wk.Dx), gxc, fma2(bc(wk.Dz), gzc, bc(wk.phi))), s, c);
+                const f2 dk = fma2(bc(wk.Dx), ex, mul2(bc(wk.Dz), ez));
+                f2 C[H + 1], S[H + 1];
+                S[1] = make_float2(__sinf(dk.x), __sinf(dk.y));
+                C[1] = make_float2(__cosf(dk.x), __cosf(dk.y));
+                const f2 qc = mul2(bc(wk.cX), c), qs = mul2(bc(wk.cX), s);
+                const f2 rc = mul2(bc(wk.cZ), c), rs = mul2(bc(wk.cZ), s);
+                const f2 yc = mul2(bc(wk.A), c), ys = mul2(bc(wk.A), s);
+                ccx = add2(ccx, qc); ccy = add2(ccy, ys); ccz = add2(ccz, rc);
+#pragma unroll
+                for (int j = 1; j <= H; ++j) {
+                    if (j > 1) {
+                        if ((j & 1) == 0) {
+                            // e^{i 2t} from e^{i t}: cos 2t = 1 - 2 sin^2 t (exact form for small t), sin 2t = 2 sin t cos t
+                            const f2 t2 = add2(S[j / 2], S[j / 2]);
+                            C[j] = fma2(make_float2(-t2.x, -t2.y), S[j / 2], bc(1.0f));
+                            S[j] = mul2(t2, C[j / 2]);
+                        } else {
+                            C[j] = fma2(C[j - 1], C[1], mul2(make_float2(-S[j - 1].x, -S[j - 1].y), S[1]));
+                            S[j] = fma2(S[j - 1], C[1], mul2(C[j - 1], S[1]));
+                        }
+                    }
+                    ax[j - 1] = fma2(qc, C[j], ax[j - 1]); bx[j - 1] = fma2(qs, S[j], bx[j - 1]);
+                    az[j - 1] = fma2(rc, C[j], az[j - 1]); bz[j - 1] = fma2(rs, S[j], bz[j - 1]);
+                    ay[j - 1] = fma2(ys, C[j], ay[j - 1]); by[j - 1] = fma2(yc, S[j], by[j - 1]);
+                }
+            }
+            px[H] = add2(px[H], ccx); py[H] = ccy; pz[H] = add2(pz[H], ccz);
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                px[H + j] = add2(px[H + j], sub2(ax[j - 1], bx[j - 1])); px[H - j] = add2(px[H - j], add2(ax[j - 1], bx[j - 1]));
+                pz[H + j] = add2(pz[H + j], sub2(az[j - 1], bz[j - 1])); pz[H - j] = add2(pz[H - j], add2(az[j - 1], bz[j - 1]));
+                py[H + j] = add2(ay[j - 1], by[j - 1]); py[H - j] = sub2(ay[j - 1], by[j - 1]);
+            }
         } else {
             const f2 gx0 = px[0], gz0 = pz[0];
             WaveK wk_next = wt.w[0];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
@@ -572,6 +637,28 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 px[0] = fma2(bc(wk.cX), c, px[0]);
                 py[0] = fma2(bc(wk.A), s, py[0]);
                 pz[0] = fma2(bc(wk.cZ), c, pz[0]);
+#if WT_CHEB
+                // Row 1 by one complex rotation, e^{i(k + dk)} = e^{ik} e^{i dk}; rows 2.. by the three-term recurrence
+                //   x_{j+1} = 2 cos(dk) x_j - x_{j-1}        (x = cos or sin of k + j dk)
+                // — one FMA per value instead of two operations.  Re-seeded every R rows, so a rounding error e of one
+                // step reaches row n as e (n - m) at most (U_{n-m-1}(cos dk) <= n - m): < 2e-6 of a unit wave over 7 rows.
+                f2 cp = c, sp = s;   // row j - 1
+                c = fma2(cp, cd, mul2(make_float2(-sp.x, -sp.y), sd));
+                s = fma2(sp, cd, mul2(cp, sd));
+                const f2 tc = add2(cd, cd);
+                px[1] = fma2(bc(wk.cX), c, px[1]);
+                py[1] = fma2(bc(wk.A), s, py[1]);
+                pz[1] = fma2(bc(wk.cZ), c, pz[1]);
+#pragma unroll
+                for (int j = 2; j < R; ++j) {
+                    const f2 cn = fma2(tc, c, make_float2(-cp.x, -cp.y));
+                    const f2 sn = fma2(tc, s, make_float2(-sp.x, -sp.y));
+                    cp = c; sp = s; c = cn; s = sn;
+                    px[j] = fma2(bc(wk.cX), c, px[j]);
+                    py[j] = fma2(bc(wk.A), s, py[j]);
+                    pz[j] = fma2(bc(wk.cZ), c, pz[j]);
+                }
+#else
 #pragma unroll
                 for (int j = 1; j < R; ++j) {
                     // e^{i(k + dk)} = e^{ik} e^{i dk}
@@ -582,6 +669,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                     py[j] = fma2(bc(wk.A), s, py[j]);
                     pz[j] = fma2(bc(wk.cZ), c, pz[j]);
                 }
+#endif
             }
         }
         if (a.dbg & 1) {

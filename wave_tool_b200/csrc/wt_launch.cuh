@@ -15,7 +15,7 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
 
 template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY>
 cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
-    constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
+    constexpr int R = MODE == 1 ? (CAP > 64 ? R_RECUR_BIG : R_RECUR) : R_EXACT;
     auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2, VARY>;
     const int smem = WARPS_PER_CTA * RingLayout<R, VARY>::BYTES_PER_WARP + g_knobs.extra_smem;
     static thread_local struct { int L = -1, rows = -1, dev = -1, slots = 0; Plan p; } cache;   // per instantiation
