@@ -96,10 +96,10 @@ extern Knobs g_knobs;
 #define WT_R_RECUR 8
 #endif
 constexpr int R_EXACT = WT_R_EXACT;   // rows per marching step, MODE 0 (keeps the undisplaced grid point of every row live)
-constexpr int DYN_ROWS_RECUR = 38;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 5 marching steps)
+constexpr int DYN_ROWS_RECUR = 46;   // rows per dynamically queued work item, MODE 1 (+2 halo rows = 6 marching steps of 8 rows, 4 of 12)
 constexpr int DYN_ROWS_EXACT = 30;   // ... MODE 0 (8 marching steps)
 constexpr int DYN_SMALL_RECUR = 14, DYN_SMALL_EXACT = 0;   // rows per item of the tail of the launch (0 = single level)
-constexpr int DYN_TAIL_PERCENT = 25;
+constexpr int DYN_TAIL_PERCENT = 15;   // measured at cfg3 (profiles/README.md): 38/14/25 % 0.4075 ms, 46/14/25 % 0.4026, 46/14/15 % 0.3982
 constexpr int R_RECUR = WT_R_RECUR;   // rows per marching step, MODE 1 (one MUFU seed per wave, row 1 by rotation, rows 2.. by the three-term recurrence)
 #ifndef WT_R_RECUR_BIG
 #define WT_R_RECUR_BIG 12

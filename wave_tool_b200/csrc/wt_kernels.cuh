@@ -233,13 +233,16 @@ __host__ __device__ __forceinline__ float key_float(unsigned k) {
 
 struct ChecksumAcc {
     unsigned long long pos = 0, nrm = 0, shd = 0, count = 0;
-    unsigned kmin = 0xffffffffu, kmax = 0u;
-    __device__ __forceinline__ void add(const float4& p, const float4& n) {
+    float ymin = 3.402823466e+38f, ymax = -3.402823466e+38f;   // +-FLT_MAX; converted to ordered keys in flush()
+    // sums and y range of one vertex; the vertex COUNT is added per vertex by add(), per work item by the production kernel
+    __device__ __forceinline__ void add_sums(const float4& p, const float4& n) {
         pos += (unsigned long long)__float_as_uint(p.x) + __float_as_uint(p.y) + __float_as_uint(p.z);
         nrm += (unsigned long long)__float_as_uint(n.x) + __float_as_uint(n.y) + __float_as_uint(n.z) + __float_as_uint(n.w);
-        unsigned k = float_key(p.y);
-        kmin = min(kmin, k);
-        kmax = max(kmax, k);
+        ymin = fminf(ymin, p.y);
+        ymax = fmaxf(ymax, p.y);
+    }
+    __device__ __forceinline__ void add(const float4& p, const float4& n) {
+        add_sums(p, n);
         count += 1;
     }
     __device__ __forceinline__ void add_shade(const float4& s) {
@@ -248,6 +251,7 @@ struct ChecksumAcc {
     // warp-reduce, then one set of atomics per warp.  While accumulating, the min_y/max_y words of
     // the record hold order-preserving keys; checksum_finalize_kernel decodes them.
     __device__ __forceinline__ void flush(wt_checksum* out) {
+        unsigned kmin = float_key(ymin), kmax = float_key(ymax);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             pos += __shfl_xor_sync(0xffffffffu, pos, o);
@@ -830,8 +834,8 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 if (stB) __stcs(pb + 32, make_float4(yn[0].y * yi.y, yn[1].y * yi.y, yn[2].y * yi.y, 0.0f));
             }
             if (CKS) {
-                if (stA) { acc.add(opA, onA); if (SHADE) acc.add_shade(sA); }
-                if (stB) { acc.add(opB, onB); if (SHADE) acc.add_shade(sB); }
+                if (stA) { acc.add_sums(opA, onA); if (SHADE) acc.add_shade(sA); }
+                if (stB) { acc.add_sums(opB, onB); if (SHADE) acc.add_shade(sB); }
             }
         };
         {
@@ -845,6 +849,8 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         }
         slot_new = slot_new + R >= RL::ROWS ? slot_new + R - RL::ROWS : slot_new + R;
     }
+    // every row of [r0, r1) was stored exactly once for each of this lane's in-range columns
+    if (CKS) acc.count += (unsigned long long)max(r1 - r0, 0) * ((outA ? 1 : 0) + (outB ? 1 : 0));
     if (a.trace && lane == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
