@@ -351,7 +351,7 @@ def run_ours(args):
         dn = (na - nb).norm(dim=1)
         dn = torch.minimum(dn, (na + nb).norm(dim=1))          # the view-facing flip is sign-ambiguous at grazing incidence
         other = {"ms_per_frame": oms, "vertex_waves_per_sec": vw_per_frame / (oms * 1e-3),
-                 "phase": "bit-faithful fp32 phase, MUFU pair per vertex-wave" if recurrence else "rotation recurrence",
+                 "phase": "bit-faithful fp32 phase, MUFU pair per vertex-wave" if recurrence else "phase recurrence",
                  "max_position_deviation_between_modes": dpos, "position_tolerance": 1e-4 * float(total_amp),
                  "max_normal_deviation_rad_between_modes": float(dn.max().item()), "normal_tolerance_rad": 1e-3,
                  "checked_on": "all %d vertices of the last timed frame, on the device" % n}
@@ -400,7 +400,9 @@ def run_ours(args):
                      "peak_source": "of measured: FFMA-only micro-kernel on this device in this run (wt_measure_peak 1; packed FFMA2: %.1f); "
                                     "MEASURED_PEAKS.json has no FP32 figure; nominal 128 FMA/clk/SM = 74.4" % (fma2_flops / 1e12),
                      "algorithmic_per_launch": alg,
-                     "note": "15 FLOP per vertex-wave (SURVEY 8d); the recurrence executes ~15.5 FLOP + 0.5 MUFU per vertex-wave"}
+                     "note": "15 FLOP per vertex-wave (SURVEY 8d) is the algorithmic count; the recurrence mode EXECUTES ~11.6 FLOP + 0.5 MUFU per "
+                             "vertex-wave at 64 waves (row 1 of a step by one complex rotation, the others by the three-term recurrence, "
+                             "1 FMA per value), so frac can exceed the FMA-pipe utilisation reported in pipes_ncu"}
         roof_hbm = {"bound": "hbm", "achieved": out_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": out_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                     "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "of fallback: 6650 GB/s",
@@ -424,7 +426,8 @@ def run_ours(args):
                                        "no data-path collective") if row_sharded else
                                       f"frame-sharded x{n_gpus} (frame f on rank f mod N), no data-path collective",
                        "l2": "each step writes %d MB of fresh output into a 2-deep ring (> 126 MB L2)" % (out_bytes // 2 ** 20),
-                       "phase": "rotation recurrence (WT_FLAG_FAST_PHASE): MUFU seed every 8 rows, complex rotation in between"
+                       "phase": "phase recurrence (WT_FLAG_FAST_PHASE): one MUFU seed per wave every 8 rows (12 above 64 waves), row 1 by complex rotation, "
+                                "rows 2.. by the three-term recurrence x[j+1] = 2 cos(dk) x[j] - x[j-1]"
                                 if recurrence else "bit-faithful fp32 phase, MUFU sin/cos pair per vertex-wave"},
             "ms_per_frame": ms_per_step,
             "roofline": primary,
@@ -470,7 +473,7 @@ def main():
     ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3",
                     help="cfg3 is the bench line (BASELINE.json's metric is quoted on it); the others are extra measurements")
     ap.add_argument("--exact-phase", action="store_true",
-                    help="time the bit-faithful-phase wave loop (one MUFU pair per vertex-wave) instead of the rotation recurrence")
+                    help="time the bit-faithful-phase wave loop (one MUFU pair per vertex-wave) instead of the phase recurrence")
     ap.add_argument("--fast-phase", action="store_true", help="(default; kept for compatibility)")
     ap.add_argument("--no-readback", action="store_true", help="skip the full output read-back (PCIe-bound) variant of e2e")
     ap.add_argument("--no-cpu-baseline", action="store_true")
