@@ -43,7 +43,7 @@ extern "C" {
 /* evaluation flags */
 #define WT_FLAG_SHADE 0x1u            /* also evaluate the vertex-evaluable fragment terms (water-grid.frag:71-73,95-111) */
 #define WT_FLAG_CHECKSUM 0x2u         /* fold the outputs into the wt_checksum record passed to the call */
-#define WT_FLAG_FAST_PHASE 0x4u       /* pre-folded 2-FMA wave phase (not bit-faithful to the reference's fp32 phase) */
+#define WT_FLAG_FAST_PHASE 0x4u       /* pre-folded 2-FMA wave phase seeded once per wave every 8 or 12 rows, per-row recurrence in between (not bit-faithful to the reference's fp32 phase; same tolerances) */
 #define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
 #define WT_FLAG_VARYINGS 0x10u        /* also write the vertex stage's other outputs (wt_eval_frame_ex): gl_Position,
                                          xyPositionNDCSpaceHeight0, heightmap_colour.r, normalVecInViewSpaceOnlyYaw */

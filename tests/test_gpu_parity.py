@@ -14,7 +14,7 @@ from wave_tool_b200 import api, scenes
 pytestmark = pytest.mark.gpu
 
 # the two phase modes of the production kernel: bit-faithful fp32 phase + MUFU pair per vertex-wave, and
-# MUFU seed + rotation recurrence (WT_FLAG_FAST_PHASE).  Both must meet the same tolerances.
+# MUFU seed + phase recurrence (WT_FLAG_FAST_PHASE).  Both must meet the same tolerances.
 MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE}
 
 
