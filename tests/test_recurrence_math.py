@@ -98,3 +98,70 @@ def test_reference_order_accumulation_is_what_parity_needs():
     print("vs the reference's fp32 result: same order", worst_seq, " summed first", worst_sum)
     assert worst_seq <= 1e-4          # following the reference's order stays inside the bar ...
     assert worst_sum > worst_seq      # ... summing first (more exact!) is further from the reference
+
+
+# --------------------------------------------------------------------------------------------------
+# The whole MODE 1 wave loop, emulated in fp32 for a few grid columns, against the ORACLE (x and z: the heightmap
+# detail and the bounce only touch y).  No GPU: this pins the algorithm — seed row, phase step, three-term chain and
+# the reference-order accumulation — to the reference's own arithmetic; the kernel is pinned to the same oracle on
+# the GPU (tests/test_gpu_parity.py).
+# --------------------------------------------------------------------------------------------------
+def _emulate_column(frame, waves, L, col, R):
+    """x, z of every row of one grid column the way surface_warp_kernel<MODE 1> computes them (steps of R rows)."""
+    bl = np.array(frame.bottomLeftGridPointInWorld[:], f32); br = np.array(frame.bottomRightGridPointInWorld[:], f32)
+    tl = np.array(frame.topLeftGridPointInWorld[:], f32); tr = np.array(frame.topRightGridPointInWorld[:], f32)
+    t = f32(frame.waveAnimationTimeInSeconds)
+    A, w, phi, Q, Dx, Dz = [waves[:, i].astype(f32) for i in range(6)]
+    W = len(A)
+    Qi = (Q / (w * A * f32(max(W, 4)))).astype(f32)             # render-engine.cpp:1073
+    cX, cZ = ((A * Qi).astype(f32) * Dx).astype(f32), ((A * Qi).astype(f32) * Dz).astype(f32)
+    wDx, wDz = (w * Dx).astype(f32), (w * Dz).astype(f32)
+    ph = np.remainder((phi * t).astype(f32).astype(np.float64) + np.pi, 2 * np.pi) - np.pi
+    ph = ph.astype(f32)
+    du = f32(1.0) / f32(L - 1)
+
+    def mix(a, b, x):
+        return f32(f32(a * f32(f32(1) - x)) + f32(b * x))
+    u = f32(col) * du
+    m1 = (mix(bl[0], br[0], u), mix(bl[2], br[2], u))
+    m2 = (mix(tl[0], tr[0], u), mix(tl[2], tr[2], u))
+    ex, ez = f32(f32(m2[0] - m1[0]) * du), f32(f32(m2[1] - m1[1]) * du)
+    out = np.zeros((L, 2), f32)
+    for row_a in range(0, L, R):
+        rows = [r for r in range(row_a, min(row_a + R, L))]
+        gx = np.array([mix(m1[0], m2[0], f32(r) * du) for r in rows], f32)
+        gz = np.array([mix(m1[1], m2[1], f32(r) * du) for r in rows], f32)
+        k0 = fma(wDx, np.full(W, gx[0], f32), fma(wDz, np.full(W, gz[0], f32), ph))
+        n = np.rint(k0.astype(np.float64) / (2 * np.pi))
+        r0 = (k0.astype(np.float64) - n * 2 * np.pi).astype(f32)       # Cody-Waite: exact to fp32 rounding
+        dk = fma(wDx, np.full(W, ex, f32), mul(wDz, np.full(W, ez, f32)))
+        c, s = chain(r0.astype(np.float64), dk.astype(np.float64), len(rows)) if len(rows) > 1 else (np.cos(r0)[None].astype(f32), np.sin(r0)[None].astype(f32))
+        for j in range(len(rows)):
+            x, z = gx[j], gz[j]
+            for i in range(W):                                          # wave order, starting from the grid position
+                x = f32(np.float64(cX[i]) * np.float64(c[j][i]) + np.float64(x))
+                z = f32(np.float64(cZ[i]) * np.float64(c[j][i]) + np.float64(z))
+            out[rows[j]] = (x, z)
+    return out
+
+
+@pytest.mark.parametrize("W,R", [(16, 8), (64, 8), (256, 12)])
+def test_emulated_recurrence_loop_matches_the_oracle(W, R):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from common import Scene
+    from oracle import oracle as orc
+    from wave_tool_b200 import scenes
+    L = 96
+    waves = scenes.seeded_waves(W, cfg=9)
+    sc = Scene(waves, scenes.camera(), scenes.animation_params(5), L, scenes.procedural_heightmap(64))
+    st, frame = sc.frame()
+    assert st == 0
+    O = orc.Oracle()
+    tol = 1e-4 * sc.total_amplitude
+    for col in (0, 58, 95):
+        got = _emulate_column(frame, sc.waves, L, col, R)
+        want = sc.oracle_eval(O, ids=np.arange(L) * L + col)["pos"]
+        err = np.abs(got.astype(np.float64) - want[:, [0, 2]].astype(np.float64)).max()
+        print(f"W={W} R={R} col={col}: max |x,z error| = {err:.2e} (bar {tol:.1e})")
+        assert err <= tol
