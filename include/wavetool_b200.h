@@ -43,10 +43,15 @@ extern "C" {
 /* evaluation flags */
 #define WT_FLAG_SHADE 0x1u            /* also evaluate the vertex-evaluable fragment terms (water-grid.frag:71-73,95-111) */
 #define WT_FLAG_CHECKSUM 0x2u         /* fold the outputs into the wt_checksum record passed to the call */
-#define WT_FLAG_FAST_PHASE 0x4u       /* pre-folded 2-FMA wave phase seeded once per wave every 8 or 12 rows, per-row recurrence in between (not bit-faithful to the reference's fp32 phase; same tolerances) */
+#define WT_FLAG_FAST_PHASE 0x4u       /* pre-folded 2-FMA wave phase seeded once per wave every 8 or 12 rows, per-row recurrence in between.  NOT
+                                         bit-faithful to the reference's fp32 phase: it meets the tolerances only inside the domain
+                                         wt_fast_phase_valid describes (small phi t, vertex spacing not too fine) — prefer WT_FLAG_AUTO_PHASE */
 #define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
 #define WT_FLAG_VARYINGS 0x10u        /* also write the vertex stage's other outputs (wt_eval_frame_ex): gl_Position,
                                          xyPositionNDCSpaceHeight0, heightmap_colour.r, normalVecInViewSpaceOnlyYaw */
+#define WT_FLAG_AUTO_PHASE 0x20u      /* per frame: the recurrence kernel (WT_FLAG_FAST_PHASE) where wt_fast_phase_valid says its deviation
+                                         from the reference stays inside the tolerances with margin, else the bit-faithful kernel.  Both run
+                                         on the GPU; wt_last_phase_mode tells which one a launch used */
 
 typedef struct wt_ctx wt_ctx;
 
@@ -164,6 +169,52 @@ int wt_project_grid(const wt_camera* cam, float displaceable_amplitude, float co
  * matrices (:278-285), sun (:289-291), bounce (:299-300), projected grid (:797-1042) -> wt_frame. */
 int wt_build_frame(const wt_camera* cam, const wt_params* params, float total_wave_amplitude, wt_frame* out);
 
+/* The wave-parameter interface in physical terms (north_star: "per-wave amplitude, wavelength, steepness, direction and
+ * speed") on top of the reference-native 5-tuple — render-engine.h:138-142: "w = 2/L (roughly), where L = wavelength",
+ * "phi = S x w, where S = speed" (GPU Gems ch.1).  convention picks the wavenumber: WT_WAVENUMBER_GPU_GEMS w = 2/L (the
+ * reference's comment), WT_WAVENUMBER_PHYSICAL w = 2 pi / L (what the seeded benchmark scenes use).  The direction is
+ * normalised like the UI does (program.cpp:398). */
+#define WT_WAVENUMBER_GPU_GEMS 0
+#define WT_WAVENUMBER_PHYSICAL 1
+int wt_wave_from_wavelength_speed(float amplitude, float wavelength, float steepness, float dir_x, float dir_z, float speed,
+                                  int convention, wt_wave* out);
+
+/* The reference's parameter surface: what its ImGui panel does to a value after an edit ("force-clamp (handle CTRL +
+ * LEFT_CLICK)", program.cpp:201-479).  Note the asymmetry the reference has: some fields are clamped at both ends
+ * (glm::clamp), others only from below (`if (v < 0) v = 0`) — a CTRL-click can push those past the slider's maximum. */
+int wt_wave_clamp_ui(wt_wave* wave);                 /* program.cpp:376-401: A, w, phi >= 0; Q in [0,1]; D clamped to [-1,1]^2, normalised, 0 -> (0,1) */
+int wt_params_clamp_ui(wt_params* params);           /* :201-204, :242-250, :410-437 */
+int wt_animation_clamp_ui(wt_animation* anim);       /* :212-215, :444-447 */
+/* the SliderFloat bounds themselves, in UI order */
+typedef struct wt_ui_range {
+    const char* field;          /* RenderEngine / GerstnerWave field name */
+    float slider_min, slider_max;
+    int clamped_below, clamped_above;   /* which ends the force-clamp code enforces */
+} wt_ui_range;
+#define WT_UI_RANGE_COUNT 23
+void wt_ui_ranges(wt_ui_range out[WT_UI_RANGE_COUNT]);
+
+/* Validity domain of WT_FLAG_FAST_PHASE.  The reference rounds every wave's phase to fp32 at every vertex
+ * (water-grid.vert:78), i.e. to ulp(w D.x + phi t): the bit-faithful kernel reproduces those roundings, the recurrence
+ * kernel evaluates a cleaner phase and therefore differs from the REFERENCE by about that noise — per wave A_i ulp(k_i) in
+ * position, and that over twice the vertex spacing in the finite-difference normal.  The report estimates both deviations
+ * for one frame (a statistical bound: variances of the unshared roundings summed over the waves; the constants are the
+ * upper envelope of deviations measured over grids 1024..16384, 8..256 waves, t = 0..3600 s and the edge cameras,
+ * profiles/parity_margins.json) and compares them with the north-star
+ * tolerances with a margin of WT_PHASE_MARGIN.  Host only; returns 1 (valid), 0 (use the bit-faithful kernel) or < 0. */
+typedef struct wt_phase_report {
+    float est_position_error, position_tolerance;      /* world units; tolerance = 1e-4 x total amplitude */
+    float est_normal_error_rad, normal_tolerance_rad;  /* radians; tolerance = 1e-3 */
+    float min_vertex_spacing;                          /* smallest distance between neighbouring grid vertices */
+    float max_phase;                                   /* largest |k| any wave reaches on this frame */
+    int valid;
+} wt_phase_report;
+#define WT_PHASE_MARGIN 1.0f        /* valid iff estimate x margin <= tolerance */
+#define WT_PHASE_K_POSITION 4.5     /* extreme of the position noise in modelled sigmas */
+#define WT_PHASE_K_NORMAL 3.7       /* height-noise term of the normal estimate: envelope 2.85 x 1.27 (the kernel's own MUFU / recurrence noise) */
+#define WT_PHASE_K_FLIP 0.35        /* flipped-rounding term: envelope 0.274 x 1.27 */
+int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* frame, unsigned grid_len, wt_phase_report* out);
+
 /* ---------------------------------------------------------------------------------------------
  * Device context
  * ------------------------------------------------------------------------------------------- */
@@ -173,6 +224,11 @@ void wt_destroy(wt_ctx* ctx);
 /* Replaces the per-wave uniform upload loop (render-engine.cpp:1067-1081): derives Q_i with
  * Count() == count and stages the table for the kernels.  count in [0, WT_MAX_WAVES]. */
 int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count);
+/* wt_fast_phase_report on the context's wave set: 1 = the recurrence kernel is inside its validity domain on this
+ * frame, 0 = not (WT_FLAG_AUTO_PHASE then runs the bit-faithful kernel), < 0 error.  report may be NULL. */
+int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, wt_phase_report* report);
+/* Phase mode of the most recent evaluation launch of this context: 0 bit-faithful, 1 recurrence, -1 none yet. */
+int wt_last_phase_mode(const wt_ctx* ctx);
 
 /* Replaces load2DTexture + create2DTexture (render-engine.cpp:1308-1322, texture.cpp:54-72):
  * tightly packed RGBA8, rows ALREADY in GL order (i.e. flipped as stbi_set_flip_vertically_on_load
@@ -245,6 +301,8 @@ typedef struct wt_compose_params {
     float viewportWidth, viewportHeight;
 } wt_compose_params;
 void wt_default_compose_params(wt_compose_params* out, const wt_camera* cam, unsigned viewport_width, unsigned viewport_height);
+/* program.cpp:254-272 (fog colour; the two fog radii push each other: edited_fog_near says which slider moved), :466-479 */
+int wt_compose_params_clamp_ui(wt_compose_params* params, int edited_fog_near);
 
 /* Replaces the three FBO attachments the water program samples (render-engine.cpp:128-188, bound at :1060,:1087-1088):
  * depth (float, window-space, GL_NEAREST), local reflections and refractions (RGBA8, GL_LINEAR), all CLAMP_TO_EDGE,
@@ -274,6 +332,7 @@ typedef struct wt_sky_params {          /* RenderEngine fields, src/render-engin
     int drawStars, drawSkysphere, drawClouds;   /* the m_isVisible switches of the three sky objects; default 1 */
 } wt_sky_params;
 void wt_default_sky_params(wt_sky_params* out);
+int wt_sky_params_clamp_ui(wt_sky_params* params);   /* program.cpp:201-204, :227-257 */
 
 /* The three source textures: the 1-D sky gradient (program.cpp:644; RGBA8, GL_LINEAR, CLAMP_TO_EDGE) and the star and
  * cloud cubemaps (six n x n RGBA8 faces in GL order, rows as loaded — cubemaps are not flipped, render-engine.cpp:1332).
@@ -340,8 +399,16 @@ int wt_measure_peak(wt_ctx* ctx, int kind, double* per_second);
  * (0 when tracing is off) or < 0.  Synchronises the device. */
 int wt_debug_read_trace(wt_ctx* ctx, uint64_t* out, unsigned max_items);
 /* Diagnostic: re-reads the WT_* development knobs (WT_DYN, WT_DYN_WARPS, WT_TRACE, WT_DBG, WT_EXTRA_SMEM) from
- * the environment; they are otherwise read once when the library is loaded. */
+ * the environment.  Only libraries compiled with -DWT_DEV_KNOBS (tools/build_variant.py) have knobs; the production
+ * library ignores the environment and this call does nothing. */
 void wt_debug_reload_env(void);
+/* Diagnostic (host only, no GPU): the canonical work layout of a grid — the row chunks [begin, end) the production
+ * kernel's work items cover for rows [row_begin, row_end), for an instantiation that marches rows_per_step rows per step
+ * in phase mode 0 (bit-faithful) or 1 (recurrence).  The layout is a function of grid_len, rows_per_step and the mode
+ * only: a chunk that meets the row range is listed with its FULL canonical extent, which is what makes the results of
+ * row shards bit-identical to the unsharded evaluation.  Writes (begin, end) pairs to out[0 .. 2 capacity) in launch
+ * order and returns the number of chunks (which may exceed capacity: nothing is written then), or < 0. */
+int wt_debug_layout(unsigned grid_len, int rows_per_step, int phase_mode, unsigned row_begin, unsigned row_end, int* out, unsigned capacity);
 
 #ifdef __cplusplus
 }

@@ -205,8 +205,13 @@ class Oracle:
 
     # --- per-vertex evaluation ----------------------------------------------------------------
     def eval(self, u: Uniforms, wave_uniforms: np.ndarray, heightmap_rgba: np.ndarray, sky_faces=None,
-             ids=None, rows=None, cols=None, shade: bool = False, extra: bool = False, f64: bool = False):
-        """Returns dict(pos (n,4), normal (n,4), shade (n,4)|None, extra (n,16)|None)."""
+             ids=None, rows=None, cols=None, shade: bool = False, extra: bool = False, f64: bool = False, clean_phase: bool = False,
+             smooth_phase: bool = False):
+        """Returns dict(pos (n,4), normal (n,4), shade (n,4)|None, extra (n,16)|None).
+        clean_phase (with f64): the time offset of every wave is the shader's fp32 product fl(phi t), everything else exact —
+        the phase a smooth evaluation (the recurrence kernel) aims at.
+        smooth_phase (fp32): phase and sin/cos in double from the same fp32 inputs, all else (products, the running fp32 sum in
+        wave order) as the shader: models a kernel that does not reproduce the reference's rounding of the phase."""
         L = int(u.gridLength)
         wu = np.ascontiguousarray(wave_uniforms)
         assert wu.dtype == WAVE_UNIFORM_DTYPE and len(wu) >= u.gerstnerWaveCount
@@ -238,6 +243,7 @@ class Oracle:
         shd = np.empty((n, 4), dt) if shade else None
         ext = np.empty((n, 16), dt) if extra else None
         fn = self.lib.wto_eval_f64 if f64 else self.lib.wto_eval_f32
+        self.lib.wto_set_time_offset_fp32(2 if (smooth_phase and not f64) else (1 if (f64 and clean_phase) else 0))
         st = fn(C.byref(u), wu.ctypes.data, C.byref(tx), ids_p, n, r0, r1, c0, c1, pos.ctypes.data, nrm.ctypes.data,
                 shd.ctypes.data if shade else None, ext.ctypes.data if extra else None)
         if st != 0:

@@ -394,6 +394,8 @@ struct wto_screen_textures {
 
 namespace {
 
+int g_time_offset_fp32 = 0;   // wto_set_time_offset_fp32: see Surface::gerstner (only changes T = double)
+
 template <typename T> struct Surface {
     const wto_uniforms& u;
     const wto_wave* waves;
@@ -417,9 +419,22 @@ template <typename T> struct Surface {
             T A = (T)waves[i].A, w = (T)waves[i].w, phi = (T)waves[i].phi, Q = (T)waves[i].Q_i;
             T Dx = (T)waves[i].Dx, Dz = (T)waves[i].Dz;
             T dxz = Dx * x + Dz * z;                 // dot(vec2, vec2): tmp.x + tmp.y
-            T k = w * dxz + phi * t;
-            T c = Q * std::cos(k);
-            V3<T> d{Dx * c, std::sin(k), Dz * c};
+            // T = double, "clean phase" variant: the time offset as the shader's fp32 product fl(phi t), everything else
+            // exact — the phase a smooth (recurrence) evaluation aims at; used to budget its distance from the reference
+            T pt = g_time_offset_fp32 ? (T)((float)waves[i].phi * (float)u.waveAnimationTimeInSeconds) : phi * t;
+            T k = w * dxz + pt;
+            T ck = std::cos(k), sk = std::sin(k);
+            if (g_time_offset_fp32 == 2) {
+                // "smooth phase" variant (meaningful for T = float): the phase and its sin / cos evaluated in double from the
+                // same fp32 inputs (time offset = the shader's fl(phi t)), everything else — products, the running fp32 sum in
+                // wave order — exactly as the shader does it.  Models an evaluation that does not reproduce the reference's
+                // rounding of k (the recurrence kernel); its distance from T = float is the price of that.
+                const double kd = (double)waves[i].w * ((double)waves[i].Dx * (double)x + (double)waves[i].Dz * (double)z) +
+                                  (double)((float)waves[i].phi * (float)u.waveAnimationTimeInSeconds);
+                ck = (T)std::cos(kd); sk = (T)std::sin(kd);
+            }
+            T c = Q * ck;
+            V3<T> d{Dx * c, sk, Dz * c};
             P = P + A * d;
         }
         return P;
@@ -721,6 +736,7 @@ int wto_eval_f32(const wto_uniforms* u, const wto_wave* waves, const wto_texture
                  long long row0, long long row1, long long col0, long long col1, float* pos4, float* nrm4, float* shade4, float* extra16) {
     return eval_vertices<float>(u, waves, tx, ids, n, row0, row1, col0, col1, pos4, nrm4, shade4, extra16);
 }
+void wto_set_time_offset_fp32(int on) { g_time_offset_fp32 = on; }
 int wto_eval_f64(const wto_uniforms* u, const wto_wave* waves, const wto_textures* tx, const long long* ids, long long n,
                  long long row0, long long row1, long long col0, long long col1, double* pos4, double* nrm4, double* shade4, double* extra16) {
     return eval_vertices<double>(u, waves, tx, ids, n, row0, row1, col0, col1, pos4, nrm4, shade4, extra16);

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.common import GOLDEN, Scene, angle_between, compare, numpy_checksum, reference_heightmap
+from tests.common import GOLDEN, Scene, angle_between, compare, deviation_stats, numpy_checksum, reference_heightmap
 from wave_tool_b200 import api, scenes
 
 pytestmark = pytest.mark.gpu
@@ -190,6 +190,69 @@ def test_cfg3_shaded_vs_oracle_on_sampled_rows(oracle, cfg3, mode):
     compare(sub, want, sc, shade=True, label="cfg3 columns")
 
 
+# --------------------------------------------------------------------------------------------------
+# the validity domain of the recurrence kernel over the reference's time slider (program.cpp:433: 0 .. 3600 s)
+# --------------------------------------------------------------------------------------------------
+ENVELOPE_CASES = {
+    # name: (grid_len, waves, rows compared against the oracle (near field first))
+    "cfg1": (513, lambda: scenes.default_waves(), None),
+    "cfg2": (1024, lambda: scenes.seeded_waves(8, cfg=2), None),
+    "cfg3": (4096, lambda: scenes.seeded_waves(64, cfg=3), list(range(0, 12)) + list(range(97, 4096, 333)) + [4094, 4095]),
+    "cfg4": (8192, lambda: scenes.seeded_waves(256, cfg=4), [0, 1, 2, 3, 4097, 8190, 8191]),
+}
+
+
+@pytest.mark.parametrize("t", [0.0, 17.0, 600.0, 3600.0])
+@pytest.mark.parametrize("name", list(ENVELOPE_CASES))
+def test_phase_envelope_over_the_time_slider(oracle, hm, name, t):
+    """Every BASELINE scene at the start, in the middle and at the top of waveAnimationTimeInSeconds' slider:
+      * the bit-faithful kernel meets the north-star tolerances at every t (it reproduces the reference's own rounding of k);
+      * WT_FLAG_AUTO_PHASE meets them at every t, running the recurrence kernel exactly where wt_fast_phase_valid allows it;
+      * the recurrence kernel meets them wherever wt_fast_phase_valid says so — and really does leave them at the top of the
+        slider (cfg2 / cfg3 / cfg4 at t = 3600 s), which is why the switch exists."""
+    torch = torch_mod()
+    L, waves, rows = ENVELOPE_CASES[name]
+    p = api.default_params()
+    p.waveAnimationTimeInSeconds = t
+    sc = Scene(waves(), scenes.camera(), p, L, hm)
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    rep = ctx.fast_phase_valid(frame, L)
+    if rows is None:
+        want = sc.oracle_eval(oracle)
+        pick = lambda got: got
+    else:
+        want = sc.oracle_eval(oracle, ids=rows_to_ids(rows, L))
+        pick = lambda got: take_rows(got, rows, L)
+    results = {}
+    for mode, fl in (("exact", 0), ("auto", api.FLAG_AUTO_PHASE), ("recurrence", api.FLAG_FAST_PHASE)):
+        if L >= 8192:      # row bands (2.15 GB per full frame)
+            parts = [gpu_eval(ctx, frame, L, flags=fl, rows=(max(r - 1, 0), min(r + 2, L))) for r in rows]
+            got = {k: np.concatenate([pp[k][(r - max(r - 1, 0)) * L:(r - max(r - 1, 0) + 1) * L] for pp, r in zip(parts, rows)]) for k in ("pos", "normal")}
+        else:
+            got = pick(gpu_eval(ctx, frame, L, flags=fl))
+        ran = ctx.last_phase_mode()
+        stats, perr, ang, band = deviation_stats(got, want, sc)
+        results[mode] = (stats, ran)
+        print("envelope", name, t, mode, "ran", ran, {k: stats[k] for k in ("pos_margin", "normal_margin", "flip_band")}, "valid", rep.valid)
+        if mode == "exact":
+            assert ran == 0
+            compare(got, want, sc, label=f"{name} t={t} exact")
+        elif mode == "auto":
+            assert ran == rep.valid
+            compare(got, want, sc, label=f"{name} t={t} auto")
+        else:
+            assert ran == 1
+            if rep.valid:
+                compare(got, want, sc, label=f"{name} t={t} recurrence inside its validity domain")
+    if t >= 3600.0 and name != "cfg1":
+        assert rep.valid == 0
+        assert results["recurrence"][0]["normal_margin"] < 1.0, "the recurrence kernel was expected to leave the tolerance at the top of the slider"
+    if t <= 17.0:
+        assert rep.valid == (1 if name == "cfg2" else 0)     # cfg3 / cfg4 under the horizon-grazing default camera: near-field spacing too fine
+
+
 @pytest.mark.parametrize("mode", list(MODES))
 def test_cfg3_full_grid_vs_reference_order_kernel(cfg3, mode):
     """Full 4096^2 coverage: the production kernel against the reference-order kernel (itself checked against
@@ -214,19 +277,17 @@ def test_row_sharded_equals_unsharded_bit_exact(cfg3, mode):
     for r in range(8):
         b, e = shard.row_shard(L, r, 8)
         part = gpu_eval(ctx, frame, L, flags=fl, rows=(b, e), checksum=True)
-        if mode == "exact":
-            # every vertex is a pure function of (col,row): the very same bits whatever the shard
-            for k in ("pos", "normal", "shade"):
-                assert np.array_equal(part[k].view(np.uint32), full[k][b * L:e * L].view(np.uint32)), (r, k)
-        else:
-            # the recurrence re-seeds every 8 rows counted from the shard's first row, so a vertex's rounding
-            # depends on where its shard starts: equal within the parity tolerance, not bit for bit
-            sub = {k: full[k][b * L:e * L] for k in ("pos", "normal", "shade")}
-            compare(part, sub, sc, pos_tol=5e-5 * sc.total_amplitude, normal_tol=5e-4, label=f"shard {r}")
-            assert tuple(part["checksum"])[:3] == numpy_checksum(part["pos"], part["normal"], part["shade"])[:3]
+        # every vertex is a pure function of (col,row): the very same bits whatever the shard.  In the recurrence mode
+        # too: the marching steps (and with them the re-seed rows) sit on the CANONICAL layout of the whole grid
+        # (wt_ctx.h), not on the shard's first row
+        for k in ("pos", "normal", "shade"):
+            assert np.array_equal(part[k].view(np.uint32), full[k][b * L:e * L].view(np.uint32)), (r, k)
         parts.append(part["checksum"])
-    if mode != "exact":
-        return
+    # uneven cuts, incl. one-row shards and cuts inside a marching step
+    for b, e in [(0, 1), (1, 2), (2, 9), (9, 500), (500, 501), (501, 1023), (1023, 1024)]:
+        part = gpu_eval(ctx, frame, L, flags=fl, rows=(b, e))
+        for k in ("pos", "normal", "shade"):
+            assert np.array_equal(part[k].view(np.uint32), full[k][b * L:e * L].view(np.uint32)), (b, e, k)
     c = shard.combine_checksums(np.array(parts))
     f = full["checksum"]
     assert (c["position_bits"], c["normal_bits"], c["shade_bits"], c["vertices"]) == (f["position_bits"], f["normal_bits"], f["shade_bits"], f["vertices"])
@@ -703,10 +764,11 @@ def test_stream_ordering_on_a_non_default_stream(hm):
                 assert np.array_equal(pos[slot * n:(slot + 1) * n].cpu().numpy().view(np.uint32), want["pos"].view(np.uint32))
 
 
-def test_large_grid_digest_is_shard_invariant(hm):
-    """Size-independent property at a BASELINE-size grid (8192^2, the two-level dynamic work queue in play): in the exact
-    mode every vertex is a pure function of (col, row), so the digest of the whole frame equals the fold of the digests
-    of an uneven set of row shards, and min/max of y fold the same way."""
+@pytest.mark.parametrize("mode", list(MODES))
+def test_large_grid_digest_is_shard_invariant(hm, mode):
+    """Size-independent property at a BASELINE-size grid (8192^2, the two-level dynamic work queue in play): in BOTH phase
+    modes every vertex is a pure function of (col, row), so the digest of the whole frame equals the fold of the digests
+    of an uneven set of row shards and of the 8 row shards of a box, and min/max of y fold the same way."""
     from wave_tool_b200 import shard
     torch = torch_mod()
     L = 8192
@@ -719,7 +781,7 @@ def test_large_grid_digest_is_shard_invariant(hm):
     sp = torch.cuda.current_stream().cuda_stream
 
     def digest(rows):
-        ctx.eval_frame(frame, L, pos.data_ptr(), nrm.data_ptr(), 0, cks.data_ptr(), flags=api.FLAG_CHECKSUM, rows=rows, stream=sp)
+        ctx.eval_frame(frame, L, pos.data_ptr(), nrm.data_ptr(), 0, cks.data_ptr(), flags=api.FLAG_CHECKSUM | MODES[mode], rows=rows, stream=sp)
         torch.cuda.synchronize()
         return cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[0].copy()
 
@@ -730,6 +792,8 @@ def test_large_grid_digest_is_shard_invariant(hm):
     c = shard.combine_checksums(parts)
     assert (c["position_bits"], c["normal_bits"], c["vertices"]) == (full["position_bits"], full["normal_bits"], full["vertices"])
     assert c["min_y"] == full["min_y"] and c["max_y"] == full["max_y"]
+    c8 = shard.combine_checksums(np.array([digest(shard.row_shard(L, r, 8)) for r in range(8)]))
+    assert (c8["position_bits"], c8["normal_bits"], c8["vertices"]) == (full["position_bits"], full["normal_bits"], full["vertices"])
     # and the frame itself is sane: y within the displaceable amplitude around the base plane
     amp = sc.total_amplitude + 1.0 + 0.1
     assert -amp <= full["min_y"] < full["max_y"] <= amp

@@ -88,3 +88,42 @@ def test_frame_sharded_gather_world_size_2_gloo(tmp_path):
     assert np.array_equal(a, b)
     assert list(a["position_bits"]) == [1000 + f for f in range(10)]
     assert shard.combine_checksums(a)["vertices"] == 40
+
+
+@pytest.mark.parametrize("L,R,mode", [(4096, 8, 1), (4096, 4, 0), (16384, 8, 1), (8192, 12, 1), (1024, 8, 1), (513, 8, 1), (513, 4, 0), (7, 8, 1), (32768, 8, 1)])
+def test_canonical_layout_is_shard_invariant(L, R, mode):
+    """The work items of a row shard are the chunks of the CANONICAL layout of the whole grid that meet the shard
+    (wt_debug_layout, host only): chunks tile [0, L) exactly, every chunk keeps its full canonical extent in every
+    shard — the property that makes recurrence-mode results bit-identical across shards, streams and devices
+    (wt_ctx.h: canonical_layout) — and the 8 row shards of a box get equal work."""
+    full = api.debug_layout(L, R, mode)
+    order = np.argsort(full[:, 0])
+    srt = full[order]
+    assert srt[0, 0] == 0 and srt[-1, 1] == L and np.array_equal(srt[1:, 0], srt[:-1, 1])       # exact tiling, no overlap
+    canon = {tuple(c) for c in full}
+    rng = np.random.default_rng(L + R)
+    cuts = sorted({0, L, *rng.integers(1, L, size=min(6, L - 1)).tolist()})
+    for world in (2, 8):
+        if L >= world:
+            cuts_w = [shard.row_shard(L, r, world) for r in range(world)]
+            sizes = []
+            for b, e in cuts_w:
+                part = api.debug_layout(L, R, mode, rows=(b, e))
+                assert {tuple(c) for c in part} <= canon
+                assert all(c[1] > b and c[0] < e for c in part)                                   # only chunks that meet the shard
+                cover = sorted(part.tolist())
+                assert cover[0][0] <= b and cover[-1][1] >= e
+                sizes.append(int((part[:, 1] - part[:, 0] + 2).sum()))
+            if L >= 4096:
+                assert max(sizes) <= 1.03 * min(sizes), sizes                                     # balanced marching work per shard
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        part = api.debug_layout(L, R, mode, rows=(b, e))
+        assert {tuple(c) for c in part} <= canon
+        got = sorted(part.tolist())
+        assert got[0][0] <= b < got[0][1] and got[-1][0] < e <= got[-1][1]
+        assert all(x[1] == y[0] for x, y in zip(got[:-1], got[1:]))
+    # big items are handed out before the small ones (the tail of the launch is filled with small pieces)
+    h = full[:, 1] - full[:, 0]
+    if len(set(h.tolist())) > 1 and L >= 4096:
+        first_small = int(np.argmax(h < h.max() - R))
+        assert np.all(h[:first_small] >= h[first_small:].max())

@@ -10,7 +10,7 @@ name, defs = sys.argv[1], sys.argv[2:]
 out_dir = os.path.join(B.PKG_DIR, "variants")
 os.makedirs(out_dir, exist_ok=True)
 out = os.path.join(out_dir, f"libwt_{name}.so")
-log = B.compile_all(out, extra_flags=defs, verbose=True, obj_dir=os.path.join(out_dir, 'obj_' + name))
+log = B.compile_all(out, extra_flags=['-DWT_DEV_KNOBS'] + defs, verbose=True, obj_dir=os.path.join(out_dir, 'obj_' + name))
 lines = log.splitlines()
 for i, l in enumerate(lines):
     if "Compiling entry function" in l and "surface_warp_kernelILi64E" in l and "ELb1ELb0E" in l:

@@ -1,0 +1,106 @@
+#!/usr/bin/env python
+"""Margin table of the parity bar (GPU + the CPU oracle): for every BASELINE configuration x animation time x phase mode,
+the largest position / normal deviation of the CUDA path from the oracle relative to the north-star tolerances, and what
+wt_fast_phase_valid predicted for the frame.     python tools/parity_margins.py [out.json] [--quick]
+-> profiles/parity_margins.json (committed copy).  Not a test: tests/test_gpu_parity.py asserts the outcomes."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from oracle import oracle as orc  # noqa: E402
+from tests.common import Scene, deviation_stats, reference_heightmap  # noqa: E402
+from wave_tool_b200 import api, scenes  # noqa: E402
+
+MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE, "auto": api.FLAG_AUTO_PHASE}
+TIMES = [0.0, 3.4, 17.0, 60.0, 600.0, 3600.0]
+
+
+def rows_to_ids(rows, L):
+    return np.concatenate([np.arange(r * L, (r + 1) * L, dtype=np.int64) for r in rows])
+
+
+def gpu_rows(ctx, frame, L, flags, bands):
+    """Evaluate the row bands on the GPU; returns dict of arrays restricted to the 'inner' rows of each band."""
+    out = {"pos": [], "normal": []}
+    for b0, b1, rows in bands:
+        n = (b1 - b0) * L
+        pos = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+        nrm = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+        ctx.eval_frame(frame, L, pos.data_ptr(), nrm.data_ptr(), flags=flags, rows=(b0, b1), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        idx = np.concatenate([np.arange((r - b0) * L, (r - b0 + 1) * L) for r in rows])
+        out["pos"].append(pos.cpu().numpy()[idx])
+        out["normal"].append(nrm.cpu().numpy()[idx])
+    return {k: np.concatenate(v) for k, v in out.items()}, ctx.last_phase_mode()
+
+
+def case_bands(L, quick):
+    """(band_begin, band_end, rows compared) — whole grid for small L, near field + strided bands otherwise."""
+    if L <= 1024:
+        return [(0, L, list(range(L)))]
+    if L == 4096 and not quick:
+        return [(0, L, list(range(L)))]
+    step = max(1, L // 24)
+    bands = [(0, 24, list(range(0, 24)))]
+    for r in range(step, L - 8, step):
+        bands.append((r, r + 4, [r + 1, r + 2]))
+    bands.append((L - 8, L, list(range(L - 8, L))))
+    return bands
+
+
+def main():
+    out_path = next((a for a in sys.argv[1:] if not a.startswith("--")), os.path.join(ROOT, "gpurun_out", "parity_margins.json"))
+    quick = "--quick" in sys.argv
+    O = orc.Oracle()
+    try:
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    hm = reference_heightmap()
+    cases = [("cfg1", 513, scenes.default_waves(), scenes.camera()), ("cfg2", 1024, scenes.seeded_waves(8, cfg=2), scenes.camera()),
+             ("cfg3", 4096, scenes.seeded_waves(64, cfg=3), scenes.camera()), ("cfg4", 8192, scenes.seeded_waves(256, cfg=4), scenes.camera()),
+             ("cfg5", 16384, scenes.seeded_waves(32, cfg=5), scenes.camera()),
+             ("cfg5_high", 16384, scenes.seeded_waves(32, cfg=5), scenes.camera(**scenes.EDGE_CAMERAS["high_looking_down"]))]
+    table = []
+    for name, L, waves, cam in cases:
+        ctx = None
+        for t in TIMES:
+            if quick and t not in (0.0, 17.0, 3600.0):
+                continue
+            p = api.default_params()
+            p.waveAnimationTimeInSeconds = t
+            sc = Scene(waves, cam, p, L, hm)
+            st, frame = sc.frame()
+            assert st == api.WT_OK
+            ctx = ctx or sc.make_context()
+            bands = case_bands(L, quick or t not in (3.4, 3600.0))
+            ids = rows_to_ids([r for b in bands for r in b[2]], L)
+            t0 = time.time()
+            want = sc.oracle_eval(O, ids=ids)
+            t_or = time.time() - t0
+            rep = ctx.fast_phase_valid(frame, L)
+            for mode, fl in MODES.items():
+                got, ran = gpu_rows(ctx, frame, L, fl, bands)
+                stats, perr, ang, band = deviation_stats(got, want, sc)
+                row = {"config": name, "grid_len": L, "waves": len(waves), "t": t, "mode": mode, "kernel": "recurrence" if ran == 1 else "bit-faithful",
+                       "vertices_compared": int(len(perr)), **{k: stats[k] for k in ("pos_max", "pos_tol", "pos_margin", "normal_max", "normal_tol", "normal_margin",
+                                                                                      "pos_over_tol", "normal_over_tol", "flip_band")},
+                       "predicted": rep.as_dict(), "passes": bool(stats["pos_margin"] >= 1.0 and stats["normal_margin"] >= 1.0)}
+                table.append(row)
+                print(f"{name:9s} t={t:6.1f} {mode:10s} ran={row['kernel']:12s} pos {stats['pos_max']:.2e} (x{stats['pos_margin']:6.2f}) normal {stats['normal_max']:.2e} (x{stats['normal_margin']:6.2f})"
+                      f" over {stats['pos_over_tol']}/{stats['normal_over_tol']} of {len(perr)}  est {rep.est_position_error:.2e}/{rep.est_normal_error_rad:.2e} valid={rep.valid}  [oracle {t_or:.1f}s]", flush=True)
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    json.dump({"tolerances": "north_star: position 1e-4 x total amplitude, normal 1e-3 rad; margin = tolerance / largest deviation from the oracle",
+               "rows": table}, open(out_path, "w"), indent=1)
+    print("wrote", out_path)
+
+
+if __name__ == "__main__":
+    main()

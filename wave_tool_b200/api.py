@@ -16,7 +16,9 @@ from . import build as _build
 WT_OK, WT_NO_GRID = 0, 1
 WT_ERR_INVALID_ARGUMENT, WT_ERR_CUDA, WT_ERR_NO_DEVICE, WT_ERR_NOT_READY, WT_ERR_DEGENERATE = -1, -2, -3, -4, -5
 WT_MAX_WAVES = 1000
-FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER, FLAG_VARYINGS = 0x1, 0x2, 0x4, 0x8, 0x10
+FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER, FLAG_VARYINGS, FLAG_AUTO_PHASE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+WAVENUMBER_GPU_GEMS, WAVENUMBER_PHYSICAL = 0, 1
+UI_RANGE_COUNT = 23
 
 # every symbol include/wavetool_b200.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTED_SYMBOLS = [
@@ -26,10 +28,12 @@ EXPORTED_SYMBOLS = [
     "wt_project_grid", "wt_build_frame",
     "wt_create", "wt_destroy", "wt_set_waves", "wt_set_heightmap_rgba8", "wt_set_skybox_rgba8",
     "wt_eval_frame", "wt_eval_batch", "wt_eval_frame_host", "wt_launch_count", "wt_measure_peak",
-    "wt_debug_read_trace", "wt_debug_reload_env", "wt_eval_frame_ex", "wt_grid_indices",
+    "wt_debug_read_trace", "wt_debug_reload_env", "wt_debug_layout", "wt_eval_frame_ex", "wt_grid_indices",
     "wt_default_animation", "wt_animation_advance", "wt_run_animation",
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
+    "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode",
 ]
 
 
@@ -83,6 +87,18 @@ class SkyParams(C.Structure):
     _fields_ = [("timeOfDayInHours", C.c_float), ("cloudProportion", C.c_float), ("overcastStrength", C.c_float), ("sunHorizonDarkness", C.c_float),
                 ("sunShininess", C.c_float), ("sunStrength", C.c_float), ("fogColourFarAtNoon", C.c_float * 4),
                 ("drawStars", C.c_int), ("drawSkysphere", C.c_int), ("drawClouds", C.c_int)]
+
+
+class PhaseReport(C.Structure):
+    _fields_ = [("est_position_error", C.c_float), ("position_tolerance", C.c_float), ("est_normal_error_rad", C.c_float),
+                ("normal_tolerance_rad", C.c_float), ("min_vertex_spacing", C.c_float), ("max_phase", C.c_float), ("valid", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class UiRange(C.Structure):
+    _fields_ = [("field", C.c_char_p), ("slider_min", C.c_float), ("slider_max", C.c_float), ("clamped_below", C.c_int), ("clamped_above", C.c_int)]
 
 
 class Outputs(C.Structure):
@@ -146,6 +162,7 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_measure_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.wt_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
     L.wt_debug_reload_env.restype = None
+    L.wt_debug_layout.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_uint]
     L.wt_eval_frame_ex.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs), C.c_uint, C.c_void_p]
     L.wt_grid_indices.argtypes = [C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.wt_default_compose_params.argtypes = [C.POINTER(ComposeParams), C.POINTER(Camera), C.c_uint, C.c_uint]
@@ -158,6 +175,17 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_step_submit.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(Params), C.c_float, C.c_uint, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_uint)]
     L.wt_step_wait.argtypes = [C.c_void_p, C.c_uint, C.POINTER(Checksum)]
+    L.wt_wave_from_wavelength_speed.argtypes = [C.c_float] * 6 + [C.c_int, C.POINTER(Wave)]
+    L.wt_wave_clamp_ui.argtypes = [C.POINTER(Wave)]
+    L.wt_params_clamp_ui.argtypes = [C.POINTER(Params)]
+    L.wt_animation_clamp_ui.argtypes = [C.POINTER(Animation)]
+    L.wt_sky_params_clamp_ui.argtypes = [C.POINTER(SkyParams)]
+    L.wt_compose_params_clamp_ui.argtypes = [C.POINTER(ComposeParams), C.c_int]
+    L.wt_ui_ranges.argtypes = [C.POINTER(UiRange)]
+    L.wt_ui_ranges.restype = None
+    L.wt_fast_phase_report.argtypes = [C.c_void_p, C.c_uint, C.POINTER(Frame), C.c_uint, C.POINTER(PhaseReport)]
+    L.wt_fast_phase_valid.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.POINTER(PhaseReport)]
+    L.wt_last_phase_mode.argtypes = [C.c_void_p]
     L.wt_default_sky_params.argtypes = [C.POINTER(SkyParams)]
     L.wt_default_sky_params.restype = None
     L.wt_set_sky_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -253,6 +281,36 @@ def grid_indices(grid_len: int) -> np.ndarray:
     out = np.empty(n.value, np.uint32)
     _check(lib().wt_grid_indices(grid_len, out.ctypes.data, n.value, C.byref(n)))
     return out
+
+
+def wave_from_wavelength_speed(amplitude, wavelength, steepness, direction, speed, convention=WAVENUMBER_PHYSICAL) -> Wave:
+    w = Wave()
+    _check(lib().wt_wave_from_wavelength_speed(amplitude, wavelength, steepness, direction[0], direction[1], speed, convention, C.byref(w)))
+    return w
+
+
+def ui_ranges() -> dict:
+    arr = (UiRange * UI_RANGE_COUNT)()
+    lib().wt_ui_ranges(arr)
+    return {r.field.decode(): (r.slider_min, r.slider_max, bool(r.clamped_below), bool(r.clamped_above)) for r in arr}
+
+
+def fast_phase_report(waves: np.ndarray, frame: Frame, grid_len: int) -> PhaseReport:
+    """wt_fast_phase_report (host only): the estimated deviation of the recurrence kernel from the reference on this frame."""
+    w = waves_array(waves)
+    rep = PhaseReport()
+    _check(lib().wt_fast_phase_report(w.ctypes.data, len(w), C.byref(frame), grid_len, C.byref(rep)))
+    return rep
+
+
+def debug_layout(grid_len: int, rows_per_step: int, phase_mode: int, rows=None) -> np.ndarray:
+    """(n,2) int32 canonical row chunks [begin, end) of the work items that meet `rows` (wt_debug_layout; host only)."""
+    r0, r1 = rows if rows is not None else (0, grid_len)
+    cap = 4 * (grid_len // 4 + 16)
+    out = np.zeros((cap, 2), np.int32)
+    n = _check(lib().wt_debug_layout(grid_len, rows_per_step, phase_mode, r0, r1, out.ctypes.data, cap))
+    assert n <= cap
+    return out[:n].copy()
 
 
 def build_frame(cam: Camera, params: Params, total_wave_amplitude: float):
@@ -404,6 +462,14 @@ class Context:
                                             shd.ctypes.data if shd is not None else None,
                                             C.byref(cks) if cks is not None else None, flags), self._h)
         return {"pos": pos, "normal": nrm, "shade": shd, "checksum": cks}
+
+    def fast_phase_valid(self, frame: Frame, grid_len: int) -> PhaseReport:
+        rep = PhaseReport()
+        _check(self._lib.wt_fast_phase_valid(self._h, C.byref(frame), grid_len, C.byref(rep)), self._h)
+        return rep
+
+    def last_phase_mode(self) -> int:
+        return int(self._lib.wt_last_phase_mode(self._h))
 
     def launch_count(self) -> int:
         return int(self._lib.wt_launch_count(self._h))

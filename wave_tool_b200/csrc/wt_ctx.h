@@ -19,6 +19,8 @@ struct wt_ctx {
     unsigned n_waves = 0;
     bool waves_set = false;
     std::vector<wt::WaveK> tab_exact, tab_fast, tab_raw;
+    std::vector<wt_wave> waves;     // as handed to wt_set_waves (wt_fast_phase_valid)
+    int last_phase_mode = -1;       // 0 bit-faithful, 1 recurrence: what the most recent evaluation launch ran
     // textures
     float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
     float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)
@@ -67,7 +69,8 @@ constexpr unsigned STEP_RING = 4;   // frames in flight between wt_step_submit a
 
 namespace wt {
 
-// Development knobs, read from the environment once (wt_debug_reload_env re-reads them):
+// Development knobs.  They exist only in builds compiled with -DWT_DEV_KNOBS (tools/build_variant.py); the
+// production library ignores the environment: its launch plans are a function of the grid alone.
 //   WT_DYN        rows per dynamically queued work item (0 = static plan; unset = built-in policy)
 //   WT_DYN_SMALL  rows per item of the tail of the dynamic plan (0 = single level), WT_DYN_TAIL = percent of the rows it covers
 //   WT_DYN_WARPS  cap on the resident warps per SM of the dynamic plan
@@ -77,10 +80,14 @@ namespace wt {
 //   WT_FANOUT     internal streams used for batches of small frames (1 = none; unset = built-in policy)
 struct Knobs {
     int dyn = -1, dyn_small = -1, dyn_tail = -1, dyn_warps = 0, trace = 0, dbg = 0, extra_smem = 0, fanout = -1;
+    unsigned generation = 0;   // bumped by every load(): cached launch plans are keyed on it
     void load() {
+#ifdef WT_DEV_KNOBS
         auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e && *e ? std::atoi(e) : dflt; };
         dyn = geti("WT_DYN", -1); dyn_small = geti("WT_DYN_SMALL", -1); dyn_tail = geti("WT_DYN_TAIL", -1); dyn_warps = geti("WT_DYN_WARPS", 0); trace = geti("WT_TRACE", 0); dbg = geti("WT_DBG", 0);
         extra_smem = geti("WT_EXTRA_SMEM", 0); fanout = geti("WT_FANOUT", -1);
+#endif
+        ++generation;
     }
     Knobs() { load(); }
 };
@@ -109,10 +116,36 @@ constexpr int R_RECUR_BIG = WT_R_RECUR_BIG;   // ... for the wave-table tiers ab
 
 struct Plan {
     int n_strips = 1, rows_per_chunk = 1, n_chunks = 1, ctas = 1;
-    int n_big = -1, rows_small = 0;   // two-level dynamic plan (n_big < 0: every chunk has rows_per_chunk rows)
 };
 
 Plan make_plan(int slots, int L, int rows, int R);
+
+// Canonical work layout of a grid: which rows form one work item.  A function of (grid_len, rows per marching
+// step, phase mode) ONLY — not of the device, the occupancy or the row range of the call — because in the
+// recurrence mode the rounding of a vertex depends on where its item's marching steps start: with a canonical
+// layout every vertex has the same bits whatever the shard, the stream or the GPU it is evaluated on.
+//   The rows are cut into `bands` equal bands (the row shards of an 8-GPU box, wave_tool_b200/shard.py:row_shard);
+//   each band holds n_big items of rows_big rows followed by items of rows_small rows (the tail that keeps every
+//   warp busy until the queue is empty); the last item of a band is clipped at the band's end.
+constexpr int NOMINAL_SMS = 148;     // B200; the layout must not depend on the device actually used
+constexpr int LAYOUT_BANDS = 8;
+constexpr int MAX_SEGS = 2 * LAYOUT_BANDS;
+struct Layout {
+    int n_strips = 1, bands = 1, rows_big = 1, rows_small = 0, tail_pct = 0;
+    void band_range(int L, int b, int& lo, int& hi) const {
+        const int base = L / bands, rem = L % bands;
+        lo = b * base + (b < rem ? b : rem);
+        hi = lo + base + (b < rem ? 1 : 0);
+    }
+    int n_big(int band_rows) const {
+        if (rows_small <= 0) return (band_rows + rows_big - 1) / rows_big;
+        return (int)((long long)band_rows * (100 - tail_pct) / 100 / rows_big);
+    }
+};
+Layout canonical_layout(int L, int R, int mode);
+// The work items of rows [row_begin, row_end) under `lay`, as segments of equally sized chunks (big items of all
+// bands first, then the small ones): fills the seg_* fields, n_seg and n_items of `a`.
+void layout_segments(const Layout& lay, int L, int row_begin, int row_end, EvalArgs& a);
 
 inline int wave_capacity(unsigned n) { return n <= 64 ? 64 : n <= 256 ? 256 : 1000; }
 

@@ -30,10 +30,10 @@ using namespace wt;
 namespace wt {
 Knobs g_knobs;
 
-// Work items are warps: n_strips strips of STRIP_COLS columns x n_chunks chunks of rows.  Every item
-// marches rows_per_chunk + 2 rows (the +-1-row stencil halo is recomputed, never exchanged), in steps
-// of R.  Cost model: the SMs hold `slots` warps at a time; a partially filled round costs as much as
-// a full one; smaller chunks balance better but pay the 2 halo rows more often.
+// Work items are warps: n_strips strips of STRIP_COLS columns x chunks of rows.  Every item marches its rows + 2
+// (the +-1-row stencil halo is recomputed, never exchanged), in steps of R.  Cost model for grids with few items:
+// the SMs hold `slots` warps at a time; a partially filled round costs as much as a full one; smaller chunks
+// balance better but pay the 2 halo rows more often.
 Plan make_plan(int slots, int L, int rows, int R) {
     Plan best;
     double best_cost = 1e300;
@@ -54,6 +54,63 @@ Plan make_plan(int slots, int L, int rows, int R) {
         }
     }
     return best;
+}
+
+Layout canonical_layout(int L, int R, int mode) {
+    Layout lay;
+    lay.n_strips = (L + STRIP_COLS - 1) / STRIP_COLS;
+    // resident warps of a B200 for this instantiation (__launch_bounds__ of surface_warp_kernel) — a constant of the
+    // layout, NOT the occupancy of the device in use
+    const int slots = NOMINAL_SMS * (mode == 1 ? (R > 8 ? WT_LB_RECUR_BIG : WT_LB_RECUR) : WT_LB_EXACT);
+    auto round_rows = [R](int want) { int r = ((want + 2 + R - 1) / R) * R - 2; return r < 1 ? R : r; };   // rows + 2 a multiple of R
+    int big = mode == 1 ? DYN_ROWS_RECUR : DYN_ROWS_EXACT, small = mode == 1 ? DYN_SMALL_RECUR : DYN_SMALL_EXACT, tail = DYN_TAIL_PERCENT;
+    const bool forced = g_knobs.dyn >= 0;           // development builds only (WT_DEV_KNOBS)
+    if (forced) big = g_knobs.dyn;
+    if (g_knobs.dyn_small >= 0) small = g_knobs.dyn_small;
+    if (g_knobs.dyn_tail >= 0) tail = g_knobs.dyn_tail;
+    if (big > 0) {
+        lay.rows_big = round_rows(big);
+        lay.rows_small = (small > 0 && small < big && tail > 0) ? round_rows(small) : 0;
+        lay.tail_pct = lay.rows_small ? tail : 0;
+        lay.bands = L >= LAYOUT_BANDS * 4 * lay.rows_big ? LAYOUT_BANDS : 1;
+        long long chunks = 0;
+        for (int b = 0; b < lay.bands; ++b) {
+            int lo, hi;
+            lay.band_range(L, b, lo, hi);
+            const int nb = lay.n_big(hi - lo);
+            chunks += nb + (lay.rows_small ? (hi - lo - nb * lay.rows_big + lay.rows_small - 1) / lay.rows_small : 0);
+        }
+        if (forced || chunks * lay.n_strips >= 2LL * slots) return lay;
+    }
+    // few items: one level of equal chunks sized to fill the machine
+    const Plan p = make_plan(slots, L, L, R);
+    lay.bands = 1; lay.rows_big = p.rows_per_chunk; lay.rows_small = 0; lay.tail_pct = 0;
+    return lay;
+}
+
+void layout_segments(const Layout& lay, int L, int row_begin, int row_end, EvalArgs& a) {
+    a.n_strips = lay.n_strips;
+    a.n_seg = 0;
+    a.seg_prefix[0] = 0;
+    auto push = [&](int row0, int rows, int end) {   // chunks of `rows` rows from row0 up to `end`, those meeting [row_begin, row_end)
+        if (rows <= 0 || row0 >= end) return;
+        const int lo = std::max(row_begin, row0), hi = std::min(row_end, end);
+        if (lo >= hi) return;
+        const int c_lo = (lo - row0) / rows, c_hi = (hi - 1 - row0) / rows;
+        const int s = a.n_seg++;
+        a.seg_row0[s] = row0 + c_lo * rows; a.seg_rows[s] = rows; a.seg_end[s] = end;
+        a.seg_prefix[s + 1] = a.seg_prefix[s] + (c_hi - c_lo + 1);
+    };
+    for (int pass = 0; pass < 2; ++pass) {           // big items of every band first, the small ones after them
+        for (int b = 0; b < lay.bands; ++b) {
+            int lo, hi;
+            lay.band_range(L, b, lo, hi);
+            const int split = lay.rows_small ? lo + lay.n_big(hi - lo) * lay.rows_big : hi;
+            if (pass == 0) push(lo, lay.rows_big, split);
+            else push(split, lay.rows_small, hi);
+        }
+    }
+    a.n_items = a.n_strips * a.seg_prefix[a.n_seg];
 }
 
 }  // namespace wt
@@ -185,8 +242,24 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
     return a;
 }
 
+// WT_FLAG_AUTO_PHASE: the recurrence kernel where its deviation from the reference's own phase rounding stays inside
+// the tolerances (wt_fast_phase_report on this frame's corners and time), the bit-faithful kernel elsewhere
+bool fast_phase_ok(const wt_ctx* ctx, const EvalArgs& a) {
+    wt_frame f;
+    std::memset(&f, 0, sizeof(f));
+    f.bottomLeftGridPointInWorld[0] = a.blx; f.bottomLeftGridPointInWorld[2] = a.blz;
+    f.bottomRightGridPointInWorld[0] = a.brx; f.bottomRightGridPointInWorld[2] = a.brz;
+    f.topLeftGridPointInWorld[0] = a.tlx; f.topLeftGridPointInWorld[2] = a.tlz;
+    f.topRightGridPointInWorld[0] = a.trx; f.topRightGridPointInWorld[2] = a.trz;
+    f.waveAnimationTimeInSeconds = a.t;
+    return wt_fast_phase_report(ctx->waves.data(), (unsigned)ctx->waves.size(), &f, (unsigned)a.L, nullptr) == 1;
+}
+
 cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
     const bool shade = flags & WT_FLAG_SHADE;
+    if ((flags & WT_FLAG_AUTO_PHASE) && !(flags & WT_FLAG_REFERENCE_ORDER))
+        flags = fast_phase_ok(ctx, a) ? (flags | WT_FLAG_FAST_PHASE) : (flags & ~WT_FLAG_FAST_PHASE);
+    ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? 0 : ((flags & WT_FLAG_FAST_PHASE) ? 1 : 0);
     if (flags & WT_FLAG_REFERENCE_ORDER) {
         switch (wave_capacity(ctx->n_waves)) {
             case 64: return shade ? launch_reference_order<64, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<64, false>(ctx, a, ctx->tab_raw, stream);
@@ -295,10 +368,19 @@ int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count) {
         ctx->tab_fast[i] = {(float)((double)w.frequency_w * w.dir_x), (float)((double)w.frequency_w * w.dir_z), w.frequency_w, w.phaseConstant_phi, cX, w.amplitude_A, cZ, 0.f};
         ctx->tab_raw[i] = {w.dir_x, w.dir_z, w.frequency_w, w.phaseConstant_phi, Qi, w.amplitude_A, 0.f, 0.f};
     }
+    ctx->waves.assign(waves, waves + count);
     ctx->n_waves = count;
     ctx->waves_set = true;
     return WT_OK;
 }
+
+int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned L, wt_phase_report* report) {
+    if (!ctx || !frame) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_fast_phase_valid: NULL argument");
+    if (!ctx->waves_set) return fail(nullptr, WT_ERR_NOT_READY, "wt_fast_phase_valid: wt_set_waves has not been called");
+    return wt_fast_phase_report(ctx->waves.data(), (unsigned)ctx->waves.size(), frame, L, report);
+}
+
+int wt_last_phase_mode(const wt_ctx* ctx) { return ctx ? ctx->last_phase_mode : -1; }
 
 int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int w, int h) {
     if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_set_heightmap_rgba8: ctx is NULL");
@@ -590,6 +672,24 @@ int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned 
 uint64_t wt_launch_count(const wt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void wt_debug_reload_env(void) { g_knobs.load(); }
+
+int wt_debug_layout(unsigned L, int rows_per_step, int phase_mode, unsigned row_begin, unsigned row_end, int* out, unsigned capacity) {
+    if (L < 2 || L > 32768 || rows_per_step < 1 || row_begin >= row_end || row_end > L || !out)
+        return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_debug_layout: bad argument");
+    EvalArgs a;
+    std::memset(&a, 0, sizeof(a));
+    layout_segments(canonical_layout((int)L, rows_per_step, phase_mode), (int)L, (int)row_begin, (int)row_end, a);
+    const int n = a.seg_prefix[a.n_seg];
+    if ((unsigned)n > capacity) return n;
+    int k = 0;
+    for (int s = 0; s < a.n_seg; ++s)
+        for (int q = a.seg_prefix[s]; q < a.seg_prefix[s + 1]; ++q, ++k) {
+            const int c0 = a.seg_row0[s] + (q - a.seg_prefix[s]) * a.seg_rows[s];
+            out[2 * k] = c0;
+            out[2 * k + 1] = std::min(c0 + a.seg_rows[s], a.seg_end[s]);
+        }
+    return n;
+}
 
 int wt_debug_read_trace(wt_ctx* ctx, uint64_t* out, unsigned max_items) {
     if (!ctx || !out) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_debug_read_trace: NULL argument");

@@ -6,6 +6,7 @@
 // Replaces: Camera (src/camera.cpp:47-146), RenderEngine::render's per-frame scalars
 // (src/render-engine.cpp:278-300) and its projected-grid block (src/render-engine.cpp:797-1042),
 // geometry::Plane/Line + utils::linePlaneIntersection (src/render-engine.h:53-124).
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -283,6 +284,197 @@ int wt_build_frame(const wt_camera* cam, const wt_params* p, float total_wave_am
     std::memcpy(out->bottomRightGridPointInWorld, c[2], 16);
     std::memcpy(out->topRightGridPointInWorld, c[3], 16);
     return WT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameter surface: the reference's sliders and their "force-clamp" code
+// ------------------------------------------------------------------------------------------------
+static inline float clamp01(float v) { return std::fmin(std::fmax(v, 0.0f), 1.0f); }   // glm::clamp(v, 0, 1)
+static inline float floor0(float v) { return v < 0.0f ? 0.0f : v; }                     // `if (v < 0) v = 0`: NaN passes through like in the reference
+
+int wt_wave_from_wavelength_speed(float amplitude, float wavelength, float steepness, float dir_x, float dir_z, float speed, int convention,
+                                  wt_wave* out) {
+    if (!out) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_wave_from_wavelength_speed: out is NULL");
+    if (!(wavelength > 0.0f) || !(amplitude >= 0.0f) || !(speed >= 0.0f) || !(steepness >= 0.0f && steepness <= 1.0f))
+        return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_wave_from_wavelength_speed: need wavelength > 0, amplitude >= 0, speed >= 0, steepness in [0,1]");
+    if (convention != WT_WAVENUMBER_GPU_GEMS && convention != WT_WAVENUMBER_PHYSICAL)
+        return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_wave_from_wavelength_speed: unknown convention");
+    const float len = std::sqrt(dir_x * dir_x + dir_z * dir_z);
+    if (!(len > 0.0f)) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_wave_from_wavelength_speed: direction is the zero vector");
+    // render-engine.h:139-140: "w = 2/L (roughly)", "phi = S x w" (GPU Gems ch.1 eq. 1-2); the physical wavenumber is 2 pi / L
+    const float w = (convention == WT_WAVENUMBER_GPU_GEMS ? 2.0f : 6.283185307179586476925286766559f) / wavelength;
+    out->amplitude_A = amplitude;
+    out->frequency_w = w;
+    out->phaseConstant_phi = speed * w;
+    out->steepness_Q = steepness;
+    out->dir_x = dir_x / len;     // glm::normalize divides by the length
+    out->dir_z = dir_z / len;
+    return WT_OK;
+}
+
+int wt_wave_clamp_ui(wt_wave* w) {   // program.cpp:376-401
+    if (!w) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_wave_clamp_ui: NULL argument");
+    w->amplitude_A = floor0(w->amplitude_A);               // :376-379 (slider 0..1, only the lower end is forced)
+    w->frequency_w = floor0(w->frequency_w);               // :380-383
+    w->phaseConstant_phi = floor0(w->phaseConstant_phi);   // :384-387 (slider 0..10)
+    w->steepness_Q = clamp01(w->steepness_Q);              // :388-391
+    float x = std::fmin(std::fmax(w->dir_x, -1.0f), 1.0f), z = std::fmin(std::fmax(w->dir_z, -1.0f), 1.0f);   // :392-394
+    const float len = std::sqrt(x * x + z * z);
+    if (len == 0.0f) { x = 0.0f; z = 1.0f; }               // :397
+    else { x /= len; z /= len; }                           // :398
+    w->dir_x = x; w->dir_z = z;
+    return WT_OK;
+}
+
+int wt_params_clamp_ui(wt_params* p) {   // program.cpp:201-204, 242-250, 410-437
+    if (!p) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_params_clamp_ui: NULL argument");
+    p->timeOfDayInHours = std::fmin(std::fmax(p->timeOfDayInHours, 0.0f), 24.0f);   // :201-204
+    p->sunShininess = floor0(p->sunShininess);                                      // :242-245 (slider 0..200)
+    p->sunStrength = clamp01(p->sunStrength);                                       // :247-250
+    p->heightmapSampleScale = floor0(p->heightmapSampleScale);                      // :410-413
+    p->heightmapDisplacementScale = floor0(p->heightmapDisplacementScale);          // :415-418
+    p->verticalBounceWaveAmplitude = floor0(p->verticalBounceWaveAmplitude);        // :420-423
+    p->verticalBounceWavePhase = clamp01(p->verticalBounceWavePhase);               // :425-428
+    p->waveAnimationTimeInSeconds = floor0(p->waveAnimationTimeInSeconds);          // :433-436 (slider 0..3600)
+    return WT_OK;
+}
+
+int wt_animation_clamp_ui(wt_animation* a) {   // program.cpp:212-215, 444-447
+    if (!a) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_animation_clamp_ui: NULL argument");
+    a->animationSpeedTimeOfDayInSecondsPerHour = floor0(a->animationSpeedTimeOfDayInSecondsPerHour);
+    a->animationSpeedVerticalBounceWavePhasePeriodInSeconds = floor0(a->animationSpeedVerticalBounceWavePhasePeriodInSeconds);
+    a->isAnimatingTimeOfDay = a->isAnimatingTimeOfDay ? 1 : 0;
+    a->isAnimatingWaves = a->isAnimatingWaves ? 1 : 0;
+    return WT_OK;
+}
+
+int wt_sky_params_clamp_ui(wt_sky_params* s) {   // program.cpp:201-204, 227-250, 254-257
+    if (!s) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_sky_params_clamp_ui: NULL argument");
+    s->timeOfDayInHours = std::fmin(std::fmax(s->timeOfDayInHours, 0.0f), 24.0f);
+    s->cloudProportion = clamp01(s->cloudProportion);          // :227-230
+    s->overcastStrength = clamp01(s->overcastStrength);        // :232-235
+    s->sunHorizonDarkness = clamp01(s->sunHorizonDarkness);    // :237-240
+    s->sunShininess = floor0(s->sunShininess);                 // :242-245
+    s->sunStrength = clamp01(s->sunStrength);                  // :247-250
+    for (int i = 0; i < 4; ++i) s->fogColourFarAtNoon[i] = clamp01(s->fogColourFarAtNoon[i]);   // :254-257
+    s->drawStars = s->drawStars ? 1 : 0; s->drawSkysphere = s->drawSkysphere ? 1 : 0; s->drawClouds = s->drawClouds ? 1 : 0;
+    return WT_OK;
+}
+
+int wt_compose_params_clamp_ui(wt_compose_params* c, int edited_fog_near) {   // program.cpp:254-272, 466-479
+    if (!c) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_compose_params_clamp_ui: NULL argument");
+    for (int i = 0; i < 4; ++i) c->fogColourFarAtNoon[i] = clamp01(c->fogColourFarAtNoon[i]);
+    if (edited_fog_near) {   // :266-271 — the slider that moved wins, the other bound is shifted
+        c->fogDepthRadiusNear = clamp01(c->fogDepthRadiusNear);
+        c->fogDepthRadiusFar = std::fmin(std::fmax(c->fogDepthRadiusFar, c->fogDepthRadiusNear), 1.0f);
+    } else {                 // :259-264
+        c->fogDepthRadiusFar = clamp01(c->fogDepthRadiusFar);
+        c->fogDepthRadiusNear = std::fmin(std::fmax(c->fogDepthRadiusNear, 0.0f), c->fogDepthRadiusFar);
+    }
+    c->tintDeltaDepthThreshold = clamp01(c->tintDeltaDepthThreshold);             // :466-469
+    c->waterClarity = clamp01(c->waterClarity);                                   // :471-474
+    c->softEdgesDeltaDepthThreshold = clamp01(c->softEdgesDeltaDepthThreshold);   // :476-479
+    return WT_OK;
+}
+
+void wt_ui_ranges(wt_ui_range out[WT_UI_RANGE_COUNT]) {   // the SliderFloat bounds of program.cpp:201-479, in UI order
+    static const wt_ui_range R[WT_UI_RANGE_COUNT] = {
+        {"timeOfDayInHours", 0.0f, 24.0f, 1, 1},                                          // :201
+        {"animationSpeedTimeOfDayInSecondsPerHour", 0.0f, 60.0f, 1, 0},                   // :212
+        {"cloudProportion", 0.0f, 1.0f, 1, 1}, {"overcastStrength", 0.0f, 1.0f, 1, 1},    // :227, :232
+        {"sunHorizonDarkness", 0.0f, 1.0f, 1, 1},                                         // :237
+        {"sunShininess", 0.0f, 200.0f, 1, 0}, {"sunStrength", 0.0f, 1.0f, 1, 1},          // :242, :247
+        {"fogDepthRadiusFar", 0.0f, 1.0f, 1, 1}, {"fogDepthRadiusNear", 0.0f, 1.0f, 1, 1},// :259, :266
+        {"amplitude_A", 0.0f, 1.0f, 1, 0}, {"frequency_w", 0.0f, 1.0f, 1, 0},             // :376, :380
+        {"phaseConstant_phi", 0.0f, 10.0f, 1, 0}, {"steepness_Q", 0.0f, 1.0f, 1, 1},      // :384, :388
+        {"xzDirection_D", -1.0f, 1.0f, 1, 1},                                             // :392
+        {"heightmapSampleScale", 0.0f, 1.0f, 1, 0}, {"heightmapDisplacementScale", 0.0f, 1.0f, 1, 0},   // :410, :415
+        {"verticalBounceWaveAmplitude", 0.0f, 1.0f, 1, 0}, {"verticalBounceWavePhase", 0.0f, 1.0f, 1, 1},// :420, :425
+        {"waveAnimationTimeInSeconds", 0.0f, 3600.0f, 1, 0},                              // :433
+        {"animationSpeedVerticalBounceWavePhasePeriodInSeconds", 0.0f, 60.0f, 1, 0},      // :444
+        {"tintDeltaDepthThreshold", 0.0f, 1.0f, 1, 1}, {"waterClarity", 0.0f, 1.0f, 1, 1},// :466, :471
+        {"softEdgesDeltaDepthThreshold", 0.0f, 1.0f, 1, 1},                               // :476
+    };
+    if (out) std::memcpy(out, R, sizeof(R));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Validity domain of WT_FLAG_FAST_PHASE
+// ------------------------------------------------------------------------------------------------
+// The reference rounds the phase of every wave at every vertex to fp32:
+//     k = fl(fl(w * fl(fl(D.x x) + fl(D.z z))) + fl(phi t))                       (water-grid.vert:78)
+// so k carries a deterministic error of up to ulp(k)/2 — 1.5e-5 rad at |k| ~ 300 (a short wave at the far side of the
+// default grid), 2e-3 rad at phi t = 36000 (the top of the reference's time slider).  The bit-faithful mode reproduces
+// those roundings bit for bit.  The recurrence mode evaluates a CLEANER phase (pre-folded w D, the time offset reduced mod
+// 2 pi in double, an affine step per row): it does not share the reference's rounding noise, so it sits ~ulp(k) x A_i
+// away from the reference per wave, and its finite-difference normals by that noise over twice the vertex spacing.  This
+// estimator adds the variances of the roundings the two paths do not share, per wave, and scales by the spacing of the
+// grid; the constants are calibrated against measured deviations (profiles/parity_margins.json).
+static inline float ulp_of(float x) {
+    x = std::fabs(x);
+    if (!(x > 0.0f)) return 0.0f;
+    int e;
+    std::frexp(x, &e);                       // x = m 2^e, m in [0.5, 1)
+    return std::ldexp(1.0f, e - 24);
+}
+
+int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f, unsigned L, wt_phase_report* out) {
+    if ((count && !waves) || !f || L < 2) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_fast_phase_report: bad argument");
+    const float* c[4] = {f->bottomLeftGridPointInWorld, f->bottomRightGridPointInWorld, f->topLeftGridPointInWorld, f->topRightGridPointInWorld};
+    double rho = 0.0, coord = 0.0;           // largest |xz| and largest |x| or |z| of the grid (the bilinear hull of its corners)
+    for (int i = 0; i < 4; ++i) {
+        rho = std::fmax(rho, std::hypot((double)c[i][0], (double)c[i][2]));
+        coord = std::fmax(coord, std::fmax(std::fabs((double)c[i][0]), std::fabs((double)c[i][2])));
+    }
+    // vertex spacing along u and along v at the four corners; the noise-to-angle gain is largest where both are small
+    auto dist = [&](int a, int b) { return std::hypot((double)c[a][0] - c[b][0], (double)c[a][2] - c[b][2]) / (double)(L - 1); };
+    const double hu[2] = {dist(0, 1), dist(2, 3)}, hv[2] = {dist(0, 2), dist(1, 3)};   // bottom / top edge, left / right edge
+    double gain = 0.0, hmin = 1e300;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+            const double u = std::fmax(hu[a], 1e-30), v = std::fmax(hv[b], 1e-30);
+            gain = std::fmax(gain, std::sqrt(1.0 / (u * u) + 1.0 / (v * v)));
+            hmin = std::fmin(hmin, std::fmin(u, v));
+        }
+    const double t = f->waveAnimationTimeInSeconds;
+    const float urho = ulp_of((float)rho);
+    const double uc = ulp_of((float)coord);
+    double var_y = 0.0, var_h = 0.0, total = 0.0, kmax = 0.0, flips = 0.0;
+    for (unsigned i = 0; i < count; ++i) {
+        const wt_wave& w = waves[i];
+        const double a = (double)w.frequency_w * rho, K = a + (double)w.phaseConstant_phi * t;
+        kmax = std::fmax(kmax, K);
+        // roundings of the reference's k the recurrence mode does not reproduce: the final add (ulp(K)), w * d (ulp(a)),
+        // d itself (two products and a sum at magnitude rho, times w); and the mode's own: two FMAs at magnitude ~a + pi and
+        // the rounding of the pre-folded w D (systematic, relative 2^-24).  Uniform rounding error: variance ulp^2 / 12.
+        const double uK = ulp_of((float)K), ua = ulp_of((float)a), ud = (double)w.frequency_w * urho, um = ulp_of((float)(a + 3.2));
+        const double var = (uK * uK + ua * ua + 3.0 * ud * ud + 2.0 * um * um) / 12.0 + (a * 5.96e-8) * (a * 5.96e-8) / 3.0;
+        const double Qi = wt_steepness_Q_i(&w, count);
+        const double ah = (double)w.amplitude_A * Qi;          // horizontal amplitude A Q_i |D|
+        var_y += (double)w.amplitude_A * w.amplitude_A * var;
+        var_h += ah * ah * var;
+        // The shader adds every wave's term to a running fp32 sum that starts at the grid coordinate (magnitude up to
+        // `coord`): a term that differs by a fraction of ulp(coord) flips a rounding of that sum now and then
+        if (uc > 0.0) flips += std::fmin(1.0, 2.0 * ah * std::sqrt(var) / uc);
+        total += w.amplitude_A;
+    }
+    wt_phase_report r;
+    std::memset(&r, 0, sizeof(r));
+    // Extremes over a frame in units of the modelled sigmas; the constants are the upper envelope of the deviations
+    // measured over grids 1024 .. 16384, 8 .. 256 waves, t = 0 .. 3600 s and the edge cameras (see the header).
+    //   position: the phase noise itself + the flipped roundings of the running sums, quantised in ulp(coord);
+    //   normal:   the height noise and those flips, each over the vertex spacing (the flips tilt the finite-difference
+    //             tangents of a sloped surface: at the start of an animation they are the larger part).
+    const double sig_n = std::sqrt(var_y) * gain, flip_n = uc * gain;
+    r.est_position_error = (float)(WT_PHASE_K_POSITION * std::sqrt(std::fmax(var_y, var_h)) + (1.0 + 2.5 * std::sqrt(flips)) * uc);
+    r.est_normal_error_rad = (float)std::sqrt(WT_PHASE_K_NORMAL * WT_PHASE_K_NORMAL * sig_n * sig_n + WT_PHASE_K_FLIP * WT_PHASE_K_FLIP * flip_n * flip_n);
+    r.position_tolerance = (float)(1e-4 * total);
+    r.normal_tolerance_rad = 1e-3f;
+    r.min_vertex_spacing = (float)hmin;
+    r.max_phase = (float)kmax;
+    r.valid = (count == 0) || (r.est_position_error * WT_PHASE_MARGIN <= r.position_tolerance && r.est_normal_error_rad * WT_PHASE_MARGIN <= r.normal_tolerance_rad);
+    if (out) *out = r;
+    return r.valid ? 1 : 0;
 }
 
 }  // extern "C"

@@ -84,11 +84,14 @@ struct EvalArgs {
     float vy[12];       // upper-left 3 rows of viewMatOnlyYaw's first three columns: vy[3*c + r]
     int L, row_begin, row_end;
     int n_strips;       // warps across a row
-    int rows_per_chunk; // output rows per work item
-    int n_chunks;
-    // two-level dynamic plan: chunks [0, n_big) hold rows_per_chunk rows, the rest rows_small rows (they are handed
-    // out last and fill the tail of the launch); static / single-level plans have n_big == n_chunks
-    int n_big, rows_small;
+    // Work items = (strip, chunk of rows).  The chunks come from the CANONICAL layout of the grid (wt_ctx.h: a function of
+    // grid_len and the kernel instantiation only), restricted to the chunks that intersect [row_begin, row_end): n_seg
+    // segments of equally sized chunks; chunk q of the launch lies in segment s with seg_prefix[s] <= q < seg_prefix[s+1]
+    // and covers rows [seg_row0[s] + (q - seg_prefix[s]) * seg_rows[s], ... + seg_rows[s]) clipped at seg_end[s].  A chunk's
+    // marching steps always start at its canonical first row - 1 (+ a multiple of R), whatever part of it the call
+    // writes, so a vertex's rounding never depends on the shard or the device.
+    int n_seg;
+    int seg_prefix[17], seg_row0[16], seg_rows[16], seg_end[16];
     int dbg;            // experiment knob (WT_DBG): bit 0 = skip heights/epilogue
     // dynamic work distribution (NULL = static: item = blockIdx.x): queue[0] = next item, queue[1] = warps done
     int* queue;
@@ -517,9 +520,12 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
     if (a.trace) t_start = global_ns();
     const int strip = item % a.n_strips, chunk = item / a.n_strips;
     const int strip0 = strip * STRIP_COLS;
-    const bool big = chunk < a.n_big;
-    const int r0 = a.row_begin + (big ? chunk * a.rows_per_chunk : a.n_big * a.rows_per_chunk + (chunk - a.n_big) * a.rows_small);
-    const int r1 = min(r0 + (big ? a.rows_per_chunk : a.rows_small), a.row_end);
+    int seg = 0;
+    while (seg + 1 < a.n_seg && chunk >= a.seg_prefix[seg + 1]) ++seg;
+    // canonical rows of the chunk [c0, c1); the rows this call writes [r0, r1)
+    const int c0 = a.seg_row0[seg] + (chunk - a.seg_prefix[seg]) * a.seg_rows[seg];
+    const int c1 = min(c0 + a.seg_rows[seg], a.seg_end[seg]);
+    const int r0 = max(c0, a.row_begin), r1 = min(c1, a.row_end);
     const int colA = strip0 - 1 + lane, colB = colA + 32;
     const bool outA = lane >= 1 && colA < a.L;
     const bool outB = lane <= 30 && colB < a.L;
@@ -527,7 +533,9 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
 
     int slot_new = 2;   // ring row that receives the first row of the next step; rows -2/-1 of the first step are never read
 
-    for (int row_a = r0 - 1; row_a <= r1; row_a += R) {
+    // marching steps sit on the chunk's own lattice (first rows c0 - 1 + k R); a call that writes only part of the
+    // chunk starts at the step that holds row r0 - 1 — every step is seeded on its own, so skipping steps changes nothing
+    for (int row_a = c0 - 1 + ((r0 - c0) / R) * R; row_a <= r1; row_a += R) {
         // water-grid.vert:123-125,87-91: u = col*du is fixed per lane, so the two inner mixes are too.  They
         // are re-derived every step (a dozen instructions) instead of living in 12 registers across the wave
         // loop; the empty asm keeps the compiler from hoisting them back out.

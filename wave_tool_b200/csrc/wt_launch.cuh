@@ -18,53 +18,33 @@ cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>&
     constexpr int R = MODE == 1 ? (CAP > 64 ? R_RECUR_BIG : R_RECUR) : R_EXACT;
     auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2, VARY>;
     const int smem = WARPS_PER_CTA * RingLayout<R, VARY>::BYTES_PER_WARP + g_knobs.extra_smem;
-    static thread_local struct { int L = -1, rows = -1, dev = -1, slots = 0; Plan p; } cache;   // per instantiation
-    const int rows = a.row_end - a.row_begin;
-    if (cache.L != a.L || cache.rows != rows || cache.dev != ctx->device) {
+    // per instantiation: occupancy and the segments of the last (grid, row range) seen
+    static thread_local struct { int L = -1, r0 = -1, r1 = -1, dev = -1, slots = 0; unsigned gen = 0; EvalArgs seg; } cache;
+    if (cache.L != a.L || cache.r0 != a.row_begin || cache.r1 != a.row_end || cache.dev != ctx->device || cache.gen != g_knobs.generation) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * WARPS_PER_CTA, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         cache.slots = ctx->sm_count * per_sm * WARPS_PER_CTA;
-        cache.p = make_plan(cache.slots, a.L, rows, R);
-        cache.L = a.L; cache.rows = rows; cache.dev = ctx->device;
+        layout_segments(canonical_layout(a.L, R, MODE), a.L, a.row_begin, a.row_end, cache.seg);
+        cache.L = a.L; cache.r0 = a.row_begin; cache.r1 = a.row_end; cache.dev = ctx->device; cache.gen = g_knobs.generation;
     }
-    Plan p = cache.p;
-    // Dynamic work distribution: the warp schedulers favour some resident warps heavily, so equal static
-    // shares finish far apart (profiles/README.md); with small items handed out through an atomic queue every
-    // warp stays busy until the queue runs dry.  Used when there are enough items to go round several times;
-    // WT_DYN overrides the rows per item (0 = static plan).
-    const bool forced = g_knobs.dyn >= 0;
-    const int dyn_rows = forced ? g_knobs.dyn : (MODE == 1 ? DYN_ROWS_RECUR : DYN_ROWS_EXACT);
+    a.n_strips = cache.seg.n_strips; a.n_seg = cache.seg.n_seg; a.n_items = cache.seg.n_items;
+    std::memcpy(a.seg_prefix, cache.seg.seg_prefix, sizeof(a.seg_prefix));
+    std::memcpy(a.seg_row0, cache.seg.seg_row0, sizeof(a.seg_row0));
+    std::memcpy(a.seg_rows, cache.seg.seg_rows, sizeof(a.seg_rows));
+    std::memcpy(a.seg_end, cache.seg.seg_end, sizeof(a.seg_end));
+    // Work distribution.  Few items (fewer than two per resident warp): one item per CTA.  Otherwise a persistent grid
+    // pulls items off an atomic queue — the warp schedulers favour some resident warps heavily, so equal static shares
+    // finish far apart (profiles/README.md); with queued items every warp stays busy until the queue runs dry.  Which
+    // warp takes which item never changes a result.
+    int slots = cache.slots;
+    if (g_knobs.dyn_warps > 0) slots = std::min(slots, ctx->sm_count * g_knobs.dyn_warps);
+    int ctas = a.n_items;
     a.queue = nullptr;
-    if (dyn_rows > 0) {
-        auto round_rows = [](int want) { int r = ((want + 2 + R - 1) / R) * R - 2; return r < 1 ? R : r; };   // rows + 2 a multiple of R
-        const int rpc = round_rows(dyn_rows);
-        // two levels: the last `tail` percent of the rows go out in small items, after all the big ones
-        const int small_want = g_knobs.dyn_small >= 0 ? g_knobs.dyn_small : (MODE == 1 ? DYN_SMALL_RECUR : DYN_SMALL_EXACT);
-        const int tail_pct = g_knobs.dyn_tail >= 0 ? g_knobs.dyn_tail : DYN_TAIL_PERCENT;
-        int n_big = (rows + rpc - 1) / rpc, n_small = 0, rps = 0;
-        if (small_want > 0 && small_want < dyn_rows && tail_pct > 0) {
-            rps = round_rows(small_want);
-            n_big = (int)((long long)rows * (100 - tail_pct) / 100 / rpc);
-            n_small = (rows - n_big * rpc + rps - 1) / rps;
-        }
-        const long long items = (long long)p.n_strips * (n_big + n_small);
-        int slots = cache.slots;
-        if (g_knobs.dyn_warps > 0) slots = std::min(slots, ctx->sm_count * g_knobs.dyn_warps);
-        if (forced || items >= 2LL * slots) {
-            p.rows_per_chunk = rpc;
-            p.n_chunks = n_big + n_small;
-            p.n_big = n_big; p.rows_small = rps;
-            p.ctas = (int)std::min<long long>(items, slots);
-            a.queue = ctx->d_queues + 2 * (ctx->queue_next++ % N_QUEUES);
-        }
+    if ((long long)a.n_items >= 2LL * slots && g_knobs.dyn != 0) {
+        ctas = slots;
+        a.queue = ctx->d_queues + 2 * (ctx->queue_next++ % N_QUEUES);
     }
-    a.n_strips = p.n_strips;
-    a.rows_per_chunk = p.rows_per_chunk;
-    a.n_chunks = p.n_chunks;
-    a.n_big = p.n_big < 0 ? p.n_chunks : p.n_big;
-    a.rows_small = p.rows_small > 0 ? p.rows_small : p.rows_per_chunk;
-    a.n_items = p.n_strips * p.n_chunks;
     a.trace = nullptr;
     {
         if (g_knobs.trace) {
@@ -90,7 +70,7 @@ cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>&
         a.cks_acc = ctx->d_cks_acc + slot;
         a.cks_done = ctx->d_cks_done + slot;
     }
-    kernel<<<p.ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
+    kernel<<<ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
 }
