@@ -1,25 +1,35 @@
 #!/usr/bin/env python
 """bench.py — vertex-waves/s of the fused water-surface kernel (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4|cfg5]
+                    [--phase auto|exact|recurrence]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one frame of the workload per GPU (frame sharding: global frame f runs on rank f mod N,
 no data-path collective; weak scaling).  Default workload = BASELINE.json configs[2], the one the
 metric ("ms per 4096^2 grid frame", ">=70% of roofline at a 4096^2 grid with 64 waves") is quoted on:
-4096x4096 projected grid, 64 seeded Gerstner waves + heightmap detail, finite-difference normals and the
-Fresnel / sky-cubemap / sun-specular terms, default camera.  Synthetic data (seeded waves, procedural
-heightmap and cubemap).  Rank 0 prints ONE JSON line.
+4096x4096 projected grid, 64 seeded Gerstner waves + heightmap detail (the reference's own heightmap,
+tests/golden fixture), finite-difference normals and the Fresnel / sky-cubemap / sun-specular terms,
+default camera.  Synthetic data (seeded waves, procedural cubemap).  Rank 0 prints ONE JSON line.
+
+Phase mode: `auto` (default) = WT_FLAG_AUTO_PHASE — the library runs the recurrence kernel where
+wt_fast_phase_valid says it stays inside the north-star tolerances against the reference, the bit-faithful
+kernel elsewhere; the line says which kernel the timed steps ran (`phase.kernel_launches`), reports the
+roofline of THAT kernel and, measured after the timed region against the CPU oracle on sampled rows of the
+last timed frame, its parity margin (`parity_margin`).
 
 Timing: W >= 3 untimed warm-up steps, then EXACTLY K steps bracketed by barrier + synchronize, timed
 with CUDA events on the stream the kernels are launched on, max over ranks.  Every step writes
 805 MB of fresh output (>> the 126 MB L2) into a 2-deep ring, so no step can be served from L2.
+After the contract's timed region the line also carries: a sustained re-run (>= 0.5 s), the other phase
+mode on the same frame, end-to-end numbers through the C ABI, and `extra_workloads` (configs[1], [3], [4]).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -42,8 +52,10 @@ WORKLOADS = {
 ROW_SHARDED = {"cfg5"}
 TRANSCENDENTALS_PER_VERTEX_WAVE = 2      # 1 sin + 1 cos (water-grid.vert:78-81), SURVEY.md §8d
 FLOP_PER_VERTEX_WAVE = 15
+NOMINAL_FP32_TFLOPS = 74.4               # 128 FMA/clk/SM x 148 SM x 1.965 GHz
 _REAL_STDOUT = sys.stdout
 SKYBOX_N = 2048                           # reference: 2048^2 faces (render-engine.h:191)
+PHASE_FLAGS = {"auto": 0x20, "exact": 0, "recurrence": 0x4}
 
 
 def measured_peaks():
@@ -72,11 +84,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0: float, t1: float):
+    def window(self, t0: float, t1: float):
+        """Summary of the samples taken in [t0, t1] (the sampler keeps running)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.12)
-        self.proc.terminate()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05] or self.rows
@@ -92,6 +104,60 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def probe_llvmpipe():
+    """north_star's CPU baseline is the reference GLSL under Mesa llvmpipe with transform feedback; BASELINE.md §3: the
+    harness may try it opportunistically.  Recorded as unavailable where no software GL can be loaded."""
+    tried = []
+    for name in ("libOSMesa.so", "libOSMesa.so.8", "libOSMesa.so.6", "libEGL.so.1", "libGL.so.1"):
+        try:
+            C.CDLL(name)
+            return {"available": True, "library": name, "note": "a GL library loads, but no headless context / GLSL harness is wired up in this image"}
+        except OSError:
+            tried.append(name)
+    return {"available": False, "tried": tried, "note": "no libOSMesa / libEGL / libGL in this image (SURVEY.md §8c): the CPU arm is the reference "
+            "shader text compiled as C++ (oracle/_ref) instead"}
+
+
+# --------------------------------------------------------------------------------------------------
+# The CPU arm: the reference's own implementation of the path on the host cores.  Touches oracle/ only — none of the
+# product's code or libraries (the scene is rebuilt here from plain numpy / ctypes values).
+# --------------------------------------------------------------------------------------------------
+def _cpu_scene(orc, O, L, W, cfg, frame_index):
+    """Uniforms of animation frame `frame_index` of workload (L, W, cfg) for the oracle / oracle/_ref, built WITHOUT the
+    product library: seeded waves (pure numpy), reference defaults (render-engine.h:224-238), default camera."""
+    from wave_tool_b200 import scenes                     # pure numpy generators; does not load libwavetool_b200.so
+    waves = scenes.seeded_waves(W, cfg=cfg)
+    cam = orc.Camera()
+    cam.fov_deg, cam.aspect, cam.z_near, cam.z_far = 72.0, 1.0, 0.1, 100.0      # render-engine.cpp:52, camera.cpp:40-45
+    cam.pos[:] = [0.0, 4.0, 70.0]
+    cam.yaw_deg, cam.pitch_deg = -90.0, 0.0
+    t = np.float32(frame_index) / np.float32(60.0)
+    hm_disp, hm_scale, bounce_amp = np.float32(1.0), np.float32(0.02), np.float32(0.1)
+    phase = np.float32(math.fmod(float(t) / 3.0, 1.0))
+    total = O.total_amplitude(waves[:, 0])                                        # running fp32 sum, render-engine.h:156-157
+    D = np.float32(np.float32(total + hm_disp) + bounce_amp)                      # render-engine.cpp:803
+    st, g = O.project_grid(cam, D)
+    assert st == 0
+    u = orc.Uniforms()
+    c = np.array(g.corners, np.float32).reshape(4, 4)
+    u.bottomLeft[:] = c[0]; u.topLeft[:] = c[1]; u.bottomRight[:] = c[2]; u.topRight[:] = c[3]
+    u.cameraPosition[:] = cam.pos[:]
+    u.gerstnerWaveCount = len(waves)
+    u.gridLength = L
+    u.heightmapDisplacementScale, u.heightmapSampleScale = float(hm_disp), float(hm_scale)
+    u.verticalBounceWaveDisplacement = float(O.bounce_displacement(bounce_amp, phase))
+    u.viewMatOnlyYaw[:] = g.view_only_yaw[:]
+    u.viewProjection[:] = g.view_proj[:]
+    u.waveAnimationTimeInSeconds = float(t)
+    u.sunPosition[:] = O.sun_position(9.0)
+    u.sunShininess, u.sunStrength = 50.0, 1.0
+    return u, O.wave_uniforms(waves)
+
 
 def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
     """The reference's own CPU implementation of the path on the host cores: the reference
@@ -99,11 +165,10 @@ def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
     else the oracle port (kind 'port').  Bounded sample: bands of whole rows of consecutive animation
     frames of the SAME workload until about `seconds_target` seconds of wall time have been spent."""
     from oracle import oracle as orc                      # cpu_baseline leg: the one place bench.py may use oracle/
-    from tests.common import Scene
     from wave_tool_b200 import scenes
     global _CPU_ARM
     if "_CPU_ARM" not in globals():
-        _CPU_ARM = (orc.Oracle(), orc.Ref(), scenes.procedural_heightmap(512))     # built once: the sample times the path, not the setup
+        _CPU_ARM = (orc.Oracle(), orc.Ref(), scenes.reference_heightmap())          # built once: the sample times the path, not the setup
     O, R, hm = _CPU_ARM
     # all the host threads this process may use — torchrun exports OMP_NUM_THREADS=1, which would otherwise
     # pin the reference arm to one core (the oracle and oracle/_ref share one OpenMP runtime)
@@ -111,12 +176,10 @@ def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
         O.set_num_threads(len(os.sched_getaffinity(0)))
     except Exception:
         O.set_num_threads(os.cpu_count() or 1)
-    waves = scenes.seeded_waves(W, cfg=cfg)
     use_ref = R.available and L <= 4096 and W <= R.max_waves()
     cores = O.num_threads()
     rows_total, t_spent, chunk, frame, row = 0, 0.0, 8, 75, 0
-    sc = Scene(waves, scenes.camera(), scenes.animation_params(frame), L, hm)
-    st, u, wu = sc.oracle_uniforms(O)
+    u, wu = _cpu_scene(orc, O, L, W, cfg, frame)
     while t_spent < seconds_target:
         hi = min(row + chunk, L)
         t0 = time.perf_counter()
@@ -130,16 +193,15 @@ def cpu_reference_rate(L, W, cfg, seconds_target=12.0, max_seconds=40.0):
         row = hi
         if row >= L:                                      # next animation frame
             frame, row = frame + 1, 0
-            sc = Scene(waves, scenes.camera(), scenes.animation_params(frame), L, hm)
-            st, u, wu = sc.oracle_uniforms(O)
+            u, wu = _cpu_scene(orc, O, L, W, cfg, frame)
         if t_spent + 2 * dt > max_seconds:
             break
         if dt < 1.0:
             chunk = min(chunk * 2, 512)
     vw = rows_total * L * W
     return {"value": vw / t_spent, "unit": "vertex-waves/s", "cores": cores, "kind": "reference" if use_ref else "port",
-            "sample": f"{rows_total} rows ({rows_total / L:.2f} frames) of the {L}x{L} grid with {W} waves, vertex stage "
-                      f"(positions + 4-neighbour normals: 5 evaluations per vertex as the shader does), {t_spent:.1f} s wall, "
+            "sample": f"{rows_total} rows ({rows_total / L:.2f} frames) of the {L}x{L} grid with {W} waves, vertex stage only "
+                      f"(positions + 4-neighbour normals: 5 evaluations per vertex as the shader does; no fragment terms), {t_spent:.1f} s wall, "
                       f"OpenMP over vertices on {cores} threads, g++ -O2 -ffp-contract=off",
             "seconds": t_spent, "vertex_waves": vw}
 
@@ -165,10 +227,54 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "grid_len": L, "waves": W, "note": "each step is a bounded row sample of one frame on the host cores"},
+            "config": {"workload": desc, "grid_len": L, "waves": W, "shade": False,
+                       "note": "each step is a bounded row sample of one frame on the host cores; the CPU arm runs the reference's VERTEX shader only "
+                               "(water-grid.vert: positions + finite-difference normals) — less work than the GPU arm, which also evaluates the fragment terms"},
             "cpu_baseline": cb, "e2e": {"value": value, "unit": "vertex-waves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "ms_per_frame_extrapolated": 1e3 * (L * L * W) / value}
+            "ms_per_frame_extrapolated": 1e3 * (L * L * W) / value, "llvmpipe": probe_llvmpipe()}
     emit(line)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def oracle_margin(api, scenes, ctx, waves, cam, params, L, hm, flags, shade_flag, torch, rows=None):
+    """Parity margin of ONE frame against the CPU oracle (test infrastructure, used here only as the checker, after the timed
+    region): near-field rows (where the vertex spacing is finest) + rows strided over the grid."""
+    from oracle import oracle as orc
+    from tests.common import Scene, deviation_stats
+    sc = Scene(waves, cam, params, L, hm)
+    st, frame = sc.frame()
+    rows = rows or sorted(set(list(range(0, 8)) + list(range(97, L - 2, max(1, L // 20))) + [L - 2, L - 1]))
+    bands, r = [], 0
+    O = orc.Oracle()
+    try:
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    ids = np.concatenate([np.arange(q * L, (q + 1) * L, dtype=np.int64) for q in rows])
+    want = sc.oracle_eval(O, ids=ids)
+    out = {}
+    for name, fl in flags.items():
+        got = {"pos": [], "normal": []}
+        for q in rows:
+            b0, b1 = max(q - 1, 0), min(q + 2, L)
+            n = (b1 - b0) * L
+            pos = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+            nrm = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+            shd = torch.empty((n, 4), dtype=torch.float32, device="cuda") if shade_flag else None
+            ctx.eval_frame(frame, L, pos.data_ptr(), nrm.data_ptr(), shd.data_ptr() if shade_flag else 0, flags=fl | shade_flag, rows=(b0, b1),
+                           stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got["pos"].append(pos[(q - b0) * L:(q - b0 + 1) * L].cpu().numpy())
+            got["normal"].append(nrm[(q - b0) * L:(q - b0 + 1) * L].cpu().numpy())
+        got = {k: np.concatenate(v) for k, v in got.items()}
+        stats, _, _, _ = deviation_stats(got, want, sc)
+        out[name] = {"kernel": "recurrence" if ctx.last_phase_mode() == 1 else "bit-faithful",
+                     **{k: stats[k] for k in ("pos_max", "pos_tol", "pos_margin", "normal_max", "normal_tol", "normal_margin", "flip_band")}}
+    rep = ctx.fast_phase_valid(frame, L)
+    return {"vertices_compared": int(len(ids)), "rows": f"{len(rows)} rows: 0-7, every {max(1, L // 20)}th, the last two",
+            "frame_time_s": float(params.waveAnimationTimeInSeconds), "modes": out, "fast_phase_report": rep.as_dict()}
 
 
 def run_ours(args):
@@ -189,17 +295,17 @@ def run_ours(args):
 
     L, W, cfg, shade, desc = WORKLOADS[args.workload]
     K, Wm = args.steps, max(3, args.warmup)
-    flags = api.FLAG_SHADE if shade else 0
-    recurrence = not args.exact_phase
-    if recurrence:
-        flags |= api.FLAG_FAST_PHASE
+    shade_flag = api.FLAG_SHADE if shade else 0
+    phase = "exact" if args.exact_phase else ("recurrence" if args.fast_phase else args.phase)
+    flags = shade_flag | PHASE_FLAGS[phase]
 
     # ---- setup (untimed): context, wave table, textures, output ring ----------------------------
     waves = scenes.seeded_waves(W, cfg=cfg)
     cam = scenes.camera()
+    hm = scenes.reference_heightmap()
     ctx = api.Context(local_rank)
     ctx.set_waves(waves)
-    ctx.set_heightmap(scenes.procedural_heightmap(512))
+    ctx.set_heightmap(hm)
     if shade:
         ctx.set_skybox(scenes.procedural_skybox(SKYBOX_N))
     # frame sharding (weak scaling): every rank evaluates whole frames, frame f on rank f mod N;
@@ -234,10 +340,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def launch(lo, hi, with_cks=False):
+    def launch(lo, hi, with_cks=False, fl=None):
         arr = (api.Frame * (hi - lo))(*frames[lo:hi])
+        f = flags if fl is None else fl
         ctx.eval_batch(arr, L, pos.data_ptr(), nrm.data_ptr(), shd.data_ptr() if shade else 0, ring,
-                       cks.data_ptr() + 40 * lo if with_cks else 0, flags=flags | (api.FLAG_CHECKSUM if with_cks else 0), rows=rows, stream=sp)
+                       cks.data_ptr() + 40 * lo if with_cks else 0, flags=f | (api.FLAG_CHECKSUM if with_cks else 0), rows=rows, stream=sp)
 
     # ---- device-timed region: W warm-up steps, then exactly K steps ------------------------------
     launch(0, Wm)
@@ -245,6 +352,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.15 if sampler else 0.0)
     l0 = ctx.launch_count()
+    m0 = ctx.phase_mode_counts()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -254,14 +362,33 @@ def run_ours(args):
     barrier()
     t_wall1 = time.time()
     launches = ctx.launch_count() - l0
+    m1 = ctx.phase_mode_counts()
+    ran = {"bit-faithful": m1[0] - m0[0], "recurrence": m1[1] - m0[1]}
     ms_local = e0.elapsed_time(e1)
     ms = shard.max_over_ranks(ms_local, dev) if world > 1 else ms_local
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+    recurrence = ran["recurrence"] > ran["bit-faithful"]               # which kernel the timed steps ran (auto decides per frame)
 
     vw_per_frame = n * W                                               # this rank's share of one step
     frames_total = K if row_sharded else n_gpus * K                    # whole frames the job evaluated in the timed region
     value = frames_total * L * L * W / (ms * 1e-3)
     ms_per_step = ms / K
+
+    # ---- sustained re-run: at least 0.5 s of back-to-back steps (same frames, cycled), with its own clock record ----
+    reps = max(1, min(400, int(math.ceil(0.6e3 / max(ms, 1e-3)))))
+    barrier()
+    ts0 = time.time()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(reps):
+        launch(Wm, Wm + K)
+    s1.record(stream)
+    barrier()
+    ts1 = time.time()
+    sus_local = s0.elapsed_time(s1) / (reps * K)
+    sustained_ms = shard.max_over_ranks(sus_local, dev) if world > 1 else sus_local
+    sustained = {"ms_per_step_sustained": sustained_ms, "steps": reps * K, "seconds": (ts1 - ts0),
+                 "clocks": sampler.window(ts0, ts1) if sampler else None}
 
     # ---- end-to-end through the C ABI with HOST inputs/outputs -----------------------------------
     # per step ONE call, wt_step_host: camera + params (host structs) -> wt_build_frame (host prologue) -> fused kernel
@@ -307,58 +434,63 @@ def run_ours(args):
         e2e[in_flight] = frames_total * L * L * W / e2e_s
     e2e_value = e2e[2]
 
-    # full read-back variant: every output byte copied to pinned host memory each step (PCIe-bound)
+    # full read-back variant, every N: every output byte of every rank's frame copied to ITS pinned host buffers each step (PCIe-bound)
     rb = None
-    if not args.no_readback and rank == 0 and world == 1 and n <= (1 << 25):
+    if not args.no_readback and n <= (1 << 25):
         hp = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         hn = torch.empty((n, 4), dtype=torch.float32).pin_memory()
         hs = torch.empty((n, 4), dtype=torch.float32).pin_memory() if shade else None
+        reps_rb = min(K, 3)
+        barrier()
         t0 = time.perf_counter()
-        reps = min(K, 3)
-        for k in range(reps):
+        for k in range(reps_rb):
             e2e_step(k)
             hp.copy_(pos[:n], non_blocking=True); hn.copy_(nrm[:n], non_blocking=True)
             if shade:
                 hs.copy_(shd[:n], non_blocking=True)
             stream.synchronize()
+        barrier()
         dt = time.perf_counter() - t0
-        rb = {"value": reps * vw_per_frame / dt, "unit": "vertex-waves/s", "d2h_bytes_per_step": n * 16 * (3 if shade else 2), "n_gpus": 1}
+        dt = shard.max_over_ranks(dt, dev) if world > 1 else dt
+        frames_rb = reps_rb if row_sharded else reps_rb * n_gpus
+        rb = {"value": frames_rb * L * L * W / dt, "unit": "vertex-waves/s", "d2h_bytes_per_step": n * 16 * (3 if shade else 2), "n_gpus": n_gpus,
+              "what": "the synchronous e2e step + every output buffer (positions, normals, shading terms) copied to pinned host memory each step, "
+                      "every rank its own frame over its own PCIe link"}
+        del hp, hn, hs
 
-    # ---- the other phase mode on the same frames (untimed region of the bench; rank 0, N=1) + deviation ----
+    # ---- the other phase mode on the same frames (untimed region of the bench; rank 0) + deviation ----
     other = None
     if rank == 0:
-        oflags = flags ^ api.FLAG_FAST_PHASE
+        oflags = shade_flag | (0 if recurrence else api.FLAG_FAST_PHASE)
+        mflags = shade_flag | (api.FLAG_FAST_PHASE if recurrence else 0)
         f_last = frames[Wm + K - 1]
-        slot_main = (Wm + K - 1) % ring                       # where the timed run left its last frame
+        slot_main = (Wm + K - 1) % ring
         slot_other = 1 - slot_main
         ctx.eval_frame(f_last, L, pos.data_ptr() + slot_main * n * 16, nrm.data_ptr() + slot_main * n * 16,
-                       (shd.data_ptr() + slot_main * n * 16) if shade else 0, flags=flags, rows=rows, stream=sp)
+                       (shd.data_ptr() + slot_main * n * 16) if shade else 0, flags=mflags, rows=rows, stream=sp)
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(3, min(K, 10))
+        reps_o = max(3, min(K, 10))
         for w_ in range(2):
             ctx.eval_frame(f_last, L, pos.data_ptr() + slot_other * n * 16, nrm.data_ptr() + slot_other * n * 16,
                            (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, rows=rows, stream=sp)
         o0.record(stream)
-        for r_ in range(reps):
+        for r_ in range(reps_o):
             ctx.eval_frame(f_last, L, pos.data_ptr() + slot_other * n * 16, nrm.data_ptr() + slot_other * n * 16,
                            (shd.data_ptr() + slot_other * n * 16) if shade else 0, flags=oflags, rows=rows, stream=sp)
         o1.record(stream)
         torch.cuda.synchronize()
-        oms = o0.elapsed_time(o1) / reps
+        oms = o0.elapsed_time(o1) / reps_o
         pa, pb = pos[slot_main * n:(slot_main + 1) * n, :3], pos[slot_other * n:(slot_other + 1) * n, :3]
         na, nb = nrm[slot_main * n:(slot_main + 1) * n, :3], nrm[slot_other * n:(slot_other + 1) * n, :3]
         dpos = float((pa - pb).abs().max().item())
         dn = (na - nb).norm(dim=1)
         dn = torch.minimum(dn, (na + nb).norm(dim=1))          # the view-facing flip is sign-ambiguous at grazing incidence
-        other = {"ms_per_frame": oms, "vertex_waves_per_sec": vw_per_frame / (oms * 1e-3),
-                 "phase": "bit-faithful fp32 phase, MUFU pair per vertex-wave" if recurrence else "phase recurrence",
-                 "max_position_deviation_between_modes": dpos, "position_tolerance": 1e-4 * float(total_amp),
-                 "max_normal_deviation_rad_between_modes": float(dn.max().item()), "normal_tolerance_rad": 1e-3,
-                 "checked_on": "all %d vertices of the last timed frame, on the device" % n}
-        if L > 8192:
-            other["note"] = ("on a 16384^2 grid the near-field vertex spacing is ~100 ulp of the fp32 coordinates: the reference's own fp32 "
-                             "evaluation sits up to ~3e-3 rad from its fp64 twin there, and the two phase modes round differently; "
-                             "tests/test_gpu_parity.py::test_cfg5_edge_cameras_16384 gates each mode against that measured noise floor")
+        other = {"kernel": "bit-faithful" if recurrence else "recurrence", "ms_per_frame": oms, "vertex_waves_per_sec": vw_per_frame / (oms * 1e-3),
+                 "max_position_deviation_between_kernels": dpos, "position_tolerance": 1e-4 * float(total_amp),
+                 "max_normal_deviation_rad_between_kernels": float(dn.max().item()), "normal_tolerance_rad": 1e-3,
+                 "checked_on": "all %d vertices of the last timed frame, on the device" % n,
+                 "note": "the bit-faithful kernel reproduces the reference's rounding of every wave phase; the recurrence kernel does not, and is "
+                         "only selected by WT_FLAG_AUTO_PHASE where wt_fast_phase_valid bounds that difference inside the tolerances"}
 
     # gather the per-frame digests of the timed frames (the only collective; after the timed region)
     launch(Wm, Wm + K, with_cks=True)
@@ -370,19 +502,36 @@ def run_ours(args):
     else:
         digest_of_digests = shard.combine_checksums(local_digests)
 
+    # ---- parity margin of the timed kernel (and of the other one) against the CPU oracle, after the timed region ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = oracle_margin(api, scenes, ctx, waves, cam, scenes.animation_params(my_frames[Wm + K - 1]), L, hm,
+                                   {"timed": PHASE_FLAGS[phase], "exact": 0, "recurrence": api.FLAG_FAST_PHASE}, shade_flag, torch)
+            parity["frame"] = "the last timed frame (global frame %d)" % my_frames[Wm + K - 1]
+        except Exception as ex:                                          # the checker must never take the bench line down
+            parity = {"error": repr(ex)}
+
+    # ---- the other BASELINE configurations, after the timed region (every rank takes part where the work is sharded) ----
+    extra = None
+    if not args.no_extra and args.workload == "cfg3":
+        del pos, nrm, shd
+        torch.cuda.empty_cache()
+        extra = extra_workloads(torch, dist, api, scenes, shard, rank, world, local_rank, dev, phase, barrier)
+
     if rank == 0:
         peaks = measured_peaks()
         kernel_ms = ms_local / K                                    # one evaluation kernel per step
         out_bytes = n * 16 * (3 if shade else 2)
         hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
-        traffic = None
+        key = args.workload + ("" if recurrence else "_exact")
+        traffic = pipes = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload + ("" if recurrence else "_exact"))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
         except Exception:
             pass
-        pipes = None
         try:
-            pipes = json.load(open(os.path.join(ROOT, "profiles", "pipes.json"))).get(args.workload + ("" if recurrence else "_exact"))
+            pipes = json.load(open(os.path.join(ROOT, "profiles", "pipes.json"))).get(key)
         except Exception:
             pass
         alg = {"vertex_waves": vw_per_frame, "transcendentals": vw_per_frame * TRANSCENDENTALS_PER_VERTEX_WAVE,
@@ -390,19 +539,19 @@ def run_ours(args):
         trans_per_s = alg["transcendentals"] / (kernel_ms * 1e-3)
         flop_per_s = alg["flop"] / (kernel_ms * 1e-3)
         sfu_peak = 2.0 * mufu_pairs                                  # measured MUFU-only micro-kernel, this device, this run
+        sfu_nominal = 16 * 148 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6
         roof_sfu = {"bound": "sfu", "achieved": trans_per_s / 1e9, "peak": sfu_peak / 1e9, "unit": "Gtranscendental/s",
-                    "frac": trans_per_s / sfu_peak, "traffic": traffic,
+                    "frac": trans_per_s / sfu_peak, "frac_of_nominal": trans_per_s / sfu_nominal, "traffic": traffic,
                     "peak_source": "of measured: MUFU-only micro-kernel (sin+cos) on this device in this run (wt_measure_peak 0); "
-                                   "nominal 16/clk/SM x 148 SM x clocks.max.sm = %.0f" % (16 * 148 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6 / 1e9),
+                                   "nominal 16/clk/SM x 148 SM x clocks.max.sm = %.0f" % (sfu_nominal / 1e9),
                     "algorithmic_per_launch": alg}
         roof_fp32 = {"bound": "fp32", "achieved": flop_per_s / 1e12, "peak": fma_flops / 1e12, "unit": "TFLOP/s",
-                     "frac": flop_per_s / fma_flops, "traffic": traffic,
+                     "frac": flop_per_s / fma_flops, "frac_of_nominal": flop_per_s / (NOMINAL_FP32_TFLOPS * 1e12), "traffic": traffic,
                      "peak_source": "of measured: FFMA-only micro-kernel on this device in this run (wt_measure_peak 1; packed FFMA2: %.1f); "
-                                    "MEASURED_PEAKS.json has no FP32 figure; nominal 128 FMA/clk/SM = 74.4" % (fma2_flops / 1e12),
+                                    "MEASURED_PEAKS.json has no FP32 figure; nominal 128 FMA/clk/SM = %.1f (frac_of_nominal)" % (fma2_flops / 1e12, NOMINAL_FP32_TFLOPS),
                      "algorithmic_per_launch": alg,
-                     "note": "15 FLOP per vertex-wave (SURVEY 8d) is the algorithmic count; the recurrence mode EXECUTES ~11.6 FLOP + 0.5 MUFU per "
-                             "vertex-wave at 64 waves (row 1 of a step by one complex rotation, the others by the three-term recurrence, "
-                             "1 FMA per value), so frac can exceed the FMA-pipe utilisation reported in pipes_ncu"}
+                     "note": "15 FLOP per vertex-wave (SURVEY 8d) is the algorithmic count; the recurrence kernel EXECUTES ~11.6 FLOP + 0.5 MUFU per "
+                             "vertex-wave at 64 waves, so frac can exceed the FMA-pipe utilisation reported in pipes_ncu"}
         roof_hbm = {"bound": "hbm", "achieved": out_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": out_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                     "peak_source": "of measured: MEASURED_PEAKS.json hbm_gbs (copy)" if peaks else "of fallback: 6650 GB/s",
@@ -426,32 +575,191 @@ def run_ours(args):
                                        "no data-path collective") if row_sharded else
                                       f"frame-sharded x{n_gpus} (frame f on rank f mod N), no data-path collective",
                        "l2": "each step writes %d MB of fresh output into a 2-deep ring (> 126 MB L2)" % (out_bytes // 2 ** 20),
-                       "phase": "phase recurrence (WT_FLAG_FAST_PHASE): one MUFU seed per wave every 8 rows (12 above 64 waves), row 1 by complex rotation, "
-                                "rows 2.. by the three-term recurrence x[j+1] = 2 cos(dk) x[j] - x[j-1]"
-                                if recurrence else "bit-faithful fp32 phase, MUFU sin/cos pair per vertex-wave"},
+                       "heightmap": "the reference's assets/textures/noise/waves/waves3/00.png (tests/golden fixture)",
+                       "phase": phase},
+            "phase": {"requested": phase, "kernel_launches": ran,
+                      "kernel": "phase recurrence: one MUFU seed per wave every 8 rows (12 above 64 waves), row 1 by complex rotation, rows 2.. by the "
+                                "three-term recurrence x[j+1] = 2 cos(dk) x[j] - x[j-1]" if recurrence else
+                                "bit-faithful fp32 phase (the reference's own rounding of k), Cody-Waite reduction, MUFU sin/cos pair per vertex-wave",
+                      "why": "WT_FLAG_AUTO_PHASE: wt_fast_phase_valid decides per frame (see parity_margin.fast_phase_report)" if phase == "auto" else "forced by --phase"},
             "ms_per_frame": ms_per_step,
             "roofline": primary,
             "roofline_secondary": secondary,
+            "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": "vertex-waves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "per step: host camera/params -> wt_step_submit (wt_build_frame, fused kernel + digest written by its last warp into mapped host memory) "
-                            "-> wt_step_wait reads the step's 40-byte digest on the host; 2 frames in flight (frame k+1 is submitted before frame k's digest is awaited)",
+                            "-> wt_step_wait reads the step's 40-byte digest on the host; 2 frames in flight (frame k+1 is submitted before frame k's digest is awaited). "
+                            "The vertex data stays on the GPU, as in the reference (a draw call's outputs feed the rasteriser); e2e_full_readback copies it all out",
                     "synchronous_value": e2e[1], "synchronous_what": "the same with one wt_step_host call per step (submit + wait back to back, nothing overlapped)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "digest_of_timed_frames": {k: (int(v) if not isinstance(v, float) else v) for k, v in digest_of_digests.items()},
+            "llvmpipe": probe_llvmpipe(),
         }
         if other:
             line["other_phase_mode"] = other
+        if parity:
+            line["parity_margin"] = parity
         if rb:
             line["e2e_full_readback"] = rb
+        if extra:
+            line["extra_workloads"] = extra
         if n_gpus == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_rate(L, W, cfg)
             cb.pop("seconds", None); cb.pop("vertex_waves", None)
             line["cpu_baseline"] = cb
+            if rb:
+                line["e2e_full_readback"]["ratio_to_cpu_baseline"] = rb["value"] / cb["value"]
         emit(line)
+    if sampler:
+        sampler.stop()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_workloads(torch, dist, api, scenes, shard, rank, world, local_rank, dev, phase, barrier):
+    """configs[1], [3], [4] measured after the timed region so that the one driver-recorded line covers them:
+    cfg2 as a 1000-frame animation through the native runner (frame-sharded), cfg4 frame-sharded, cfg5 ROW-sharded when
+    N > 1 — with the fold of the shards' digests checked against rank 0's evaluation of the whole frame."""
+    out = {}
+    hm = scenes.reference_heightmap()
+    cam = scenes.camera()
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    peaks = measured_peaks() or {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    pf = PHASE_FLAGS[phase]
+
+    def timed(fn):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        barrier()
+        ms = a.elapsed_time(b)
+        return shard.max_over_ranks(ms, dev) if world > 1 else ms
+
+    def kernel_name(ctx, before):
+        after = ctx.phase_mode_counts()
+        return "recurrence" if after[1] - before[1] > after[0] - before[0] else "bit-faithful"
+
+    # cfg2: 1024^2 x 8 waves, 1000-frame animation (frame f on rank f mod N), 4-deep ring, per-frame digests
+    try:
+        L, W = 1024, 8
+        waves = scenes.seeded_waves(W, cfg=2)
+        ctx = api.Context(local_rank)
+        ctx.set_waves(waves); ctx.set_heightmap(hm)
+        n = L * L
+        ring = 4
+        pos = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
+        nrm = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
+        total_frames = 1000
+        mine = len(range(rank, total_frames, world))
+        cks = torch.zeros(40 * mine, dtype=torch.uint8, device=dev)
+        anim = api.default_animation()
+        total_amp = api.total_amplitude(waves)
+
+        def run():
+            p = api.default_params()
+            for _ in range(rank):
+                api.animation_advance(p, anim, 1.0 / 60.0)
+            ctx.run_animation(cam, p, anim, total_amp, 1.0 / 60.0, mine, L, pos.data_ptr(), nrm.data_ptr(), 0, ring, cks.data_ptr(),
+                              flags=api.FLAG_CHECKSUM | pf, frame_stride=world, stream=sp)
+        run()
+        before = ctx.phase_mode_counts()
+        ms = timed(run)
+        gbs = total_frames * n * 32 / (ms * 1e-3) / 1e9
+        out["cfg2_animation"] = {"workload": WORKLOADS["cfg2"][4], "frames": total_frames, "ms_per_frame": ms / total_frames * world, "ms_total": ms,
+                                 "vertex_waves_per_sec": total_frames * n * W / (ms * 1e-3), "hbm_gbs_written": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak / world,
+                                 "kernel": kernel_name(ctx, before), "n_gpus": world,
+                                 "what": "wt_run_animation (native frame loop: advance state, build frame, launch), t from 0 to 16.7 s, 4-deep ring, digest per frame; "
+                                         "HBM-write-bound tier (33.5 MB per frame): hbm_frac is per GPU against MEASURED_PEAKS hbm_gbs"}
+        del pos, nrm, cks, ctx
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["cfg2_animation"] = {"error": repr(ex)}
+
+    # cfg4: 8192^2 x 256 waves, frame-sharded
+    try:
+        L, W = 8192, 256
+        waves = scenes.seeded_waves(W, cfg=4)
+        ctx = api.Context(local_rank)
+        ctx.set_waves(waves); ctx.set_heightmap(hm)
+        n = L * L
+        pos = torch.empty((2 * n, 4), dtype=torch.float32, device=dev)
+        nrm = torch.empty((2 * n, 4), dtype=torch.float32, device=dev)
+        per_rank = 4
+        frames = scenes.frames_for_animation(cam, waves, first=rank, count=per_rank + 1, stride=world)
+        arr = (api.Frame * (per_rank + 1))(*frames)
+
+        def run(lo=1, hi=per_rank + 1):
+            sub = (api.Frame * (hi - lo))(*frames[lo:hi])
+            ctx.eval_batch(sub, L, pos.data_ptr(), nrm.data_ptr(), 0, 2, 0, flags=pf, stream=sp)
+        run(0, 1)
+        before = ctx.phase_mode_counts()
+        ms = timed(run)
+        out["cfg4"] = {"workload": WORKLOADS["cfg4"][4], "frames": per_rank * world, "ms_per_frame": ms / per_rank,
+                       "vertex_waves_per_sec": per_rank * world * n * W / (ms * 1e-3), "kernel": kernel_name(ctx, before), "n_gpus": world}
+        del pos, nrm, ctx
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["cfg4"] = {"error": repr(ex)}
+
+    # cfg5: 16384^2 x 32 waves; row-sharded across the ranks (strong scaling); shard digests must fold into the whole frame's
+    try:
+        L, W = 16384, 32
+        waves = scenes.seeded_waves(W, cfg=5)
+        ctx = api.Context(local_rank)
+        ctx.set_waves(waves); ctx.set_heightmap(hm)
+        rows = shard.row_shard(L, rank, world)
+        n = (rows[1] - rows[0]) * L
+        pos = torch.empty((2 * n, 4), dtype=torch.float32, device=dev)
+        nrm = torch.empty((2 * n, 4), dtype=torch.float32, device=dev)
+        nf = 3
+        frames = scenes.frames_for_animation(cam, waves, first=0, count=nf + 1)
+        cks = torch.zeros(40 * (nf + 1), dtype=torch.uint8, device=dev)
+
+        def run(lo=1, hi=nf + 1, with_cks=False):
+            sub = (api.Frame * (hi - lo))(*frames[lo:hi])
+            ctx.eval_batch(sub, L, pos.data_ptr(), nrm.data_ptr(), 0, 2, cks.data_ptr() + 40 * lo if with_cks else 0,
+                           flags=pf | (api.FLAG_CHECKSUM if with_cks else 0), rows=rows, stream=sp)
+        run(0, 1)
+        before = ctx.phase_mode_counts()
+        ms = timed(run)
+        run(1, nf + 1, with_cks=True)
+        torch.cuda.synchronize()
+        local = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)[1:nf + 1]
+        entry = {"workload": WORKLOADS["cfg5"][4], "frames": nf, "ms_per_frame": ms / nf, "vertex_waves_per_sec": nf * L * L * W / (ms * 1e-3),
+                 "kernel": kernel_name(ctx, before), "n_gpus": world,
+                 "parallelism": f"row-sharded x{world}: rank g evaluates rows [g L/N, (g+1) L/N) of every frame, halo rows recomputed, no collective on the data path"}
+        if world > 1:
+            allr = shard.all_gather_checksums(local, dev)                          # (world, nf)
+            del pos, nrm
+            torch.cuda.empty_cache()
+            if rank == 0:
+                # the whole frame on ONE GPU (8.6 GB of output) for the digest comparison; untimed
+                nfull = L * L
+                fp = torch.empty((nfull, 4), dtype=torch.float32, device=dev)
+                fn_ = torch.empty((nfull, 4), dtype=torch.float32, device=dev)
+                fc = torch.zeros(40, dtype=torch.uint8, device=dev)
+                same = True
+                for k in range(nf):
+                    ctx.eval_frame(frames[1 + k], L, fp.data_ptr(), fn_.data_ptr(), 0, fc.data_ptr(), flags=pf | api.FLAG_CHECKSUM, stream=sp)
+                    torch.cuda.synchronize()
+                    full = fc.cpu().numpy().view(api.CHECKSUM_DTYPE)[0]
+                    fold = shard.combine_checksums(allr[:, k])
+                    same = same and (fold["position_bits"], fold["normal_bits"], fold["vertices"]) == (int(full["position_bits"]), int(full["normal_bits"]), int(full["vertices"])) \
+                        and fold["min_y"] == float(full["min_y"]) and fold["max_y"] == float(full["max_y"])
+                entry["row_shard_digests_fold_into_the_single_gpu_digest"] = bool(same)
+                del fp, fn_, fc
+        out["cfg5"] = entry
+        del ctx
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["cfg5"] = {"error": repr(ex)}
+    return out
 
 
 def emit(line: dict) -> None:
@@ -472,11 +780,14 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=list(WORKLOADS), default="cfg3",
                     help="cfg3 is the bench line (BASELINE.json's metric is quoted on it); the others are extra measurements")
-    ap.add_argument("--exact-phase", action="store_true",
-                    help="time the bit-faithful-phase wave loop (one MUFU pair per vertex-wave) instead of the phase recurrence")
-    ap.add_argument("--fast-phase", action="store_true", help="(default; kept for compatibility)")
+    ap.add_argument("--phase", choices=list(PHASE_FLAGS), default="auto",
+                    help="auto (default): WT_FLAG_AUTO_PHASE, the library picks the kernel per frame; exact / recurrence force one")
+    ap.add_argument("--exact-phase", action="store_true", help="same as --phase exact")
+    ap.add_argument("--fast-phase", action="store_true", help="same as --phase recurrence")
     ap.add_argument("--no-readback", action="store_true", help="skip the full output read-back (PCIe-bound) variant of e2e")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the last timed frame")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_workloads (configs 2, 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

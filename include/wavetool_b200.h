@@ -229,6 +229,8 @@ int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count);
 int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, wt_phase_report* report);
 /* Phase mode of the most recent evaluation launch of this context: 0 bit-faithful, 1 recurrence, -1 none yet. */
 int wt_last_phase_mode(const wt_ctx* ctx);
+/* Evaluation launches of this context so far by phase mode: out[0] bit-faithful (incl. reference-order), out[1] recurrence. */
+void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[2]);
 
 /* Replaces load2DTexture + create2DTexture (render-engine.cpp:1308-1322, texture.cpp:54-72):
  * tightly packed RGBA8, rows ALREADY in GL order (i.e. flipped as stbi_set_flip_vertically_on_load

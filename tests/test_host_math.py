@@ -141,3 +141,103 @@ def test_animation_advance_matches_reference_state_machine():
             assert f(p.waveAnimationTimeInSeconds) == t and f(p.verticalBounceWavePhase) == ph and f(p.timeOfDayInHours) == tod, k
     d = api.default_animation()
     assert (d.animationSpeedTimeOfDayInSecondsPerHour, d.animationSpeedVerticalBounceWavePhasePeriodInSeconds, d.isAnimatingTimeOfDay, d.isAnimatingWaves) == (1.0, 3.0, 0, 1)
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter surface: the reference's sliders, their force-clamp code, the physical wave constructor
+# --------------------------------------------------------------------------------------------------
+def test_wave_from_wavelength_speed_conventions():
+    """render-engine.h:139-140: 'w = 2/L (roughly)', 'phi = S x w'.  The physical convention (w = 2 pi / L) reproduces the
+    seeded benchmark sets (wave_tool_b200/scenes.py) to fp32 rounding."""
+    import ctypes as C
+    w = api.wave_from_wavelength_speed(0.25, 8.0, 0.5, (3.0, 4.0), 2.0, api.WAVENUMBER_GPU_GEMS)
+    assert (w.amplitude_A, w.frequency_w, w.phaseConstant_phi, w.steepness_Q) == (0.25, 0.25, 0.5, 0.5)
+    assert abs(w.dir_x - 0.6) < 1e-7 and abs(w.dir_z - 0.8) < 1e-7
+    w = api.wave_from_wavelength_speed(0.25, 8.0, 0.5, (0.0, -2.0), 2.0, api.WAVENUMBER_PHYSICAL)
+    assert abs(w.frequency_w - 2 * np.pi / 8) < 1e-7 and abs(w.phaseConstant_phi - 2 * 2 * np.pi / 8) < 2e-7 and (w.dir_x, w.dir_z) == (0.0, -1.0)
+    rows = scenes.seeded_waves(64, cfg=3)
+    for A, wn, phi, Q, dx, dz in rows[::7]:
+        lam = 2 * np.pi / float(wn)
+        speed = float(phi) / float(wn)                      # deep-water phase speed sqrt(g lambda / 2 pi)
+        assert abs(speed - np.sqrt(9.8 * lam / (2 * np.pi))) < 1e-5 * speed
+        got = api.wave_from_wavelength_speed(float(A), lam, float(Q), (float(dx), float(dz)), speed)
+        want = np.array([A, wn, phi, Q, dx, dz], np.float32)
+        have = np.array([got.amplitude_A, got.frequency_w, got.phaseConstant_phi, got.steepness_Q, got.dir_x, got.dir_z], np.float32)
+        assert np.all(np.abs(have - want) <= 4 * np.spacing(np.abs(want)) + 1e-7), (have, want)
+        # and the result is a wave wt_set_waves' validation (render-engine.h:147-154) accepts: unit direction, ranges
+        assert abs(np.hypot(got.dir_x, got.dir_z) - 1.0) < 1e-6
+    for bad in [dict(wavelength=0.0), dict(amplitude=-1.0), dict(speed=-0.1), dict(steepness=1.5), dict(direction=(0.0, 0.0))]:
+        kw = dict(amplitude=0.1, wavelength=4.0, steepness=0.5, direction=(1.0, 0.0), speed=1.0)
+        kw.update(bad)
+        with pytest.raises(api.WaveToolError):
+            api.wave_from_wavelength_speed(**kw)
+
+
+def test_ui_ranges_and_force_clamps_at_the_range_ends():
+    """program.cpp:201-479: slider bounds and the asymmetric 'force-clamp (handle CTRL + LEFT_CLICK)' code — glm::clamp on
+    some fields, only `if (v < 0) v = 0` on others (a CTRL-click can exceed their slider maximum)."""
+    L = api.lib()
+    r = api.ui_ranges()
+    assert len(r) == api.UI_RANGE_COUNT
+    assert r["waveAnimationTimeInSeconds"] == (0.0, 3600.0, True, False)         # :433
+    assert r["sunShininess"] == (0.0, 200.0, True, False) and r["sunStrength"] == (0.0, 1.0, True, True)   # :242, :247
+    assert r["phaseConstant_phi"] == (0.0, 10.0, True, False) and r["steepness_Q"] == (0.0, 1.0, True, True)   # :384, :388
+    assert r["amplitude_A"] == (0.0, 1.0, True, False) and r["frequency_w"] == (0.0, 1.0, True, False)
+    assert r["timeOfDayInHours"] == (0.0, 24.0, True, True) and r["xzDirection_D"] == (-1.0, 1.0, True, True)
+    # params: both ends of every range + beyond
+    p = api.default_params()
+    p.timeOfDayInHours, p.sunShininess, p.sunStrength = 25.0, 200.0, 1.0
+    p.heightmapSampleScale, p.heightmapDisplacementScale, p.verticalBounceWaveAmplitude = 1.0, 1.0, 1.0
+    p.verticalBounceWavePhase, p.waveAnimationTimeInSeconds = 1.0, 3600.0
+    L.wt_params_clamp_ui(C.byref(p))
+    assert (p.timeOfDayInHours, p.sunShininess, p.sunStrength, p.heightmapSampleScale, p.heightmapDisplacementScale,
+            p.verticalBounceWaveAmplitude, p.verticalBounceWavePhase, p.waveAnimationTimeInSeconds) == (24.0, 200.0, 1.0, 1.0, 1.0, 1.0, 1.0, 3600.0)
+    p.timeOfDayInHours, p.sunShininess, p.sunStrength = -1.0, -5.0, 1.5
+    p.heightmapSampleScale, p.heightmapDisplacementScale, p.verticalBounceWaveAmplitude = -0.1, 3.0, -2.0
+    p.verticalBounceWavePhase, p.waveAnimationTimeInSeconds = -0.5, 7200.0
+    L.wt_params_clamp_ui(C.byref(p))
+    assert (p.timeOfDayInHours, p.sunShininess, p.sunStrength, p.heightmapSampleScale, p.heightmapDisplacementScale,
+            p.verticalBounceWaveAmplitude, p.verticalBounceWavePhase, p.waveAnimationTimeInSeconds) == (0.0, 0.0, 1.0, 0.0, 3.0, 0.0, 0.0, 7200.0)
+    p.sunShininess = 250.0                                                         # above the slider: NOT clamped by the reference (:244)
+    L.wt_params_clamp_ui(C.byref(p))
+    assert p.sunShininess == 250.0
+    # waves
+    w = api.Wave(1.0, 1.0, 10.0, 1.0, 1.0, 1.0)
+    L.wt_wave_clamp_ui(C.byref(w))
+    assert (w.amplitude_A, w.frequency_w, w.phaseConstant_phi, w.steepness_Q) == (1.0, 1.0, 10.0, 1.0)
+    assert abs(w.dir_x - np.float32(1 / np.sqrt(np.float32(2)))) < 1e-7 and w.dir_x == w.dir_z              # normalised (:398)
+    w = api.Wave(-1.0, -0.5, -3.0, 1.7, 0.0, 0.0)
+    L.wt_wave_clamp_ui(C.byref(w))
+    assert (w.amplitude_A, w.frequency_w, w.phaseConstant_phi, w.steepness_Q, w.dir_x, w.dir_z) == (0.0, 0.0, 0.0, 1.0, 0.0, 1.0)   # :397 zero vector -> (0,1)
+    w = api.Wave(2.0, 3.0, 12.0, -0.2, -5.0, 0.0)
+    L.wt_wave_clamp_ui(C.byref(w))
+    assert (w.amplitude_A, w.frequency_w, w.phaseConstant_phi, w.steepness_Q, w.dir_x, w.dir_z) == (2.0, 3.0, 12.0, 0.0, -1.0, 0.0)
+    # a clamped wave always passes the GerstnerWave constructor's constraints (render-engine.h:147-154) ...
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        v = rng.uniform(-2, 12, size=6)
+        w = api.Wave(*[float(x) for x in v])
+        L.wt_wave_clamp_ui(C.byref(w))
+        assert w.amplitude_A >= 0 and w.frequency_w >= 0 and w.phaseConstant_phi >= 0 and 0 <= w.steepness_Q <= 1
+        assert abs(np.hypot(w.dir_x, w.dir_z) - 1) <= 1e-3
+    # animation, sky, compose
+    a = api.default_animation()
+    a.animationSpeedTimeOfDayInSecondsPerHour, a.animationSpeedVerticalBounceWavePhasePeriodInSeconds = -1.0, 60.0
+    L.wt_animation_clamp_ui(C.byref(a))
+    assert (a.animationSpeedTimeOfDayInSecondsPerHour, a.animationSpeedVerticalBounceWavePhasePeriodInSeconds) == (0.0, 60.0)
+    s = api.default_sky_params()
+    s.cloudProportion, s.overcastStrength, s.sunHorizonDarkness, s.sunShininess, s.sunStrength, s.timeOfDayInHours = 1.5, -0.5, 1.0, 201.0, 2.0, 24.0
+    s.fogColourFarAtNoon[:] = [2.0, -1.0, 0.5, 1.0]
+    L.wt_sky_params_clamp_ui(C.byref(s))
+    assert (s.cloudProportion, s.overcastStrength, s.sunHorizonDarkness, s.sunShininess, s.sunStrength, s.timeOfDayInHours) == (1.0, 0.0, 1.0, 201.0, 1.0, 24.0)
+    assert list(s.fogColourFarAtNoon) == [1.0, 0.0, 0.5, 1.0]
+    c = api.default_compose_params(api.default_camera(), 8, 8)
+    c.fogDepthRadiusFar, c.fogDepthRadiusNear = 0.25, 0.75                          # the FAR slider moved below near: near follows (:259-264)
+    L.wt_compose_params_clamp_ui(C.byref(c), 0)
+    assert (c.fogDepthRadiusFar, c.fogDepthRadiusNear) == (0.25, 0.25)
+    c.fogDepthRadiusFar, c.fogDepthRadiusNear = 0.25, 0.75                          # the NEAR slider moved above far: far follows (:266-271)
+    L.wt_compose_params_clamp_ui(C.byref(c), 1)
+    assert (c.fogDepthRadiusFar, c.fogDepthRadiusNear) == (0.75, 0.75)
+    c.tintDeltaDepthThreshold, c.waterClarity, c.softEdgesDeltaDepthThreshold = 1.0, 0.0, 7.0
+    L.wt_compose_params_clamp_ui(C.byref(c), 0)
+    assert (c.tintDeltaDepthThreshold, c.waterClarity, c.softEdgesDeltaDepthThreshold) == (1.0, 0.0, 1.0)

@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
     "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
-    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts",
 ]
 
 
@@ -186,6 +186,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_fast_phase_report.argtypes = [C.c_void_p, C.c_uint, C.POINTER(Frame), C.c_uint, C.POINTER(PhaseReport)]
     L.wt_fast_phase_valid.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.POINTER(PhaseReport)]
     L.wt_last_phase_mode.argtypes = [C.c_void_p]
+    L.wt_phase_mode_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.wt_phase_mode_counts.restype = None
     L.wt_default_sky_params.argtypes = [C.POINTER(SkyParams)]
     L.wt_default_sky_params.restype = None
     L.wt_set_sky_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -470,6 +472,12 @@ class Context:
 
     def last_phase_mode(self) -> int:
         return int(self._lib.wt_last_phase_mode(self._h))
+
+    def phase_mode_counts(self):
+        """(bit-faithful launches, recurrence launches) of this context so far."""
+        out = (C.c_uint64 * 2)()
+        self._lib.wt_phase_mode_counts(self._h, out)
+        return int(out[0]), int(out[1])
 
     def launch_count(self) -> int:
         return int(self._lib.wt_launch_count(self._h))

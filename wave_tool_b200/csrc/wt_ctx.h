@@ -21,6 +21,7 @@ struct wt_ctx {
     std::vector<wt::WaveK> tab_exact, tab_fast, tab_raw;
     std::vector<wt_wave> waves;     // as handed to wt_set_waves (wt_fast_phase_valid)
     int last_phase_mode = -1;       // 0 bit-faithful, 1 recurrence: what the most recent evaluation launch ran
+    uint64_t mode_launches[2] = {0, 0};   // evaluation launches per phase mode (wt_phase_mode_counts)
     // textures
     float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
     float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)

@@ -207,7 +207,7 @@ int validate_eval(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, u
     if ((flags & WT_FLAG_SHADE) && !d_shade) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_SHADE needs a shade buffer");
     if ((flags & WT_FLAG_CHECKSUM) && !d_cks) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_CHECKSUM needs a checksum buffer");
     if (!ctx->waves_set) return fail(ctx, WT_ERR_NOT_READY, "wt_set_waves has not been called");
-    if (!ctx->d_hm_r) return fail(ctx, WT_ERR_NOT_READY, "wt_set_heightmap_rgba8 has not been called (the reference draws no water without a heightmap, program.cpp:721)");
+    if (!ctx->d_hm_r || !ctx->d_hm_quads) return fail(ctx, WT_ERR_NOT_READY, "wt_set_heightmap_rgba8 has not been called (the reference draws no water without a heightmap, program.cpp:721)");
     return WT_OK;
 }
 
@@ -260,6 +260,7 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
     if ((flags & WT_FLAG_AUTO_PHASE) && !(flags & WT_FLAG_REFERENCE_ORDER))
         flags = fast_phase_ok(ctx, a) ? (flags | WT_FLAG_FAST_PHASE) : (flags & ~WT_FLAG_FAST_PHASE);
     ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? 0 : ((flags & WT_FLAG_FAST_PHASE) ? 1 : 0);
+    ctx->mode_launches[ctx->last_phase_mode]++;
     if (flags & WT_FLAG_REFERENCE_ORDER) {
         switch (wave_capacity(ctx->n_waves)) {
             case 64: return shade ? launch_reference_order<64, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<64, false>(ctx, a, ctx->tab_raw, stream);
@@ -299,21 +300,28 @@ int wt_create(wt_ctx** out, int device) {
     wt_ctx* ctx = new wt_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    WT_CUDA(nullptr, cudaMalloc(&ctx->s_cks, sizeof(wt_checksum)));
-    WT_CUDA(nullptr, cudaMalloc(&ctx->d_sky_black, 6 * sizeof(uchar4)));
-    WT_CUDA(nullptr, cudaMemset(ctx->d_sky_black, 0, 6 * sizeof(uchar4)));
-    {
+    // every allocation of the context; on any failure the half-built context is destroyed again
+    auto init = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaMalloc(&ctx->s_cks, sizeof(wt_checksum))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ctx->d_sky_black, 6 * sizeof(uchar4))) != cudaSuccess) return e;
+        if ((e = cudaMemset(ctx->d_sky_black, 0, 6 * sizeof(uchar4))) != cudaSuccess) return e;
         const uint8_t black[4] = {0, 0, 0, 0};
         const uint8_t* const faces[6] = {black, black, black, black, black, black};
-        WT_CUDA(nullptr, make_sky_atlas(faces, 1, &ctx->sky_array_black, &ctx->sky_tex_black));
+        if ((e = make_sky_atlas(faces, 1, &ctx->sky_array_black, &ctx->sky_tex_black)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ctx->d_cks_acc, N_QUEUES * sizeof(wt_checksum))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ctx->d_cks_done, N_QUEUES * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMemset(ctx->d_cks_done, 0, N_QUEUES * sizeof(int))) != cudaSuccess) return e;
+        checksum_init_kernel<<<(N_QUEUES + 127) / 128, 128>>>(ctx->d_cks_acc, (int)N_QUEUES);   // armed: zero sums, min/max keys at their identities
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ctx->d_queues, 2 * N_QUEUES * sizeof(int))) != cudaSuccess) return e;
+        return cudaMemset(ctx->d_queues, 0, 2 * N_QUEUES * sizeof(int));
+    };
+    const cudaError_t e = init();
+    if (e != cudaSuccess) {
+        wt_destroy(ctx);
+        return fail(nullptr, WT_ERR_CUDA, std::string("wt_create: ") + cudaGetErrorString(e));
     }
-    WT_CUDA(nullptr, cudaMalloc(&ctx->d_cks_acc, N_QUEUES * sizeof(wt_checksum)));
-    WT_CUDA(nullptr, cudaMalloc(&ctx->d_cks_done, N_QUEUES * sizeof(int)));
-    WT_CUDA(nullptr, cudaMemset(ctx->d_cks_done, 0, N_QUEUES * sizeof(int)));
-    checksum_init_kernel<<<(N_QUEUES + 127) / 128, 128>>>(ctx->d_cks_acc, (int)N_QUEUES);   // armed: zero sums, min/max keys at their identities
-    WT_CUDA(nullptr, cudaDeviceSynchronize());
-    WT_CUDA(nullptr, cudaMalloc(&ctx->d_queues, 2 * N_QUEUES * sizeof(int)));
-    WT_CUDA(nullptr, cudaMemset(ctx->d_queues, 0, 2 * N_QUEUES * sizeof(int)));
     *out = ctx;
     return WT_OK;
 }
@@ -382,21 +390,41 @@ int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned L, wt
 
 int wt_last_phase_mode(const wt_ctx* ctx) { return ctx ? ctx->last_phase_mode : -1; }
 
+void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[2]) {
+    if (!out) return;
+    out[0] = ctx ? ctx->mode_launches[0] : 0;
+    out[1] = ctx ? ctx->mode_launches[1] : 0;
+}
+
 int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int w, int h) {
     if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_set_heightmap_rgba8: ctx is NULL");
-    if (!rgba || w <= 0 || h <= 0 || w > 16384 || h > 16384) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_heightmap_rgba8: bad image");
+    // the footprint table takes 64 bytes per texel: 4096 x 4096 texels = 1 GiB is the most it is allowed to grow to
+    if (!rgba || w <= 0 || h <= 0 || w > 8192 || h > 8192 || (long long)w * h > (1LL << 24))
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_heightmap_rgba8: bad image (need 1 <= width, height <= 8192 and width * height <= 2^24)");
     DeviceGuard g(ctx->device);
     // water-grid.vert:106-111 reads only .r; stage it as the exact unorm value c/255.0f
     std::vector<float> r((size_t)w * h);
     for (size_t i = 0; i < r.size(); ++i) r[i] = (float)rgba[4 * i] / 255.0f;
+    // build into temporaries; the context changes only after every step has succeeded
+    float* d_r = nullptr;
+    float4* d_quads = nullptr;
+    auto build = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaMalloc(&d_r, r.size() * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMemcpy(d_r, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&d_quads, 4 * r.size() * sizeof(float4))) != cudaSuccess) return e;
+        build_heightmap_quads_kernel<<<ctx->sm_count * 4, 256>>>(d_r, w, h, d_quads);
+        ctx->launches++;
+        return cudaDeviceSynchronize();
+    };
+    const cudaError_t e = build();
+    if (e != cudaSuccess) {
+        cudaFree(d_r); cudaFree(d_quads);
+        cudaGetLastError();
+        return fail(ctx, WT_ERR_CUDA, std::string("wt_set_heightmap_rgba8: ") + cudaGetErrorString(e) + " (the previous heightmap, if any, is still in place)");
+    }
     cudaFree(ctx->d_hm_r); cudaFree(ctx->d_hm_quads);
-    ctx->d_hm_r = nullptr; ctx->d_hm_quads = nullptr;
-    WT_CUDA(ctx, cudaMalloc(&ctx->d_hm_r, r.size() * sizeof(float)));
-    WT_CUDA(ctx, cudaMemcpy(ctx->d_hm_r, r.data(), r.size() * sizeof(float), cudaMemcpyHostToDevice));
-    WT_CUDA(ctx, cudaMalloc(&ctx->d_hm_quads, 4 * r.size() * sizeof(float4)));
-    build_heightmap_quads_kernel<<<ctx->sm_count * 4, 256>>>(ctx->d_hm_r, w, h, ctx->d_hm_quads);
-    ctx->launches++;
-    WT_CUDA(ctx, cudaDeviceSynchronize());
+    ctx->d_hm_r = d_r; ctx->d_hm_quads = d_quads;
     ctx->hm_w = w; ctx->hm_h = h;
     return WT_OK;
 }
@@ -406,15 +434,31 @@ int wt_set_skybox_rgba8(wt_ctx* ctx, const uint8_t* const faces[6], int n) {
     if (!faces || n <= 0 || n > 16384) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: bad cubemap");
     for (int f = 0; f < 6; ++f) if (!faces[f]) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_set_skybox_rgba8: face pointer is NULL");
     DeviceGuard g(ctx->device);
-    cudaFree(ctx->d_sky);
-    ctx->d_sky = nullptr;
-    if (ctx->sky_surf) { cudaDestroySurfaceObject(ctx->sky_surf); ctx->sky_surf = 0; }
-    if (ctx->sky_tex) { cudaDestroyTextureObject(ctx->sky_tex); ctx->sky_tex = 0; }
-    if (ctx->sky_array) { cudaFreeArray(ctx->sky_array); ctx->sky_array = nullptr; }
+    // build into temporaries; the context changes only after every step has succeeded
     const size_t face_bytes = (size_t)n * n * 4;
-    WT_CUDA(ctx, cudaMalloc(&ctx->d_sky, 6 * face_bytes));
-    for (int f = 0; f < 6; ++f) WT_CUDA(ctx, cudaMemcpy((uint8_t*)ctx->d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice));
-    WT_CUDA(ctx, make_sky_atlas(faces, n, &ctx->sky_array, &ctx->sky_tex));
+    uchar4* d_sky = nullptr;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    auto build = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaMalloc(&d_sky, 6 * face_bytes)) != cudaSuccess) return e;
+        for (int f = 0; f < 6; ++f)
+            if ((e = cudaMemcpy((uint8_t*)d_sky + f * face_bytes, faces[f], face_bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        return make_sky_atlas(faces, n, &arr, &tex);
+    };
+    const cudaError_t e = build();
+    if (e != cudaSuccess) {
+        cudaFree(d_sky);
+        if (tex) cudaDestroyTextureObject(tex);
+        if (arr) cudaFreeArray(arr);
+        cudaGetLastError();
+        return fail(ctx, WT_ERR_CUDA, std::string("wt_set_skybox_rgba8: ") + cudaGetErrorString(e) + " (the previous skybox, if any, is still in place)");
+    }
+    cudaFree(ctx->d_sky);
+    if (ctx->sky_surf) { cudaDestroySurfaceObject(ctx->sky_surf); ctx->sky_surf = 0; }
+    if (ctx->sky_tex) cudaDestroyTextureObject(ctx->sky_tex);
+    if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
+    ctx->d_sky = d_sky; ctx->sky_array = arr; ctx->sky_tex = tex;
     ctx->sky_n = n;
     ctx->sky_surface_ok = false;   // this array was not created for surface writes: a later synthesis re-creates it
     return WT_OK;
@@ -538,7 +582,11 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
         const size_t off = (size_t)(f % ring_depth) * slot;
         EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
-        WT_CUDA(ctx, launch_eval(ctx, a, flags, fan.stream_for(f)));
+        const cudaError_t e = launch_eval(ctx, a, flags, fan.stream_for(f));
+        if (e != cudaSuccess) {   // the internal streams were forked off the caller's: join them before reporting
+            fan.end();
+            return fail(ctx, WT_ERR_CUDA, std::string("wt_eval_batch: ") + cudaGetErrorString(e));
+        }
     }
     WT_CUDA(ctx, fan.end());
     if (ref_cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
@@ -567,23 +615,33 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     unsigned drawn = 0;
     FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
     WT_CUDA(ctx, fan.begin());
+    std::vector<unsigned> not_drawn;
+    // after begin() the internal streams have been forked off the caller's: every exit path joins them again
+    auto bail = [&](int code, const std::string& msg) { fan.end(); return fail(ctx, code, msg); };
     for (unsigned k = 0; k < n_frames; ++k) {
         wt_frame frame;
         st = wt_build_frame(cam, params, total_amp, &frame);
-        if (st < 0) return fail(ctx, st, std::string("wt_run_animation: ") + wt_last_error(nullptr));
+        if (st < 0) return bail(st, std::string("wt_run_animation: ") + wt_last_error(nullptr));
         if (st == WT_OK) {
             const size_t off = (size_t)(k % ring_depth) * slot;
             EvalArgs a = make_args(ctx, frame, L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
-            WT_CUDA(ctx, launch_eval(ctx, a, flags, fan.stream_for(k)));
+            const cudaError_t e = launch_eval(ctx, a, flags, fan.stream_for(k));
+            if (e != cudaSuccess) return bail(WT_ERR_CUDA, std::string("wt_run_animation: ") + cudaGetErrorString(e));
             ++drawn;
-        } else if (cks && !ref_cks) {
-            WT_CUDA(ctx, cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), fan.stream_for(k)));   // nothing drawn: zero digest
+        } else if (cks) {
+            if (ref_cks) not_drawn.push_back(k);   // the finalize kernel below would turn the armed record into NaN extrema
+            else if (cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), fan.stream_for(k)) != cudaSuccess)
+                return bail(WT_ERR_CUDA, "wt_run_animation: cudaMemsetAsync failed");   // nothing drawn: zero digest
         }
         for (unsigned s_ = 0; s_ < stride; ++s_) wt_animation_advance(params, anim, dt);
     }
     WT_CUDA(ctx, fan.end());
-    if (ref_cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
+    if (ref_cks) {
+        checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames);
+        ctx->launches++;
+        for (unsigned k : not_drawn) WT_CUDA(ctx, cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), stream));   // documented: zero digest
+    }
     WT_CUDA(ctx, cudaGetLastError());
     if (n_evaluated) *n_evaluated = drawn;
     return WT_OK;
@@ -604,21 +662,28 @@ int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, f
     if (st < 0) return fail(ctx, st, std::string("wt_step_submit: ") + wt_last_error(nullptr));
     DeviceGuard g(ctx->device);
     if (!ctx->h_cks_pinned) {
-        WT_CUDA(ctx, cudaHostAlloc(&ctx->h_cks_pinned, STEP_RING * sizeof(wt_checksum), cudaHostAllocMapped));
-        for (unsigned i = 0; i < STEP_RING; ++i) WT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->step_event[i], cudaEventDisableTiming));
+        // the events first: the mapped records are only published once everything a ticket needs exists
+        for (unsigned i = 0; i < STEP_RING; ++i)
+            if (!ctx->step_event[i]) WT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->step_event[i], cudaEventDisableTiming));
+        wt_checksum* h = nullptr;
+        WT_CUDA(ctx, cudaHostAlloc(&h, STEP_RING * sizeof(wt_checksum), cudaHostAllocMapped));
+        ctx->h_cks_pinned = h;
     }
-    const unsigned t = ctx->step_next++;
+    // a ticket is only handed out for a frame that really was enqueued (or that legitimately draws nothing): on an
+    // evaluation error nothing is consumed and no slot is left waiting for an event that was never recorded
+    const unsigned t = ctx->step_next;
     const unsigned slot = t % STEP_RING;
-    *ticket = t;
-    ctx->step_status[slot] = st;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (st == WT_OK) {
         // the kernel's last warp writes the finished digest straight into the mapped host record: no copy to enqueue
-        st = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned + slot, flags | WT_FLAG_CHECKSUM, stream_);
-        if (st != WT_OK) return st;
+        const int ev = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned + slot, flags | WT_FLAG_CHECKSUM, stream_);
+        if (ev != WT_OK) return ev;
     }
     WT_CUDA(ctx, cudaEventRecord(ctx->step_event[slot], stream));
-    return ctx->step_status[slot];
+    ctx->step_status[slot] = st;
+    ctx->step_next = t + 1;
+    *ticket = t;
+    return st;
 }
 
 int wt_step_wait(wt_ctx* ctx, unsigned ticket, wt_checksum* h_out) {

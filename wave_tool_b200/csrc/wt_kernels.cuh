@@ -25,6 +25,11 @@
 
 #include "../../include/wavetool_b200.h"
 
+// build-time switches used by the helpers below (the kernel's own knobs are defined next to it)
+#ifndef WT_HM_SCALAR_BLEND
+#define WT_HM_SCALAR_BLEND 1    // heightmap footprint blended per column in scalar form (no register moves to pair the two columns' texels up)
+#endif
+
 namespace wt {
 
 // One wave, pre-folded on the host (wt_set_waves).  MODE 0 reads (Dx,Dz,w); MODE 1 is handed a
@@ -352,10 +357,22 @@ __device__ __forceinline__ f2 hm_finish2(const EvalArgs& a, const HmTap& h, f2 p
     const float one = a.one;
     f2 oma = sub2(bc(1.0f), h.al), omb = sub2(bc(1.0f), h.be);
     f2 w00 = mul2(oma, omb), w10 = mul2(h.al, omb), w01 = mul2(oma, h.be), w11 = mul2(h.al, h.be);
+#if WT_HM_SCALAR_BLEND
+    // The two columns' texels arrive in two separate 16-byte loads: blending them as scalars (same operations, same
+    // order, same roundings) costs the FMA pipe exactly what the packed form costs and saves the eight register moves
+    // that would pair (qa.k, qb.k) up
+    float aA = mul_rn(w00.x, h.qa.x), aB = mul_rn(w00.y, h.qb.x);
+    aA = add_rn(mul_rn(w10.x, h.qa.y), aA); aB = add_rn(mul_rn(w10.y, h.qb.y), aB);
+    aA = add_rn(mul_rn(w01.x, h.qa.z), aA); aB = add_rn(mul_rn(w01.y, h.qb.z), aB);
+    aA = add_rn(mul_rn(w11.x, h.qa.w), aA); aB = add_rn(mul_rn(w11.y, h.qb.w), aB);
+    f2 acc = make_float2(aA, aB);
+    (void)one;
+#else
     f2 acc = mul2(w00, make_float2(h.qa.x, h.qb.x));
     acc = add2x(mul2(w10, make_float2(h.qa.y, h.qb.y)), acc, one);
     acc = add2x(mul2(w01, make_float2(h.qa.z, h.qb.z)), acc, one);
     acc = add2x(mul2(w11, make_float2(h.qa.w, h.qb.w)), acc, one);
+#endif
     texel_r = acc;   // heightmap_colour.r (:141)
     f2 bump = mul2(bc(a.hm_disp), mul2(bc(2.0f), sub2(acc, bc(0.5f))));
     return add2(add2x(bump, py, one), bc(a.bounce));
