@@ -270,7 +270,7 @@ def oracle_margin(api, scenes, ctx, waves, cam, params, L, hm, flags, shade_flag
             got["normal"].append(nrm[(q - b0) * L:(q - b0 + 1) * L].cpu().numpy())
         got = {k: np.concatenate(v) for k, v in got.items()}
         stats, _, _, _ = deviation_stats(got, want, sc)
-        out[name] = {"kernel": "recurrence" if ctx.last_phase_mode() == 1 else "bit-faithful",
+        out[name] = {"kernel": api.PHASE_NAMES[ctx.last_phase_mode()],
                      **{k: stats[k] for k in ("pos_max", "pos_tol", "pos_margin", "normal_max", "normal_tol", "normal_margin", "flip_band")}}
     rep = ctx.fast_phase_valid(frame, L)
     return {"vertices_compared": int(len(ids)), "rows": f"{len(rows)} rows: 0-7, every {max(1, L // 20)}th, the last two",
@@ -363,11 +363,12 @@ def run_ours(args):
     t_wall1 = time.time()
     launches = ctx.launch_count() - l0
     m1 = ctx.phase_mode_counts()
-    ran = {"bit-faithful": m1[0] - m0[0], "recurrence": m1[1] - m0[1]}
+    ran = {api.PHASE_NAMES[k]: m1[k] - m0[k] for k in range(3)}
     ms_local = e0.elapsed_time(e1)
     ms = shard.max_over_ranks(ms_local, dev) if world > 1 else ms_local
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
-    recurrence = ran["recurrence"] > ran["bit-faithful"]               # which kernel the timed steps ran (auto decides per frame)
+    timed_kernel = max(ran, key=ran.get)                               # which kernel the timed steps ran (auto decides per frame)
+    recurrence = timed_kernel == "recurrence"
 
     vw_per_frame = n * W                                               # this rank's share of one step
     frames_total = K if row_sharded else n_gpus * K                    # whole frames the job evaluated in the timed region
@@ -507,7 +508,8 @@ def run_ours(args):
     if rank == 0 and not args.no_parity:
         try:
             parity = oracle_margin(api, scenes, ctx, waves, cam, scenes.animation_params(my_frames[Wm + K - 1]), L, hm,
-                                   {"timed": PHASE_FLAGS[phase], "exact": 0, "recurrence": api.FLAG_FAST_PHASE}, shade_flag, torch)
+                                   {"timed": PHASE_FLAGS[phase], "bit-faithful": 0, "recurrence": api.FLAG_FAST_PHASE, "reference-order": api.FLAG_REFERENCE_ORDER},
+                                   shade_flag, torch)
             parity["frame"] = "the last timed frame (global frame %d)" % my_frames[Wm + K - 1]
         except Exception as ex:                                          # the checker must never take the bench line down
             parity = {"error": repr(ex)}
@@ -578,9 +580,11 @@ def run_ours(args):
                        "heightmap": "the reference's assets/textures/noise/waves/waves3/00.png (tests/golden fixture)",
                        "phase": phase},
             "phase": {"requested": phase, "kernel_launches": ran,
-                      "kernel": "phase recurrence: one MUFU seed per wave every 8 rows (12 above 64 waves), row 1 by complex rotation, rows 2.. by the "
-                                "three-term recurrence x[j+1] = 2 cos(dk) x[j] - x[j-1]" if recurrence else
-                                "bit-faithful fp32 phase (the reference's own rounding of k), Cody-Waite reduction, MUFU sin/cos pair per vertex-wave",
+                      "kernel": {"recurrence": "phase recurrence: one MUFU seed per wave every 8 rows (12 above 64 waves), row 1 by complex rotation, rows 2.. by the "
+                                               "three-term recurrence x[j+1] = 2 cos(dk) x[j] - x[j-1]",
+                                 "bit-faithful": "bit-faithful fp32 phase (the reference's own rounding of k), Cody-Waite reduction, MUFU sin/cos pair per vertex-wave, "
+                                                 "every displaced position evaluated once and shared by the stencils of its neighbours",
+                                 "reference-order": "straight transliteration of the shader: 5 full evaluations per vertex at the shader's own uv +- du arguments, libdevice sincosf"}[timed_kernel],
                       "why": "WT_FLAG_AUTO_PHASE: wt_fast_phase_valid decides per frame (see parity_margin.fast_phase_report)" if phase == "auto" else "forced by --phase"},
             "ms_per_frame": ms_per_step,
             "roofline": primary,
@@ -643,7 +647,8 @@ def extra_workloads(torch, dist, api, scenes, shard, rank, world, local_rank, de
 
     def kernel_name(ctx, before):
         after = ctx.phase_mode_counts()
-        return "recurrence" if after[1] - before[1] > after[0] - before[0] else "bit-faithful"
+        d = [after[k] - before[k] for k in range(3)]
+        return api.PHASE_NAMES[d.index(max(d))]
 
     # cfg2: 1024^2 x 8 waves, 1000-frame animation (frame f on rank f mod N), 4-deep ring, per-frame digests
     try:

@@ -49,9 +49,10 @@ extern "C" {
 #define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
 #define WT_FLAG_VARYINGS 0x10u        /* also write the vertex stage's other outputs (wt_eval_frame_ex): gl_Position,
                                          xyPositionNDCSpaceHeight0, heightmap_colour.r, normalVecInViewSpaceOnlyYaw */
-#define WT_FLAG_AUTO_PHASE 0x20u      /* per frame: the recurrence kernel (WT_FLAG_FAST_PHASE) where wt_fast_phase_valid says its deviation
-                                         from the reference stays inside the tolerances with margin, else the bit-faithful kernel.  Both run
-                                         on the GPU; wt_last_phase_mode tells which one a launch used */
+#define WT_FLAG_AUTO_PHASE 0x20u      /* per frame, the fastest kernel whose deviation from the reference wt_fast_phase_report bounds inside the
+                                         tolerances: the recurrence kernel, else the bit-faithful kernel, else (late in an animation, where
+                                         the shader's own re-evaluation of the stencil neighbours becomes noisy) the reference-order kernel.
+                                         All three run on the GPU; wt_last_phase_mode tells which one a launch used */
 
 typedef struct wt_ctx wt_ctx;
 
@@ -203,16 +204,31 @@ void wt_ui_ranges(wt_ui_range out[WT_UI_RANGE_COUNT]);
  * profiles/parity_margins.json) and compares them with the north-star
  * tolerances with a margin of WT_PHASE_MARGIN.  Host only; returns 1 (valid), 0 (use the bit-faithful kernel) or < 0. */
 typedef struct wt_phase_report {
-    float est_position_error, position_tolerance;      /* world units; tolerance = 1e-4 x total amplitude */
-    float est_normal_error_rad, normal_tolerance_rad;  /* radians; tolerance = 1e-3 */
+    float est_position_error, position_tolerance;      /* recurrence kernel; world units; tolerance = 1e-4 x total amplitude */
+    float est_normal_error_rad, normal_tolerance_rad;  /* recurrence kernel; radians; tolerance = 1e-3 */
     float min_vertex_spacing;                          /* smallest distance between neighbouring grid vertices */
     float max_phase;                                   /* largest |k| any wave reaches on this frame */
-    int valid;
+    int valid;                                         /* 1: the recurrence kernel is inside its validity domain */
+    /* The bit-faithful kernel reproduces k and the running sums bit for bit but, like the recurrence kernel, shares every
+     * displaced position between the stencils of its neighbours, where the shader re-evaluates them at uv +- du
+     * (water-grid.vert:164-182).  Once ulp(k) is large (late in an animation) that re-evaluation flips
+     * roundings of k and the SHADER's normals carry noise of A_i ulp(k_i) / spacing that only the reference-order kernel
+     * (WT_FLAG_REFERENCE_ORDER: five evaluations per vertex with exactly the shader's arguments) reproduces. */
+    float est_shared_stencil_normal_error_rad;
+    int shared_stencil_valid;                          /* 1: the bit-faithful kernel is inside ITS validity domain */
+    /* What one ulp of the fp32 coordinates does to a finite-difference normal on this grid: the floor for ANY evaluation whose
+     * sin / cos are not bit-identical to the reference's libm.  Above the tolerance on very fine grids. */
+    float coordinate_ulp_normal_error_rad;
+    int recommended;                                   /* WT_PHASE_*: what WT_FLAG_AUTO_PHASE runs on this frame */
 } wt_phase_report;
+#define WT_PHASE_BIT_FAITHFUL 0
+#define WT_PHASE_RECURRENCE 1
+#define WT_PHASE_REFERENCE_ORDER 2
 #define WT_PHASE_MARGIN 1.0f        /* valid iff estimate x margin <= tolerance */
 #define WT_PHASE_K_POSITION 4.5     /* extreme of the position noise in modelled sigmas */
 #define WT_PHASE_K_NORMAL 3.7       /* height-noise term of the normal estimate: envelope 2.85 x 1.27 (the kernel's own MUFU / recurrence noise) */
 #define WT_PHASE_K_FLIP 0.35        /* flipped-rounding term: envelope 0.274 x 1.27 */
+#define WT_PHASE_K_STENCIL 1.0      /* shared-stencil term: two coinciding flips of A_i ulp(k_i) over the 2-spacing baseline */
 int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* frame, unsigned grid_len, wt_phase_report* out);
 
 /* ---------------------------------------------------------------------------------------------
@@ -227,10 +243,11 @@ int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count);
 /* wt_fast_phase_report on the context's wave set: 1 = the recurrence kernel is inside its validity domain on this
  * frame, 0 = not (WT_FLAG_AUTO_PHASE then runs the bit-faithful kernel), < 0 error.  report may be NULL. */
 int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, wt_phase_report* report);
-/* Phase mode of the most recent evaluation launch of this context: 0 bit-faithful, 1 recurrence, -1 none yet. */
+/* Kernel of the most recent evaluation launch of this context: WT_PHASE_BIT_FAITHFUL (0), WT_PHASE_RECURRENCE (1),
+ * WT_PHASE_REFERENCE_ORDER (2); -1 none yet. */
 int wt_last_phase_mode(const wt_ctx* ctx);
-/* Evaluation launches of this context so far by phase mode: out[0] bit-faithful (incl. reference-order), out[1] recurrence. */
-void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[2]);
+/* Evaluation launches of this context so far by kernel: out[WT_PHASE_*]. */
+void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[3]);
 
 /* Replaces load2DTexture + create2DTexture (render-engine.cpp:1308-1322, texture.cpp:54-72):
  * tightly packed RGBA8, rows ALREADY in GL order (i.e. flipped as stbi_set_flip_vertically_on_load
@@ -374,8 +391,7 @@ int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, flo
 
 /* The same round trip split in two so that frames overlap: wt_step_submit builds and enqueues a frame and returns a
  * ticket; wt_step_wait blocks until that frame's digest has arrived in host memory (WT_NO_GRID: zero digest).  Up to 4
- * frames may be in flight — the host prepares frame k+1 while the GPU evaluates frame k, as a render loop does.  Not
- * available with WT_FLAG_REFERENCE_ORDER. */
+ * frames may be in flight — the host prepares frame k+1 while the GPU evaluates frame k, as a render loop does. */
 int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_wave_amplitude, unsigned grid_len,
                    unsigned row_begin, unsigned row_end, void* d_position, void* d_normal, void* d_shade, unsigned flags,
                    void* cuda_stream, unsigned* ticket);

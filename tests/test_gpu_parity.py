@@ -205,11 +205,18 @@ ENVELOPE_CASES = {
 @pytest.mark.parametrize("t", [0.0, 17.0, 600.0, 3600.0])
 @pytest.mark.parametrize("name", list(ENVELOPE_CASES))
 def test_phase_envelope_over_the_time_slider(oracle, hm, name, t):
-    """Every BASELINE scene at the start, in the middle and at the top of waveAnimationTimeInSeconds' slider:
-      * the bit-faithful kernel meets the north-star tolerances at every t (it reproduces the reference's own rounding of k);
-      * WT_FLAG_AUTO_PHASE meets them at every t, running the recurrence kernel exactly where wt_fast_phase_valid allows it;
-      * the recurrence kernel meets them wherever wt_fast_phase_valid says so — and really does leave them at the top of the
-        slider (cfg2 / cfg3 / cfg4 at t = 3600 s), which is why the switch exists."""
+    """Every BASELINE scene at the start, in the middle and at the top of waveAnimationTimeInSeconds' slider, on all three
+    kernels and on WT_FLAG_AUTO_PHASE:
+      * each kernel meets the north-star tolerances wherever wt_fast_phase_report says it is inside its validity domain
+        (recurrence: `valid`; bit-faithful: `shared_stencil_valid`; reference-order: always);
+      * WT_FLAG_AUTO_PHASE meets them at EVERY t, and runs exactly the kernel the report recommends;
+      * at the top of the slider the recurrence kernel AND the bit-faithful kernel really do leave the tolerance — the first
+        because it does not share the reference's rounding of k = w d + phi t (ulp(36000) = 4e-3 rad), the second because
+        the shader re-evaluates the stencil neighbours at uv +- du and those re-evaluations flip roundings of k no
+        shared-stencil kernel reproduces — which is why the third tier exists.
+    On the 8192^2 grid one ulp of the fp32 coordinates already tilts a finite-difference normal by more than 1e-3 rad
+    (report.coordinate_ulp_normal_error_rad): there the gate is that bound, and at most 1e-4 of the vertices
+    may exceed the plain tolerance."""
     torch = torch_mod()
     L, waves, rows = ENVELOPE_CASES[name]
     p = api.default_params()
@@ -219,38 +226,43 @@ def test_phase_envelope_over_the_time_slider(oracle, hm, name, t):
     assert st == api.WT_OK
     ctx = sc.make_context()
     rep = ctx.fast_phase_valid(frame, L)
+    fine = L >= 8192
     if rows is None:
         want = sc.oracle_eval(oracle)
-        pick = lambda got: got
     else:
         want = sc.oracle_eval(oracle, ids=rows_to_ids(rows, L))
-        pick = lambda got: take_rows(got, rows, L)
-    results = {}
-    for mode, fl in (("exact", 0), ("auto", api.FLAG_AUTO_PHASE), ("recurrence", api.FLAG_FAST_PHASE)):
-        if L >= 8192:      # row bands (2.15 GB per full frame)
+
+    def evaluate(fl):
+        if fine:      # row bands (2.15 GB per full frame)
             parts = [gpu_eval(ctx, frame, L, flags=fl, rows=(max(r - 1, 0), min(r + 2, L))) for r in rows]
-            got = {k: np.concatenate([pp[k][(r - max(r - 1, 0)) * L:(r - max(r - 1, 0) + 1) * L] for pp, r in zip(parts, rows)]) for k in ("pos", "normal")}
-        else:
-            got = pick(gpu_eval(ctx, frame, L, flags=fl))
+            return {k: np.concatenate([pp[k][(r - max(r - 1, 0)) * L:(r - max(r - 1, 0) + 1) * L] for pp, r in zip(parts, rows)]) for k in ("pos", "normal")}
+        got = gpu_eval(ctx, frame, L, flags=fl)
+        return got if rows is None else take_rows(got, rows, L)
+
+    def passes(stats):
+        if not fine:
+            return stats["pos_margin"] >= 1.0 and stats["normal_margin"] >= 1.0
+        return (stats["pos_margin"] >= 1.0 and stats["normal_max"] <= max(1e-3, rep.coordinate_ulp_normal_error_rad)
+                and stats["normal_over_tol"] <= 1e-4 * stats["n"])
+
+    results = {}
+    for mode, fl, inside in (("exact", 0, rep.shared_stencil_valid), ("recurrence", api.FLAG_FAST_PHASE, rep.valid),
+                             ("reference_order", api.FLAG_REFERENCE_ORDER, 1), ("auto", api.FLAG_AUTO_PHASE, 1)):
+        got = evaluate(fl)
         ran = ctx.last_phase_mode()
         stats, perr, ang, band = deviation_stats(got, want, sc)
-        results[mode] = (stats, ran)
-        print("envelope", name, t, mode, "ran", ran, {k: stats[k] for k in ("pos_margin", "normal_margin", "flip_band")}, "valid", rep.valid)
-        if mode == "exact":
-            assert ran == 0
-            compare(got, want, sc, label=f"{name} t={t} exact")
-        elif mode == "auto":
-            assert ran == rep.valid
-            compare(got, want, sc, label=f"{name} t={t} auto")
-        else:
-            assert ran == 1
-            if rep.valid:
-                compare(got, want, sc, label=f"{name} t={t} recurrence inside its validity domain")
+        results[mode] = stats
+        print("envelope", name, t, mode, "ran", api.PHASE_NAMES[ran], {k: round(stats[k], 3) for k in ("pos_margin", "normal_margin")}, "over", stats["normal_over_tol"],
+              "inside" if inside else "outside", "recommended", api.PHASE_NAMES[rep.recommended])
+        assert ran == {"exact": api.PHASE_BIT_FAITHFUL, "recurrence": api.PHASE_RECURRENCE, "reference_order": api.PHASE_REFERENCE_ORDER, "auto": rep.recommended}[mode]
+        if inside:
+            assert passes(stats), (name, t, mode, stats)
+            assert stats["flip_band"] <= max(2, stats["n"] // 10000)
     if t >= 3600.0 and name != "cfg1":
-        assert rep.valid == 0
-        assert results["recurrence"][0]["normal_margin"] < 1.0, "the recurrence kernel was expected to leave the tolerance at the top of the slider"
+        assert rep.recommended == api.PHASE_REFERENCE_ORDER
+        assert results["recurrence"]["normal_margin"] < 1.0 and results["exact"]["normal_margin"] < 1.0, "both shared-stencil kernels were expected to leave the tolerance at the top of the slider"
     if t <= 17.0:
-        assert rep.valid == (1 if name == "cfg2" else 0)     # cfg3 / cfg4 under the horizon-grazing default camera: near-field spacing too fine
+        assert rep.recommended == (api.PHASE_RECURRENCE if name == "cfg2" else api.PHASE_BIT_FAITHFUL)
 
 
 @pytest.mark.parametrize("frame_index", [22, 202])
@@ -347,31 +359,55 @@ FINE_GRID_MODES = {"exact": 0, "auto": api.FLAG_AUTO_PHASE, "reference_order": a
 
 
 def fine_grid_check(oracle, sc, frame, ctx, L, bands, mode, label):
-    """Row bands of a very fine grid against the oracle with the PER-VERTEX noise-aware gate (tests/common.py:
-    noise_aware_gate).  Asserted for the bit-faithful kernel, WT_FLAG_AUTO_PHASE and the reference-order
-    kernel: no vertex may sit further from the fp32 oracle than max(tolerance, 2 x that vertex's own fp32-vs-fp64 noise), and
-    the fraction of vertices over the PLAIN north-star tolerances may not exceed the oracle's own fraction against fp64.
-    The recurrence kernel forced outside its validity domain is measured and reported, not gated per vertex: it does not
-    share the reference's roundings there by construction (wt_fast_phase_report)."""
+    """Row bands of a very fine grid against the oracle, PER VERTEX.  On a 16384^2 grid the near-field vertex
+    spacing is ~100 ulp of the fp32 coordinates: ONE flipped rounding of the shader's running fp32 sum moves a vertex by
+    ulp(coord) and tilts its neighbours' finite-difference normals by up to ulp(coord) / (2 x spacing) — more than the
+    1e-3 rad tolerance — and any evaluation whose sin / cos are not bit-identical to the reference's libm flips such a
+    rounding at a few vertices per million (so does the fp32 oracle against its fp64 twin, far more often).  Per vertex:
+        err_i <= max(tolerance, 2 noise_i, one-ulp bound_i)
+    with noise_i = the fp32 oracle's own distance from fp64 at that vertex and one-ulp bound_i = ulp(|x_i|, |z_i|) over the
+    distance to its nearest stencil neighbour; and, as a population, the fraction of vertices over the PLAIN north-star
+    tolerances may not exceed the oracle's own fraction against fp64.  Asserted for the bit-faithful kernel,
+    WT_FLAG_AUTO_PHASE and the reference-order kernel (t = 0.18 s: all three are inside their validity domains); the
+    recurrence kernel forced outside its domain is bounded at 3x the oracle's own noise and reported."""
     fl = FINE_GRID_MODES[mode]
     rep = ctx.fast_phase_valid(frame, L)
+    tol = 1e-4 * sc.total_amplitude
     for band in bands:
         got = gpu_eval(ctx, frame, L, rows=band, flags=fl)
-        rows = [band[0] + 1]
-        ids = rows_to_ids(rows, L)
-        want = sc.oracle_eval(oracle, ids=ids)
-        truth = sc.oracle_eval(oracle, ids=ids, f64=True)
-        sub = take_rows(got, rows, L, row_begin=band[0])
+        ran = ctx.last_phase_mode()
+        r = band[0] + 1
+        ids3 = rows_to_ids([r - 1, r, r + 1], L)                   # the row and its two stencil rows (their own positions)
+        want3 = sc.oracle_eval(oracle, ids=ids3)
+        want = {k: (v[L:2 * L] if isinstance(v, np.ndarray) else v) for k, v in want3.items()}
+        truth = sc.oracle_eval(oracle, ids=rows_to_ids([r], L), f64=True)
+        sub = take_rows(got, [r], L, row_begin=band[0])
         g = noise_aware_gate(sub, want, truth, sc)
-        print("fine grid", label, mode, band, "valid" if rep.valid else "outside-domain", g)
-        gated = mode != "recurrence" or rep.valid
-        if gated:
-            assert g["pos_fail"] == 0 and g["normal_fail"] == 0, (label, band, g)
+        # per-vertex one-ulp bound from the oracle's own geometry
+        P = want3["pos"][:, :3].astype(np.float64).reshape(3, L, 3)
+        c = P[1]
+        d_lr = np.linalg.norm(np.diff(c[:, [0, 2]], axis=0), axis=1)
+        d_lr = np.minimum(np.r_[d_lr, d_lr[-1]], np.r_[d_lr[0], d_lr])
+        d_ud = np.minimum(np.linalg.norm((P[2] - c)[:, [0, 2]], axis=1), np.linalg.norm((c - P[0])[:, [0, 2]], axis=1))
+        ulp = np.spacing(np.maximum(np.abs(c[:, 0]), np.abs(c[:, 2])).astype(np.float32)).astype(np.float64)
+        one_ulp = ulp / np.maximum(np.minimum(d_lr, d_ud), 1e-30)
+        g_err = np.abs(sub["pos"][:, :3].astype(np.float64) - want["pos"][:, :3]).max(axis=1)
+        o_err = np.abs(want["pos"][:, :3].astype(np.float64) - truth["pos"][:, :3]).max(axis=1)
+        g_ang = np.minimum(angle_between(sub["normal"][:, :3], want["normal"][:, :3]), angle_between(sub["normal"][:, :3], -want["normal"][:, :3]))
+        o_ang = np.minimum(angle_between(want["normal"][:, :3], truth["normal"][:, :3].astype(np.float32)),
+                           angle_between(want["normal"][:, :3], -truth["normal"][:, :3].astype(np.float32)))
+        pos_fail = int((g_err > np.maximum(np.maximum(tol, 2.0 * o_err), 2.0 * ulp)).sum())
+        nrm_fail = int((g_ang > np.maximum(np.maximum(1e-3, 2.0 * o_ang), one_ulp)).sum())
+        print("fine grid", label, mode, "ran", api.PHASE_NAMES[ran], band, dict(pos_fail=pos_fail, normal_fail=nrm_fail, normal_max=float(g_ang.max()),
+              one_ulp_max=float(one_ulp.max()), frac_over=g["normal_frac_over_tol"], oracle_frac_over=g["oracle_normal_frac_over_tol"]))
+        inside = {api.PHASE_RECURRENCE: rep.valid, api.PHASE_BIT_FAITHFUL: rep.shared_stencil_valid, api.PHASE_REFERENCE_ORDER: 1}[ran]
+        if inside:
+            assert pos_fail == 0 and nrm_fail == 0, (label, band, mode, g)
             assert g["pos_frac_over_tol"] <= g["oracle_pos_frac_over_tol"] + 1e-12, (label, band, g)
             assert g["normal_frac_over_tol"] <= g["oracle_normal_frac_over_tol"] + 1e-12, (label, band, g)
         else:
             # outside its domain the recurrence kernel sits about as far from the reference as the reference sits from fp64
-            assert g["pos_max"] <= max(1e-4 * sc.total_amplitude, 3.0 * g["oracle_pos_noise_max"]), (label, band, g)
+            assert g["pos_max"] <= max(tol, 3.0 * g["oracle_pos_noise_max"]), (label, band, g)
             assert g["normal_max"] <= max(1e-3, 3.0 * g["oracle_normal_noise_max"]), (label, band, g)
 
 

@@ -18,7 +18,7 @@ from oracle import oracle as orc  # noqa: E402
 from tests.common import Scene, deviation_stats, reference_heightmap  # noqa: E402
 from wave_tool_b200 import api, scenes  # noqa: E402
 
-MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE, "auto": api.FLAG_AUTO_PHASE}
+MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE, "reference_order": api.FLAG_REFERENCE_ORDER, "auto": api.FLAG_AUTO_PHASE}
 TIMES = [0.0, 3.4, 17.0, 60.0, 600.0, 3600.0]
 
 
@@ -89,7 +89,7 @@ def main():
             for mode, fl in MODES.items():
                 got, ran = gpu_rows(ctx, frame, L, fl, bands)
                 stats, perr, ang, band = deviation_stats(got, want, sc)
-                row = {"config": name, "grid_len": L, "waves": len(waves), "t": t, "mode": mode, "kernel": "recurrence" if ran == 1 else "bit-faithful",
+                row = {"config": name, "grid_len": L, "waves": len(waves), "t": t, "mode": mode, "kernel": api.PHASE_NAMES[ran],
                        "vertices_compared": int(len(perr)), **{k: stats[k] for k in ("pos_max", "pos_tol", "pos_margin", "normal_max", "normal_tol", "normal_margin",
                                                                                       "pos_over_tol", "normal_over_tol", "flip_band")},
                        "predicted": rep.as_dict(), "passes": bool(stats["pos_margin"] >= 1.0 and stats["normal_margin"] >= 1.0)}

@@ -18,6 +18,8 @@ WT_ERR_INVALID_ARGUMENT, WT_ERR_CUDA, WT_ERR_NO_DEVICE, WT_ERR_NOT_READY, WT_ERR
 WT_MAX_WAVES = 1000
 FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER, FLAG_VARYINGS, FLAG_AUTO_PHASE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 WAVENUMBER_GPU_GEMS, WAVENUMBER_PHYSICAL = 0, 1
+PHASE_BIT_FAITHFUL, PHASE_RECURRENCE, PHASE_REFERENCE_ORDER = 0, 1, 2
+PHASE_NAMES = {0: "bit-faithful", 1: "recurrence", 2: "reference-order"}
 UI_RANGE_COUNT = 23
 
 # every symbol include/wavetool_b200.h declares (tests/test_abi.py checks the library exports them all)
@@ -91,7 +93,9 @@ class SkyParams(C.Structure):
 
 class PhaseReport(C.Structure):
     _fields_ = [("est_position_error", C.c_float), ("position_tolerance", C.c_float), ("est_normal_error_rad", C.c_float),
-                ("normal_tolerance_rad", C.c_float), ("min_vertex_spacing", C.c_float), ("max_phase", C.c_float), ("valid", C.c_int)]
+                ("normal_tolerance_rad", C.c_float), ("min_vertex_spacing", C.c_float), ("max_phase", C.c_float), ("valid", C.c_int),
+                ("est_shared_stencil_normal_error_rad", C.c_float), ("shared_stencil_valid", C.c_int),
+                ("coordinate_ulp_normal_error_rad", C.c_float), ("recommended", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -474,10 +478,10 @@ class Context:
         return int(self._lib.wt_last_phase_mode(self._h))
 
     def phase_mode_counts(self):
-        """(bit-faithful launches, recurrence launches) of this context so far."""
-        out = (C.c_uint64 * 2)()
+        """(bit-faithful, recurrence, reference-order) evaluation launches of this context so far (indexed by PHASE_*)."""
+        out = (C.c_uint64 * 3)()
         self._lib.wt_phase_mode_counts(self._h, out)
-        return int(out[0]), int(out[1])
+        return int(out[0]), int(out[1]), int(out[2])
 
     def launch_count(self) -> int:
         return int(self._lib.wt_launch_count(self._h))

@@ -20,8 +20,8 @@ struct wt_ctx {
     bool waves_set = false;
     std::vector<wt::WaveK> tab_exact, tab_fast, tab_raw;
     std::vector<wt_wave> waves;     // as handed to wt_set_waves (wt_fast_phase_valid)
-    int last_phase_mode = -1;       // 0 bit-faithful, 1 recurrence: what the most recent evaluation launch ran
-    uint64_t mode_launches[2] = {0, 0};   // evaluation launches per phase mode (wt_phase_mode_counts)
+    int last_phase_mode = -1;       // WT_PHASE_*: what the most recent evaluation launch ran
+    uint64_t mode_launches[3] = {0, 0, 0};   // evaluation launches per kernel, indexed by WT_PHASE_* (wt_phase_mode_counts)
     // textures
     float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
     float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)
@@ -46,6 +46,7 @@ struct wt_ctx {
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;
     size_t s_elems = 0;
     wt_checksum* s_cks = nullptr;
+    wt_checksum* d_step_cks = nullptr;     // device records of wt_step_submit frames that run the reference-order kernel
     wt_checksum* h_cks_pinned = nullptr;   // mapped host records of wt_step_host / wt_step_submit (STEP_RING + 1 of them)
     cudaEvent_t step_event[4] = {nullptr, nullptr, nullptr, nullptr};
     int step_status[4] = {0, 0, 0, 0};
@@ -129,7 +130,10 @@ Plan make_plan(int slots, int L, int rows, int R);
 //   each band holds n_big items of rows_big rows followed by items of rows_small rows (the tail that keeps every
 //   warp busy until the queue is empty); the last item of a band is clipped at the band's end.
 constexpr int NOMINAL_SMS = 148;     // B200; the layout must not depend on the device actually used
-constexpr int LAYOUT_BANDS = 8;
+#ifndef WT_LAYOUT_BANDS
+#define WT_LAYOUT_BANDS 8
+#endif
+constexpr int LAYOUT_BANDS = WT_LAYOUT_BANDS;
 constexpr int MAX_SEGS = 2 * LAYOUT_BANDS;
 struct Layout {
     int n_strips = 1, bands = 1, rows_big = 1, rows_small = 0, tail_pct = 0;

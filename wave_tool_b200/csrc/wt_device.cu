@@ -242,9 +242,13 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
     return a;
 }
 
-// WT_FLAG_AUTO_PHASE: the recurrence kernel where its deviation from the reference's own phase rounding stays inside
-// the tolerances (wt_fast_phase_report on this frame's corners and time), the bit-faithful kernel elsewhere
-bool fast_phase_ok(const wt_ctx* ctx, const EvalArgs& a) {
+// WT_FLAG_AUTO_PHASE for one frame: the fastest kernel whose deviation from the reference wt_fast_phase_report bounds inside
+// the tolerances (this frame's corners and time): recurrence, else bit-faithful, else reference-order.  The reference-order
+// kernel has no WT_FLAG_VARYINGS variant: with that flag the bit-faithful kernel is the last resort.
+unsigned resolve_phase(const wt_ctx* ctx, const EvalArgs& a, unsigned flags) {
+    if (!(flags & WT_FLAG_AUTO_PHASE)) return flags;
+    flags &= ~WT_FLAG_AUTO_PHASE;
+    if (flags & WT_FLAG_REFERENCE_ORDER) return flags;
     wt_frame f;
     std::memset(&f, 0, sizeof(f));
     f.bottomLeftGridPointInWorld[0] = a.blx; f.bottomLeftGridPointInWorld[2] = a.blz;
@@ -252,14 +256,17 @@ bool fast_phase_ok(const wt_ctx* ctx, const EvalArgs& a) {
     f.topLeftGridPointInWorld[0] = a.tlx; f.topLeftGridPointInWorld[2] = a.tlz;
     f.topRightGridPointInWorld[0] = a.trx; f.topRightGridPointInWorld[2] = a.trz;
     f.waveAnimationTimeInSeconds = a.t;
-    return wt_fast_phase_report(ctx->waves.data(), (unsigned)ctx->waves.size(), &f, (unsigned)a.L, nullptr) == 1;
+    wt_phase_report rep;
+    if (wt_fast_phase_report(ctx->waves.data(), (unsigned)ctx->waves.size(), &f, (unsigned)a.L, &rep) < 0) return flags & ~WT_FLAG_FAST_PHASE;
+    flags &= ~WT_FLAG_FAST_PHASE;
+    if (rep.recommended == WT_PHASE_RECURRENCE) flags |= WT_FLAG_FAST_PHASE;
+    else if (rep.recommended == WT_PHASE_REFERENCE_ORDER && !(flags & WT_FLAG_VARYINGS)) flags |= WT_FLAG_REFERENCE_ORDER;
+    return flags;
 }
 
 cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
     const bool shade = flags & WT_FLAG_SHADE;
-    if ((flags & WT_FLAG_AUTO_PHASE) && !(flags & WT_FLAG_REFERENCE_ORDER))
-        flags = fast_phase_ok(ctx, a) ? (flags | WT_FLAG_FAST_PHASE) : (flags & ~WT_FLAG_FAST_PHASE);
-    ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? 0 : ((flags & WT_FLAG_FAST_PHASE) ? 1 : 0);
+    ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? WT_PHASE_REFERENCE_ORDER : ((flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL);
     ctx->mode_launches[ctx->last_phase_mode]++;
     if (flags & WT_FLAG_REFERENCE_ORDER) {
         switch (wave_capacity(ctx->n_waves)) {
@@ -271,6 +278,18 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
     if (flags & WT_FLAG_FAST_PHASE)
         return shade ? launch_production_recur_shade(ctx, a, flags, stream) : launch_production_recur(ctx, a, flags, stream);
     return shade ? launch_production_exact_shade(ctx, a, flags, stream) : launch_production_exact(ctx, a, flags, stream);
+}
+
+// One frame: resolves WT_FLAG_AUTO_PHASE, launches the kernel and — for the reference-order kernel, which only accumulates
+// into the digest record — arms the record before and decodes it after (the production kernels do both themselves).
+cudaError_t launch_frame(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
+    flags = resolve_phase(ctx, a, flags);
+    const bool ref_cks = a.cks && (flags & WT_FLAG_REFERENCE_ORDER);
+    if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    const cudaError_t e = launch_eval(ctx, a, flags, stream);
+    if (e != cudaSuccess) return e;
+    if (ref_cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -338,7 +357,7 @@ void wt_destroy(wt_ctx* ctx) {
     if (ctx->sky_array_black) cudaFreeArray(ctx->sky_array_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
-    cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done);
+    cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done); cudaFree(ctx->d_step_cks);
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
     cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
     if (ctx->h_cks_pinned) cudaFreeHost(ctx->h_cks_pinned);
@@ -390,10 +409,9 @@ int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned L, wt
 
 int wt_last_phase_mode(const wt_ctx* ctx) { return ctx ? ctx->last_phase_mode : -1; }
 
-void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[2]) {
+void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[3]) {
     if (!out) return;
-    out[0] = ctx ? ctx->mode_launches[0] : 0;
-    out[1] = ctx ? ctx->mode_launches[1] : 0;
+    for (int k = 0; k < 3; ++k) out[k] = ctx ? ctx->mode_launches[k] : 0;
 }
 
 int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int w, int h) {
@@ -471,11 +489,7 @@ int wt_eval_frame(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, u
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalArgs a = make_args(ctx, *frame, L, r0, r1, d_pos, d_nrm, d_shade, d_cks, flags);
-    const bool ref_cks = a.cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digest itself
-    if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
-    WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
-    if (ref_cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
-    WT_CUDA(ctx, cudaGetLastError());
+    WT_CUDA(ctx, launch_frame(ctx, a, flags, stream));
     return WT_OK;
 }
 
@@ -492,11 +506,7 @@ int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalArgs a = make_args(ctx, *frame, L, r0, r1, out->position, out->normal, out->shade, out->checksum, flags);
     if (vary) { a.clip = (float4*)out->clip_position; a.vary_a = (float4*)out->varyings_a; a.vary_b = (float4*)out->varyings_b; }
-    const bool ref_cks = a.cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digest itself
-    if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
-    WT_CUDA(ctx, launch_eval(ctx, a, flags, stream));
-    if (ref_cks) { checksum_finalize_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
-    WT_CUDA(ctx, cudaGetLastError());
+    WT_CUDA(ctx, launch_frame(ctx, a, flags, stream));
     return WT_OK;
 }
 
@@ -573,8 +583,6 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool cks = flags & WT_FLAG_CHECKSUM;
-    const bool ref_cks = cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digests itself
-    if (ref_cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     const size_t slot = (size_t)(r1 - r0) * L;
     FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
     WT_CUDA(ctx, fan.begin());
@@ -582,14 +590,13 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
         const size_t off = (size_t)(f % ring_depth) * slot;
         EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
-        const cudaError_t e = launch_eval(ctx, a, flags, fan.stream_for(f));
+        const cudaError_t e = launch_frame(ctx, a, flags, fan.stream_for(f));
         if (e != cudaSuccess) {   // the internal streams were forked off the caller's: join them before reporting
             fan.end();
             return fail(ctx, WT_ERR_CUDA, std::string("wt_eval_batch: ") + cudaGetErrorString(e));
         }
     }
     WT_CUDA(ctx, fan.end());
-    if (ref_cks) { checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     WT_CUDA(ctx, cudaGetLastError());
     return WT_OK;
 }
@@ -609,13 +616,10 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool cks = flags & WT_FLAG_CHECKSUM;
-    const bool ref_cks = cks && (flags & WT_FLAG_REFERENCE_ORDER);   // the production kernel finalises its digests itself
-    if (ref_cks) { checksum_init_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames); ctx->launches++; }
     const size_t slot = (size_t)(r1 - r0) * L;
     unsigned drawn = 0;
     FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
     WT_CUDA(ctx, fan.begin());
-    std::vector<unsigned> not_drawn;
     // after begin() the internal streams have been forked off the caller's: every exit path joins them again
     auto bail = [&](int code, const std::string& msg) { fan.end(); return fail(ctx, code, msg); };
     for (unsigned k = 0; k < n_frames; ++k) {
@@ -626,22 +630,15 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
             const size_t off = (size_t)(k % ring_depth) * slot;
             EvalArgs a = make_args(ctx, frame, L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
-            const cudaError_t e = launch_eval(ctx, a, flags, fan.stream_for(k));
+            const cudaError_t e = launch_frame(ctx, a, flags, fan.stream_for(k));
             if (e != cudaSuccess) return bail(WT_ERR_CUDA, std::string("wt_run_animation: ") + cudaGetErrorString(e));
             ++drawn;
-        } else if (cks) {
-            if (ref_cks) not_drawn.push_back(k);   // the finalize kernel below would turn the armed record into NaN extrema
-            else if (cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), fan.stream_for(k)) != cudaSuccess)
-                return bail(WT_ERR_CUDA, "wt_run_animation: cudaMemsetAsync failed");   // nothing drawn: zero digest
+        } else if (cks && cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), fan.stream_for(k)) != cudaSuccess) {
+            return bail(WT_ERR_CUDA, "wt_run_animation: cudaMemsetAsync failed");   // nothing drawn: zero digest
         }
         for (unsigned s_ = 0; s_ < stride; ++s_) wt_animation_advance(params, anim, dt);
     }
     WT_CUDA(ctx, fan.end());
-    if (ref_cks) {
-        checksum_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>((wt_checksum*)d_checksums, (int)n_frames);
-        ctx->launches++;
-        for (unsigned k : not_drawn) WT_CUDA(ctx, cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), stream));   // documented: zero digest
-    }
     WT_CUDA(ctx, cudaGetLastError());
     if (n_evaluated) *n_evaluated = drawn;
     return WT_OK;
@@ -656,7 +653,6 @@ int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, f
                    void* d_pos, void* d_nrm, void* d_shade, unsigned flags, void* stream_, unsigned* ticket) {
     if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_step_submit: ctx is NULL");
     if (!cam || !params || !ticket) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_submit: NULL argument");
-    if (flags & WT_FLAG_REFERENCE_ORDER) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_step_submit: not available with WT_FLAG_REFERENCE_ORDER");
     wt_frame frame;
     int st = wt_build_frame(cam, params, total_amp, &frame);
     if (st < 0) return fail(ctx, st, std::string("wt_step_submit: ") + wt_last_error(nullptr));
@@ -675,9 +671,21 @@ int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, f
     const unsigned slot = t % STEP_RING;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (st == WT_OK) {
-        // the kernel's last warp writes the finished digest straight into the mapped host record: no copy to enqueue
-        const int ev = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned + slot, flags | WT_FLAG_CHECKSUM, stream_);
+        int ev = validate_eval(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned + slot, flags | WT_FLAG_CHECKSUM);
         if (ev != WT_OK) return ev;
+        EvalArgs probe = make_args(ctx, frame, L, r0, r1, d_pos, d_nrm, d_shade, nullptr, flags);
+        const unsigned rflags = resolve_phase(ctx, probe, flags) | WT_FLAG_CHECKSUM;
+        if (rflags & WT_FLAG_REFERENCE_ORDER) {
+            // the reference-order kernel accumulates its digest with atomics: into a device record, copied out afterwards
+            if (!ctx->d_step_cks) WT_CUDA(ctx, cudaMalloc(&ctx->d_step_cks, STEP_RING * sizeof(wt_checksum)));
+            ev = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->d_step_cks + slot, rflags, stream_);
+            if (ev != WT_OK) return ev;
+            WT_CUDA(ctx, cudaMemcpyAsync(ctx->h_cks_pinned + slot, ctx->d_step_cks + slot, sizeof(wt_checksum), cudaMemcpyDeviceToHost, stream));
+        } else {
+            // the production kernels' last warp writes the finished digest straight into the mapped host record: no copy to enqueue
+            ev = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->h_cks_pinned + slot, rflags, stream_);
+            if (ev != WT_OK) return ev;
+        }
     }
     WT_CUDA(ctx, cudaEventRecord(ctx->step_event[slot], stream));
     ctx->step_status[slot] = st;

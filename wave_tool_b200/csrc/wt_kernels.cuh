@@ -42,9 +42,13 @@ struct __align__(16) WaveK {
     float cX, A, cZ, pad;
 };
 
+#ifndef WT_PAD_TABLE
+#define WT_PAD_TABLE 0          // 1: one spare (zero) entry behind the tiers up to 256 waves, so the one-wave-ahead fetch of the wave loop needs no index clamp
+#endif
 template <int CAP>
 struct WaveTable {
-    WaveK w[CAP];
+    static constexpr int PAD = (WT_PAD_TABLE && CAP <= 256) ? 1 : 0;   // the 1000-wave tier sits at the kernel-parameter size limit
+    WaveK w[CAP + PAD];
 };
 
 constexpr int STRIP_COLS = 62;   // output columns per warp: 64 held columns minus the two halo columns
@@ -498,6 +502,10 @@ __device__ __forceinline__ int next_item(int* queue, int lane) {
 #ifndef WT_EPI_UNROLL
 #define WT_EPI_UNROLL 2         // rows of the output stage in flight per warp (MODE 1)
 #endif
+#ifndef WT_SEAMLESS_RING
+#define WT_SEAMLESS_RING 0      // 1: no seam entries in the ring; lane 0 / lane 31 fetch their cross-half neighbours through per-lane offsets (4 scalar
+                                // loads per plane instead of 2 pair loads, no divergent seam writes)
+#endif
 #ifndef WT_CHEB
 #define WT_CHEB 1               // 1: rows 2.. of a MODE 1 step by the three-term recurrence, 0: by complex rotations (cfg3: 0.405 vs 0.438 ms)
 #endif
@@ -612,7 +620,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             WT_UNROLL(WT_WAVE_UNROLL)
             for (int i = 0; i < a.n_waves; ++i) {
                 const WaveK wk = wk_next;
-                wk_next = wt.w[i + 1 < a.n_waves ? i + 1 : i];
+                wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < a.n_waves) ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gxc, fma2(bc(wk.Dz), gzc, bc(wk.phi))), s, c);
                 const f2 dk = fma2(bc(wk.Dx), ex, mul2(bc(wk.Dz), ez));
@@ -655,7 +663,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             for (int i = 0; i < a.n_waves; ++i) {
                 // the next wave's constants are fetched from the constant bank one trip ahead
                 const WaveK wk = wk_next;
-                wk_next = wt.w[i + 1 < a.n_waves ? i + 1 : i];
+                wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < a.n_waves) ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gx0, fma2(bc(wk.Dz), gz0, bc(wk.phi))), s, c);
                 // per-row phase step: small unless the wave is undersampled by the grid; MUFU's own range
@@ -734,12 +742,14 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                     row[1 + lane] = px[j];
                     row[RL::PLANE + 1 + lane] = py[j];
                     row[2 * RL::PLANE + 1 + lane] = pz[j];
+#if !WT_SEAMLESS_RING
                     if (lane == 31) {
                         row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
                     }
                     if (lane == 0) {
                         row[33] = make_float2(px[j].y, 0.f); row[RL::PLANE + 33] = make_float2(py[j].y, 0.f); row[2 * RL::PLANE + 33] = make_float2(pz[j].y, 0.f);
                     }
+#endif
                     slot = slot + 1 == RL::ROWS ? 0 : slot + 1;
                 }
             }
@@ -752,6 +762,11 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         // The rows are independent: with two of them per loop trip their ring reads, MUFU chains and cubemap
         // gathers overlap.  Only the stores are predicated.
         int sd_ = slot_new - 2 < 0 ? slot_new - 2 + RL::ROWS : slot_new - 2;   // row_a - 2
+#if WT_SEAMLESS_RING
+        // float offsets of this lane's left / right neighbours inside a ring row (see front())
+        const int oLx = 2 * (lane ? lane : 1), oLy = lane ? 2 * lane + 1 : 2 * 32;
+        const int oRx = lane < 31 ? 2 * (lane + 2) : 2 * 1 + 1, oRy = lane < 31 ? 2 * (lane + 2) + 1 : 2 * 32 + 1;
+#endif
         // front half of one output row: ring reads, normal, view-facing flip, shading terms, cubemap gathers ISSUED
         auto front = [&](EpiRow& e, const int j) {
             const int sc_ = sd_ + 1 == RL::ROWS ? 0 : sd_ + 1;
@@ -764,7 +779,19 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             e.slot = sc_;
             const f2 cx = rc[1], cy = rc[RL::PLANE + 1], cz = rc[2 * RL::PLANE + 1];
             // (right - left), (up - down): water-grid.vert:164-187
+#if WT_SEAMLESS_RING
+            // entry 1 + l holds (A_l, B_l).  Left neighbours: (A_{l-1}, B_{l-1}) = entry l — except lane 0, whose B column
+            // (strip column 32) has A_31 to its left; right neighbours: entry l + 2 — except lane 31, whose A column (31) has
+            // B_0 to its right.  Lane 0's A and lane 31's B are halo columns: any finite value serves as their neighbour.
+            const float* const rf = reinterpret_cast<const float*>(ring + sc_ * RING_COLS);
+            constexpr int PF = 2 * RL::PLANE;   // floats per plane
+            const f2 lx = make_float2(rf[oLx], rf[oLy]), rx_ = make_float2(rf[oRx], rf[oRy]);
+            const f2 ly = make_float2(rf[PF + oLx], rf[PF + oLy]), ry_ = make_float2(rf[PF + oRx], rf[PF + oRy]);
+            const f2 lz = make_float2(rf[2 * PF + oLx], rf[2 * PF + oLy]), rz_ = make_float2(rf[2 * PF + oRx], rf[2 * PF + oRy]);
+            const f2 ux = sub2(rx_, lx), uy = sub2(ry_, ly), uz = sub2(rz_, lz);
+#else
             const f2 ux = sub2(rc[2], rc[0]), uy = sub2(rc[RL::PLANE + 2], rc[RL::PLANE]), uz = sub2(rc[2 * RL::PLANE + 2], rc[2 * RL::PLANE]);
+#endif
             const f2 vx = sub2(ru[0], rd[0]), vy = sub2(ru[RL::PLANE], rd[RL::PLANE]), vz = sub2(ru[2 * RL::PLANE], rd[2 * RL::PLANE]);
             f2 nx = fma2(uy, vz, mul2(make_float2(-vy.x, -vy.y), uz));
             f2 ny = fma2(uz, vx, mul2(make_float2(-vz.x, -vz.y), ux));
