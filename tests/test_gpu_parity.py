@@ -866,6 +866,31 @@ def test_skybox_synthesis_argument_checks(hm):
         ctx.synthesize_skybox(api.default_sky_params(), 0)
 
 
+@pytest.mark.parametrize("scale", [1.0, 60.0])
+def test_heightmap_sample_scale_extremes(oracle, hm, scale):
+    """heightmapSampleScale at the top of its slider (1.0, program.cpp:410) and far beyond (a CTRL-click is only clamped from
+    below): the bit-faithful kernel floors the sample coordinates with a magic-number add while they are far inside +-2^22
+    texels and with FRND / F2I beyond (scale 60: ~3e6 texels).  With zero waves the positions must be bit-exact either way."""
+    p = scenes.animation_params(9)
+    p.heightmapSampleScale = scale
+    for waves, exact in ((np.zeros((0, 6), np.float32), True), (scenes.seeded_waves(8, cfg=2), False)):
+        sc = Scene(waves, scenes.camera(), p, 257, hm)
+        st, frame = sc.frame()
+        ctx = sc.make_context()
+        want = sc.oracle_eval(oracle)
+        for fl in (0, api.FLAG_FAST_PHASE):
+            got = gpu_eval(ctx, frame, 257, flags=fl)
+            if exact:
+                assert np.array_equal(got["pos"].view(np.uint32), want["pos"].view(np.uint32)), (scale, fl)
+            else:
+                # the bump of a 1-texel-wide sample footprint is discontinuous in the sample position: only positions far from a
+                # texel boundary are comparable at scale 60; at scale 1 the usual bar holds
+                if scale <= 1.0:
+                    compare(got, want, sc, normal_tol=1.0, label=f"scale {scale}")
+                perr = np.abs(got["pos"][:, :3].astype(np.float64) - want["pos"][:, :3]).max(axis=1)
+                assert np.median(perr) <= 1e-5 and (perr > 1e-3).mean() < (0.02 if scale > 1.0 else 1e-9)
+
+
 def test_non_power_of_two_heightmap(oracle):
     hm = scenes.procedural_heightmap(200)[:150]      # 200 x 150 texels
     sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(), scenes.animation_params(3), 300, hm)

@@ -20,6 +20,7 @@ struct wt_ctx {
     bool waves_set = false;
     std::vector<wt::WaveK> tab_exact, tab_fast, tab_raw;
     std::vector<wt_wave> waves;     // as handed to wt_set_waves (wt_fast_phase_valid)
+    float max_horizontal = 0.0f;    // sum_i |A_i Q_i D_i|_1: the furthest a vertex can move sideways
     int last_phase_mode = -1;       // WT_PHASE_*: what the most recent evaluation launch ran
     uint64_t mode_launches[3] = {0, 0, 0};   // evaluation launches per kernel, indexed by WT_PHASE_* (wt_phase_mode_counts)
     // textures

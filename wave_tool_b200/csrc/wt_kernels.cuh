@@ -26,6 +26,9 @@
 #include "../../include/wavetool_b200.h"
 
 // build-time switches used by the helpers below (the kernel's own knobs are defined next to it)
+#ifndef WT_HM_MAGIC_FLOOR
+#define WT_HM_MAGIC_FLOOR 1     // bit-faithful kernel: floor / float->int of the heightmap coordinates on the FP32 and integer pipes instead of the XU pipe
+#endif
 #ifndef WT_HM_SCALAR_BLEND
 #define WT_HM_SCALAR_BLEND 1    // heightmap footprint blended per column in scalar form (no register moves to pair the two columns' texels up)
 #endif
@@ -43,7 +46,7 @@ struct __align__(16) WaveK {
 };
 
 #ifndef WT_PAD_TABLE
-#define WT_PAD_TABLE 0          // 1: one spare (zero) entry behind the tiers up to 256 waves, so the one-wave-ahead fetch of the wave loop needs no index clamp
+#define WT_PAD_TABLE 1          // 1: one spare (zero) entry behind the tiers up to 256 waves, so the one-wave-ahead fetch of the wave loop needs no index clamp
 #endif
 template <int CAP>
 struct WaveTable {
@@ -65,6 +68,7 @@ struct EvalArgs {
     // heightmap, reference-order kernel: R channel as exact unorm floats (c/255.0f), row-major, GL row order
     const float* hm_r;
     int hm_w, hm_h, hm_pow2;
+    int hm_magic_floor;   // production kernel, bit-faithful mode: every heightmap sample coordinate of this frame is far inside +-2^22 texels (hm_fetch2)
     // heightmap, production kernel: GL_MIRRORED_REPEAT unrolled into a (2w x 2h) table of bilinear
     // footprints (t00, t10, t01, t11) so that one 16-byte load serves a sample
     const float4* hm_quads;
@@ -336,18 +340,31 @@ static __device__ __noinline__ int4 wrap_period4_any(int4 v, int w2, int h2) {
 // Split in two so that the table loads of several rows are in flight together: hm_fetch2 computes the
 // bilinear weights and issues the two 16-byte footprint loads, hm_finish2 blends and applies :141-147.
 struct HmTap { f2 al, be; float4 qa, qb; };
-template <bool POW2>
+template <bool POW2, bool MAGIC_FLOOR>
 __device__ __forceinline__ HmTap hm_fetch2(const EvalArgs& a, f2 px, f2 pz) {
     const float one = a.one;
     f2 s = mul2(bc(a.hm_scale), px);
     f2 t = mul2(bc(-a.hm_scale), pz);
     f2 um = sub2x(mul2(s, bc((float)a.hm_w)), bc(0.5f), one);
     f2 vm = sub2x(mul2(t, bc((float)a.hm_h)), bc(0.5f), one);
-    f2 fu = make_float2(floorf(um.x), floorf(um.y)), fv = make_float2(floorf(vm.x), floorf(vm.y));
+    f2 fu, fv;
+    int4 ij;
+    if (MAGIC_FLOOR && a.hm_magic_floor) {
+        // floor() and the float -> int conversion without the XU pipe (FRND and F2I issue at a quarter of the FP32 rate, and
+        // the bit-faithful kernel is bound by that pipe): for |x| < 2^22 the sum x + 1.5 * 2^23 is a positive number with a
+        // unit in the last place of 1, so adding with round-toward-zero floors x exactly; the integer sits in the mantissa.
+        // The launcher clears hm_magic_floor when the sample coordinates of a frame could leave that range.
+        const float M = 12582912.0f;
+        const f2 tu = __fadd2_rz(um, bc(M)), tv = __fadd2_rz(vm, bc(M));
+        fu = add2(tu, bc(-M)); fv = add2(tv, bc(-M));
+        ij = make_int4(__float_as_int(tu.x) - 0x4B400000, __float_as_int(tu.y) - 0x4B400000, __float_as_int(tv.x) - 0x4B400000, __float_as_int(tv.y) - 0x4B400000);
+    } else {
+        fu = make_float2(floorf(um.x), floorf(um.y)); fv = make_float2(floorf(vm.x), floorf(vm.y));
+        ij = make_int4((int)fu.x, (int)fu.y, (int)fv.x, (int)fv.y);
+    }
     HmTap h;
     h.al = sub2(um, fu); h.be = sub2(vm, fv);
     const int w2 = 2 * a.hm_w, h2 = 2 * a.hm_h;
-    int4 ij = make_int4((int)fu.x, (int)fu.y, (int)fv.x, (int)fv.y);
     if (POW2) {
         ij.x &= w2 - 1; ij.y &= w2 - 1; ij.z &= h2 - 1; ij.w &= h2 - 1;
     } else {
@@ -730,7 +747,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 HmTap tap[HM_BATCH];
 #pragma unroll
                 for (int jj = 0; jj < HM_BATCH; ++jj)
-                    if (j0 + jj < R) tap[jj] = hm_fetch2<HMP2>(a, px[j0 + jj], pz[j0 + jj]);
+                    if (j0 + jj < R) tap[jj] = hm_fetch2<HMP2, MODE == 0 && WT_HM_MAGIC_FLOOR>(a, px[j0 + jj], pz[j0 + jj]);
 #pragma unroll
                 for (int jj = 0; jj < HM_BATCH; ++jj) {
                     const int j = j0 + jj;
