@@ -360,6 +360,9 @@ int wt_set_sky_layers(wt_ctx* ctx, const uint8_t* gradient_rgba, int gradient_le
                       const uint8_t* const clouds[6], int clouds_n);
 /* Synthesizes the 6 x n x n skybox into the context (exactly as if wt_set_skybox_rgba8 had been called with the result). */
 int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* params, int n, void* cuda_stream);
+/* Diagnostic: how many texels of the most recent wt_synthesize_skybox were recomputed on the exact path (IEEE division, libdevice
+ * powf) because the approximate path (MUFU lg2 / ex2, reciprocal multiply) could not exclude a different byte.  Synchronises. */
+int wt_debug_sky_exact_texels(wt_ctx* ctx, uint64_t* out);
 /* Copies the context's current skybox faces (6 * n * n RGBA8) to HOST memory; out may be NULL to query n.  Synchronises. */
 int wt_get_skybox_rgba8(wt_ctx* ctx, uint8_t* out, int* n_out);
 

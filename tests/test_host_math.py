@@ -241,3 +241,37 @@ def test_ui_ranges_and_force_clamps_at_the_range_ends():
     c.tintDeltaDepthThreshold, c.waterClarity, c.softEdgesDeltaDepthThreshold = 1.0, 0.0, 7.0
     L.wt_compose_params_clamp_ui(C.byref(c), 0)
     assert (c.tintDeltaDepthThreshold, c.waterClarity, c.softEdgesDeltaDepthThreshold) == (1.0, 0.0, 1.0)
+
+
+def test_division_by_a_uniform_divisor_is_ieee_division():
+    """wt_kernels.cuh:div_by_uniform — x / c as q = fl(x rc), q' = fma(fma(-q, c, x), rc, q) with rc = fl(1 / c) (the compose
+    pass uses it for the divisors that are the same for every vertex of a launch).  Emulated with exact rational arithmetic
+    (one rounding per fp32 operation) against correctly rounded division, on the operand ranges the pass feeds it."""
+    from fractions import Fraction
+    f32 = np.float32
+
+    def rn(fr):            # round a Fraction to the nearest fp32 (ties to even), via float64 only when that is exact enough
+        d = float(fr)      # correctly rounded to fp64
+        r = f32(d)
+        # double rounding: fix up by comparing the two neighbouring fp32 values exactly
+        lo, hi = np.nextafter(r, f32(-np.inf)), np.nextafter(r, f32(np.inf))
+        best = min((abs(Fraction(float(c)) - fr), c) for c in (lo, r, hi) if np.isfinite(c))
+        cands = [c for c in (lo, r, hi) if np.isfinite(c) and abs(Fraction(float(c)) - fr) == best[0]]
+        if len(cands) == 1:
+            return cands[0]
+        return [c for c in cands if (np.frombuffer(f32(c).tobytes(), np.uint32)[0] & 1) == 0][0]
+
+    rng = np.random.default_rng(11)
+    divisors = [f32(v) for v in (100.0, 1920.0, 1080.0, 1024.0, 0.1, 0.05, 1.0, 0.3, 3.0, 7.0, 96.0, 64.0, 0.999, 1e-3, 2.4)] + \
+               [f32(v) for v in rng.uniform(1e-3, 4e3, size=40)]
+    bad = 0
+    for c in divisors:
+        rc = f32(1.0) / c
+        xs = np.concatenate([rng.uniform(0.0, 2.0 * float(c), size=150), rng.uniform(0.0, 1.0, size=100), [0.0, float(c), 1.0]]).astype(f32)
+        for x in xs:
+            q = rn(Fraction(float(x)) * Fraction(float(rc)))
+            rem = rn(Fraction(float(x)) - Fraction(float(q)) * Fraction(float(c)))
+            q2 = rn(Fraction(float(q)) + Fraction(float(rem)) * Fraction(float(rc)))
+            want = rn(Fraction(float(x)) / Fraction(float(c)))
+            bad += int(q2 != want)
+    assert bad == 0, bad

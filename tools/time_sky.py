@@ -27,5 +27,6 @@ for k in range(20):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 out_b = 6 * n * n * 4
+print("texels recomputed on the exact path in the last synthesis:", ctx.sky_exact_texels(), "of", 6 * n * n)
 print(f"skybox synthesis {n}^2 faces from {src}^2 star/cloud cubemaps: {ms*1e3:.1f} us per cubemap (synthesis + atlas), "
       f"{(2*out_b + 6*(n+2)*(n+2)*4 + 2*6*src*src*4)/(ms*1e-3)/1e9:.0f} GB/s of algorithmic traffic")

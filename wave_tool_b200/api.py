@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
     "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
-    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels",
 ]
 
 
@@ -197,6 +197,7 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_set_sky_layers.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     L.wt_synthesize_skybox.argtypes = [C.c_void_p, C.POINTER(SkyParams), C.c_int, C.c_void_p]
     L.wt_get_skybox_rgba8.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    L.wt_debug_sky_exact_texels.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.wt_default_animation.argtypes = [C.POINTER(Animation)]
     L.wt_default_animation.restype = None
     L.wt_animation_advance.argtypes = [C.POINTER(Params), C.POINTER(Animation), C.c_float]
@@ -416,6 +417,11 @@ class Context:
 
     def synthesize_skybox(self, params: "SkyParams", n: int, stream: int = 0):
         return _check(self._lib.wt_synthesize_skybox(self._h, C.byref(params), n, stream or None), self._h)
+
+    def sky_exact_texels(self) -> int:
+        v = C.c_uint64()
+        _check(self._lib.wt_debug_sky_exact_texels(self._h, C.byref(v)), self._h)
+        return int(v.value)
 
     def get_skybox(self) -> np.ndarray:
         n = C.c_int()

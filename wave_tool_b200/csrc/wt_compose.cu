@@ -21,6 +21,8 @@ struct ComposeArgs {
     long long n;
     float fog[4], fog_far, fog_near, soft_edges, tint_threshold, clarity, z_near, z_far, vw, vh;
     float camx, camy, camz, sun_y;
+    // reciprocals of the per-launch divisors (div_by_uniform) and the hoisted viewport halves
+    float r_zfar, r_vw, r_vh, r_tint, r_soft, r_fog, half_vw, half_vh;
     // clip == NULL: gl_Position, the height-0 NDC position and the yaw-only view-space normal are recomputed here from
     // position and normal (the same FMA chains as the surface kernel's WT_FLAG_VARYINGS) instead of being read back
     float vp[16], vy[12];
@@ -32,21 +34,25 @@ __device__ __forceinline__ int clamp_i(int i, int n) { return i < 0 ? 0 : (i > n
 
 // texture(sampler2D, st) of an RGBA8 texture: GL_LINEAR, GL_CLAMP_TO_EDGE, exact fp32 weights, the oracle's operation order
 __device__ __forceinline__ float4 sample_rgba8_clamp_linear(const uchar4* tex, int w, int h, float s, float t) {
+    // s, t in [0, 1] (the callers clamp them): um, vm in [-0.5, w] — floor and the float -> int conversion by the magic-number
+    // add, the byte -> float conversions by a byte permute (none of them on the XU pipe, which bounded this pass)
     const float um = __fsub_rn(__fmul_rn(s, (float)w), 0.5f), vm = __fsub_rn(__fmul_rn(t, (float)h), 0.5f);
-    const float fu = floorf(um), fv = floorf(vm);
+    int iu, iv;
+    const float fu = floor_small(um, iu), fv = floor_small(vm, iv);
     const float a = __fsub_rn(um, fu), b = __fsub_rn(vm, fv);
-    const int i0 = clamp_i((int)fu, w), i1 = clamp_i((int)fu + 1, w), j0 = clamp_i((int)fv, h), j1 = clamp_i((int)fv + 1, h);
-    const uchar4 t00 = __ldg(tex + (size_t)j0 * w + i0), t10 = __ldg(tex + (size_t)j0 * w + i1);
-    const uchar4 t01 = __ldg(tex + (size_t)j1 * w + i0), t11 = __ldg(tex + (size_t)j1 * w + i1);
+    const int i0 = clamp_i(iu, w), i1 = clamp_i(iu + 1, w), j0 = clamp_i(iv, h), j1 = clamp_i(iv + 1, h);
+    const unsigned* const tx = reinterpret_cast<const unsigned*>(tex);
+    const unsigned t00 = __ldg(tx + (size_t)j0 * w + i0), t10 = __ldg(tx + (size_t)j0 * w + i1);
+    const unsigned t01 = __ldg(tx + (size_t)j1 * w + i0), t11 = __ldg(tx + (size_t)j1 * w + i1);
     const float oma = __fsub_rn(1.0f, a), omb = __fsub_rn(1.0f, b);
     const float w00 = __fmul_rn(oma, omb), w10 = __fmul_rn(a, omb), w01 = __fmul_rn(oma, b), w11 = __fmul_rn(a, b);
-    auto ch = [&](unsigned c00, unsigned c10, unsigned c01, unsigned c11) {
-        float acc = __fmul_rn(w00, unorm8(c00));
-        acc = __fadd_rn(acc, __fmul_rn(w10, unorm8(c10)));
-        acc = __fadd_rn(acc, __fmul_rn(w01, unorm8(c01)));
-        return __fadd_rn(acc, __fmul_rn(w11, unorm8(c11)));
+    auto ch = [&](unsigned k) {
+        float acc = __fmul_rn(w00, unorm8f(byte_f(t00, k)));
+        acc = __fadd_rn(acc, __fmul_rn(w10, unorm8f(byte_f(t10, k))));
+        acc = __fadd_rn(acc, __fmul_rn(w01, unorm8f(byte_f(t01, k))));
+        return __fadd_rn(acc, __fmul_rn(w11, unorm8f(byte_f(t11, k))));
     };
-    return make_float4(ch(t00.x, t10.x, t01.x, t11.x), ch(t00.y, t10.y, t01.y, t11.y), ch(t00.z, t10.z, t01.z, t11.z), ch(t00.w, t10.w, t01.w, t11.w));
+    return make_float4(ch(0), ch(1), ch(2), ch(3));
 }
 
 __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
@@ -76,15 +82,19 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
         auto linearize = [&](float d) { return __fdiv_rn(__fmul_rn(a.z_near, d), __fsub_rn(a.z_far, __fmul_rn(d, __fsub_rn(a.z_far, a.z_near)))); };   // frag:66-69
         const float wx = __fsub_rn(a.camx, P.x), wy = __fsub_rn(a.camy, P.y), wz = __fsub_rn(a.camz, P.z);
         const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(wx, wx), __fmul_rn(wy, wy)), __fmul_rn(wz, wz)));   // frag:71
-        const float vdc = clamp_f(__fdiv_rn(len, a.z_far), 0.0f, 1.0f);                                                  // frag:72
+        const float vdc = clamp_f(div_by_uniform(len, a.z_far, a.r_zfar), 0.0f, 1.0f);                                   // frag:72
         // gl_FragCoord: viewport transform of gl_Position (GL 4.1 section 2.14.1, default depth range)
         const float ndx = __fdiv_rn(C.x, C.w), ndy = __fdiv_rn(C.y, C.w), ndz = __fdiv_rn(C.z, C.w);
-        const float fx = __fmul_rn(__fadd_rn(ndx, 1.0f), __fdiv_rn(a.vw, 2.0f)), fy = __fmul_rn(__fadd_rn(ndy, 1.0f), __fdiv_rn(a.vh, 2.0f));
-        const float fz = __fdiv_rn(__fadd_rn(ndz, 1.0f), 2.0f);
-        const float uvx = __fdiv_rn(fx, a.vw), uvy = __fdiv_rn(fy, a.vh);                                                // frag:79
-        const float h0x = __fdiv_rn(__fadd_rn(A.x, 1.0f), 2.0f), h0y = __fdiv_rn(__fadd_rn(A.y, 1.0f), 2.0f);             // frag:81
+        const float fx = __fmul_rn(__fadd_rn(ndx, 1.0f), a.half_vw), fy = __fmul_rn(__fadd_rn(ndy, 1.0f), a.half_vh);   // x / 2 == x * 0.5 exactly
+        const float fz = __fmul_rn(__fadd_rn(ndz, 1.0f), 0.5f);
+        const float uvx = div_by_uniform(fx, a.vw, a.r_vw), uvy = div_by_uniform(fy, a.vh, a.r_vh);                      // frag:79
+        const float h0x = __fmul_rn(__fadd_rn(A.x, 1.0f), 0.5f), h0y = __fmul_rn(__fadd_rn(A.y, 1.0f), 0.5f);             // frag:81
         // texture(depthTexture2D, uv).x: GL_NEAREST, CLAMP_TO_EDGE (render-engine.cpp:128-136)
-        const int di = clamp_i((int)floorf(__fmul_rn(uvx, (float)a.w)), a.w), dj = clamp_i((int)floorf(__fmul_rn(uvy, (float)a.h)), a.h);
+        // (screen coordinates of vertices the frustum-padded grid places far off screen are clamped before the conversion)
+        int di, dj;
+        floor_small(clamp_f(__fmul_rn(uvx, (float)a.w), -1.0f, (float)a.w), di);
+        floor_small(clamp_f(__fmul_rn(uvy, (float)a.h), -1.0f, (float)a.h), dj);
+        di = clamp_i(di, a.w); dj = clamp_i(dj, a.h);
         const float back = linearize(__ldg(a.depth + (size_t)dj * a.w + di));                                            // frag:84
         const float hack = back > 0.999f ? 0.0f : 1.0f;                                                                 // frag:86
         const float dcl = clamp_f(__fsub_rn(back, linearize(fz)), 0.0f, 1.0f);                                           // frag:87-91
@@ -96,7 +106,7 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
         const float4 refl = sample_rgba8_clamp_linear(a.refl, a.w, a.h, rlx, rly);
         const float4 refr = sample_rgba8_clamp_linear(a.refr, a.w, a.h, rrx, rry);
         // frag:136-151 tint, transmission, reflection, Fresnel mix
-        const float tint_f = a.tint_threshold == 0.0f ? 0.0f : __fmul_rn(hack, __fsub_rn(1.0f, clamp_f(__fdiv_rn(dcl, a.tint_threshold), 0.0f, 1.0f)));
+        const float tint_f = a.tint_threshold == 0.0f ? 0.0f : __fmul_rn(hack, __fsub_rn(1.0f, clamp_f(div_by_uniform(dcl, a.tint_threshold, a.r_tint), 0.0f, 1.0f)));
         const float t_w = __fmul_rn(__fmul_rn(a.clarity, refr.w), __fsub_rn(1.0f, dcl));
         auto channel = [&](float deep, float shallow, float refr_c, float sky_c, float refl_c) {
             const float tint = __fmul_rn(a.sun_y, mix_f(deep, shallow, tint_f));
@@ -106,10 +116,10 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
         };
         const float cr = channel(0.0f, 0.3f, refr.x, S.x, refl.x), cg = channel(0.341f, 0.941f, refr.y, S.y, refl.y), cb = channel(0.482f, 0.903f, refr.z, S.z, refl.z);
         // frag:154-156 soft edges
-        const float hard = a.soft_edges == 0.0f ? 1.0f : __fsub_rn(1.0f, __fmul_rn(hack, __fsub_rn(1.0f, clamp_f(__fdiv_rn(dcl, a.soft_edges), 0.0f, 1.0f))));
+        const float hard = a.soft_edges == 0.0f ? 1.0f : __fsub_rn(1.0f, __fmul_rn(hack, __fsub_rn(1.0f, clamp_f(div_by_uniform(dcl, a.soft_edges, a.r_soft), 0.0f, 1.0f))));
         // frag:160-162 fog
         const float fog_a = vdc >= a.fog_far ? a.fog[3] : vdc <= a.fog_near ? 0.0f
-                            : __fmul_rn(a.fog[3], __fdiv_rn(__fsub_rn(vdc, a.fog_near), __fsub_rn(a.fog_far, a.fog_near)));
+                            : __fmul_rn(a.fog[3], div_by_uniform(__fsub_rn(vdc, a.fog_near), __fsub_rn(a.fog_far, a.fog_near), a.r_fog));
         __stcs(a.colour + k, make_float4(mix_f(cr, a.fog[0], fog_a), mix_f(cg, a.fog[1], fog_a), mix_f(cb, a.fog[2], fog_a), hard));
     }
 }
@@ -186,6 +196,11 @@ int wt_compose_frame(wt_ctx* ctx, const wt_frame* frame, const wt_compose_params
     a.vw = p->viewportWidth; a.vh = p->viewportHeight;
     a.camx = frame->cameraPosition[0]; a.camy = frame->cameraPosition[1]; a.camz = frame->cameraPosition[2];
     a.sun_y = sy;
+    a.r_zfar = 1.0f / a.z_far; a.r_vw = 1.0f / a.vw; a.r_vh = 1.0f / a.vh;
+    a.r_tint = a.tint_threshold != 0.0f ? 1.0f / a.tint_threshold : 0.0f;
+    a.r_soft = a.soft_edges != 0.0f ? 1.0f / a.soft_edges : 0.0f;
+    a.r_fog = 1.0f / (a.fog_far - a.fog_near);      // only read where fog_near < vdc < fog_far
+    a.half_vw = a.vw / 2.0f; a.half_vh = a.vh / 2.0f;
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);

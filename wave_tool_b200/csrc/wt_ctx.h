@@ -38,6 +38,7 @@ struct wt_ctx {
     uchar4 *d_stars = nullptr, *d_clouds = nullptr;
     int stars_n = 0, clouds_n = 0;
     bool sky_surface_ok = false;
+    unsigned long long* d_sky_unsure = nullptr;   // texels of the last synthesis that took the exact path (wt_debug_sky_exact_texels)
     cudaSurfaceObject_t sky_surf = 0;
     // screen-space inputs of the compose pass (wt_set_screen_textures)
     float* d_depth = nullptr;

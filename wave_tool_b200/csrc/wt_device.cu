@@ -370,7 +370,7 @@ void wt_destroy(wt_ctx* ctx) {
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
     cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done); cudaFree(ctx->d_step_cks);
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
-    cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds);
+    cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds); cudaFree(ctx->d_sky_unsure);
     if (ctx->h_cks_pinned) cudaFreeHost(ctx->h_cks_pinned);
     for (unsigned i = 0; i < STEP_RING; ++i) if (ctx->step_event[i]) cudaEventDestroy(ctx->step_event[i]);
     for (int i = 0; i < 4; ++i) {

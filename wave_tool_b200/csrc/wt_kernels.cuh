@@ -27,7 +27,8 @@
 
 // build-time switches used by the helpers below (the kernel's own knobs are defined next to it)
 #ifndef WT_HM_MAGIC_FLOOR
-#define WT_HM_MAGIC_FLOOR 1     // bit-faithful kernel: floor / float->int of the heightmap coordinates on the FP32 and integer pipes instead of the XU pipe
+#define WT_HM_MAGIC_FLOOR 0     // 1: bit-faithful kernel floors the heightmap coordinates on the FP32 / integer pipes instead of the XU pipe (FRND, F2I).
+                                // Measured 1.2 % SLOWER at cfg3 (0.703 vs 0.695 ms): the XU pipe is not what the per-vertex stage waits for
 #endif
 #ifndef WT_HM_SCALAR_BLEND
 #define WT_HM_SCALAR_BLEND 1    // heightmap footprint blended per column in scalar form (no register moves to pair the two columns' texels up)
@@ -147,6 +148,30 @@ __device__ __forceinline__ float unorm8(unsigned c) {
     float q = f * R;
     float rem = __fmaf_rn(-q, 255.0f, f);
     return __fmaf_rn(rem, R, q);
+}
+
+// Byte and floor conversions kept off the XU pipe (I2F / F2I / FRND issue at a quarter of the FP32 rate):
+//  * byte k of a word -> float: PRMT builds the bit pattern of 2^23 + c, one add removes the 2^23 (exact);
+//  * floor(x) for |x| < 2^22: x + 1.5 * 2^23 is positive, so adding with round-toward-zero floors it (exact).
+__device__ __forceinline__ float byte_f(unsigned word, unsigned k) { return __fadd_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | k)), -8388608.0f); }
+__device__ __forceinline__ float unorm8f(float f) {   // exact c / 255.0f for integer-valued f in [0,255] (see unorm8)
+    const float R = 1.0f / 255.0f;
+    const float q = __fmul_rn(f, R);
+    return __fmaf_rn(__fmaf_rn(-q, 255.0f, f), R, q);
+}
+__device__ __forceinline__ float floor_small(float x, int& as_int) {
+    const float MAGIC = 12582912.0f;
+    const float t = __fadd_rz(x, MAGIC);
+    as_int = __float_as_int(t) - 0x4B400000;
+    return __fsub_rn(t, MAGIC);
+}
+// x / c for a divisor c that is the same for every vertex of a launch, given rc = fl(1 / c): the quotient estimate x rc is
+// corrected with its exact FMA residual — correctly rounded like IEEE division (Markstein 1990; what __fdiv_rn's own fast
+// path does after computing the reciprocal), three FP32-pipe operations instead of a reciprocal on the XU pipe plus ~8.
+// Needs finite, normal x / c (the callers' operands are screen coordinates, depths and thresholds in [0, 1e5]).
+__device__ __forceinline__ float div_by_uniform(float x, float c, float rc) {
+    const float q = __fmul_rn(x, rc);
+    return __fmaf_rn(__fmaf_rn(-q, c, x), rc, q);
 }
 
 // GL_MIRRORED_REPEAT on a texel index (GL 4.1 core §3.8.9): (size-1) - mirror((i mod 2 size) - size)

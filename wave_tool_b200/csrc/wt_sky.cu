@@ -24,23 +24,11 @@ struct SkyArgs {
     float shininess, strength, alpha1;
     float omp, overcast;         // oneMinusCloudProportion, overcastStrength
     float fog[4];
+    float inv_gamma;             // fl(1 / 2.4) as the shader's constant expression folds it (skybox-clouds.frag:54)
+    float inv_one_minus_omp;     // 1 / (1 - omp) for the approximate path
+    unsigned long long* unsure_count;   // diagnostic (may be NULL): texels that took the exact path
+    int fast;                    // 1: approximate path with guard bands + exact fallback per texel; 0: exact path only (WT_SKY_EXACT build / debugging)
 };
-
-// Byte and floor conversions kept off the XU pipe (I2F / F2I / FRND issue at a quarter of the FP32 rate):
-//  * byte k of a word -> float: PRMT builds the bit pattern of 2^23 + c, one add removes the 2^23 (exact);
-//  * floor(x) for |x| < 2^22: x + 1.5 * 2^23 is positive, so adding with round-toward-zero floors it (exact).
-__device__ __forceinline__ float byte_f(unsigned word, unsigned k) { return __fadd_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | k)), -8388608.0f); }
-__device__ __forceinline__ float unorm8f(float f) {   // exact c / 255.0f for integer-valued f in [0,255] (see unorm8)
-    const float R = 1.0f / 255.0f;
-    const float q = __fmul_rn(f, R);
-    return __fmaf_rn(__fmaf_rn(-q, 255.0f, f), R, q);
-}
-__device__ __forceinline__ float floor_small(float x, int& as_int) {
-    const float MAGIC = 12582912.0f;
-    const float t = __fadd_rz(x, MAGIC);
-    as_int = __float_as_int(t) - 0x4B400000;
-    return __fsub_rn(t, MAGIC);
-}
 
 __device__ __forceinline__ float mixs(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
 __device__ __forceinline__ float sat(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
@@ -76,22 +64,121 @@ __device__ __forceinline__ float4 cube_rgba8(const uchar4* faces, int n, float r
 
 // one layer into the RGBA8 destination: operands clamped to [0,1], Cd' = Cs As + Cd (1 - As) on all four channels,
 // converted back to unorm8 with round-to-nearest (GL 4.1 sections 4.1.7, 2.1.5)
-// dst holds the attachment's bytes as integer-valued floats
-__device__ __forceinline__ void blend(float dst[4], float r, float g, float b, float a) {
+// dst holds the attachment's bytes as integer-valued floats.
+// FAST instantiation: the source colour / alpha carry absolute error bounds (err_rgb, err_a: they came out of MUFU
+// approximations of pow); `unsure` is raised when a channel's value before the final floor lies so close to an integer that
+// the bound cannot exclude a different byte.  A texel that raises it is recomputed on the exact path.
+template <bool FAST>
+__device__ __forceinline__ void blend(float dst[4], float r, float g, float b, float a, float err_rgb, float err_a, bool& unsure) {
     const float src[4] = {sat(r), sat(g), sat(b), sat(a)};
     // As == 0: Cs * 0 + Cd * 1 = Cd = c / 255, which converts back to the same byte c: nothing to do
-    if (src[3] == 0.0f) return;
+    // (a shortcut, not a discontinuity: blending with As = 0 leaves the same bytes — so an approximate As near 0 needs no guard)
+    if (src[3] == 0.0f && (!FAST || err_a == 0.0f)) return;
     const float oma = __fsub_rn(1.0f, src[3]);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const float d = unorm8f(dst[c]);   // what the blender reads back from the RGBA8 attachment: c / 255
         const float v = sat(__fadd_rn(__fmul_rn(src[c], src[3]), __fmul_rn(d, oma)));
+        const float t = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
         int unused;
-        dst[c] = floor_small(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f), unused);
+        const float q = floor_small(t, unused);
+        if (FAST) {
+            // d(out)/d(src_c) = As <= 1, d(out)/d(As) = src_c - d in [-1, 1] (the alpha channel: 2 As - d in [-1, 2]); 255 byte units
+            // per unit, plus the roundings of the blend itself (a few ulp of a value <= 1, 1e-4 byte units is ample)
+            const float e = 255.0f * ((c < 3 ? err_rgb : err_a) + 2.0f * err_a) + 1e-4f;
+            const float fr = __fsub_rn(t, q);
+            unsure = unsure || ((err_rgb != 0.0f || err_a != 0.0f) && (fr < e || fr > 1.0f - e));
+        }
+        dst[c] = q;
     }
 }
 
-__global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
+// All layers of one texel (direction d) into dst.  FAST = false is the exact evaluation: IEEE division / square root and
+// libdevice powf, bit-compatible with the oracle's restatement of the sky shaders.  FAST = true replaces the two powf by
+// MUFU lg2 / ex2 and the per-texel division by (1 - omp) by a multiplication with its reciprocal, carries bounds on the error
+// this introduces, and raises `unsure` wherever a comparison or a byte conversion could come out differently.
+template <bool FAST>
+__device__ __forceinline__ void sky_texel(const SkyArgs& a, float dx, float dy, float dz, float dst[4], bool& unsure) {
+    dst[0] = dst[1] = dst[2] = dst[3] = 255.0f;                          // glClearColor(1,1,1,1), render-engine.cpp:694,330
+    if (a.stars) {                                                       // skybox-stars.frag:41
+        const float4 s = cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
+        blend<FAST>(dst, s.x, s.y, s.z, 1.0f, 0.0f, 0.0f, unsure);
+    }
+    if (a.draw_sphere) {                                                 // skysphere.frag:48-76
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+        const float nx = __fmul_rn(dx, inv), ny = __fmul_rn(dy, inv), nz = __fmul_rn(dz, inv);
+        const float a3 = __fadd_rn(__fadd_rn(__fmul_rn(nx, a.Lx), __fmul_rn(ny, a.Ly)), __fmul_rn(nz, a.Lz));
+        float spec = 0.0f, err = 0.0f;
+        if (a3 > 0.0f) {
+            if (FAST) {
+                // pow(a3, shininess) = 2^(shininess log2 a3): lg2.approx is within 2^-21 absolute, ex2.approx within 2^-21 relative
+                const float p = ex2_approx(__fmul_rn(a.shininess, lg2_approx(a3)));
+                spec = __fmul_rn(__fmul_rn(a.strength, 1.0f), p);
+                err = __fmul_rn(spec, __fmaf_rn(a.shininess, 4e-7f, 1e-6f)) + 1e-30f;
+                if (a.shininess == 0.0f) { spec = __fmul_rn(a.strength, 1.0f); err = 0.0f; }    // pow(x, 0) = 1
+            } else {
+                spec = __fmul_rn(__fmul_rn(a.strength, 1.0f), powf(a3, a.shininess));
+            }
+        }
+        const float night = __fmul_rn(fabsf(a3), __fsub_rn(1.0f, fabsf(a.Ly)));
+        float col[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float diffuse = a3 >= 0.0f ? mixs(a.horizon[c], a.peak[c], a3) : mixs(a.horizon[c], 0.0f, night);
+            col[c] = __fadd_rn(diffuse, spec);
+        }
+        const float alpha = fmaxf(a.alpha1, __fmul_rn(__fadd_rn(a3, 1.0f), 0.5f));   // x / 2.0 == x * 0.5 exactly
+        blend<FAST>(dst, col[0], col[1], col[2], alpha, err, 0.0f, unsure);
+    }
+    if (a.clouds) {                                                      // skybox-clouds.frag:46-67
+        const float4 raw = cube_rgba8(a.clouds, a.clouds_n, dx, dy, dz);
+        const float lin = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, raw.x), __fmul_rn(0.7152f, raw.y)), __fmul_rn(0.0722f, raw.z));
+        float srgb, es = 0.0f;
+        if (lin <= 0.0031308f) {
+            srgb = __fmul_rn(12.92f, lin);
+        } else if (FAST) {
+            const float p = ex2_approx(__fmul_rn(a.inv_gamma, lg2_approx(lin)));
+            srgb = __fsub_rn(__fmul_rn(1.055f, p), 0.055f);
+            es = 2e-6f;                                                  // |p| <= 1: (1/2.4 2^-21 ln 2 + 2^-21) 1.055 + roundings < 1e-6
+        } else {
+            srgb = __fsub_rn(__fmul_rn(1.055f, powf(lin, a.inv_gamma)), 0.055f);
+        }
+        const float intensity = fminf(fmaxf(a.sun_y, 0.2f), 1.0f);
+        const float oc = __fmul_rn(sat(a.sun_y), a.overcast);
+        if (FAST && fabsf(__fsub_rn(srgb, a.omp)) <= es && es != 0.0f) unsure = true;   // the branch itself hangs on the approximation
+        if (srgb > a.omp) {
+            float ca, eca = 0.0f;
+            if (FAST) {
+                ca = __fmul_rn(__fsub_rn(srgb, a.omp), a.inv_one_minus_omp);
+                eca = __fmaf_rn(es, a.inv_one_minus_omp, 2e-7f * fabsf(ca) + 1e-30f);   // the approximation + one rounding of the reciprocal form
+            } else {
+                ca = __fdiv_rn(__fsub_rn(srgb, a.omp), __fsub_rn(1.0f, a.omp));
+            }
+            const float v = mixs(intensity, srgb, oc);
+            blend<FAST>(dst, v, v, v, mixs(ca, 1.0f, oc), es, eca, unsure);
+        } else {
+            blend<FAST>(dst, 0.5f, 0.5f, 0.5f, oc, 0.0f, 0.0f, unsure);
+        }
+    }
+    blend<FAST>(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3], 0.0f, 0.0f, unsure);   // screen-space-quad.frag:45
+}
+
+// pack the four integer-valued floats (0..255) into RGBA8: 2^23 + c has c in its low mantissa byte
+__device__ __forceinline__ unsigned pack_rgba8(const float dst[4]) {
+    const unsigned b0 = __float_as_uint(__fadd_rn(dst[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rn(dst[1], 8388608.0f));
+    const unsigned b2 = __float_as_uint(__fadd_rn(dst[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rn(dst[3], 8388608.0f));
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+}
+
+// the exact evaluation, out of line: only the texels the approximate path is unsure about come here
+static __device__ __noinline__ unsigned sky_texel_exact(const SkyArgs& a, float dx, float dy, float dz) {
+    float dst[4];
+    bool unused = false;
+    sky_texel<false>(a, dx, dy, dz, dst, unused);
+    return pack_rgba8(dst);
+}
+
+__global__ void __launch_bounds__(256) sky_synth_kernel(const __grid_constant__ SkyArgs a) {
     // grid = (ceil(n / 256), n, 6): the face and the row come from the block index (no integer divisions, and the face
     // switch below is uniform per block)
     const int face = blockIdx.z, j = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,45 +198,18 @@ __global__ void __launch_bounds__(256) sky_synth_kernel(const SkyArgs a) {
             case 4: dx = sc; dy = -tc; dz = 1.0f; break;
             default: dx = -sc; dy = -tc; dz = -1.0f; break;
         }
-        float dst[4] = {255.0f, 255.0f, 255.0f, 255.0f};                 // glClearColor(1,1,1,1), render-engine.cpp:694,330
-        if (a.stars) {                                                   // skybox-stars.frag:41
-            const float4 s = cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
-            blend(dst, s.x, s.y, s.z, 1.0f);
+        unsigned rgba;
+        bool unsure = !a.fast;
+        if (a.fast) {
+            float dst[4];
+            sky_texel<true>(a, dx, dy, dz, dst, unsure);
+            rgba = pack_rgba8(dst);
         }
-        if (a.draw_sphere) {                                             // skysphere.frag:48-76
-            const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
-            const float nx = __fmul_rn(dx, inv), ny = __fmul_rn(dy, inv), nz = __fmul_rn(dz, inv);
-            const float a3 = __fadd_rn(__fadd_rn(__fmul_rn(nx, a.Lx), __fmul_rn(ny, a.Ly)), __fmul_rn(nz, a.Lz));
-            const float spec = a3 > 0.0f ? __fmul_rn(__fmul_rn(a.strength, 1.0f), powf(a3, a.shininess)) : 0.0f;
-            const float night = __fmul_rn(fabsf(a3), __fsub_rn(1.0f, fabsf(a.Ly)));
-            float col[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float diffuse = a3 >= 0.0f ? mixs(a.horizon[c], a.peak[c], a3) : mixs(a.horizon[c], 0.0f, night);
-                col[c] = __fadd_rn(diffuse, spec);
-            }
-            const float alpha = fmaxf(a.alpha1, __fdiv_rn(__fadd_rn(a3, 1.0f), 2.0f));
-            blend(dst, col[0], col[1], col[2], alpha);
+        if (unsure) {                                                    // a byte (or a branch) within the error bound of a boundary
+            rgba = sky_texel_exact(a, dx, dy, dz);
+            if (a.unsure_count) atomicAdd(a.unsure_count, 1ULL);
         }
-        if (a.clouds) {                                                  // skybox-clouds.frag:46-67
-            const float4 raw = cube_rgba8(a.clouds, a.clouds_n, dx, dy, dz);
-            const float lin = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, raw.x), __fmul_rn(0.7152f, raw.y)), __fmul_rn(0.0722f, raw.z));
-            const float srgb = lin <= 0.0031308f ? __fmul_rn(12.92f, lin) : __fsub_rn(__fmul_rn(1.055f, powf(lin, __fdiv_rn(1.0f, 2.4f))), 0.055f);
-            const float intensity = fminf(fmaxf(a.sun_y, 0.2f), 1.0f);
-            const float oc = __fmul_rn(sat(a.sun_y), a.overcast);
-            if (srgb > a.omp) {
-                const float ca = __fdiv_rn(__fsub_rn(srgb, a.omp), __fsub_rn(1.0f, a.omp));
-                const float v = mixs(intensity, srgb, oc);
-                blend(dst, v, v, v, mixs(ca, 1.0f, oc));
-            } else {
-                blend(dst, 0.5f, 0.5f, 0.5f, oc);
-            }
-        }
-        blend(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3]);             // screen-space-quad.frag:45
-        // pack the four integer-valued floats (0..255) into RGBA8: 2^23 + c has c in its low mantissa byte
-        const unsigned b0 = __float_as_uint(__fadd_rn(dst[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rn(dst[1], 8388608.0f));
-        const unsigned b2 = __float_as_uint(__fadd_rn(dst[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rn(dst[3], 8388608.0f));
-        reinterpret_cast<unsigned*>(a.out)[k] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        reinterpret_cast<unsigned*>(a.out)[k] = rgba;
     }
 }
 
@@ -290,10 +350,20 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* strea
         // the star layer left in the attachment cannot reach the result — skip sampling it (same bytes, a third less work)
         if (a.draw_sphere && a.alpha1 == 1.0f) a.stars = nullptr;
         a.omp = 1.0f - p->cloudProportion;                               // render-engine.cpp:297
+        a.inv_gamma = 1.0f / 2.4f;
+        a.inv_one_minus_omp = 1.0f / (1.0f - a.omp);                     // only read where srgb > omp, i.e. omp < 1
+#ifdef WT_SKY_EXACT
+        a.fast = 0;
+#else
+        a.fast = std::isfinite(a.inv_one_minus_omp) ? 1 : 0;
+#endif
         a.overcast = p->overcastStrength;
         const float sy = std::fmin(std::fmax(sun[1], 0.0f), 1.0f);
         for (int c = 0; c < 3; ++c) a.fog[c] = sy * p->fogColourFarAtNoon[c];   // :295
         a.fog[3] = p->fogColourFarAtNoon[3];
+        if (!ctx->d_sky_unsure) e = cudaMalloc(&ctx->d_sky_unsure, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_sky_unsure, 0, sizeof(unsigned long long), stream);
+        a.unsure_count = e == cudaSuccess ? ctx->d_sky_unsure : nullptr;
         sky_synth_kernel<<<dim3((n + 255) / 256, n, 6), 256, 0, stream>>>(a);
         ctx->launches++;
         e = cudaGetLastError();
@@ -302,6 +372,22 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* strea
     if (e == cudaSuccess) { ctx->sky_n = n; ctx->sky_surface_ok = true; }
     if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(WT_ERR_CUDA, cudaGetErrorString(e));
+    return WT_OK;
+}
+
+int wt_debug_sky_exact_texels(wt_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_debug_sky_exact_texels: NULL argument");
+    *out = 0;
+    if (!ctx->d_sky_unsure) return WT_OK;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    unsigned long long v = 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(&v, ctx->d_sky_unsure, sizeof(v), cudaMemcpyDeviceToHost);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return set_thread_error(WT_ERR_CUDA, ctx->err.c_str()); }
+    *out = v;
     return WT_OK;
 }
 
