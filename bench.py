@@ -363,7 +363,7 @@ def run_ours(args):
     t_wall1 = time.time()
     launches = ctx.launch_count() - l0
     m1 = ctx.phase_mode_counts()
-    ran = {api.PHASE_NAMES[k]: m1[k] - m0[k] for k in range(3)}
+    ran = {api.PHASE_NAMES[k]: m1[k] - m0[k] for k in range(4)}
     ms_local = e0.elapsed_time(e1)
     ms = shard.max_over_ranks(ms_local, dev) if world > 1 else ms_local
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
@@ -508,7 +508,7 @@ def run_ours(args):
     if rank == 0 and not args.no_parity:
         try:
             parity = oracle_margin(api, scenes, ctx, waves, cam, scenes.animation_params(my_frames[Wm + K - 1]), L, hm,
-                                   {"timed": PHASE_FLAGS[phase], "bit-faithful": 0, "recurrence": api.FLAG_FAST_PHASE, "reference-order": api.FLAG_REFERENCE_ORDER},
+                                   {"timed": PHASE_FLAGS[phase], "bit-faithful": 0, "recurrence": api.FLAG_FAST_PHASE, "stencil-order": api.FLAG_STENCIL_ORDER},
                                    shade_flag, torch)
             parity["frame"] = "the last timed frame (global frame %d)" % my_frames[Wm + K - 1]
         except Exception as ex:                                          # the checker must never take the bench line down
@@ -584,7 +584,8 @@ def run_ours(args):
                                                "three-term recurrence x[j+1] = 2 cos(dk) x[j] - x[j-1]",
                                  "bit-faithful": "bit-faithful fp32 phase (the reference's own rounding of k), Cody-Waite reduction, MUFU sin/cos pair per vertex-wave, "
                                                  "every displaced position evaluated once and shared by the stencils of its neighbours",
-                                 "reference-order": "straight transliteration of the shader: 5 full evaluations per vertex at the shader's own uv +- du arguments, libdevice sincosf"}[timed_kernel],
+                                 "reference-order": "straight transliteration of the shader: 5 full evaluations per vertex at the shader's own uv +- du arguments, libdevice sincosf",
+                                 "stencil-order": "the shader's structure (5 full evaluations per vertex at its own uv +- du arguments) with Cody-Waite + MUFU sin/cos"}[timed_kernel],
                       "why": "WT_FLAG_AUTO_PHASE: wt_fast_phase_valid decides per frame (see parity_margin.fast_phase_report)" if phase == "auto" else "forced by --phase"},
             "ms_per_frame": ms_per_step,
             "roofline": primary,
@@ -647,7 +648,7 @@ def extra_workloads(torch, dist, api, scenes, shard, rank, world, local_rank, de
 
     def kernel_name(ctx, before):
         after = ctx.phase_mode_counts()
-        d = [after[k] - before[k] for k in range(3)]
+        d = [after[k] - before[k] for k in range(4)]
         return api.PHASE_NAMES[d.index(max(d))]
 
     # cfg2: 1024^2 x 8 waves, 1000-frame animation (frame f on rank f mod N), 4-deep ring, per-frame digests

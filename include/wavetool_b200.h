@@ -49,9 +49,12 @@ extern "C" {
 #define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
 #define WT_FLAG_VARYINGS 0x10u        /* also write the vertex stage's other outputs (wt_eval_frame_ex): gl_Position,
                                          xyPositionNDCSpaceHeight0, heightmap_colour.r, normalVecInViewSpaceOnlyYaw */
+#define WT_FLAG_STENCIL_ORDER 0x40u    /* the shader's own structure — five full evaluations per vertex, the four stencil neighbours at uv +- du exactly as
+                                         water-grid.vert:164-182 forms them — with the production kernels' trigonometry (Cody-Waite + MUFU): reproduces
+                                         the reference at any animation time, at ~4x the cost of the bit-faithful kernel */
 #define WT_FLAG_AUTO_PHASE 0x20u      /* per frame, the fastest kernel whose deviation from the reference wt_fast_phase_report bounds inside the
                                          tolerances: the recurrence kernel, else the bit-faithful kernel, else (late in an animation, where
-                                         the shader's own re-evaluation of the stencil neighbours becomes noisy) the reference-order kernel.
+                                         the shader's own re-evaluation of the stencil neighbours becomes noisy) the stencil-order kernel.
                                          All three run on the GPU; wt_last_phase_mode tells which one a launch used */
 
 typedef struct wt_ctx wt_ctx;
@@ -212,8 +215,8 @@ typedef struct wt_phase_report {
     /* The bit-faithful kernel reproduces k and the running sums bit for bit but, like the recurrence kernel, shares every
      * displaced position between the stencils of its neighbours, where the shader re-evaluates them at uv +- du
      * (water-grid.vert:164-182).  Once ulp(k) is large (late in an animation) that re-evaluation flips
-     * roundings of k and the SHADER's normals carry noise of A_i ulp(k_i) / spacing that only the reference-order kernel
-     * (WT_FLAG_REFERENCE_ORDER: five evaluations per vertex with exactly the shader's arguments) reproduces. */
+     * roundings of k and the SHADER's normals carry noise of A_i ulp(k_i) / spacing that only the five-evaluation kernels
+     * (WT_FLAG_STENCIL_ORDER / WT_FLAG_REFERENCE_ORDER: exactly the shader's arguments) reproduce. */
     float est_shared_stencil_normal_error_rad;
     int shared_stencil_valid;                          /* 1: the bit-faithful kernel is inside ITS validity domain */
     /* What one ulp of the fp32 coordinates does to a finite-difference normal on this grid: the floor for ANY evaluation whose
@@ -224,6 +227,7 @@ typedef struct wt_phase_report {
 #define WT_PHASE_BIT_FAITHFUL 0
 #define WT_PHASE_RECURRENCE 1
 #define WT_PHASE_REFERENCE_ORDER 2
+#define WT_PHASE_STENCIL_ORDER 3
 #define WT_PHASE_MARGIN 1.0f        /* valid iff estimate x margin <= tolerance */
 #define WT_PHASE_K_POSITION 4.5     /* extreme of the position noise in modelled sigmas */
 #define WT_PHASE_K_NORMAL 3.7       /* height-noise term of the normal estimate: envelope 2.85 x 1.27 (the kernel's own MUFU / recurrence noise) */
@@ -244,10 +248,10 @@ int wt_set_waves(wt_ctx* ctx, const wt_wave* waves, unsigned count);
  * frame, 0 = not (WT_FLAG_AUTO_PHASE then runs the bit-faithful kernel), < 0 error.  report may be NULL. */
 int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, wt_phase_report* report);
 /* Kernel of the most recent evaluation launch of this context: WT_PHASE_BIT_FAITHFUL (0), WT_PHASE_RECURRENCE (1),
- * WT_PHASE_REFERENCE_ORDER (2); -1 none yet. */
+ * WT_PHASE_REFERENCE_ORDER (2), WT_PHASE_STENCIL_ORDER (3); -1 none yet. */
 int wt_last_phase_mode(const wt_ctx* ctx);
 /* Evaluation launches of this context so far by kernel: out[WT_PHASE_*]. */
-void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[3]);
+void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[4]);
 
 /* Replaces load2DTexture + create2DTexture (render-engine.cpp:1308-1322, texture.cpp:54-72):
  * tightly packed RGBA8, rows ALREADY in GL order (i.e. flipped as stbi_set_flip_vertically_on_load

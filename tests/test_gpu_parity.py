@@ -208,7 +208,8 @@ def test_phase_envelope_over_the_time_slider(oracle, hm, name, t):
     """Every BASELINE scene at the start, in the middle and at the top of waveAnimationTimeInSeconds' slider, on all three
     kernels and on WT_FLAG_AUTO_PHASE:
       * each kernel meets the north-star tolerances wherever wt_fast_phase_report says it is inside its validity domain
-        (recurrence: `valid`; bit-faithful: `shared_stencil_valid`; reference-order: always);
+        (recurrence: `valid`; bit-faithful: `shared_stencil_valid`; the two five-evaluation kernels — reference-order with
+        libdevice sincosf, stencil-order with the production trigonometry — always);
       * WT_FLAG_AUTO_PHASE meets them at EVERY t, and runs exactly the kernel the report recommends;
       * at the top of the slider the recurrence kernel AND the bit-faithful kernel really do leave the tolerance — the first
         because it does not share the reference's rounding of k = w d + phi t (ulp(36000) = 4e-3 rad), the second because
@@ -247,19 +248,20 @@ def test_phase_envelope_over_the_time_slider(oracle, hm, name, t):
 
     results = {}
     for mode, fl, inside in (("exact", 0, rep.shared_stencil_valid), ("recurrence", api.FLAG_FAST_PHASE, rep.valid),
-                             ("reference_order", api.FLAG_REFERENCE_ORDER, 1), ("auto", api.FLAG_AUTO_PHASE, 1)):
+                             ("reference_order", api.FLAG_REFERENCE_ORDER, 1), ("stencil_order", api.FLAG_STENCIL_ORDER, 1), ("auto", api.FLAG_AUTO_PHASE, 1)):
         got = evaluate(fl)
         ran = ctx.last_phase_mode()
         stats, perr, ang, band = deviation_stats(got, want, sc)
         results[mode] = stats
         print("envelope", name, t, mode, "ran", api.PHASE_NAMES[ran], {k: round(stats[k], 3) for k in ("pos_margin", "normal_margin")}, "over", stats["normal_over_tol"],
               "inside" if inside else "outside", "recommended", api.PHASE_NAMES[rep.recommended])
-        assert ran == {"exact": api.PHASE_BIT_FAITHFUL, "recurrence": api.PHASE_RECURRENCE, "reference_order": api.PHASE_REFERENCE_ORDER, "auto": rep.recommended}[mode]
+        assert ran == {"exact": api.PHASE_BIT_FAITHFUL, "recurrence": api.PHASE_RECURRENCE, "reference_order": api.PHASE_REFERENCE_ORDER,
+                       "stencil_order": api.PHASE_STENCIL_ORDER, "auto": rep.recommended}[mode]
         if inside:
             assert passes(stats), (name, t, mode, stats)
             assert stats["flip_band"] <= max(2, stats["n"] // 10000)
     if t >= 3600.0 and name != "cfg1":
-        assert rep.recommended == api.PHASE_REFERENCE_ORDER
+        assert rep.recommended == api.PHASE_STENCIL_ORDER
         assert results["recurrence"]["normal_margin"] < 1.0 and results["exact"]["normal_margin"] < 1.0, "both shared-stencil kernels were expected to leave the tolerance at the top of the slider"
     if t <= 17.0:
         assert rep.recommended == (api.PHASE_RECURRENCE if name == "cfg2" else api.PHASE_BIT_FAITHFUL)
@@ -355,7 +357,8 @@ def test_cfg4_8192_grid_256_waves_row_bands(oracle, hm, mode):
 # --------------------------------------------------------------------------------------------------
 # configs[4]: 16384^2 grid, 32 waves, horizon-grazing / high-altitude projector edge cases
 # --------------------------------------------------------------------------------------------------
-FINE_GRID_MODES = {"exact": 0, "auto": api.FLAG_AUTO_PHASE, "reference_order": api.FLAG_REFERENCE_ORDER, "recurrence": api.FLAG_FAST_PHASE}
+FINE_GRID_MODES = {"exact": 0, "auto": api.FLAG_AUTO_PHASE, "reference_order": api.FLAG_REFERENCE_ORDER, "stencil_order": api.FLAG_STENCIL_ORDER,
+                   "recurrence": api.FLAG_FAST_PHASE}
 
 
 def fine_grid_check(oracle, sc, frame, ctx, L, bands, mode, label):
@@ -400,7 +403,7 @@ def fine_grid_check(oracle, sc, frame, ctx, L, bands, mode, label):
         nrm_fail = int((g_ang > np.maximum(np.maximum(1e-3, 2.0 * o_ang), one_ulp)).sum())
         print("fine grid", label, mode, "ran", api.PHASE_NAMES[ran], band, dict(pos_fail=pos_fail, normal_fail=nrm_fail, normal_max=float(g_ang.max()),
               one_ulp_max=float(one_ulp.max()), frac_over=g["normal_frac_over_tol"], oracle_frac_over=g["oracle_normal_frac_over_tol"]))
-        inside = {api.PHASE_RECURRENCE: rep.valid, api.PHASE_BIT_FAITHFUL: rep.shared_stencil_valid, api.PHASE_REFERENCE_ORDER: 1}[ran]
+        inside = {api.PHASE_RECURRENCE: rep.valid, api.PHASE_BIT_FAITHFUL: rep.shared_stencil_valid, api.PHASE_REFERENCE_ORDER: 1, api.PHASE_STENCIL_ORDER: 1}[ran]
         if inside:
             assert pos_fail == 0 and nrm_fail == 0, (label, band, mode, g)
             assert g["pos_frac_over_tol"] <= g["oracle_pos_frac_over_tol"] + 1e-12, (label, band, g)
@@ -721,7 +724,7 @@ def test_step_host_round_trip(oracle, hm):
     st, frame = sc.frame()
     n = L * L
     b = [torch.empty((n, 4), dtype=torch.float32, device="cuda") for _ in range(3)]
-    for flags in (api.FLAG_SHADE, api.FLAG_SHADE | api.FLAG_FAST_PHASE, 0):
+    for flags in (api.FLAG_SHADE, api.FLAG_SHADE | api.FLAG_FAST_PHASE, 0, api.FLAG_STENCIL_ORDER, api.FLAG_SHADE | api.FLAG_REFERENCE_ORDER):
         want = gpu_eval(ctx, frame, L, flags=flags, checksum=True)["checksum"]
         st, got = ctx.step_host(sc.cam, sc.params, sc.total_amplitude, L, b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr() if flags & 1 else 0,
                                 flags=flags, stream=torch.cuda.current_stream().cuda_stream)
@@ -748,6 +751,47 @@ def test_step_host_round_trip(oracle, hm):
         ctx.step_wait(tickets[0])            # that record has been reused since
     with pytest.raises(api.WaveToolError):
         ctx.step_wait(999)
+
+
+def test_auto_phase_through_batches_and_steps(hm):
+    """WT_FLAG_AUTO_PHASE is resolved per FRAME wherever frames are evaluated — wt_eval_frame, wt_eval_batch (incl. the fan-out
+    over internal streams), wt_step_host — and always to the kernel wt_fast_phase_report recommends: the digests equal those of
+    the same frames evaluated with that kernel's explicit flag.  The frames span all three tiers."""
+    torch = torch_mod()
+    L = 1024
+    waves = scenes.seeded_waves(8, cfg=2)
+    sc = Scene(waves, scenes.camera(), api.default_params(), L, hm)
+    ctx = sc.make_context()
+    explicit = {api.PHASE_RECURRENCE: api.FLAG_FAST_PHASE, api.PHASE_BIT_FAITHFUL: 0, api.PHASE_STENCIL_ORDER: api.FLAG_STENCIL_ORDER}
+    frames, params, want, tiers = [], [], [], []
+    for t in (0.0, 2.5, 250.0, 300.0, 3000.0, 3600.0):
+        p = api.default_params()
+        p.waveAnimationTimeInSeconds = t
+        st, fr = api.build_frame(sc.cam, p, sc.total_amplitude)
+        assert st == api.WT_OK
+        tier = ctx.fast_phase_valid(fr, L).recommended
+        got = gpu_eval(ctx, fr, L, flags=explicit[tier], checksum=True)
+        assert ctx.last_phase_mode() == tier
+        auto = gpu_eval(ctx, fr, L, flags=api.FLAG_AUTO_PHASE, checksum=True)
+        assert ctx.last_phase_mode() == tier and tuple(auto["checksum"]) == tuple(got["checksum"])
+        frames.append(fr); params.append(p); want.append(tuple(got["checksum"])); tiers.append(tier)
+    assert set(tiers) == {api.PHASE_RECURRENCE, api.PHASE_BIT_FAITHFUL, api.PHASE_STENCIL_ORDER}, tiers
+    n = L * L
+    ring = [torch.empty((4 * n, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
+    cks = torch.zeros(40 * len(frames), dtype=torch.uint8, device="cuda")
+    before = ctx.phase_mode_counts()
+    ctx.eval_batch(frames, L, ring[0].data_ptr(), ring[1].data_ptr(), 0, 4, cks.data_ptr(), flags=api.FLAG_CHECKSUM | api.FLAG_AUTO_PHASE,
+                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    after = ctx.phase_mode_counts()
+    got = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
+    for k in range(len(frames)):
+        assert tuple(got[k]) == want[k], (k, tiers[k])
+    assert [after[m] - before[m] for m in range(4)] == [tiers.count(m) for m in range(4)]
+    for k, p in enumerate(params):
+        st, d = ctx.step_host(sc.cam, p, sc.total_amplitude, L, ring[0].data_ptr(), ring[1].data_ptr(), flags=api.FLAG_AUTO_PHASE,
+                              stream=torch.cuda.current_stream().cuda_stream)
+        assert st == api.WT_OK and d.as_tuple() == want[k], (k, tiers[k])
 
 
 def test_cpp_host_program_matches_python_driver(tmp_path):

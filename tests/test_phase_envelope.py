@@ -62,7 +62,7 @@ def test_report_bounds_the_smooth_phase_model(oracle, name, t):
     # the bit-faithful (shared-stencil) kernel: inside its domain for the first minutes of an animation on every scene,
     # outside at the top of the slider, where only the reference-order kernel reproduces the shader's neighbour evaluations
     assert rep.shared_stencil_valid == (1 if t <= 17.0 else 0 if t >= 3600.0 else rep.shared_stencil_valid)
-    assert rep.recommended == (api.PHASE_RECURRENCE if rep.valid else api.PHASE_BIT_FAITHFUL if rep.shared_stencil_valid else api.PHASE_REFERENCE_ORDER)
+    assert rep.recommended == (api.PHASE_RECURRENCE if rep.valid else api.PHASE_BIT_FAITHFUL if rep.shared_stencil_valid else api.PHASE_STENCIL_ORDER)
     assert rep.coordinate_ulp_normal_error_rad > 0.0
 
 

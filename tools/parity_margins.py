@@ -18,7 +18,7 @@ from oracle import oracle as orc  # noqa: E402
 from tests.common import Scene, deviation_stats, reference_heightmap  # noqa: E402
 from wave_tool_b200 import api, scenes  # noqa: E402
 
-MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE, "reference_order": api.FLAG_REFERENCE_ORDER, "auto": api.FLAG_AUTO_PHASE}
+MODES = {"exact": 0, "recurrence": api.FLAG_FAST_PHASE, "stencil_order": api.FLAG_STENCIL_ORDER, "reference_order": api.FLAG_REFERENCE_ORDER, "auto": api.FLAG_AUTO_PHASE}
 TIMES = [0.0, 3.4, 17.0, 60.0, 600.0, 3600.0]
 
 
@@ -94,7 +94,7 @@ def main():
                                                                                       "pos_over_tol", "normal_over_tol", "flip_band")},
                        "predicted": rep.as_dict(), "passes": bool(stats["pos_margin"] >= 1.0 and stats["normal_margin"] >= 1.0)}
                 table.append(row)
-                print(f"{name:9s} t={t:6.1f} {mode:10s} ran={row['kernel']:12s} pos {stats['pos_max']:.2e} (x{stats['pos_margin']:6.2f}) normal {stats['normal_max']:.2e} (x{stats['normal_margin']:6.2f})"
+                print(f"{name:9s} t={t:6.1f} {mode:15s} ran={row['kernel']:15s} pos {stats['pos_max']:.2e} (x{stats['pos_margin']:6.2f}) normal {stats['normal_max']:.2e} (x{stats['normal_margin']:6.2f})"
                       f" over {stats['pos_over_tol']}/{stats['normal_over_tol']} of {len(perr)}  est {rep.est_position_error:.2e}/{rep.est_normal_error_rad:.2e} valid={rep.valid}  [oracle {t_or:.1f}s]", flush=True)
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     json.dump({"tolerances": "north_star: position 1e-4 x total amplitude, normal 1e-3 rad; margin = tolerance / largest deviation from the oracle",

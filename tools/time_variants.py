@@ -16,7 +16,7 @@ def run(spec, steps=20, warm=3):
     names = [f for f in fl.split(",") if f]
     flags = 0
     for f in names:
-        flags |= {"shade": api.FLAG_SHADE, "fast": api.FLAG_FAST_PHASE, "ref": api.FLAG_REFERENCE_ORDER, "cks": api.FLAG_CHECKSUM}[f]
+        flags |= {"shade": api.FLAG_SHADE, "fast": api.FLAG_FAST_PHASE, "ref": api.FLAG_REFERENCE_ORDER, "stencil": api.FLAG_STENCIL_ORDER, "auto": api.FLAG_AUTO_PHASE, "cks": api.FLAG_CHECKSUM}[f]
     waves = scenes.seeded_waves(W, cfg=3) if W else scenes.seeded_waves(1, cfg=3)[:0]
     ctx = api.Context(0)
     ctx.set_waves(waves)

@@ -16,10 +16,10 @@ from . import build as _build
 WT_OK, WT_NO_GRID = 0, 1
 WT_ERR_INVALID_ARGUMENT, WT_ERR_CUDA, WT_ERR_NO_DEVICE, WT_ERR_NOT_READY, WT_ERR_DEGENERATE = -1, -2, -3, -4, -5
 WT_MAX_WAVES = 1000
-FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER, FLAG_VARYINGS, FLAG_AUTO_PHASE = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+FLAG_SHADE, FLAG_CHECKSUM, FLAG_FAST_PHASE, FLAG_REFERENCE_ORDER, FLAG_VARYINGS, FLAG_AUTO_PHASE, FLAG_STENCIL_ORDER = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 WAVENUMBER_GPU_GEMS, WAVENUMBER_PHYSICAL = 0, 1
-PHASE_BIT_FAITHFUL, PHASE_RECURRENCE, PHASE_REFERENCE_ORDER = 0, 1, 2
-PHASE_NAMES = {0: "bit-faithful", 1: "recurrence", 2: "reference-order"}
+PHASE_BIT_FAITHFUL, PHASE_RECURRENCE, PHASE_REFERENCE_ORDER, PHASE_STENCIL_ORDER = 0, 1, 2, 3
+PHASE_NAMES = {0: "bit-faithful", 1: "recurrence", 2: "reference-order", 3: "stencil-order"}
 UI_RANGE_COUNT = 23
 
 # every symbol include/wavetool_b200.h declares (tests/test_abi.py checks the library exports them all)
@@ -484,10 +484,10 @@ class Context:
         return int(self._lib.wt_last_phase_mode(self._h))
 
     def phase_mode_counts(self):
-        """(bit-faithful, recurrence, reference-order) evaluation launches of this context so far (indexed by PHASE_*)."""
-        out = (C.c_uint64 * 3)()
+        """(bit-faithful, recurrence, reference-order, stencil-order) evaluation launches of this context so far (indexed by PHASE_*)."""
+        out = (C.c_uint64 * 4)()
         self._lib.wt_phase_mode_counts(self._h, out)
-        return int(out[0]), int(out[1]), int(out[2])
+        return tuple(int(v) for v in out)
 
     def launch_count(self) -> int:
         return int(self._lib.wt_launch_count(self._h))

@@ -40,7 +40,9 @@ __global__ void build_heightmap_quads_kernel(const float* r, int w, int h, float
 // ------------------------------------------------------------------------------------------------
 // Reference-order kernel: one thread per vertex, the shader's own structure (water-grid.vert:114-194)
 // ------------------------------------------------------------------------------------------------
-template <int CAP>
+// MUFU_TRIG = false: libdevice sincosf (the straight transliteration); true: the production kernels' Cody-Waite reduction + MUFU.SIN / MUFU.COS
+// (WT_FLAG_STENCIL_ORDER: the shader's five evaluations per vertex at a third of the cost)
+template <int CAP, bool MUFU_TRIG>
 __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const WaveTable<CAP>& wt, float u, float v) {
     // :87-91
     float x = mix_rn(mix_rn(a.blx, a.brx, u), mix_rn(a.tlx, a.trx, u), v);
@@ -50,7 +52,8 @@ __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const
         const WaveK wk = wt.w[i];
         float k = add_rn(mul_rn(wk.w, add_rn(mul_rn(wk.Dx, x), mul_rn(wk.Dz, z))), mul_rn(wk.phi, a.t));
         float s, c;
-        sincosf(k, &s, &c);
+        if (MUFU_TRIG) sincos_mufu(k, s, c);
+        else sincosf(k, &s, &c);
         float qc = mul_rn(wk.cX, c);
         p.x = add_rn(p.x, mul_rn(wk.A, mul_rn(wk.Dx, qc)));
         p.y = add_rn(p.y, mul_rn(wk.A, s));
@@ -60,7 +63,7 @@ __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const
     return p;
 }
 
-template <int CAP, bool SHADE>
+template <int CAP, bool SHADE, bool MUFU_TRIG>
 __global__ void __launch_bounds__(256) surface_reference_order_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
     const long long n = (long long)(a.row_end - a.row_begin) * a.L;
     ChecksumAcc acc;
@@ -68,11 +71,11 @@ __global__ void __launch_bounds__(256) surface_reference_order_kernel(const __gr
         const int row = a.row_begin + (int)(k / a.L), col = (int)(k % a.L);
         const float du = a.du;
         const float u = mul_rn((float)col, du), v = mul_rn((float)row, du);   // :123-125
-        P3 c = displaced_reference_order<CAP>(a, wt, u, v);
-        P3 left = displaced_reference_order<CAP>(a, wt, sub_rn(u, du), v);    // :164-167: uv -/+ du
-        P3 right = displaced_reference_order<CAP>(a, wt, add_rn(u, du), v);
-        P3 down = displaced_reference_order<CAP>(a, wt, u, sub_rn(v, du));
-        P3 up = displaced_reference_order<CAP>(a, wt, u, add_rn(v, du));
+        P3 c = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, u, v);
+        P3 left = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, sub_rn(u, du), v);    // :164-167: uv -/+ du
+        P3 right = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, add_rn(u, du), v);
+        P3 down = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, u, sub_rn(v, du));
+        P3 up = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, u, add_rn(v, du));
         // :187-190 with IEEE sqrt/div like the CPU reference
         float ux = sub_rn(right.x, left.x), uy = sub_rn(right.y, left.y), uz = sub_rn(right.z, left.z);
         float vx = sub_rn(up.x, down.x), vy = sub_rn(up.y, down.y), vz = sub_rn(up.z, down.z);

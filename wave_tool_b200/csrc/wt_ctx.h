@@ -22,7 +22,7 @@ struct wt_ctx {
     std::vector<wt_wave> waves;     // as handed to wt_set_waves (wt_fast_phase_valid)
     float max_horizontal = 0.0f;    // sum_i |A_i Q_i D_i|_1: the furthest a vertex can move sideways
     int last_phase_mode = -1;       // WT_PHASE_*: what the most recent evaluation launch ran
-    uint64_t mode_launches[3] = {0, 0, 0};   // evaluation launches per kernel, indexed by WT_PHASE_* (wt_phase_mode_counts)
+    uint64_t mode_launches[4] = {0, 0, 0, 0};   // evaluation launches per kernel, indexed by WT_PHASE_* (wt_phase_mode_counts)
     // textures
     float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)
     float4* d_hm_quads = nullptr;   // mirrored-repeat footprint table (production kernel)

@@ -187,16 +187,27 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
 }
 
-template <int CAP, bool SHADE>
+template <int CAP, bool SHADE, bool MUFU_TRIG>
 cudaError_t launch_reference_order(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
     static thread_local WaveTable<CAP> table;
     fill_table(table, tab);
     const long long n = (long long)(a.row_end - a.row_begin) * a.L;
     int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
-    surface_reference_order_kernel<CAP, SHADE><<<std::max(blocks, 1), 256, 0, stream>>>(a, table);
+    surface_reference_order_kernel<CAP, SHADE, MUFU_TRIG><<<std::max(blocks, 1), 256, 0, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
 }
+
+template <bool MUFU_TRIG>
+cudaError_t launch_five_eval(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t stream) {
+    switch (wave_capacity(ctx->n_waves)) {
+        case 64: return shade ? launch_reference_order<64, true, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<64, false, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream);
+        case 256: return shade ? launch_reference_order<256, true, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<256, false, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream);
+        default: return shade ? launch_reference_order<1000, true, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<1000, false, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream);
+    }
+}
+
+constexpr unsigned FIVE_EVAL_FLAGS = WT_FLAG_REFERENCE_ORDER | WT_FLAG_STENCIL_ORDER;   // one thread per vertex, the shader's own five evaluations
 
 int validate_eval(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
                   void* d_cks, unsigned flags) {
@@ -259,7 +270,7 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
 unsigned resolve_phase(const wt_ctx* ctx, const EvalArgs& a, unsigned flags) {
     if (!(flags & WT_FLAG_AUTO_PHASE)) return flags;
     flags &= ~WT_FLAG_AUTO_PHASE;
-    if (flags & WT_FLAG_REFERENCE_ORDER) return flags;
+    if (flags & FIVE_EVAL_FLAGS) return flags;
     wt_frame f;
     std::memset(&f, 0, sizeof(f));
     f.bottomLeftGridPointInWorld[0] = a.blx; f.bottomLeftGridPointInWorld[2] = a.blz;
@@ -271,21 +282,17 @@ unsigned resolve_phase(const wt_ctx* ctx, const EvalArgs& a, unsigned flags) {
     if (wt_fast_phase_report(ctx->waves.data(), (unsigned)ctx->waves.size(), &f, (unsigned)a.L, &rep) < 0) return flags & ~WT_FLAG_FAST_PHASE;
     flags &= ~WT_FLAG_FAST_PHASE;
     if (rep.recommended == WT_PHASE_RECURRENCE) flags |= WT_FLAG_FAST_PHASE;
-    else if (rep.recommended == WT_PHASE_REFERENCE_ORDER && !(flags & WT_FLAG_VARYINGS)) flags |= WT_FLAG_REFERENCE_ORDER;
+    else if (rep.recommended == WT_PHASE_STENCIL_ORDER && !(flags & WT_FLAG_VARYINGS)) flags |= WT_FLAG_STENCIL_ORDER;
     return flags;
 }
 
 cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
     const bool shade = flags & WT_FLAG_SHADE;
-    ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? WT_PHASE_REFERENCE_ORDER : ((flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL);
+    ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? WT_PHASE_REFERENCE_ORDER : (flags & WT_FLAG_STENCIL_ORDER) ? WT_PHASE_STENCIL_ORDER
+                           : (flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL;
     ctx->mode_launches[ctx->last_phase_mode]++;
-    if (flags & WT_FLAG_REFERENCE_ORDER) {
-        switch (wave_capacity(ctx->n_waves)) {
-            case 64: return shade ? launch_reference_order<64, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<64, false>(ctx, a, ctx->tab_raw, stream);
-            case 256: return shade ? launch_reference_order<256, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<256, false>(ctx, a, ctx->tab_raw, stream);
-            default: return shade ? launch_reference_order<1000, true>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<1000, false>(ctx, a, ctx->tab_raw, stream);
-        }
-    }
+    if (flags & WT_FLAG_REFERENCE_ORDER) return launch_five_eval<false>(ctx, a, shade, stream);
+    if (flags & WT_FLAG_STENCIL_ORDER) return launch_five_eval<true>(ctx, a, shade, stream);
     if (flags & WT_FLAG_FAST_PHASE)
         return shade ? launch_production_recur_shade(ctx, a, flags, stream) : launch_production_recur(ctx, a, flags, stream);
     return shade ? launch_production_exact_shade(ctx, a, flags, stream) : launch_production_exact(ctx, a, flags, stream);
@@ -295,7 +302,7 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
 // into the digest record — arms the record before and decodes it after (the production kernels do both themselves).
 cudaError_t launch_frame(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
     flags = resolve_phase(ctx, a, flags);
-    const bool ref_cks = a.cks && (flags & WT_FLAG_REFERENCE_ORDER);
+    const bool ref_cks = a.cks && (flags & FIVE_EVAL_FLAGS);
     if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     const cudaError_t e = launch_eval(ctx, a, flags, stream);
     if (e != cudaSuccess) return e;
@@ -422,9 +429,9 @@ int wt_fast_phase_valid(const wt_ctx* ctx, const wt_frame* frame, unsigned L, wt
 
 int wt_last_phase_mode(const wt_ctx* ctx) { return ctx ? ctx->last_phase_mode : -1; }
 
-void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[3]) {
+void wt_phase_mode_counts(const wt_ctx* ctx, uint64_t out[4]) {
     if (!out) return;
-    for (int k = 0; k < 3; ++k) out[k] = ctx ? ctx->mode_launches[k] : 0;
+    for (int k = 0; k < 4; ++k) out[k] = ctx ? ctx->mode_launches[k] : 0;
 }
 
 int wt_set_heightmap_rgba8(wt_ctx* ctx, const uint8_t* rgba, int w, int h) {
@@ -513,8 +520,8 @@ int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0
     const bool vary = flags & WT_FLAG_VARYINGS;
     if (vary && (!out->clip_position || !out->varyings_a || !out->varyings_b))
         return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS needs the clip_position, varyings_a and varyings_b buffers");
-    if (vary && (flags & WT_FLAG_REFERENCE_ORDER))
-        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS is not available with WT_FLAG_REFERENCE_ORDER");
+    if (vary && (flags & FIVE_EVAL_FLAGS))
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS is not available with WT_FLAG_REFERENCE_ORDER / WT_FLAG_STENCIL_ORDER");
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalArgs a = make_args(ctx, *frame, L, r0, r1, out->position, out->normal, out->shade, out->checksum, flags);
@@ -688,8 +695,8 @@ int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, f
         if (ev != WT_OK) return ev;
         EvalArgs probe = make_args(ctx, frame, L, r0, r1, d_pos, d_nrm, d_shade, nullptr, flags);
         const unsigned rflags = resolve_phase(ctx, probe, flags) | WT_FLAG_CHECKSUM;
-        if (rflags & WT_FLAG_REFERENCE_ORDER) {
-            // the reference-order kernel accumulates its digest with atomics: into a device record, copied out afterwards
+        if (rflags & FIVE_EVAL_FLAGS) {
+            // the five-evaluation kernels accumulate its digest with atomics: into a device record, copied out afterwards
             if (!ctx->d_step_cks) WT_CUDA(ctx, cudaMalloc(&ctx->d_step_cks, STEP_RING * sizeof(wt_checksum)));
             ev = wt_eval_frame(ctx, &frame, L, r0, r1, d_pos, d_nrm, d_shade, ctx->d_step_cks + slot, rflags, stream_);
             if (ev != WT_OK) return ev;

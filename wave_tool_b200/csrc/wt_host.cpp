@@ -479,8 +479,8 @@ int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f
     // (SURVEY.md H4).  That difference is harmless while k is fine-grained; once ulp(k) is large it flips the rounding of k
     // in the shader's neighbour evaluation, moving that neighbour by A_i ulp(k_i): the shader's normal then carries noise no
     // shared-stencil kernel can reproduce.  Bound: the largest A_i ulp(k_i) of the frame over the vertex spacing (two such
-    // flips do coincide somewhere on a 16 M-vertex grid).  Only the reference-order kernel (5 evaluations per vertex, exactly
-    // the shader's arguments) is free of it.
+    // flips do coincide somewhere on a 16 M-vertex grid).  Only the five-evaluation kernels (WT_FLAG_STENCIL_ORDER,
+    // WT_FLAG_REFERENCE_ORDER: exactly the shader's arguments) are free of it.
     double a_ulp = 0.0;
     for (unsigned i = 0; i < count; ++i) {
         const double K = (double)waves[i].frequency_w * rho + (double)waves[i].phaseConstant_phi * t;
@@ -491,7 +491,7 @@ int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f
     // not bit-identical to the reference's libm (one flipped rounding of the running sum moves a neighbour by ulp(coord))
     r.coordinate_ulp_normal_error_rad = (float)(0.5 * uc * gain);
     r.shared_stencil_valid = (count == 0) || (r.est_shared_stencil_normal_error_rad * WT_PHASE_MARGIN <= r.normal_tolerance_rad);
-    r.recommended = r.valid ? WT_PHASE_RECURRENCE : (r.shared_stencil_valid ? WT_PHASE_BIT_FAITHFUL : WT_PHASE_REFERENCE_ORDER);
+    r.recommended = r.valid ? WT_PHASE_RECURRENCE : (r.shared_stencil_valid ? WT_PHASE_BIT_FAITHFUL : WT_PHASE_STENCIL_ORDER);
     if (out) *out = r;
     return r.valid ? 1 : 0;
 }

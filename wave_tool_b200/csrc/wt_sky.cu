@@ -26,7 +26,7 @@ struct SkyArgs {
     float fog[4];
     float inv_gamma;             // fl(1 / 2.4) as the shader's constant expression folds it (skybox-clouds.frag:54)
     float inv_one_minus_omp;     // 1 / (1 - omp) for the approximate path
-    unsigned long long* unsure_count;   // diagnostic (may be NULL): texels that took the exact path
+    unsigned long long* unsure_count;   // diagnostic (may be NULL): layers that were redone on the exact path
     int fast;                    // 1: approximate path with guard bands + exact fallback per texel; 0: exact path only (WT_SKY_EXACT build / debugging)
 };
 
@@ -85,7 +85,7 @@ __device__ __forceinline__ void blend(float dst[4], float r, float g, float b, f
         if (FAST) {
             // d(out)/d(src_c) = As <= 1, d(out)/d(As) = src_c - d in [-1, 1] (the alpha channel: 2 As - d in [-1, 2]); 255 byte units
             // per unit, plus the roundings of the blend itself (a few ulp of a value <= 1, 1e-4 byte units is ample)
-            const float e = 255.0f * ((c < 3 ? err_rgb : err_a) + 2.0f * err_a) + 1e-4f;
+            const float e = 255.0f * (c < 3 ? err_rgb + err_a : 2.0f * err_a) + 1e-4f;
             const float fr = __fsub_rn(t, q);
             unsure = unsure || ((err_rgb != 0.0f || err_a != 0.0f) && (fr < e || fr > 1.0f - e));
         }
@@ -93,74 +93,98 @@ __device__ __forceinline__ void blend(float dst[4], float r, float g, float b, f
     }
 }
 
-// All layers of one texel (direction d) into dst.  FAST = false is the exact evaluation: IEEE division / square root and
-// libdevice powf, bit-compatible with the oracle's restatement of the sky shaders.  FAST = true replaces the two powf by
-// MUFU lg2 / ex2 and the per-texel division by (1 - omp) by a multiplication with its reciprocal, carries bounds on the error
-// this introduces, and raises `unsure` wherever a comparison or a byte conversion could come out differently.
-template <bool FAST>
-__device__ __forceinline__ void sky_texel(const SkyArgs& a, float dx, float dy, float dz, float dst[4], bool& unsure) {
+// All layers of one texel (direction d) into dst (integer-valued floats 0..255).
+// The two pow() of the sky shaders are first evaluated with MUFU lg2 / ex2 and the division by (1 - omp) as a multiplication
+// by its reciprocal; the blend carries bounds on the error this introduces and tells when a comparison or a byte conversion
+// could come out differently.  Only then the layer is redone exactly (libdevice powf, IEEE division) from the bytes the
+// previous layers left — every layer starts from exact bytes, so the fallback is local to the layer.  With a.fast == 0 the
+// exact forms are used throughout.
+__device__ __forceinline__ void sky_texel(const SkyArgs& a, float dx, float dy, float dz, float dst[4], unsigned& n_exact) {
     dst[0] = dst[1] = dst[2] = dst[3] = 255.0f;                          // glClearColor(1,1,1,1), render-engine.cpp:694,330
+    bool unused = false;
     if (a.stars) {                                                       // skybox-stars.frag:41
         const float4 s = cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
-        blend<FAST>(dst, s.x, s.y, s.z, 1.0f, 0.0f, 0.0f, unsure);
+        blend<false>(dst, s.x, s.y, s.z, 1.0f, 0.0f, 0.0f, unused);
     }
     if (a.draw_sphere) {                                                 // skysphere.frag:48-76
         const float inv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
         const float nx = __fmul_rn(dx, inv), ny = __fmul_rn(dy, inv), nz = __fmul_rn(dz, inv);
         const float a3 = __fadd_rn(__fadd_rn(__fmul_rn(nx, a.Lx), __fmul_rn(ny, a.Ly)), __fmul_rn(nz, a.Lz));
+        const float night = __fmul_rn(fabsf(a3), __fsub_rn(1.0f, fabsf(a.Ly)));
+        float diffuse[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) diffuse[c] = a3 >= 0.0f ? mixs(a.horizon[c], a.peak[c], a3) : mixs(a.horizon[c], 0.0f, night);
+        const float alpha = fmaxf(a.alpha1, __fmul_rn(__fadd_rn(a3, 1.0f), 0.5f));   // x / 2.0 == x * 0.5 exactly
+        const float s1 = __fmul_rn(a.strength, 1.0f);
         float spec = 0.0f, err = 0.0f;
+        bool exact = !a.fast || a3 <= 0.0f || a.shininess == 0.0f;
         if (a3 > 0.0f) {
-            if (FAST) {
-                // pow(a3, shininess) = 2^(shininess log2 a3): lg2.approx is within 2^-21 absolute, ex2.approx within 2^-21 relative
-                const float p = ex2_approx(__fmul_rn(a.shininess, lg2_approx(a3)));
-                spec = __fmul_rn(__fmul_rn(a.strength, 1.0f), p);
-                err = __fmul_rn(spec, __fmaf_rn(a.shininess, 4e-7f, 1e-6f)) + 1e-30f;
-                if (a.shininess == 0.0f) { spec = __fmul_rn(a.strength, 1.0f); err = 0.0f; }    // pow(x, 0) = 1
+            if (exact) {
+                spec = __fmul_rn(s1, powf(a3, a.shininess));
             } else {
-                spec = __fmul_rn(__fmul_rn(a.strength, 1.0f), powf(a3, a.shininess));
+                // pow(a3, shininess) = 2^(shininess log2 a3): lg2.approx is within 2^-22 absolute on [0.5, 2] and 2 ulp elsewhere, ex2.approx within 2 ulp;
+                // the product's own rounding adds 2^-24 |shininess lg|
+                const float lg = lg2_approx(a3);
+                spec = __fmul_rn(s1, ex2_approx(__fmul_rn(a.shininess, lg)));
+                err = __fmul_rn(spec, __fmaf_rn(a.shininess, 2.5e-7f * (1.0f + fabsf(lg)), 6e-7f)) + 1e-30f;
             }
         }
-        const float night = __fmul_rn(fabsf(a3), __fsub_rn(1.0f, fabsf(a.Ly)));
-        float col[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float diffuse = a3 >= 0.0f ? mixs(a.horizon[c], a.peak[c], a3) : mixs(a.horizon[c], 0.0f, night);
-            col[c] = __fadd_rn(diffuse, spec);
+        const float keep[4] = {dst[0], dst[1], dst[2], dst[3]};
+        bool unsure = false;
+        blend<true>(dst, __fadd_rn(diffuse[0], spec), __fadd_rn(diffuse[1], spec), __fadd_rn(diffuse[2], spec), alpha, err, 0.0f, unsure);
+        if (unsure) {                                                    // a byte within the error bound of a boundary: this layer again, exactly
+            spec = __fmul_rn(s1, powf(a3, a.shininess));
+            dst[0] = keep[0]; dst[1] = keep[1]; dst[2] = keep[2]; dst[3] = keep[3];
+            blend<false>(dst, __fadd_rn(diffuse[0], spec), __fadd_rn(diffuse[1], spec), __fadd_rn(diffuse[2], spec), alpha, 0.0f, 0.0f, unused);
+            ++n_exact;
         }
-        const float alpha = fmaxf(a.alpha1, __fmul_rn(__fadd_rn(a3, 1.0f), 0.5f));   // x / 2.0 == x * 0.5 exactly
-        blend<FAST>(dst, col[0], col[1], col[2], alpha, err, 0.0f, unsure);
     }
     if (a.clouds) {                                                      // skybox-clouds.frag:46-67
         const float4 raw = cube_rgba8(a.clouds, a.clouds_n, dx, dy, dz);
         const float lin = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, raw.x), __fmul_rn(0.7152f, raw.y)), __fmul_rn(0.0722f, raw.z));
-        float srgb, es = 0.0f;
-        if (lin <= 0.0031308f) {
-            srgb = __fmul_rn(12.92f, lin);
-        } else if (FAST) {
-            const float p = ex2_approx(__fmul_rn(a.inv_gamma, lg2_approx(lin)));
-            srgb = __fsub_rn(__fmul_rn(1.055f, p), 0.055f);
-            es = 2e-6f;                                                  // |p| <= 1: (1/2.4 2^-21 ln 2 + 2^-21) 1.055 + roundings < 1e-6
-        } else {
-            srgb = __fsub_rn(__fmul_rn(1.055f, powf(lin, a.inv_gamma)), 0.055f);
-        }
         const float intensity = fminf(fmaxf(a.sun_y, 0.2f), 1.0f);
         const float oc = __fmul_rn(sat(a.sun_y), a.overcast);
-        if (FAST && fabsf(__fsub_rn(srgb, a.omp)) <= es && es != 0.0f) unsure = true;   // the branch itself hangs on the approximation
-        if (srgb > a.omp) {
-            float ca, eca = 0.0f;
-            if (FAST) {
-                ca = __fmul_rn(__fsub_rn(srgb, a.omp), a.inv_one_minus_omp);
-                eca = __fmaf_rn(es, a.inv_one_minus_omp, 2e-7f * fabsf(ca) + 1e-30f);   // the approximation + one rounding of the reciprocal form
+        const float keep[4] = {dst[0], dst[1], dst[2], dst[3]};
+        // the layer for a given srgb value: exact (IEEE division) or with the reciprocal form and the error bounds es / eca
+        auto layer = [&](float srgb, float es, bool approx, bool& unsure) {
+            if (approx && fabsf(__fsub_rn(srgb, a.omp)) <= es) unsure = true;     // the branch itself hangs on the approximation
+            if (srgb > a.omp) {
+                float ca, eca = 0.0f;
+                if (approx) {
+                    ca = __fmul_rn(__fsub_rn(srgb, a.omp), a.inv_one_minus_omp);
+                    eca = __fmaf_rn(es, a.inv_one_minus_omp, 1.3e-7f * fabsf(ca) + 1e-30f);   // the approximation + the rounding of the reciprocal form
+                } else {
+                    ca = __fdiv_rn(__fsub_rn(srgb, a.omp), __fsub_rn(1.0f, a.omp));
+                }
+                const float v = mixs(intensity, srgb, oc);
+                if (approx) blend<true>(dst, v, v, v, mixs(ca, 1.0f, oc), __fmul_rn(es, oc), __fmul_rn(eca, __fsub_rn(1.0f, oc)), unsure);
+                else blend<false>(dst, v, v, v, mixs(ca, 1.0f, oc), 0.0f, 0.0f, unsure);
             } else {
-                ca = __fdiv_rn(__fsub_rn(srgb, a.omp), __fsub_rn(1.0f, a.omp));
+                blend<false>(dst, 0.5f, 0.5f, 0.5f, oc, 0.0f, 0.0f, unsure);
             }
-            const float v = mixs(intensity, srgb, oc);
-            blend<FAST>(dst, v, v, v, mixs(ca, 1.0f, oc), es, eca, unsure);
+        };
+        if (lin <= 0.0031308f) {
+            bool u = false;
+            layer(__fmul_rn(12.92f, lin), 0.0f, a.fast != 0, u);          // srgb itself is exact here; only the reciprocal form is approximate
+            if (u) { dst[0] = keep[0]; dst[1] = keep[1]; dst[2] = keep[2]; dst[3] = keep[3]; layer(__fmul_rn(12.92f, lin), 0.0f, false, unused); ++n_exact; }
+        } else if (a.fast) {
+            const float lg = lg2_approx(lin);
+            const float p = ex2_approx(__fmul_rn(a.inv_gamma, lg));
+            const float srgb = __fsub_rn(__fmul_rn(1.055f, p), 0.055f);
+            // exponent error inv_gamma |lg| 2^-22 (+ its rounding), ex2 2^-22 relative, two more roundings; p <= 1
+            const float es = __fmul_rn(p, __fmaf_rn(fabsf(lg), 1.0e-7f, 4.5e-7f)) + 7e-8f;
+            bool u = false;
+            layer(srgb, es, true, u);
+            if (u) {
+                dst[0] = keep[0]; dst[1] = keep[1]; dst[2] = keep[2]; dst[3] = keep[3];
+                layer(__fsub_rn(__fmul_rn(1.055f, powf(lin, a.inv_gamma)), 0.055f), 0.0f, false, unused);
+                ++n_exact;
+            }
         } else {
-            blend<FAST>(dst, 0.5f, 0.5f, 0.5f, oc, 0.0f, 0.0f, unsure);
+            layer(__fsub_rn(__fmul_rn(1.055f, powf(lin, a.inv_gamma)), 0.055f), 0.0f, false, unused);
         }
     }
-    blend<FAST>(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3], 0.0f, 0.0f, unsure);   // screen-space-quad.frag:45
+    blend<false>(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3], 0.0f, 0.0f, unused);   // screen-space-quad.frag:45
 }
 
 // pack the four integer-valued floats (0..255) into RGBA8: 2^23 + c has c in its low mantissa byte
@@ -168,14 +192,6 @@ __device__ __forceinline__ unsigned pack_rgba8(const float dst[4]) {
     const unsigned b0 = __float_as_uint(__fadd_rn(dst[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rn(dst[1], 8388608.0f));
     const unsigned b2 = __float_as_uint(__fadd_rn(dst[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rn(dst[3], 8388608.0f));
     return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
-}
-
-// the exact evaluation, out of line: only the texels the approximate path is unsure about come here
-static __device__ __noinline__ unsigned sky_texel_exact(const SkyArgs& a, float dx, float dy, float dz) {
-    float dst[4];
-    bool unused = false;
-    sky_texel<false>(a, dx, dy, dz, dst, unused);
-    return pack_rgba8(dst);
 }
 
 __global__ void __launch_bounds__(256) sky_synth_kernel(const __grid_constant__ SkyArgs a) {
@@ -198,17 +214,11 @@ __global__ void __launch_bounds__(256) sky_synth_kernel(const __grid_constant__ 
             case 4: dx = sc; dy = -tc; dz = 1.0f; break;
             default: dx = -sc; dy = -tc; dz = -1.0f; break;
         }
-        unsigned rgba;
-        bool unsure = !a.fast;
-        if (a.fast) {
-            float dst[4];
-            sky_texel<true>(a, dx, dy, dz, dst, unsure);
-            rgba = pack_rgba8(dst);
-        }
-        if (unsure) {                                                    // a byte (or a branch) within the error bound of a boundary
-            rgba = sky_texel_exact(a, dx, dy, dz);
-            if (a.unsure_count) atomicAdd(a.unsure_count, 1ULL);
-        }
+        float dst[4];
+        unsigned n_exact = 0;
+        sky_texel(a, dx, dy, dz, dst, n_exact);
+        const unsigned rgba = pack_rgba8(dst);
+        if (a.unsure_count && n_exact) atomicAdd(a.unsure_count, (unsigned long long)n_exact);
         reinterpret_cast<unsigned*>(a.out)[k] = rgba;
     }
 }
