@@ -414,6 +414,10 @@ int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned grid_len, un
  * ------------------------------------------------------------------------------------------- */
 /* Number of kernels this ctx has launched so far (evaluation + helper kernels). */
 uint64_t wt_launch_count(const wt_ctx* ctx);
+/* Frames this ctx has evaluated inside GROUPED launches: wt_eval_batch / wt_run_animation put consecutive small frames (<= 4 M
+ * vertices, <= 64 waves, no shading terms / extra varyings, same kernel) that write different ring slots into one persistent
+ * launch — one work queue across the frames, one launch per group instead of one per frame. */
+uint64_t wt_batched_frame_count(const wt_ctx* ctx);
 /* Micro-benchmarks for the roofline denominators: kind 0 = MUFU (sin+cos pairs/s),
  * 1 = FP32 FMA (FLOP/s), 2 = HBM float4 store stream (bytes/s), 3 = packed FP32 FFMA2 (FLOP/s).
  * Synchronous; result in *per_second. */

@@ -148,9 +148,12 @@ def test_cfg2_animation_frames_and_batch(oracle, hm, mode):
     ring_p = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
     ring_n = torch.empty((2 * n, 4), dtype=torch.float32, device="cuda")
     cks = torch.zeros(40 * len(frames), dtype=torch.uint8, device="cuda")
+    b0, l0 = ctx.batched_frame_count(), ctx.launch_count()
     ctx.eval_batch(frames, L, ring_p.data_ptr(), ring_n.data_ptr(), 0, 2, cks.data_ptr(), flags=api.FLAG_CHECKSUM | fl,
                    stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+    # small frames are evaluated in grouped launches: 4 frames on a 2-deep ring = 2 groups of 2 (+ 1 launch each to arm the digests)
+    assert ctx.batched_frame_count() - b0 == len(frames) and ctx.launch_count() - l0 == 4
     digests = cks.cpu().numpy().view(api.CHECKSUM_DTYPE)
     for k, s in enumerate(singles):
         assert digests[k] == s["checksum"], k
@@ -776,6 +779,11 @@ def test_auto_phase_through_batches_and_steps(hm):
         assert ctx.last_phase_mode() == tier and tuple(auto["checksum"]) == tuple(got["checksum"])
         frames.append(fr); params.append(p); want.append(tuple(got["checksum"])); tiers.append(tier)
     assert set(tiers) == {api.PHASE_RECURRENCE, api.PHASE_BIT_FAITHFUL, api.PHASE_STENCIL_ORDER}, tiers
+    # the stencil-order kernel evaluates the vertex itself with the bit-faithful kernel's arithmetic: identical POSITION bits
+    # (the normals differ: it re-evaluates the four neighbours at the shader's uv +- du instead of sharing them)
+    a = gpu_eval(ctx, frames[-1], L, flags=0)
+    b = gpu_eval(ctx, frames[-1], L, flags=api.FLAG_STENCIL_ORDER)
+    assert np.array_equal(a["pos"].view(np.uint32), b["pos"].view(np.uint32))
     n = L * L
     ring = [torch.empty((4 * n, 4), dtype=torch.float32, device="cuda") for _ in range(2)]
     cks = torch.zeros(40 * len(frames), dtype=torch.uint8, device="cuda")

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
     "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
-    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count",
 ]
 
 
@@ -163,6 +163,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
                                      C.c_void_p, C.c_uint]
     L.wt_launch_count.restype = C.c_uint64
     L.wt_launch_count.argtypes = [C.c_void_p]
+    L.wt_batched_frame_count.restype = C.c_uint64
+    L.wt_batched_frame_count.argtypes = [C.c_void_p]
     L.wt_measure_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.wt_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
     L.wt_debug_reload_env.restype = None
@@ -488,6 +490,9 @@ class Context:
         out = (C.c_uint64 * 4)()
         self._lib.wt_phase_mode_counts(self._h, out)
         return tuple(int(v) for v in out)
+
+    def batched_frame_count(self) -> int:
+        return int(self._lib.wt_batched_frame_count(self._h))
 
     def launch_count(self) -> int:
         return int(self._lib.wt_launch_count(self._h))

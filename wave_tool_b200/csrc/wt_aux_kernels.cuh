@@ -48,16 +48,25 @@ __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const
     float x = mix_rn(mix_rn(a.blx, a.brx, u), mix_rn(a.tlx, a.trx, u), v);
     float z = mix_rn(mix_rn(a.blz, a.brz, u), mix_rn(a.tlz, a.trz, u), v);
     P3 p = {x, 0.0f, z};
-    for (int i = 0; i < a.n_waves; ++i) {   // :76-82, table holds the raw uniforms: cX = Q_i here
+    for (int i = 0; i < a.n_waves; ++i) {   // :76-82
         const WaveK wk = wt.w[i];
         float k = add_rn(mul_rn(wk.w, add_rn(mul_rn(wk.Dx, x), mul_rn(wk.Dz, z))), mul_rn(wk.phi, a.t));
         float s, c;
-        if (MUFU_TRIG) sincos_mufu(k, s, c);
-        else sincosf(k, &s, &c);
-        float qc = mul_rn(wk.cX, c);
-        p.x = add_rn(p.x, mul_rn(wk.A, mul_rn(wk.Dx, qc)));
-        p.y = add_rn(p.y, mul_rn(wk.A, s));
-        p.z = add_rn(p.z, mul_rn(wk.A, mul_rn(wk.Dz, qc)));
+        if (MUFU_TRIG) {
+            // the bit-faithful production kernel's arithmetic on the same k: table = tab_exact (cX = A Q_i D.x, cZ = A Q_i D.z folded
+            // on the host), one FMA per component — so the centre vertex gets the very position bits that kernel produces
+            sincos_mufu(k, s, c);
+            p.x = __fmaf_rn(wk.cX, c, p.x);
+            p.y = __fmaf_rn(wk.A, s, p.y);
+            p.z = __fmaf_rn(wk.cZ, c, p.z);
+        } else {
+            // the literal operation order of the shader; table = tab_raw: cX holds Q_i
+            sincosf(k, &s, &c);
+            float qc = mul_rn(wk.cX, c);
+            p.x = add_rn(p.x, mul_rn(wk.A, mul_rn(wk.Dx, qc)));
+            p.y = add_rn(p.y, mul_rn(wk.A, s));
+            p.z = add_rn(p.z, mul_rn(wk.A, mul_rn(wk.Dz, qc)));
+        }
     }
     p.y = finish_height(a, p.x, p.y, p.z);
     return p;

@@ -54,6 +54,7 @@ struct wt_ctx {
     int step_status[4] = {0, 0, 0, 0};
     unsigned step_next = 0;
     uint64_t launches = 0;
+    uint64_t batched_frames = 0;    // frames evaluated inside grouped launches (wt_launch.cuh: launch_warp_batch)
     // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
     int* d_queues = nullptr;
     unsigned queue_next = 0;
@@ -162,5 +163,8 @@ cudaError_t launch_production_exact(wt_ctx* ctx, EvalArgs& a, unsigned flags, cu
 cudaError_t launch_production_exact_shade(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
 cudaError_t launch_production_recur(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
 cudaError_t launch_production_recur_shade(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream);
+// several small frames in one persistent launch (wt_launch.cuh: launch_warp_batch)
+cudaError_t launch_production_batch_exact(wt_ctx* ctx, std::vector<EvalArgs>& frames, cudaStream_t stream);
+cudaError_t launch_production_batch_recur(wt_ctx* ctx, std::vector<EvalArgs>& frames, cudaStream_t stream);
 
 }  // namespace wt

@@ -200,10 +200,11 @@ cudaError_t launch_reference_order(wt_ctx* ctx, EvalArgs& a, const std::vector<W
 
 template <bool MUFU_TRIG>
 cudaError_t launch_five_eval(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t stream) {
+    const std::vector<WaveK>& tab = MUFU_TRIG ? ctx->tab_exact : ctx->tab_raw;   // see displaced_reference_order
     switch (wave_capacity(ctx->n_waves)) {
-        case 64: return shade ? launch_reference_order<64, true, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<64, false, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream);
-        case 256: return shade ? launch_reference_order<256, true, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<256, false, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream);
-        default: return shade ? launch_reference_order<1000, true, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream) : launch_reference_order<1000, false, MUFU_TRIG>(ctx, a, ctx->tab_raw, stream);
+        case 64: return shade ? launch_reference_order<64, true, MUFU_TRIG>(ctx, a, tab, stream) : launch_reference_order<64, false, MUFU_TRIG>(ctx, a, tab, stream);
+        case 256: return shade ? launch_reference_order<256, true, MUFU_TRIG>(ctx, a, tab, stream) : launch_reference_order<256, false, MUFU_TRIG>(ctx, a, tab, stream);
+        default: return shade ? launch_reference_order<1000, true, MUFU_TRIG>(ctx, a, tab, stream) : launch_reference_order<1000, false, MUFU_TRIG>(ctx, a, tab, stream);
     }
 }
 
@@ -590,6 +591,57 @@ struct FanOut {
         return cudaSuccess;
     }
 };
+
+// Groups consecutive SMALL frames of a batch / an animation into single persistent launches (wt_launch.cuh: launch_warp_batch).
+// A frame joins a group when it resolves to one of the two production kernels without shading terms or extra varyings; a group
+// holds frames of ONE kernel that write different ring slots (at most ring_depth of them).  Everything else is launched on its
+// own, after the pending group, so the stream order of the frames is kept.
+struct FrameBatcher {
+    wt_ctx* ctx;
+    cudaStream_t stream;
+    unsigned ring_depth;
+    bool enabled;
+    std::vector<EvalArgs> group;
+    unsigned group_flags = 0;
+    FrameBatcher(wt_ctx* c, cudaStream_t s, unsigned ring, unsigned n_frames, unsigned L, unsigned rows, unsigned flags)
+        : ctx(c), stream(s), ring_depth(ring),
+          enabled(ring >= 2 && n_frames >= 2 && c->n_waves <= 64 && (unsigned long long)L * rows <= (1ull << 22) && g_knobs.fanout != 1 &&
+                  !(flags & (FIVE_EVAL_FLAGS | WT_FLAG_SHADE | WT_FLAG_VARYINGS))) {}
+    cudaError_t flush() {
+        if (group.empty()) return cudaSuccess;
+        cudaError_t e;
+        if (group.size() == 1) {
+            e = launch_frame(ctx, group[0], group_flags, stream);
+        } else {
+            const int mode = (group_flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL;
+            if (group[0].cks) {   // the frames' digest records are consecutive: arm them (zero sums, min / max keys at their identities)
+                checksum_init_kernel<<<1, 32, 0, stream>>>(group[0].cks, (int)group.size());
+                ctx->launches++;
+            }
+            ctx->last_phase_mode = mode;
+            ctx->mode_launches[mode] += group.size();
+            ctx->batched_frames += group.size();
+            e = mode == WT_PHASE_RECURRENCE ? launch_production_batch_recur(ctx, group, stream) : launch_production_batch_exact(ctx, group, stream);
+        }
+        group.clear();
+        return e;
+    }
+    // `a` with flags as the caller passed them (WT_FLAG_AUTO_PHASE unresolved); other_stream: where a frame that cannot be grouped goes
+    cudaError_t add(EvalArgs& a, unsigned flags, cudaStream_t other_stream) {
+        const unsigned rflags = resolve_phase(ctx, a, flags);
+        const bool groupable = enabled && !(rflags & (FIVE_EVAL_FLAGS | WT_FLAG_SHADE | WT_FLAG_VARYINGS));
+        cudaError_t e;
+        if (!groupable) {
+            if ((e = flush()) != cudaSuccess) return e;
+            return launch_frame(ctx, a, rflags, enabled ? stream : other_stream);
+        }
+        if (!group.empty() && (group.size() >= ring_depth || ((rflags ^ group_flags) & WT_FLAG_FAST_PHASE) || (group[0].cks && a.cks != group[0].cks + group.size())))
+            if ((e = flush()) != cudaSuccess) return e;
+        group.push_back(a);
+        group_flags = rflags;
+        return cudaSuccess;
+    }
+};
 }  // namespace
 
 extern "C" {
@@ -604,13 +656,19 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool cks = flags & WT_FLAG_CHECKSUM;
     const size_t slot = (size_t)(r1 - r0) * L;
-    FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
+    FrameBatcher batcher(ctx, stream, ring_depth, n_frames, L, r1 - r0, flags);
+    FanOut fan(ctx, stream, batcher.enabled ? 1 : ring_depth, n_frames, L, r1 - r0);   // grouped frames need no fan-out
     WT_CUDA(ctx, fan.begin());
-    for (unsigned f = 0; f < n_frames; ++f) {
-        const size_t off = (size_t)(f % ring_depth) * slot;
-        EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
-                               d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
-        const cudaError_t e = launch_frame(ctx, a, flags, fan.stream_for(f));
+    for (unsigned f = 0; f <= n_frames; ++f) {
+        cudaError_t e;
+        if (f < n_frames) {
+            const size_t off = (size_t)(f % ring_depth) * slot;
+            EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
+                                   d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
+            e = batcher.add(a, flags, fan.stream_for(f));
+        } else {
+            e = batcher.flush();
+        }
         if (e != cudaSuccess) {   // the internal streams were forked off the caller's: join them before reporting
             fan.end();
             return fail(ctx, WT_ERR_CUDA, std::string("wt_eval_batch: ") + cudaGetErrorString(e));
@@ -638,7 +696,8 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     const bool cks = flags & WT_FLAG_CHECKSUM;
     const size_t slot = (size_t)(r1 - r0) * L;
     unsigned drawn = 0;
-    FanOut fan(ctx, stream, ring_depth, n_frames, L, r1 - r0);
+    FrameBatcher batcher(ctx, stream, ring_depth, n_frames, L, r1 - r0, flags);
+    FanOut fan(ctx, stream, batcher.enabled ? 1 : ring_depth, n_frames, L, r1 - r0);   // grouped frames need no fan-out
     WT_CUDA(ctx, fan.begin());
     // after begin() the internal streams have been forked off the caller's: every exit path joins them again
     auto bail = [&](int code, const std::string& msg) { fan.end(); return fail(ctx, code, msg); };
@@ -650,13 +709,18 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
             const size_t off = (size_t)(k % ring_depth) * slot;
             EvalArgs a = make_args(ctx, frame, L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
-            const cudaError_t e = launch_frame(ctx, a, flags, fan.stream_for(k));
+            const cudaError_t e = batcher.add(a, flags, fan.stream_for(k));
             if (e != cudaSuccess) return bail(WT_ERR_CUDA, std::string("wt_run_animation: ") + cudaGetErrorString(e));
             ++drawn;
-        } else if (cks && cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), fan.stream_for(k)) != cudaSuccess) {
-            return bail(WT_ERR_CUDA, "wt_run_animation: cudaMemsetAsync failed");   // nothing drawn: zero digest
+        } else if (cks) {   // nothing drawn: zero digest (after the pending group, which may hold the neighbouring records)
+            if (batcher.flush() != cudaSuccess || cudaMemsetAsync((wt_checksum*)d_checksums + k, 0, sizeof(wt_checksum), batcher.enabled ? stream : fan.stream_for(k)) != cudaSuccess)
+                return bail(WT_ERR_CUDA, "wt_run_animation: zeroing a digest failed");
         }
         for (unsigned s_ = 0; s_ < stride; ++s_) wt_animation_advance(params, anim, dt);
+    }
+    {
+        const cudaError_t e = batcher.flush();
+        if (e != cudaSuccess) return bail(WT_ERR_CUDA, std::string("wt_run_animation: ") + cudaGetErrorString(e));
     }
     WT_CUDA(ctx, fan.end());
     WT_CUDA(ctx, cudaGetLastError());
@@ -763,6 +827,8 @@ int wt_eval_frame_host(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned 
 }
 
 uint64_t wt_launch_count(const wt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t wt_batched_frame_count(const wt_ctx* ctx) { return ctx ? ctx->batched_frames : 0; }
 
 void wt_debug_reload_env(void) { g_knobs.load(); }
 

@@ -110,6 +110,13 @@ struct EvalArgs {
     // dynamic work distribution (NULL = static: item = blockIdx.x): queue[0] = next item, queue[1] = warps done
     int* queue;
     int n_items;
+    // batched launch (BATCH instantiations: several small frames in ONE persistent launch): item = frame * items_per_frame + the
+    // frame's own work item; the frame's EvalArgs (corners, time, outputs, digest record ...) and its per-wave phase offsets are
+    // read from device memory into shared memory when a warp moves on to another frame
+    const EvalArgs* batch;
+    const float* batch_phi;      // [frame * CAP + wave]: fl(phi t) of the frame (reduced mod 2 pi for the recurrence kernel)
+    int* batch_done;             // per frame: finished work items (the last one decodes the frame's digest record)
+    int items_per_frame;
     unsigned long long* trace;   // experiment knob (WT_TRACE): per work item {smid, item, t_start, t_end} in globaltimer ns
 };
 
@@ -571,13 +578,17 @@ struct RingLayout {
     static constexpr int BYTES_PER_WARP = PLANES * PLANE * (int)sizeof(float2);
 };
 
-template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY>
+template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY, bool BATCH = false>
 __global__ void __launch_bounds__(32, MODE == 1 ? (R > 8 ? WT_LB_RECUR_BIG : WT_LB_RECUR) : WT_LB_EXACT)
 surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
     extern __shared__ float2 ring_all[];
     using RL = RingLayout<R, VARY>;
     const int lane = threadIdx.x;
     float2* const ring = ring_all;
+    // BATCH: behind the ring, this warp's copy of the current frame's arguments and phase offsets
+    EvalArgs* const sA = reinterpret_cast<EvalArgs*>(ring_all + RL::PLANES * RL::PLANE);
+    float* const sphi = reinterpret_cast<float*>(sA + 1);
+    int cur_frame = -1;
     const bool dyn = a.queue != nullptr;
     int item = blockIdx.x;
     if (dyn) item = next_item(a.queue, lane);
@@ -585,18 +596,31 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
   while (item < a.n_items) {
     unsigned long long t_start = 0;
     if (a.trace) t_start = global_ns();
-    const int strip = item % a.n_strips, chunk = item / a.n_strips;
+    int fitem = item;
+    if (BATCH) {
+        const int frame = item / a.items_per_frame;
+        fitem = item - frame * a.items_per_frame;
+        if (frame != cur_frame) {
+            const unsigned* const src = reinterpret_cast<const unsigned*>(a.batch + frame);
+            for (int w = lane; w < (int)(sizeof(EvalArgs) / sizeof(unsigned)); w += 32) reinterpret_cast<unsigned*>(sA)[w] = __ldg(src + w);
+            for (int w = lane; w < a.n_waves; w += 32) sphi[w] = __ldg(a.batch_phi + (size_t)frame * CAP + w);
+            __syncwarp();
+            cur_frame = frame;
+        }
+    }
+    const EvalArgs& A = BATCH ? *sA : a;
+    const int strip = fitem % A.n_strips, chunk = fitem / A.n_strips;
     const int strip0 = strip * STRIP_COLS;
     int seg = 0;
-    while (seg + 1 < a.n_seg && chunk >= a.seg_prefix[seg + 1]) ++seg;
+    while (seg + 1 < A.n_seg && chunk >= A.seg_prefix[seg + 1]) ++seg;
     // canonical rows of the chunk [c0, c1); the rows this call writes [r0, r1)
-    const int c0 = a.seg_row0[seg] + (chunk - a.seg_prefix[seg]) * a.seg_rows[seg];
-    const int c1 = min(c0 + a.seg_rows[seg], a.seg_end[seg]);
-    const int r0 = max(c0, a.row_begin), r1 = min(c1, a.row_end);
+    const int c0 = A.seg_row0[seg] + (chunk - A.seg_prefix[seg]) * A.seg_rows[seg];
+    const int c1 = min(c0 + A.seg_rows[seg], A.seg_end[seg]);
+    const int r0 = max(c0, A.row_begin), r1 = min(c1, A.row_end);
     const int colA = strip0 - 1 + lane, colB = colA + 32;
-    const bool outA = lane >= 1 && colA < a.L;
-    const bool outB = lane <= 30 && colB < a.L;
-    const float one = a.one;
+    const bool outA = lane >= 1 && colA < A.L;
+    const bool outB = lane <= 30 && colB < A.L;
+    const float one = A.one;
 
     int slot_new = 2;   // ring row that receives the first row of the next step; rows -2/-1 of the first step are never read
 
@@ -608,17 +632,17 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         // loop; the empty asm keeps the compiler from hoisting them back out.
         int col_a = colA;
         asm volatile("" : "+r"(col_a));
-        const f2 u = make_float2(mul_rn((float)col_a, a.du), mul_rn((float)(col_a + 32), a.du));
+        const f2 u = make_float2(mul_rn((float)col_a, A.du), mul_rn((float)(col_a + 32), A.du));
         const f2 omu = sub2(bc(1.0f), u);
-        const f2 m1x = add2x(mul2(bc(a.blx), omu), mul2(bc(a.brx), u), one), m1z = add2x(mul2(bc(a.blz), omu), mul2(bc(a.brz), u), one);
-        const f2 m2x = add2x(mul2(bc(a.tlx), omu), mul2(bc(a.trx), u), one), m2z = add2x(mul2(bc(a.tlz), omu), mul2(bc(a.trz), u), one);
+        const f2 m1x = add2x(mul2(bc(A.blx), omu), mul2(bc(A.brx), u), one), m1z = add2x(mul2(bc(A.blz), omu), mul2(bc(A.brz), u), one);
+        const f2 m2x = add2x(mul2(bc(A.tlx), omu), mul2(bc(A.trx), u), one), m2z = add2x(mul2(bc(A.tlz), omu), mul2(bc(A.trz), u), one);
         // MODE 1: world-space step between consecutive rows of this column (the grid is bilinear, hence
         // affine in the row index along a column), so every wave's phase advances by a constant per row
-        const f2 ex = mul2(sub2(m2x, m1x), bc(a.du)), ez = mul2(sub2(m2z, m1z), bc(a.du));
+        const f2 ex = mul2(sub2(m2x, m1x), bc(A.du)), ez = mul2(sub2(m2z, m1z), bc(A.du));
         f2 px[R], py[R], pz[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const float v = mul_rn((float)(row_a + j), a.du);
+            const float v = mul_rn((float)(row_a + j), A.du);
             const float omv = sub_rn(1.0f, v);
             px[j] = add2x(mul2(m1x, bc(omv)), mul2(m2x, bc(v)), one);
             pz[j] = add2x(mul2(m1z, bc(omv)), mul2(m2z, bc(v)), one);
@@ -630,8 +654,9 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < R; ++j) { gx[j] = px[j]; gz[j] = pz[j]; }
             WT_UNROLL(WT_WAVE_UNROLL_EXACT)
-            for (int i = 0; i < a.n_waves; ++i) {
-                const WaveK wk = wt.w[i];   // phi holds fl(phaseConstant_phi * t) for this launch
+            for (int i = 0; i < A.n_waves; ++i) {
+                WaveK wk = wt.w[i];   // phi holds fl(phaseConstant_phi * t) for this launch
+                if (BATCH) wk.phi = sphi[i];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     // frequency_w * dot(D, xz) + phi * t, every operation rounded as GLSL/GLM does
@@ -660,9 +685,10 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             f2 ccx = bc(0.0f), ccy = bc(0.0f), ccz = bc(0.0f);
             WaveK wk_next = wt.w[0];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
             WT_UNROLL(WT_WAVE_UNROLL)
-            for (int i = 0; i < a.n_waves; ++i) {
-                const WaveK wk = wk_next;
-                wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < a.n_waves) ? i + 1 : i];
+            for (int i = 0; i < A.n_waves; ++i) {
+                WaveK wk = wk_next;
+                if (BATCH) wk.phi = sphi[i];
+                wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < A.n_waves) ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gxc, fma2(bc(wk.Dz), gzc, bc(wk.phi))), s, c);
                 const f2 dk = fma2(bc(wk.Dx), ex, mul2(bc(wk.Dz), ez));
@@ -702,10 +728,11 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             const f2 gx0 = px[0], gz0 = pz[0];
             WaveK wk_next = wt.w[0];   // (Dx,Dz) hold w*D, phi holds fl(phi*t) reduced mod 2pi
             WT_UNROLL(WT_WAVE_UNROLL)
-            for (int i = 0; i < a.n_waves; ++i) {
+            for (int i = 0; i < A.n_waves; ++i) {
                 // the next wave's constants are fetched from the constant bank one trip ahead
-                const WaveK wk = wk_next;
-                wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < a.n_waves) ? i + 1 : i];
+                WaveK wk = wk_next;
+                if (BATCH) wk.phi = sphi[i];
+                wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < A.n_waves) ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gx0, fma2(bc(wk.Dz), gz0, bc(wk.phi))), s, c);
                 // per-row phase step: small unless the wave is undersampled by the grid; MUFU's own range
@@ -752,11 +779,11 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
 #endif
             }
         }
-        if (a.dbg & 1) {
+        if (A.dbg & 1) {
             f2 t = bc(0.f);
 #pragma unroll
             for (int j = 0; j < R; ++j) t = add2(t, add2(px[j], add2(py[j], pz[j])));
-            if (t.x + t.y == 123.456f) a.pos[0] = make_float4(t.x, t.y, 0.f, 0.f);
+            if (t.x + t.y == 123.456f) A.pos[0] = make_float4(t.x, t.y, 0.f, 0.f);
             continue;
         }
         // ---- heightmap detail + bounce, final positions into the ring ----
@@ -772,13 +799,13 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 HmTap tap[HM_BATCH];
 #pragma unroll
                 for (int jj = 0; jj < HM_BATCH; ++jj)
-                    if (j0 + jj < R) tap[jj] = hm_fetch2<HMP2, MODE == 0 && WT_HM_MAGIC_FLOOR>(a, px[j0 + jj], pz[j0 + jj]);
+                    if (j0 + jj < R) tap[jj] = hm_fetch2<HMP2, MODE == 0 && WT_HM_MAGIC_FLOOR>(A, px[j0 + jj], pz[j0 + jj]);
 #pragma unroll
                 for (int jj = 0; jj < HM_BATCH; ++jj) {
                     const int j = j0 + jj;
                     if (j >= R) break;
                     f2 texel_r;
-                    py[j] = hm_finish2(a, tap[jj], py[j], texel_r);
+                    py[j] = hm_finish2(A, tap[jj], py[j], texel_r);
                     float2* const row = ring + slot * RING_COLS;
                     if (VARY) row[3 * RL::PLANE + 1 + lane] = texel_r;
                     row[1 + lane] = px[j];
@@ -840,7 +867,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             f2 nz = fma2(ux, vy, mul2(make_float2(-vx.x, -vx.y), uy));
             const f2 n2 = fma2(nx, nx, fma2(ny, ny, mul2(nz, nz)));
             f2 inv = make_float2(rsq_approx(n2.x), rsq_approx(n2.y));
-            const f2 wx = sub2(bc(a.camx), cx), wy = sub2(bc(a.camy), cy), wz = sub2(bc(a.camz), cz);   // viewVecRaw, :158
+            const f2 wx = sub2(bc(A.camx), cx), wy = sub2(bc(A.camy), cy), wz = sub2(bc(A.camz), cz);   // viewVecRaw, :158
             // :190 — the sign of dot(normal, normalize(viewVecRaw)) is the sign of the unnormalised dot
             const f2 facing = fma2(nx, wx, fma2(ny, wy, mul2(nz, wz)));
             inv.x = facing.x < 0.0f ? -inv.x : inv.x;
@@ -857,15 +884,15 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 // R = reflect(-viewVec, normal) = -viewVec + 2 dot(normal, viewVec) normal   (frag:95)
                 const f2 rx = fma2(nx, f2x, make_float2(-e_x.x, -e_x.y)), ry = fma2(ny, f2x, make_float2(-e_y.x, -e_y.y)),
                          rz = fma2(nz, f2x, make_float2(-e_z.x, -e_z.y));
-                e.skyA = sky_fetch(a, rx.x, ry.x, rz.x);                                          // frag:96
-                e.skyB = sky_fetch(a, rx.y, ry.y, rz.y);
-                f2 sdot = fma2(rx, bc(a.sunx), fma2(ry, bc(a.suny), mul2(rz, bc(a.sunz))));
+                e.skyA = sky_fetch(A, rx.x, ry.x, rz.x);                                          // frag:96
+                e.skyB = sky_fetch(A, rx.y, ry.y, rz.y);
+                f2 sdot = fma2(rx, bc(A.sunx), fma2(ry, bc(A.suny), mul2(rz, bc(A.sunz))));
                 sdot = make_float2(fminf(fmaxf(sdot.x, 0.0f), 1.0f), fminf(fmaxf(sdot.y, 0.0f), 1.0f));
                 // pow(sd, shininess) (frag:100) = 2^(shininess log2 sd): 0^y = 0 for y > 0; 0^0 = 1 is patched below
-                const f2 lg = mul2(make_float2(lg2_approx(sdot.x), lg2_approx(sdot.y)), bc(a.sun_shininess));
+                const f2 lg = mul2(make_float2(lg2_approx(sdot.x), lg2_approx(sdot.y)), bc(A.sun_shininess));
                 f2 sp = make_float2(ex2_approx(lg.x), ex2_approx(lg.y));
-                if (a.sun_shininess == 0.0f) sp = bc(1.0f);
-                e.sp = mul2(sp, bc(a.sun_strength));
+                if (A.sun_shininess == 0.0f) sp = bc(1.0f);
+                e.sp = mul2(sp, bc(A.sun_strength));
                 const f2 om = sub2(bc(1.0f), f);                                                     // frag:110-111
                 const f2 om2 = mul2(om, om);
                 e.fres = fma2(mul2(mul2(om2, om2), om), bc(1.0f - 0.02f), bc(0.02f));
@@ -884,24 +911,24 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 sB = make_float4(skyB.x, skyB.y, skyB.z, e.sp.y);
             }
             // one element offset per row; the stores themselves are the only predicated instructions
-            const size_t o = (size_t)(row - a.row_begin) * a.L + colA;
+            const size_t o = (size_t)(row - A.row_begin) * A.L + colA;
             const bool stA = outA && valid, stB = outB && valid;
             const float4 opA = make_float4(cx.x, cy.x, cz.x, 1.0f), onA = make_float4(e.nx.x, e.ny.x, e.nz.x, e.fres.x);
             const float4 opB = make_float4(cx.y, cy.y, cz.y, 1.0f), onB = make_float4(e.nx.y, e.ny.y, e.nz.y, e.fres.y);
-            float4* const pp = a.pos + o;
-            float4* const pn = a.nrm + o;
+            float4* const pp = A.pos + o;
+            float4* const pn = A.nrm + o;
             if (stA) __stcs(pp, opA);
             if (stB) __stcs(pp + 32, opB);
             if (stA) __stcs(pn, onA);
             if (stB) __stcs(pn + 32, onB);
             if (SHADE) {
-                float4* const ps = a.shade + o;
+                float4* const ps = A.shade + o;
                 if (stA) __stcs(ps, sA);
                 if (stB) __stcs(ps + 32, sB);
             }
             if (VARY) {
                 // gl_Position = viewProjection * position (:150); the same with y = 0, .xy / .w (:153-154)
-                const float* const m = a.vp;
+                const float* const m = A.vp;
                 f2 cl[4], c0[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -911,16 +938,16 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 const f2 iw = make_float2(__fdividef(1.0f, c0[3].x), __fdividef(1.0f, c0[3].y));
                 const f2 ndx = mul2(c0[0], iw), ndy = mul2(c0[1], iw);
                 // normalVecInViewSpaceOnlyYaw = normalize((viewMatOnlyYaw * vec4(normal, 0)).xyz) (:193)
-                const float* const y = a.vy;
+                const float* const y = A.vy;
                 f2 yn[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) yn[r] = fma2(bc(y[6 + r]), e.nz, fma2(bc(y[3 + r]), e.ny, mul2(bc(y[r]), e.nx)));
                 const f2 y2 = fma2(yn[0], yn[0], fma2(yn[1], yn[1], mul2(yn[2], yn[2])));
                 const f2 yi = make_float2(rsq_approx(y2.x), rsq_approx(y2.y));
                 const f2 hr = rc[3 * RL::PLANE + 1];
-                float4* const pc = a.clip + o;
-                float4* const pa = a.vary_a + o;
-                float4* const pb = a.vary_b + o;
+                float4* const pc = A.clip + o;
+                float4* const pa = A.vary_a + o;
+                float4* const pb = A.vary_b + o;
                 if (stA) __stcs(pc, make_float4(cl[0].x, cl[1].x, cl[2].x, cl[3].x));
                 if (stB) __stcs(pc + 32, make_float4(cl[0].y, cl[1].y, cl[2].y, cl[3].y));
                 if (stA) __stcs(pa, make_float4(ndx.x, ndy.x, hr.x, 0.0f));
@@ -946,6 +973,22 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
     }
     // every row of [r0, r1) was stored exactly once for each of this lane's in-range columns
     if (CKS) acc.count += (unsigned long long)max(r1 - r0, 0) * ((outA ? 1 : 0) + (outB ? 1 : 0));
+    if (BATCH && CKS) {
+        // one digest per FRAME: the frame's own record (armed by the launcher) takes this item's sums; the item that completes the
+        // frame decodes the record in place
+        acc.flush(A.cks);
+        acc = ChecksumAcc();
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(a.batch_done + cur_frame, 1) == a.items_per_frame - 1) {
+                __threadfence();
+                wt_checksum* const r = A.cks;
+                const float lo = key_float(atomicAdd((unsigned*)&r->min_y, 0u)), hi = key_float(atomicAdd((unsigned*)&r->max_y, 0u));
+                r->min_y = lo; r->max_y = hi;
+                a.batch_done[cur_frame] = 0;
+            }
+        }
+    }
     if (a.trace && lane == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -960,7 +1003,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         // the last warp to run dry re-arms the queue for the next launch that uses it
         if (atomicAdd(a.queue + 1, 1) == (int)gridDim.x - 1) { a.queue[1] = 0; __threadfence(); a.queue[0] = 0; }
     }
-    if (CKS) {
+    if (CKS && !BATCH) {
         acc.flush(a.cks_acc);
         if (lane == 0) {
             __threadfence();

@@ -92,6 +92,79 @@ cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab,
 }
 
 
+// Several SMALL frames in ONE persistent launch (wt_eval_batch / wt_run_animation; <= 64 waves, no shading terms, no extra
+// varyings): the work items of all frames go through one queue, so the SMs stay busy across frame boundaries and the host
+// pays one launch per group instead of one per frame.  Per-frame arguments (corners, time offsets, outputs, digest record)
+// travel through a stream-ordered device allocation; every warp keeps the current frame's copy in shared memory.
+// The frames of a group must write different ring slots (the caller groups them so) and share grid_len / row range.
+template <int MODE, bool CKS, bool HMP2>
+cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std::vector<WaveK>& tab, cudaStream_t stream) {
+    constexpr int CAP = 64;
+    constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
+    auto kernel = surface_warp_kernel<CAP, R, MODE, false, CKS, HMP2, false, true>;
+    const int F = (int)fa.size();
+    const int smem = WARPS_PER_CTA * RingLayout<R, false>::BYTES_PER_WARP + (int)sizeof(EvalArgs) + CAP * (int)sizeof(float);
+    static thread_local struct { int dev = -1, slots = 0; } cache;
+    if (cache.dev != ctx->device) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * WARPS_PER_CTA, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache.slots = ctx->sm_count * per_sm * WARPS_PER_CTA;
+        cache.dev = ctx->device;
+    }
+    EvalArgs& a0 = fa[0];
+    layout_segments(canonical_layout(a0.L, R, MODE), a0.L, a0.row_begin, a0.row_end, a0);
+    std::vector<float> phi((size_t)F * CAP, 0.0f);
+    for (int f = 0; f < F; ++f) {
+        EvalArgs& a = fa[f];
+        a.n_strips = a0.n_strips; a.n_seg = a0.n_seg; a.n_items = a0.n_items;
+        std::memcpy(a.seg_prefix, a0.seg_prefix, sizeof(a.seg_prefix));
+        std::memcpy(a.seg_row0, a0.seg_row0, sizeof(a.seg_row0));
+        std::memcpy(a.seg_rows, a0.seg_rows, sizeof(a.seg_rows));
+        std::memcpy(a.seg_end, a0.seg_end, sizeof(a.seg_end));
+        a.queue = nullptr; a.trace = nullptr; a.dbg = 0;
+        for (size_t i = 0; i < tab.size(); ++i) {
+            const float c = tab[i].phi * a.t;   // fl(phi * t), water-grid.vert:78
+            phi[(size_t)f * CAP + i] = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
+        }
+    }
+    // one stream-ordered allocation: [F x EvalArgs][F x CAP phase offsets][F finished-item counters]
+    const size_t b_args = (size_t)F * sizeof(EvalArgs), b_phi = phi.size() * sizeof(float), b_done = (size_t)F * sizeof(int);
+    char* blob = nullptr;
+    cudaError_t e = cudaMallocAsync(&blob, b_args + b_phi + b_done, stream);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(blob, fa.data(), b_args, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(blob + b_args, phi.data(), b_phi, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(blob + b_args + b_phi, 0, b_done, stream)) != cudaSuccess) return e;
+    EvalArgs top = a0;
+    top.batch = reinterpret_cast<const EvalArgs*>(blob);
+    top.batch_phi = reinterpret_cast<const float*>(blob + b_args);
+    top.batch_done = reinterpret_cast<int*>(blob + b_args + b_phi);
+    top.items_per_frame = a0.n_items;
+    top.n_items = a0.n_items * F;
+    int ctas = top.n_items;
+    top.queue = nullptr;
+    if ((long long)top.n_items >= 2LL * cache.slots) {
+        ctas = cache.slots;
+        top.queue = ctx->d_queues + 2 * (ctx->queue_next++ % N_QUEUES);
+    }
+    static thread_local WaveTable<CAP> table;
+    fill_table(table, tab);
+    kernel<<<ctas, 32 * WARPS_PER_CTA, smem, stream>>>(top, table);
+    ctx->launches++;
+    e = cudaGetLastError();
+    cudaFreeAsync(blob, stream);
+    return e;
+}
+
+template <int MODE>
+cudaError_t launch_production_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, cudaStream_t stream) {
+    const std::vector<WaveK>& tab = MODE == 1 ? ctx->tab_fast : ctx->tab_exact;
+    const bool cks = fa[0].cks != nullptr, p2 = fa[0].hm_pow2 != 0;
+    if (cks) return p2 ? launch_warp_batch<MODE, true, true>(ctx, fa, tab, stream) : launch_warp_batch<MODE, true, false>(ctx, fa, tab, stream);
+    return p2 ? launch_warp_batch<MODE, false, true>(ctx, fa, tab, stream) : launch_warp_batch<MODE, false, false>(ctx, fa, tab, stream);
+}
+
 // One (MODE, SHADE) slice of the dispatch: wave-table capacity tier, checksum, heightmap wrap.
 template <int MODE, bool SHADE>
 cudaError_t launch_production(wt_ctx* ctx, EvalArgs& a, cudaStream_t stream) {
