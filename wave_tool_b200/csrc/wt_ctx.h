@@ -58,6 +58,8 @@ struct wt_ctx {
     // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
     int* d_queues = nullptr;
     unsigned queue_next = 0;
+    int* d_batch_done = nullptr;    // grouped launches: per group BATCH_MAX_FRAMES finished-item counters (self re-arming)
+    unsigned batch_next = 0;
     // small frames: internal streams on which consecutive frames of a batch overlap (created on first use)
     cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -353,7 +353,9 @@ int wt_create(wt_ctx** out, int device) {
         checksum_init_kernel<<<(N_QUEUES + 127) / 128, 128>>>(ctx->d_cks_acc, (int)N_QUEUES);   // armed: zero sums, min/max keys at their identities
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
         if ((e = cudaMalloc(&ctx->d_queues, 2 * N_QUEUES * sizeof(int))) != cudaSuccess) return e;
-        return cudaMemset(ctx->d_queues, 0, 2 * N_QUEUES * sizeof(int));
+        if ((e = cudaMemset(ctx->d_queues, 0, 2 * N_QUEUES * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&ctx->d_batch_done, BATCH_MAX_FRAMES * N_QUEUES * sizeof(int))) != cudaSuccess) return e;
+        return cudaMemset(ctx->d_batch_done, 0, BATCH_MAX_FRAMES * N_QUEUES * sizeof(int));
     };
     const cudaError_t e = init();
     if (e != cudaSuccess) {
@@ -375,7 +377,7 @@ void wt_destroy(wt_ctx* ctx) {
     if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
     if (ctx->sky_array_black) cudaFreeArray(ctx->sky_array_black);
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
-    cudaFree(ctx->d_queues); cudaFree(ctx->d_trace);
+    cudaFree(ctx->d_queues); cudaFree(ctx->d_trace); cudaFree(ctx->d_batch_done);
     cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done); cudaFree(ctx->d_step_cks);
     cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
     cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds); cudaFree(ctx->d_sky_unsure);
@@ -635,7 +637,7 @@ struct FrameBatcher {
             if ((e = flush()) != cudaSuccess) return e;
             return launch_frame(ctx, a, rflags, enabled ? stream : other_stream);
         }
-        if (!group.empty() && (group.size() >= ring_depth || ((rflags ^ group_flags) & WT_FLAG_FAST_PHASE) || (group[0].cks && a.cks != group[0].cks + group.size())))
+        if (!group.empty() && (group.size() >= ring_depth || group.size() >= (size_t)BATCH_MAX_FRAMES || ((rflags ^ group_flags) & WT_FLAG_FAST_PHASE) || (group[0].cks && a.cks != group[0].cks + group.size())))
             if ((e = flush()) != cudaSuccess) return e;
         group.push_back(a);
         group_flags = rflags;

@@ -55,6 +55,9 @@ struct WaveTable {
     WaveK w[CAP + PAD];
 };
 
+struct EvalArgs;
+constexpr int BATCH_MAX_FRAMES = 8;   // frames per grouped launch: 8 x (680 + 256) bytes of kernel parameters
+struct NoBatch { int unused; };
 constexpr int STRIP_COLS = 62;   // output columns per warp: 64 held columns minus the two halo columns
 
 struct EvalArgs {
@@ -111,14 +114,29 @@ struct EvalArgs {
     int* queue;
     int n_items;
     // batched launch (BATCH instantiations: several small frames in ONE persistent launch): item = frame * items_per_frame + the
-    // frame's own work item; the frame's EvalArgs (corners, time, outputs, digest record ...) and its per-wave phase offsets are
-    // read from device memory into shared memory when a warp moves on to another frame
-    const EvalArgs* batch;
-    const float* batch_phi;      // [frame * CAP + wave]: fl(phi t) of the frame (reduced mod 2 pi for the recurrence kernel)
-    int* batch_done;             // per frame: finished work items (the last one decodes the frame's digest record)
+    // frame's own work item; the frames' own EvalArgs and phase offsets travel in a third kernel parameter (BatchTable)
+    int* batch_done;             // per frame of the group: finished work items (the last one decodes the frame's digest record and re-arms the counter)
     int items_per_frame;
     unsigned long long* trace;   // experiment knob (WT_TRACE): per work item {smid, item, t_start, t_end} in globaltimer ns
 };
+
+// the per-frame arguments of a grouped launch, passed by value as a kernel parameter (constant bank, indexed by the frame)
+struct BatchTable {
+    EvalArgs fa[BATCH_MAX_FRAMES];
+    float phi[BATCH_MAX_FRAMES][64];   // fl(phi t) per wave (reduced mod 2 pi for the recurrence kernel)
+};
+template <bool BATCH> struct BatchParam { typedef NoBatch type; };
+template <> struct BatchParam<true> { typedef BatchTable type; };
+template <bool BATCH, class BT>
+__device__ __forceinline__ const EvalArgs& frame_args(const EvalArgs& a, const BT& bt, int frame) {
+    if constexpr (BATCH) return bt.fa[frame];
+    else return a;
+}
+template <bool BATCH, class BT>
+__device__ __forceinline__ float frame_phi(const BT& bt, int frame, int wave, float dflt) {
+    if constexpr (BATCH) return bt.phi[frame][wave];
+    else return dflt;
+}
 
 // ------------------------------------------------------------------------------------------------
 // small helpers
@@ -580,15 +598,11 @@ struct RingLayout {
 
 template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY, bool BATCH = false>
 __global__ void __launch_bounds__(32, MODE == 1 ? (R > 8 ? WT_LB_RECUR_BIG : WT_LB_RECUR) : WT_LB_EXACT)
-surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
+surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt, const __grid_constant__ typename BatchParam<BATCH>::type bt) {
     extern __shared__ float2 ring_all[];
     using RL = RingLayout<R, VARY>;
     const int lane = threadIdx.x;
     float2* const ring = ring_all;
-    // BATCH: behind the ring, this warp's copy of the current frame's arguments and phase offsets
-    EvalArgs* const sA = reinterpret_cast<EvalArgs*>(ring_all + RL::PLANES * RL::PLANE);
-    float* const sphi = reinterpret_cast<float*>(sA + 1);
-    int cur_frame = -1;
     const bool dyn = a.queue != nullptr;
     int item = blockIdx.x;
     if (dyn) item = next_item(a.queue, lane);
@@ -596,19 +610,12 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
   while (item < a.n_items) {
     unsigned long long t_start = 0;
     if (a.trace) t_start = global_ns();
-    int fitem = item;
+    int fitem = item, cur_frame = 0;
     if (BATCH) {
-        const int frame = item / a.items_per_frame;
-        fitem = item - frame * a.items_per_frame;
-        if (frame != cur_frame) {
-            const unsigned* const src = reinterpret_cast<const unsigned*>(a.batch + frame);
-            for (int w = lane; w < (int)(sizeof(EvalArgs) / sizeof(unsigned)); w += 32) reinterpret_cast<unsigned*>(sA)[w] = __ldg(src + w);
-            for (int w = lane; w < a.n_waves; w += 32) sphi[w] = __ldg(a.batch_phi + (size_t)frame * CAP + w);
-            __syncwarp();
-            cur_frame = frame;
-        }
+        cur_frame = item / a.items_per_frame;
+        fitem = item - cur_frame * a.items_per_frame;
     }
-    const EvalArgs& A = BATCH ? *sA : a;
+    const EvalArgs& A = frame_args<BATCH>(a, bt, cur_frame);
     const int strip = fitem % A.n_strips, chunk = fitem / A.n_strips;
     const int strip0 = strip * STRIP_COLS;
     int seg = 0;
@@ -656,7 +663,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             WT_UNROLL(WT_WAVE_UNROLL_EXACT)
             for (int i = 0; i < A.n_waves; ++i) {
                 WaveK wk = wt.w[i];   // phi holds fl(phaseConstant_phi * t) for this launch
-                if (BATCH) wk.phi = sphi[i];
+                wk.phi = frame_phi<BATCH>(bt, cur_frame, i, wk.phi);
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     // frequency_w * dot(D, xz) + phi * t, every operation rounded as GLSL/GLM does
@@ -687,7 +694,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             WT_UNROLL(WT_WAVE_UNROLL)
             for (int i = 0; i < A.n_waves; ++i) {
                 WaveK wk = wk_next;
-                if (BATCH) wk.phi = sphi[i];
+                wk.phi = frame_phi<BATCH>(bt, cur_frame, i, wk.phi);
                 wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < A.n_waves) ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gxc, fma2(bc(wk.Dz), gzc, bc(wk.phi))), s, c);
@@ -731,7 +738,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             for (int i = 0; i < A.n_waves; ++i) {
                 // the next wave's constants are fetched from the constant bank one trip ahead
                 WaveK wk = wk_next;
-                if (BATCH) wk.phi = sphi[i];
+                wk.phi = frame_phi<BATCH>(bt, cur_frame, i, wk.phi);
                 wk_next = wt.w[(WaveTable<CAP>::PAD || i + 1 < A.n_waves) ? i + 1 : i];
                 f2 s, c;
                 sincos2(fma2(bc(wk.Dx), gx0, fma2(bc(wk.Dz), gz0, bc(wk.phi))), s, c);

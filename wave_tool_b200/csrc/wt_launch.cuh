@@ -70,7 +70,7 @@ cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>&
         a.cks_acc = ctx->d_cks_acc + slot;
         a.cks_done = ctx->d_cks_done + slot;
     }
-    kernel<<<ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table);
+    kernel<<<ctas, 32 * WARPS_PER_CTA, smem, stream>>>(a, table, NoBatch{0});
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -94,8 +94,8 @@ cudaError_t launch_warp(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab,
 
 // Several SMALL frames in ONE persistent launch (wt_eval_batch / wt_run_animation; <= 64 waves, no shading terms, no extra
 // varyings): the work items of all frames go through one queue, so the SMs stay busy across frame boundaries and the host
-// pays one launch per group instead of one per frame.  Per-frame arguments (corners, time offsets, outputs, digest record)
-// travel through a stream-ordered device allocation; every warp keeps the current frame's copy in shared memory.
+// pays one launch per group instead of one per frame.  The frames' own arguments (corners, time offsets, outputs, digest
+// record) travel as a third kernel parameter (BatchTable, constant bank, indexed by the frame of the work item).
 // The frames of a group must write different ring slots (the caller groups them so) and share grid_len / row range.
 template <int MODE, bool CKS, bool HMP2>
 cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std::vector<WaveK>& tab, cudaStream_t stream) {
@@ -103,7 +103,8 @@ cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std:
     constexpr int R = MODE == 1 ? R_RECUR : R_EXACT;
     auto kernel = surface_warp_kernel<CAP, R, MODE, false, CKS, HMP2, false, true>;
     const int F = (int)fa.size();
-    const int smem = WARPS_PER_CTA * RingLayout<R, false>::BYTES_PER_WARP + (int)sizeof(EvalArgs) + CAP * (int)sizeof(float);
+    if (F < 1 || F > BATCH_MAX_FRAMES) return cudaErrorInvalidValue;
+    const int smem = WARPS_PER_CTA * RingLayout<R, false>::BYTES_PER_WARP;
     static thread_local struct { int dev = -1, slots = 0; } cache;
     if (cache.dev != ctx->device) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -114,7 +115,7 @@ cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std:
     }
     EvalArgs& a0 = fa[0];
     layout_segments(canonical_layout(a0.L, R, MODE), a0.L, a0.row_begin, a0.row_end, a0);
-    std::vector<float> phi((size_t)F * CAP, 0.0f);
+    static thread_local BatchTable bt;
     for (int f = 0; f < F; ++f) {
         EvalArgs& a = fa[f];
         a.n_strips = a0.n_strips; a.n_seg = a0.n_seg; a.n_items = a0.n_items;
@@ -123,23 +124,14 @@ cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std:
         std::memcpy(a.seg_rows, a0.seg_rows, sizeof(a.seg_rows));
         std::memcpy(a.seg_end, a0.seg_end, sizeof(a.seg_end));
         a.queue = nullptr; a.trace = nullptr; a.dbg = 0;
+        bt.fa[f] = a;
         for (size_t i = 0; i < tab.size(); ++i) {
             const float c = tab[i].phi * a.t;   // fl(phi * t), water-grid.vert:78
-            phi[(size_t)f * CAP + i] = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
+            bt.phi[f][i] = MODE == 1 ? (float)std::remainder((double)c, 6.283185307179586476925) : c;
         }
     }
-    // one stream-ordered allocation: [F x EvalArgs][F x CAP phase offsets][F finished-item counters]
-    const size_t b_args = (size_t)F * sizeof(EvalArgs), b_phi = phi.size() * sizeof(float), b_done = (size_t)F * sizeof(int);
-    char* blob = nullptr;
-    cudaError_t e = cudaMallocAsync(&blob, b_args + b_phi + b_done, stream);
-    if (e != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(blob, fa.data(), b_args, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(blob + b_args, phi.data(), b_phi, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(blob + b_args + b_phi, 0, b_done, stream)) != cudaSuccess) return e;
     EvalArgs top = a0;
-    top.batch = reinterpret_cast<const EvalArgs*>(blob);
-    top.batch_phi = reinterpret_cast<const float*>(blob + b_args);
-    top.batch_done = reinterpret_cast<int*>(blob + b_args + b_phi);
+    top.batch_done = ctx->d_batch_done + BATCH_MAX_FRAMES * (ctx->batch_next++ % N_QUEUES);   // self re-arming, like the work queues
     top.items_per_frame = a0.n_items;
     top.n_items = a0.n_items * F;
     int ctas = top.n_items;
@@ -150,11 +142,9 @@ cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std:
     }
     static thread_local WaveTable<CAP> table;
     fill_table(table, tab);
-    kernel<<<ctas, 32 * WARPS_PER_CTA, smem, stream>>>(top, table);
+    kernel<<<ctas, 32 * WARPS_PER_CTA, smem, stream>>>(top, table, bt);
     ctx->launches++;
-    e = cudaGetLastError();
-    cudaFreeAsync(blob, stream);
-    return e;
+    return cudaGetLastError();
 }
 
 template <int MODE>
