@@ -38,9 +38,7 @@ Plan make_plan(int slots, int L, int rows, int R) {
     Plan best;
     double best_cost = 1e300;
     const int n_strips = (L + STRIP_COLS - 1) / STRIP_COLS;
-    for (int rounds = 1; rounds <= 6; ++rounds) {
-        long long want = std::max<long long>(1, (long long)rounds * slots / n_strips);
-        int rpc = (int)((rows + want - 1) / want);
+    auto consider = [&](int rpc) {
         rpc = ((rpc + 2 + R - 1) / R) * R - 2;   // rpc + 2 a multiple of R: no marching step is partly wasted
         if (rpc < 1) rpc = R - 2 > 0 ? R - 2 : 1;
         const int n_chunks = (rows + rpc - 1) / rpc;
@@ -52,7 +50,14 @@ Plan make_plan(int slots, int L, int rows, int R) {
             best.n_strips = n_strips; best.rows_per_chunk = rpc; best.n_chunks = n_chunks;
             best.ctas = (int)((items + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
         }
+    };
+    for (int rounds = 1; rounds <= 6; ++rounds) {
+        const long long want = std::max<long long>(1, (long long)rounds * slots / n_strips);
+        consider((int)((rows + want - 1) / want));
     }
+    // ... and chunks that do not fill the machine once but pay the 2 halo rows less often (a 1024^2 grid: 14-row items in one
+    // round instead of 6-row items in two — the same time for a single frame, a quarter less work in a grouped launch)
+    for (int steps = 2; steps <= 4; ++steps) consider(steps * R - 2);
     return best;
 }
 
