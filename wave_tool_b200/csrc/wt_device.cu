@@ -76,6 +76,18 @@ Layout canonical_layout(int L, int R, int mode) {
     if (big > 0) {
         lay.rows_big = round_rows(big);
         lay.rows_small = (small > 0 && small < big && tail > 0) ? round_rows(small) : 0;
+        if (!lay.rows_small && !forced) {
+            // One level of equal items (the bit-faithful kernel): the launch takes ceil(items / resident warps) rounds of one item
+            // each, an item costs its rows + the 2 halo rows — pick the item height that minimises the product (measured at 4096^2,
+            // profiles/README.md: 26 rows 0.685 ms = 3 rounds of 28, 30 rows 0.697 = 3 x 32, 38 rows 0.740 = 3 x 40, 42 rows 0.697 = 2 x 44)
+            long long best = -1;
+            for (int m = 4; m <= 24; ++m) {
+                const int r = m * R - 2;
+                const long long items = (long long)lay.n_strips * ((L + r - 1) / r);
+                const long long cost = ((items + slots - 1) / slots) * (r + 2);
+                if (items >= 2LL * slots && (best < 0 || cost < best)) { best = cost; lay.rows_big = r; }
+            }
+        }
         lay.tail_pct = lay.rows_small ? tail : 0;
         // bands only matter for a two-level layout (they give every row shard of a box its own share of small items); a single
         // level of equal items is balanced as it is, and measured 2 % faster in one band (profiles/README.md)

@@ -399,7 +399,7 @@ __device__ __forceinline__ HmTap hm_fetch2(const EvalArgs& a, f2 px, f2 pz) {
     f2 vm = sub2x(mul2(t, bc((float)a.hm_h)), bc(0.5f), one);
     f2 fu, fv;
     int4 ij;
-    if (MAGIC_FLOOR && a.hm_magic_floor) {
+    if (MAGIC_FLOOR && (WT_HM_MAGIC_FLOOR == 2 || a.hm_magic_floor)) {   // (2: experiment, no fallback compiled in)
         // floor() and the float -> int conversion without the XU pipe (FRND and F2I issue at a quarter of the FP32 rate, and
         // the bit-faithful kernel is bound by that pipe): for |x| < 2^22 the sum x + 1.5 * 2^23 is a positive number with a
         // unit in the last place of 1, so adding with round-toward-zero floors x exactly; the integer sits in the mantissa.
