@@ -28,6 +28,9 @@ struct SkyArgs {
     float inv_one_minus_omp;     // 1 / (1 - omp) for the approximate path
     unsigned long long* unsure_count;   // diagnostic (may be NULL): layers that were redone on the exact path
     int fast;                    // 1: approximate path with guard bands + exact fallback per texel; 0: exact path only (WT_SKY_EXACT build / debugging)
+    cudaSurfaceObject_t atlas;   // the padded gather atlas the surface kernel samples: written by the same kernel (0: not written)
+    int fog_identity;            // fog alpha == 0: the fog quad leaves every byte as it is
+    unsigned fog_lut[256];       // the fog quad's blend per destination byte d: byte c of entry d = the byte channel c holds afterwards
 };
 
 __device__ __forceinline__ float mixs(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
@@ -75,35 +78,55 @@ __device__ __forceinline__ void blend(float dst[4], float r, float g, float b, f
     // (a shortcut, not a discontinuity: blending with As = 0 leaves the same bytes — so an approximate As near 0 needs no guard)
     if (src[3] == 0.0f && (!FAST || err_a == 0.0f)) return;
     const float oma = __fsub_rn(1.0f, src[3]);
+    const bool opaque = src[3] == 1.0f && (!FAST || err_a == 0.0f);   // Cs * 1 + Cd * 0 == Cs exactly (Cd is finite): the destination is not read
+    float edge = 0.0f;                     // FAST: the largest distance of a guarded channel from the integer it rounds to
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float d = unorm8f(dst[c]);   // what the blender reads back from the RGBA8 attachment: c / 255
-        const float v = sat(__fadd_rn(__fmul_rn(src[c], src[3]), __fmul_rn(d, oma)));
-        const float t = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
-        int unused;
-        const float q = floor_small(t, unused);
-        if (FAST) {
-            // d(out)/d(src_c) = As <= 1, d(out)/d(As) = src_c - d in [-1, 1] (the alpha channel: 2 As - d in [-1, 2]); 255 byte units
-            // per unit, plus the roundings of the blend itself (a few ulp of a value <= 1, 1e-4 byte units is ample)
-            const float e = 255.0f * (c < 3 ? err_rgb + err_a : 2.0f * err_a) + 1e-4f;
-            const float fr = __fsub_rn(t, q);
-            unsure = unsure || ((err_rgb != 0.0f || err_a != 0.0f) && (fr < e || fr > 1.0f - e));
+        float v;
+        if (opaque) {
+            v = src[c];
+        } else {
+            const float d = unorm8f(dst[c]);   // what the blender reads back from the RGBA8 attachment: c / 255
+            // in [0, 1 + 2^-23]: the conversion's clamp to [0,1] cannot change the byte (255 (1 + 2^-23) + 1/2 still floors to 255)
+            v = __fadd_rn(__fmul_rn(src[c], src[3]), __fmul_rn(d, oma));
         }
+        const float s = __fmul_rn(v, 255.0f);
+        int unused;
+        const float q = floor_small(__fadd_rn(s, 0.5f), unused);
+        // the alpha channel depends on As alone: exact, and left out of the guard, when As is
+        if (FAST && (c < 3 || err_a != 0.0f)) edge = fmaxf(edge, fabsf(__fsub_rn(s, q)));
         dst[c] = q;
+    }
+    if (FAST) {
+        // q = round-half-up(s): a different byte needs s to move across q +- 1/2.  d(out)/d(src_c) = As <= 1, d(out)/d(As) =
+        // src_c - d in [-1, 1] (the alpha channel: 2 As - d in [-1, 2]); 255 byte units per unit, plus the roundings of the blend
+        // itself (a few ulp of a value <= 1 and of s + 1/2: 1e-4 byte units is ample)
+        const float e = 255.0f * fmaxf(err_rgb + err_a, 2.0f * err_a) + 1e-4f;
+        unsure = unsure || ((err_rgb != 0.0f || err_a != 0.0f) && edge > 0.5f - e);
     }
 }
 
-// All layers of one texel (direction d) into dst (integer-valued floats 0..255).
+// texture(samplerCube, d) for the direction through the centre of texel k of a cubemap of the SAME power-of-two size as the
+// target (the reference's own configuration: 2048^2 star / cloud assets, CUBEMAP_LENGTH 2048 — program.cpp:616,656,
+// render-engine.h:191): face selection returns the target's face (the major component is exactly +-1, the others are
+// smaller), s n - 1/2 is exactly the texel's own index, so the bilinear weights are (1, 0, 0, 0) and 1 v + 0 + 0 + 0 == v.
+__device__ __forceinline__ float4 cube_rgba8_aligned(const uchar4* faces, size_t k) {
+    const unsigned t = __ldg(reinterpret_cast<const unsigned*>(faces) + k);
+    return make_float4(unorm8f(byte_f(t, 0)), unorm8f(byte_f(t, 1)), unorm8f(byte_f(t, 2)), 1.0f);
+}
+
+// All layers of one texel (direction d) into dst (integer-valued floats 0..255), the fog quad excepted (fog_layer below).
 // The two pow() of the sky shaders are first evaluated with MUFU lg2 / ex2 and the division by (1 - omp) as a multiplication
 // by its reciprocal; the blend carries bounds on the error this introduces and tells when a comparison or a byte conversion
 // could come out differently.  Only then the layer is redone exactly (libdevice powf, IEEE division) from the bytes the
 // previous layers left — every layer starts from exact bytes, so the fallback is local to the layer.  With a.fast == 0 the
 // exact forms are used throughout.
-__device__ __forceinline__ void sky_texel(const SkyArgs& a, float dx, float dy, float dz, float dst[4], unsigned& n_exact) {
+template <bool ALIGNED>
+__device__ __forceinline__ void sky_texel(const SkyArgs& a, size_t k, float dx, float dy, float dz, float dst[4], unsigned& n_exact) {
     dst[0] = dst[1] = dst[2] = dst[3] = 255.0f;                          // glClearColor(1,1,1,1), render-engine.cpp:694,330
     bool unused = false;
     if (a.stars) {                                                       // skybox-stars.frag:41
-        const float4 s = cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
+        const float4 s = ALIGNED ? cube_rgba8_aligned(a.stars, k) : cube_rgba8(a.stars, a.stars_n, dx, dy, dz);
         blend<false>(dst, s.x, s.y, s.z, 1.0f, 0.0f, 0.0f, unused);
     }
     if (a.draw_sphere) {                                                 // skysphere.frag:48-76
@@ -140,7 +163,7 @@ __device__ __forceinline__ void sky_texel(const SkyArgs& a, float dx, float dy, 
         }
     }
     if (a.clouds) {                                                      // skybox-clouds.frag:46-67
-        const float4 raw = cube_rgba8(a.clouds, a.clouds_n, dx, dy, dz);
+        const float4 raw = ALIGNED ? cube_rgba8_aligned(a.clouds, k) : cube_rgba8(a.clouds, a.clouds_n, dx, dy, dz);
         const float lin = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, raw.x), __fmul_rn(0.7152f, raw.y)), __fmul_rn(0.0722f, raw.z));
         const float intensity = fminf(fmaxf(a.sun_y, 0.2f), 1.0f);
         const float oc = __fmul_rn(sat(a.sun_y), a.overcast);
@@ -184,7 +207,14 @@ __device__ __forceinline__ void sky_texel(const SkyArgs& a, float dx, float dy, 
             layer(__fsub_rn(__fmul_rn(1.055f, powf(lin, a.inv_gamma)), 0.055f), 0.0f, false, unused);
         }
     }
-    blend<false>(dst, a.fog[0], a.fog[1], a.fog[2], a.fog[3], 0.0f, 0.0f, unused);   // screen-space-quad.frag:45
+}
+
+// The fog quad (screen-space-quad.frag:45) blends a per-frame constant colour and alpha over the attachment: its result is a
+// function of the destination byte alone, tabulated once per frame by the host (fog_table below, same operations as blend()).
+// Returns the packed texel.
+__device__ __forceinline__ unsigned fog_layer(const unsigned* lut, unsigned rgba) {
+    const unsigned r = lut[rgba & 255u], g = lut[(rgba >> 8) & 255u], b = lut[(rgba >> 16) & 255u], al = lut[rgba >> 24];
+    return __byte_perm(__byte_perm(r, g, 0x0050), __byte_perm(b, al, 0x0072), 0x5410);
 }
 
 // pack the four integer-valued floats (0..255) into RGBA8: 2^23 + c has c in its low mantissa byte
@@ -194,12 +224,18 @@ __device__ __forceinline__ unsigned pack_rgba8(const float dst[4]) {
     return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
 }
 
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256) sky_synth_kernel(const __grid_constant__ SkyArgs a) {
     // grid = (ceil(n / 256), n, 6): the face and the row come from the block index (no integer divisions, and the face
     // switch below is uniform per block)
     const int face = blockIdx.z, j = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned lut[256];
+    if (!a.fog_identity) {
+        lut[threadIdx.x] = a.fog_lut[threadIdx.x];
+        __syncthreads();
+    }
     if (i < a.n) {
-        const size_t k = ((size_t)face * a.n + j) * a.n + i;
+        const unsigned k = ((unsigned)face * a.n + j) * a.n + i;     // 6 n^2 <= 6 * 2^28 for n <= 16384
         // direction through the centre of texel (i, j) of the face (inverse of the GL cube-map face table)
         // (2 (i + 1/2)) / n - 1; for a power-of-two n the division is a multiplication by the exact reciprocal
         const float ni = __fmul_rn(2.0f, __fadd_rn((float)i, 0.5f)), nj = __fmul_rn(2.0f, __fadd_rn((float)j, 0.5f));
@@ -216,10 +252,24 @@ __global__ void __launch_bounds__(256) sky_synth_kernel(const __grid_constant__ 
         }
         float dst[4];
         unsigned n_exact = 0;
-        sky_texel(a, dx, dy, dz, dst, n_exact);
-        const unsigned rgba = pack_rgba8(dst);
+        sky_texel<ALIGNED>(a, k, dx, dy, dz, dst, n_exact);
+        unsigned rgba = pack_rgba8(dst);
+        if (!a.fog_identity) rgba = fog_layer(lut, rgba);
         if (a.unsure_count && n_exact) atomicAdd(a.unsure_count, (unsigned long long)n_exact);
         reinterpret_cast<unsigned*>(a.out)[k] = rgba;
+        if (a.atlas) {
+            // the gather atlas: tile column = face / 2, tile row = face % 2, 1-texel border replicating the edge
+            const int tile = a.n + 2, x0 = (face / 2) * tile, y0 = (face % 2) * tile;
+            const uchar4 v = make_uchar4(rgba & 255u, (rgba >> 8) & 255u, (rgba >> 16) & 255u, rgba >> 24);
+            auto put_row = [&](int y) {
+                surf2Dwrite(v, a.atlas, (x0 + i + 1) * 4, y);
+                if (i == 0) surf2Dwrite(v, a.atlas, x0 * 4, y);
+                if (i == a.n - 1) surf2Dwrite(v, a.atlas, (x0 + a.n + 1) * 4, y);
+            };
+            put_row(y0 + j + 1);
+            if (j == 0) put_row(y0);                                                    // uniform per block (j = blockIdx.y)
+            if (j == a.n - 1) put_row(y0 + a.n + 1);
+        }
     }
 }
 
@@ -234,10 +284,11 @@ __global__ void __launch_bounds__(256) sky_atlas_kernel(const uchar4* faces, int
     }
 }
 
-cudaError_t rebuild_sky_atlas(wt_ctx* ctx, const uchar4* d_faces, int n, cudaArray_t* arr, cudaTextureObject_t* tex, bool allocate, cudaStream_t stream) {
+// (re)allocates the atlas array, its texture object and the surface object the kernels write it through
+static cudaError_t allocate_sky_atlas(wt_ctx* ctx, int n, cudaArray_t* arr, cudaTextureObject_t* tex) {
     cudaError_t e;
     const int tile = n + 2, W = 3 * tile, H = 2 * tile;
-    if (allocate) {
+    {
         if (*tex) { cudaDestroyTextureObject(*tex); *tex = 0; }
         if (*arr) { cudaFreeArray(*arr); *arr = nullptr; }
         cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
@@ -256,6 +307,13 @@ cudaError_t rebuild_sky_atlas(wt_ctx* ctx, const uchar4* d_faces, int n, cudaArr
         if (ctx->sky_surf) { cudaDestroySurfaceObject(ctx->sky_surf); ctx->sky_surf = 0; }
         if ((e = cudaCreateSurfaceObject(&ctx->sky_surf, &res)) != cudaSuccess) return e;   // kept for the life of the array
     }
+    return cudaSuccess;
+}
+
+cudaError_t rebuild_sky_atlas(wt_ctx* ctx, const uchar4* d_faces, int n, cudaArray_t* arr, cudaTextureObject_t* tex, bool allocate, cudaStream_t stream) {
+    cudaError_t e;
+    const int tile = n + 2;
+    if (allocate && (e = allocate_sky_atlas(ctx, n, arr, tex)) != cudaSuccess) return e;
     sky_atlas_kernel<<<dim3((tile + 255) / 256, tile, 6), 256, 0, stream>>>(d_faces, n, ctx->sky_surf);
     ctx->launches++;
     return cudaGetLastError();
@@ -270,6 +328,26 @@ static void gradient_sample(const std::vector<uint8_t>& g, float s, float out[3]
     const long long iu = (long long)fu;
     const int i0 = (int)std::min<long long>(std::max<long long>(iu, 0), len - 1), i1 = (int)std::min<long long>(std::max<long long>(iu + 1, 0), len - 1);
     for (int c = 0; c < 3; ++c) out[c] = (1.0f - a) * ((float)g[4 * i0 + c] / 255.0f) + a * ((float)g[4 * i1 + c] / 255.0f);
+}
+
+// The fog quad's blend for every destination byte (same operations, in the same order, as the device blend<false>():
+// plain fp32, no contraction — x86-64 host code has no fused multiply-add unless asked for).
+static void fog_table(const float fog[4], unsigned lut[256]) {
+    auto sat = [](float x) { return std::fmin(std::fmax(x, 0.0f), 1.0f); };
+    const float src[4] = {sat(fog[0]), sat(fog[1]), sat(fog[2]), sat(fog[3])};
+    const volatile float oma = 1.0f - src[3];
+    for (int d = 0; d < 256; ++d) {
+        unsigned e = 0;
+        for (int c = 0; c < 4; ++c) {
+            const volatile float dn = (float)d / 255.0f;
+            const volatile float t0 = src[c] * src[3], t1 = dn * oma;
+            const volatile float v = sat(t0 + t1);
+            const volatile float t2 = v * 255.0f;
+            const float q = std::floor(t2 + 0.5f);
+            e |= (unsigned)q << (8 * c);
+        }
+        lut[d] = e;
+    }
 }
 
 }  // namespace wt
@@ -374,11 +452,20 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* strea
         if (!ctx->d_sky_unsure) e = cudaMalloc(&ctx->d_sky_unsure, sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_sky_unsure, 0, sizeof(unsigned long long), stream);
         a.unsure_count = e == cudaSuccess ? ctx->d_sky_unsure : nullptr;
-        sky_synth_kernel<<<dim3((n + 255) / 256, n, 6), 256, 0, stream>>>(a);
-        ctx->launches++;
-        e = cudaGetLastError();
+        a.fog_identity = !(std::fmin(std::fmax(a.fog[3], 0.0f), 1.0f) > 0.0f);   // As == 0 (or NaN): Cd comes back as the same byte
+        if (!a.fog_identity) fog_table(a.fog, a.fog_lut);
+        if (e == cudaSuccess && fresh) e = allocate_sky_atlas(ctx, n, &ctx->sky_array, &ctx->sky_tex);
+        a.atlas = ctx->sky_surf;
+        if (e == cudaSuccess) {
+            // star / cloud cubemaps of the target's own power-of-two size are read texel for texel (cube_rgba8_aligned)
+            const bool aligned = a.inv_n_exact != 0.0f && (!a.stars || a.stars_n == n) && (!a.clouds || a.clouds_n == n);
+            const dim3 grid((n + 255) / 256, n, 6);
+            if (aligned) sky_synth_kernel<true><<<grid, 256, 0, stream>>>(a);
+            else sky_synth_kernel<false><<<grid, 256, 0, stream>>>(a);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
     }
-    if (e == cudaSuccess) e = rebuild_sky_atlas(ctx, ctx->d_sky, n, &ctx->sky_array, &ctx->sky_tex, fresh, stream);
     if (e == cudaSuccess) { ctx->sky_n = n; ctx->sky_surface_ok = true; }
     if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return fail(WT_ERR_CUDA, cudaGetErrorString(e));
