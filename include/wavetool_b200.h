@@ -362,7 +362,11 @@ int wt_sky_params_clamp_ui(wt_sky_params* params);   /* program.cpp:201-204, :22
  * stars / clouds may be NULL (layer not drawn).  HOST pointers, copied during the call. */
 int wt_set_sky_layers(wt_ctx* ctx, const uint8_t* gradient_rgba, int gradient_len, const uint8_t* const stars[6], int stars_n,
                       const uint8_t* const clouds[6], int clouds_n);
-/* Synthesizes the 6 x n x n skybox into the context (exactly as if wt_set_skybox_rgba8 had been called with the result). */
+/* Synthesizes the 6 x n x n skybox into the context (exactly as if wt_set_skybox_rgba8 had been called with the result).
+ * One kernel: all layers, the RGBA8 faces and the gather atlas the surface kernel samples.  Star / cloud cubemaps of the
+ * target's own power-of-two size (the reference's configuration: 2048^2 assets, CUBEMAP_LENGTH 2048 — program.cpp:616,656,
+ * render-engine.h:191) are read texel for texel, which is what the cube-map sampler returns there; other sizes go through the
+ * bilinear sampler.  Same bytes either way. */
 int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* params, int n, void* cuda_stream);
 /* Diagnostic: how many texels of the most recent wt_synthesize_skybox were recomputed on the exact path (IEEE division, libdevice
  * powf) because the approximate path (MUFU lg2 / ex2, reciprocal multiply) could not exclude a different byte.  Synchronises. */

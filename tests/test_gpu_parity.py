@@ -692,7 +692,7 @@ def test_skybox_synthesis_matches_oracle(oracle, hm, hours, cp, oc, layers):
     check_sky_synthesis(oracle, hm, hours, cp, oc, layers, 96, 24, 20)
 
 
-@pytest.mark.parametrize("n,fog_alpha", [(64, 0.1), (128, 0.0), (64, 1.0), (2, 0.35), (1, 0.1)])
+@pytest.mark.parametrize("n,fog_alpha", [(64, 0.1), (128, 0.0), (64, 1.0), (2, 0.35), (1, 0.1), (512, 0.1)])
 @pytest.mark.parametrize("hours,layers", [(9.0, (1, 1, 1)), (2.0, (1, 1, 1)), (18.6, (1, 0, 1))])
 def test_skybox_synthesis_same_size_sources(oracle, hm, n, fog_alpha, hours, layers):
     """The reference's own configuration — star / cloud cubemaps of the target's power-of-two size (2048^2 assets,

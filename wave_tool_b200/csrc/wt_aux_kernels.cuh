@@ -40,9 +40,8 @@ __global__ void build_heightmap_quads_kernel(const float* r, int w, int h, float
 // ------------------------------------------------------------------------------------------------
 // Reference-order kernel: one thread per vertex, the shader's own structure (water-grid.vert:114-194)
 // ------------------------------------------------------------------------------------------------
-// MUFU_TRIG = false: libdevice sincosf (the straight transliteration); true: the production kernels' Cody-Waite reduction + MUFU.SIN / MUFU.COS
-// (WT_FLAG_STENCIL_ORDER: the shader's five evaluations per vertex at a third of the cost)
-template <int CAP, bool MUFU_TRIG>
+// Table = tab_raw (cX holds Q_i): libdevice sincosf and the literal operation order of the shader.
+template <int CAP>
 __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const WaveTable<CAP>& wt, float u, float v) {
     // :87-91
     float x = mix_rn(mix_rn(a.blx, a.brx, u), mix_rn(a.tlx, a.trx, u), v);
@@ -52,27 +51,60 @@ __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const
         const WaveK wk = wt.w[i];
         float k = add_rn(mul_rn(wk.w, add_rn(mul_rn(wk.Dx, x), mul_rn(wk.Dz, z))), mul_rn(wk.phi, a.t));
         float s, c;
-        if (MUFU_TRIG) {
-            // the bit-faithful production kernel's arithmetic on the same k: table = tab_exact (cX = A Q_i D.x, cZ = A Q_i D.z folded
-            // on the host), one FMA per component — so the centre vertex gets the very position bits that kernel produces
-            sincos_mufu(k, s, c);
-            p.x = __fmaf_rn(wk.cX, c, p.x);
-            p.y = __fmaf_rn(wk.A, s, p.y);
-            p.z = __fmaf_rn(wk.cZ, c, p.z);
-        } else {
-            // the literal operation order of the shader; table = tab_raw: cX holds Q_i
-            sincosf(k, &s, &c);
-            float qc = mul_rn(wk.cX, c);
-            p.x = add_rn(p.x, mul_rn(wk.A, mul_rn(wk.Dx, qc)));
-            p.y = add_rn(p.y, mul_rn(wk.A, s));
-            p.z = add_rn(p.z, mul_rn(wk.A, mul_rn(wk.Dz, qc)));
-        }
+        sincosf(k, &s, &c);
+        float qc = mul_rn(wk.cX, c);
+        p.x = add_rn(p.x, mul_rn(wk.A, mul_rn(wk.Dx, qc)));
+        p.y = add_rn(p.y, mul_rn(wk.A, s));
+        p.z = add_rn(p.z, mul_rn(wk.A, mul_rn(wk.Dz, qc)));
     }
     p.y = finish_height(a, p.x, p.y, p.z);
     return p;
 }
 
-template <int CAP, bool SHADE, bool MUFU_TRIG>
+// Normal, view-facing flip, shading terms and the stores of one vertex from its five evaluated points (:164-190, frag:71-111),
+// with IEEE sqrt / div like the CPU reference.  Shared by the two five-evaluation kernels.
+template <bool SHADE>
+__device__ __forceinline__ void finish_five_eval(const EvalArgs& a, long long k, const P3& c, const P3& left, const P3& right, const P3& down, const P3& up,
+                                                 ChecksumAcc& acc) {
+    float ux = sub_rn(right.x, left.x), uy = sub_rn(right.y, left.y), uz = sub_rn(right.z, left.z);
+    float vx = sub_rn(up.x, down.x), vy = sub_rn(up.y, down.y), vz = sub_rn(up.z, down.z);
+    float nx = sub_rn(mul_rn(uy, vz), mul_rn(vy, uz));
+    float ny = sub_rn(mul_rn(uz, vx), mul_rn(vz, ux));
+    float nz = sub_rn(mul_rn(ux, vy), mul_rn(vx, uy));
+    float inv = __fdiv_rn(1.0f, __fsqrt_rn(add_rn(add_rn(mul_rn(nx, nx), mul_rn(ny, ny)), mul_rn(nz, nz))));
+    nx = mul_rn(nx, inv); ny = mul_rn(ny, inv); nz = mul_rn(nz, inv);
+    float wx = sub_rn(a.camx, c.x), wy = sub_rn(a.camy, c.y), wz = sub_rn(a.camz, c.z);
+    float ww = add_rn(add_rn(mul_rn(wx, wx), mul_rn(wy, wy)), mul_rn(wz, wz));
+    float winv = __fdiv_rn(1.0f, __fsqrt_rn(ww));
+    float ex = mul_rn(wx, winv), ey = mul_rn(wy, winv), ez = mul_rn(wz, winv);
+    float facing = add_rn(add_rn(mul_rn(nx, ex), mul_rn(ny, ey)), mul_rn(nz, ez));
+    if (facing < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+    float4 on = make_float4(nx, ny, nz, 0.0f), os = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SHADE) {
+        // frag:71-73 viewVec = viewVecRaw / length
+        float len = __fsqrt_rn(ww);
+        float fx = __fdiv_rn(wx, len), fy = __fdiv_rn(wy, len), fz = __fdiv_rn(wz, len);
+        // frag:95 reflect(-viewVec, normal) = I - N * dot(N, I) * 2
+        float ix = -fx, iy = -fy, iz = -fz;
+        float d = add_rn(add_rn(mul_rn(nx, ix), mul_rn(ny, iy)), mul_rn(nz, iz));
+        float rx = sub_rn(ix, mul_rn(mul_rn(nx, d), 2.0f)), ry = sub_rn(iy, mul_rn(mul_rn(ny, d), 2.0f)), rz = sub_rn(iz, mul_rn(mul_rn(nz, d), 2.0f));
+        float3 sky = make_float3(0.f, 0.f, 0.f);
+        if (a.sky) sky = sky_rgb(a, rx, ry, rz);
+        float sd = add_rn(add_rn(mul_rn(rx, a.sunx), mul_rn(ry, a.suny)), mul_rn(rz, a.sunz));
+        sd = fminf(fmaxf(sd, 0.0f), 1.0f);
+        float sun = mul_rn(a.sun_strength, powf(sd, a.sun_shininess));
+        float ct = add_rn(add_rn(mul_rn(nx, fx), mul_rn(ny, fy)), mul_rn(nz, fz));
+        on.w = add_rn(0.02f, mul_rn(sub_rn(1.0f, 0.02f), powf(sub_rn(1.0f, ct), 5.0f)));
+        os = make_float4(sky.x, sky.y, sky.z, sun);
+    }
+    float4 op = make_float4(c.x, c.y, c.z, 1.0f);
+    a.pos[k] = op;
+    a.nrm[k] = on;
+    if (SHADE) a.shade[k] = os;
+    if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(os); }
+}
+
+template <int CAP, bool SHADE>
 __global__ void __launch_bounds__(256) surface_reference_order_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
     const long long n = (long long)(a.row_end - a.row_begin) * a.L;
     ChecksumAcc acc;
@@ -80,48 +112,70 @@ __global__ void __launch_bounds__(256) surface_reference_order_kernel(const __gr
         const int row = a.row_begin + (int)(k / a.L), col = (int)(k % a.L);
         const float du = a.du;
         const float u = mul_rn((float)col, du), v = mul_rn((float)row, du);   // :123-125
-        P3 c = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, u, v);
-        P3 left = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, sub_rn(u, du), v);    // :164-167: uv -/+ du
-        P3 right = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, add_rn(u, du), v);
-        P3 down = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, u, sub_rn(v, du));
-        P3 up = displaced_reference_order<CAP, MUFU_TRIG>(a, wt, u, add_rn(v, du));
-        // :187-190 with IEEE sqrt/div like the CPU reference
-        float ux = sub_rn(right.x, left.x), uy = sub_rn(right.y, left.y), uz = sub_rn(right.z, left.z);
-        float vx = sub_rn(up.x, down.x), vy = sub_rn(up.y, down.y), vz = sub_rn(up.z, down.z);
-        float nx = sub_rn(mul_rn(uy, vz), mul_rn(vy, uz));
-        float ny = sub_rn(mul_rn(uz, vx), mul_rn(vz, ux));
-        float nz = sub_rn(mul_rn(ux, vy), mul_rn(vx, uy));
-        float inv = __fdiv_rn(1.0f, __fsqrt_rn(add_rn(add_rn(mul_rn(nx, nx), mul_rn(ny, ny)), mul_rn(nz, nz))));
-        nx = mul_rn(nx, inv); ny = mul_rn(ny, inv); nz = mul_rn(nz, inv);
-        float wx = sub_rn(a.camx, c.x), wy = sub_rn(a.camy, c.y), wz = sub_rn(a.camz, c.z);
-        float ww = add_rn(add_rn(mul_rn(wx, wx), mul_rn(wy, wy)), mul_rn(wz, wz));
-        float winv = __fdiv_rn(1.0f, __fsqrt_rn(ww));
-        float ex = mul_rn(wx, winv), ey = mul_rn(wy, winv), ez = mul_rn(wz, winv);
-        float facing = add_rn(add_rn(mul_rn(nx, ex), mul_rn(ny, ey)), mul_rn(nz, ez));
-        if (facing < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
-        float4 on = make_float4(nx, ny, nz, 0.0f), os = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (SHADE) {
-            // frag:71-73 viewVec = viewVecRaw / length
-            float len = __fsqrt_rn(ww);
-            float fx = __fdiv_rn(wx, len), fy = __fdiv_rn(wy, len), fz = __fdiv_rn(wz, len);
-            // frag:95 reflect(-viewVec, normal) = I - N * dot(N, I) * 2
-            float ix = -fx, iy = -fy, iz = -fz;
-            float d = add_rn(add_rn(mul_rn(nx, ix), mul_rn(ny, iy)), mul_rn(nz, iz));
-            float rx = sub_rn(ix, mul_rn(mul_rn(nx, d), 2.0f)), ry = sub_rn(iy, mul_rn(mul_rn(ny, d), 2.0f)), rz = sub_rn(iz, mul_rn(mul_rn(nz, d), 2.0f));
-            float3 sky = make_float3(0.f, 0.f, 0.f);
-            if (a.sky) sky = sky_rgb(a, rx, ry, rz);
-            float sd = add_rn(add_rn(mul_rn(rx, a.sunx), mul_rn(ry, a.suny)), mul_rn(rz, a.sunz));
-            sd = fminf(fmaxf(sd, 0.0f), 1.0f);
-            float sun = mul_rn(a.sun_strength, powf(sd, a.sun_shininess));
-            float ct = add_rn(add_rn(mul_rn(nx, fx), mul_rn(ny, fy)), mul_rn(nz, fz));
-            on.w = add_rn(0.02f, mul_rn(sub_rn(1.0f, 0.02f), powf(sub_rn(1.0f, ct), 5.0f)));
-            os = make_float4(sky.x, sky.y, sky.z, sun);
+        P3 c = displaced_reference_order<CAP>(a, wt, u, v);
+        P3 left = displaced_reference_order<CAP>(a, wt, sub_rn(u, du), v);    // :164-167: uv -/+ du
+        P3 right = displaced_reference_order<CAP>(a, wt, add_rn(u, du), v);
+        P3 down = displaced_reference_order<CAP>(a, wt, u, sub_rn(v, du));
+        P3 up = displaced_reference_order<CAP>(a, wt, u, add_rn(v, du));
+        finish_five_eval<SHADE>(a, k, c, left, right, down, up, acc);
+    }
+    if (a.cks) acc.flush(a.cks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stencil-order kernel (WT_FLAG_STENCIL_ORDER): the shader's five evaluations per vertex with the bit-faithful production
+// kernel's arithmetic — k rounded like the shader's, Cody-Waite + MUFU, folded coefficients (table = tab_exact), one FMA per
+// component — so the centre vertex gets the very position bits that kernel produces and the neighbours are evaluated at
+// uv -/+ du like the shader's.  One thread per PAIR of consecutive vertices: the two vertices' five points are
+// the halves of five packed evaluations that run through ONE wave loop (the wave constants are fetched once per wave into
+// uniform registers, 12 packed + 2 scalar + 4 MUFU instructions per point pair and wave, as in the production kernel).
+// ------------------------------------------------------------------------------------------------
+template <int CAP, bool SHADE>
+__global__ void __launch_bounds__(128) surface_stencil_order_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt) {
+    const long long n = (long long)(a.row_end - a.row_begin) * a.L;
+    const float du = a.du, one = a.one;
+    ChecksumAcc acc;
+    for (long long k0 = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); k0 < n; k0 += 2 * (long long)gridDim.x * blockDim.x) {
+        const bool two = k0 + 1 < n;                       // an odd count: the last thread evaluates its one vertex in both halves
+        const long long k1 = two ? k0 + 1 : k0;
+        const int row0 = a.row_begin + (int)(k0 / a.L), col0 = (int)(k0 % a.L);
+        const int row1 = a.row_begin + (int)(k1 / a.L), col1 = (int)(k1 % a.L);
+        const f2 u = make_float2(mul_rn((float)col0, du), mul_rn((float)col1, du));   // :123-125
+        const f2 v = make_float2(mul_rn((float)row0, du), mul_rn((float)row1, du));
+        // the five points: centre, left, right, down, up (:164-167: uv -/+ du)
+        const f2 pu[5] = {u, sub2(u, bc(du)), add2(u, bc(du)), u, u};
+        const f2 pv[5] = {v, v, v, sub2(v, bc(du)), add2(v, bc(du))};
+        f2 x[5], z[5], ax[5], ay[5], az[5];
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {                      // :87-91
+            x[p] = make_float2(mix_rn(mix_rn(a.blx, a.brx, pu[p].x), mix_rn(a.tlx, a.trx, pu[p].x), pv[p].x),
+                               mix_rn(mix_rn(a.blx, a.brx, pu[p].y), mix_rn(a.tlx, a.trx, pu[p].y), pv[p].y));
+            z[p] = make_float2(mix_rn(mix_rn(a.blz, a.brz, pu[p].x), mix_rn(a.tlz, a.trz, pu[p].x), pv[p].x),
+                               mix_rn(mix_rn(a.blz, a.brz, pu[p].y), mix_rn(a.tlz, a.trz, pu[p].y), pv[p].y));
+            ax[p] = x[p]; ay[p] = bc(0.0f); az[p] = z[p];
         }
-        float4 op = make_float4(c.x, c.y, c.z, 1.0f);
-        a.pos[k] = op;
-        a.nrm[k] = on;
-        if (SHADE) a.shade[k] = os;
-        if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(os); }
+        for (int i = 0; i < a.n_waves; ++i) {              // :76-82
+            const WaveK wk = wt.w[i];
+            const float pt = mul_rn(wk.phi, a.t);
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const f2 d = add2x(mul2(bc(wk.Dx), x[p]), mul2(bc(wk.Dz), z[p]), one);
+                const f2 k = add2x(mul2(bc(wk.w), d), bc(pt), one);
+                f2 s, c;
+                sincos2(k, s, c);
+                ax[p] = fma2(bc(wk.cX), c, ax[p]);
+                ay[p] = fma2(bc(wk.A), s, ay[p]);
+                az[p] = fma2(bc(wk.cZ), c, az[p]);
+            }
+        }
+        P3 lo[5], hi[5];
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+            lo[p] = {ax[p].x, finish_height(a, ax[p].x, ay[p].x, az[p].x), az[p].x};
+            hi[p] = {ax[p].y, finish_height(a, ax[p].y, ay[p].y, az[p].y), az[p].y};
+        }
+        finish_five_eval<SHADE>(a, k0, lo[0], lo[1], lo[2], lo[3], lo[4], acc);
+        if (two) finish_five_eval<SHADE>(a, k1, hi[0], hi[1], hi[2], hi[3], hi[4], acc);
     }
     if (a.cks) acc.flush(a.cks);
 }

@@ -204,24 +204,41 @@ void fill_table(WaveTable<CAP>& t, const std::vector<WaveK>& src) {
     std::memcpy(t.w, src.data(), src.size() * sizeof(WaveK));
 }
 
-template <int CAP, bool SHADE, bool MUFU_TRIG>
-cudaError_t launch_reference_order(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
+template <int CAP, bool SHADE>
+cudaError_t launch_reference_order(wt_ctx* ctx, EvalArgs& a, cudaStream_t stream) {
     static thread_local WaveTable<CAP> table;
-    fill_table(table, tab);
+    fill_table(table, ctx->tab_raw);
     const long long n = (long long)(a.row_end - a.row_begin) * a.L;
     int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
-    surface_reference_order_kernel<CAP, SHADE, MUFU_TRIG><<<std::max(blocks, 1), 256, 0, stream>>>(a, table);
+    surface_reference_order_kernel<CAP, SHADE><<<std::max(blocks, 1), 256, 0, stream>>>(a, table);
     ctx->launches++;
     return cudaGetLastError();
 }
 
-template <bool MUFU_TRIG>
-cudaError_t launch_five_eval(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t stream) {
-    const std::vector<WaveK>& tab = MUFU_TRIG ? ctx->tab_exact : ctx->tab_raw;   // see displaced_reference_order
+template <int CAP, bool SHADE>
+cudaError_t launch_stencil_order(wt_ctx* ctx, EvalArgs& a, cudaStream_t stream) {
+    static thread_local WaveTable<CAP> table;
+    fill_table(table, ctx->tab_exact);
+    const long long pairs = ((long long)(a.row_end - a.row_begin) * a.L + 1) / 2;
+    int blocks = (int)std::min<long long>((pairs + 127) / 128, (long long)ctx->sm_count * 32);
+    surface_stencil_order_kernel<CAP, SHADE><<<std::max(blocks, 1), 128, 0, stream>>>(a, table);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stencil(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t stream) {
     switch (wave_capacity(ctx->n_waves)) {
-        case 64: return shade ? launch_reference_order<64, true, MUFU_TRIG>(ctx, a, tab, stream) : launch_reference_order<64, false, MUFU_TRIG>(ctx, a, tab, stream);
-        case 256: return shade ? launch_reference_order<256, true, MUFU_TRIG>(ctx, a, tab, stream) : launch_reference_order<256, false, MUFU_TRIG>(ctx, a, tab, stream);
-        default: return shade ? launch_reference_order<1000, true, MUFU_TRIG>(ctx, a, tab, stream) : launch_reference_order<1000, false, MUFU_TRIG>(ctx, a, tab, stream);
+        case 64: return shade ? launch_stencil_order<64, true>(ctx, a, stream) : launch_stencil_order<64, false>(ctx, a, stream);
+        case 256: return shade ? launch_stencil_order<256, true>(ctx, a, stream) : launch_stencil_order<256, false>(ctx, a, stream);
+        default: return shade ? launch_stencil_order<1000, true>(ctx, a, stream) : launch_stencil_order<1000, false>(ctx, a, stream);
+    }
+}
+
+cudaError_t launch_reference(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t stream) {
+    switch (wave_capacity(ctx->n_waves)) {
+        case 64: return shade ? launch_reference_order<64, true>(ctx, a, stream) : launch_reference_order<64, false>(ctx, a, stream);
+        case 256: return shade ? launch_reference_order<256, true>(ctx, a, stream) : launch_reference_order<256, false>(ctx, a, stream);
+        default: return shade ? launch_reference_order<1000, true>(ctx, a, stream) : launch_reference_order<1000, false>(ctx, a, stream);
     }
 }
 
@@ -309,8 +326,8 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
     ctx->last_phase_mode = (flags & WT_FLAG_REFERENCE_ORDER) ? WT_PHASE_REFERENCE_ORDER : (flags & WT_FLAG_STENCIL_ORDER) ? WT_PHASE_STENCIL_ORDER
                            : (flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL;
     ctx->mode_launches[ctx->last_phase_mode]++;
-    if (flags & WT_FLAG_REFERENCE_ORDER) return launch_five_eval<false>(ctx, a, shade, stream);
-    if (flags & WT_FLAG_STENCIL_ORDER) return launch_five_eval<true>(ctx, a, shade, stream);
+    if (flags & WT_FLAG_REFERENCE_ORDER) return launch_reference(ctx, a, shade, stream);
+    if (flags & WT_FLAG_STENCIL_ORDER) return launch_stencil(ctx, a, shade, stream);
     if (flags & WT_FLAG_FAST_PHASE)
         return shade ? launch_production_recur_shade(ctx, a, flags, stream) : launch_production_recur(ctx, a, flags, stream);
     return shade ? launch_production_exact_shade(ctx, a, flags, stream) : launch_production_exact(ctx, a, flags, stream);
