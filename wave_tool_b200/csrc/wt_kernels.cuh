@@ -798,8 +798,6 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         {
             // HM_BATCH rows at a time: all their footprint loads are issued before the first blend
             constexpr int HM_BATCH = R < WT_HM_BATCH ? R : WT_HM_BATCH;
-            const bool seam = lane == 0 || lane == 31;
-            const int seam_col = lane ? 0 : 33;
             int slot = slot_new;
 #pragma unroll
             for (int j0 = 0; j0 < R; j0 += HM_BATCH) {
