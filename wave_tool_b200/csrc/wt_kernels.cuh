@@ -311,6 +311,21 @@ struct ChecksumAcc {
         add_sums(p, n);
         count += 1;
     }
+    // Both vertices of a lane's output row, branch-free: lanes 0 and 31 hold one halo column each (never stored, never counted),
+    // and a branch around the per-column sums made every warp diverge twice per row (2-3 % of the kernel's time).  Each column's
+    // words are summed first (at most 2^34), masked as a whole, then the two columns go into the running sum together.
+    __device__ __forceinline__ void add_pair(const float4& pa, const float4& na, const float4& sa, bool keep_a,
+                                             const float4& pb, const float4& nb, const float4& sb, bool keep_b, bool shade) {
+        const unsigned long long ma = 0ull - (unsigned long long)keep_a, mb = 0ull - (unsigned long long)keep_b;
+        auto w = [](float f) { return (unsigned long long)__float_as_uint(f); };
+        pos += ((w(pa.x) + w(pa.y) + w(pa.z)) & ma) + ((w(pb.x) + w(pb.y) + w(pb.z)) & mb);
+        nrm += ((w(na.x) + w(na.y) + w(na.z) + w(na.w)) & ma) + ((w(nb.x) + w(nb.y) + w(nb.z) + w(nb.w)) & mb);
+        if (shade) shd += ((w(sa.x) + w(sa.y) + w(sa.z) + w(sa.w)) & ma) + ((w(sb.x) + w(sb.y) + w(sb.z) + w(sb.w)) & mb);
+        const float ya = keep_a ? pa.y : ymin, yb = keep_b ? pb.y : ymin;     // the running value itself is neutral
+        ymin = fminf(ymin, fminf(ya, yb));
+        const float za = keep_a ? pa.y : ymax, zb = keep_b ? pb.y : ymax;
+        ymax = fmaxf(ymax, fmaxf(za, zb));
+    }
     __device__ __forceinline__ void add_shade(const float4& s) {
         shd += (unsigned long long)__float_as_uint(s.x) + __float_as_uint(s.y) + __float_as_uint(s.z) + __float_as_uint(s.w);
     }
@@ -594,6 +609,9 @@ struct RingLayout {
     static constexpr int PLANE = ROWS * RING_COLS;                   // float2 entries per component
     static constexpr int PLANES = VARY ? 4 : 3;                      // x, y, z (+ the heightmap sample with WT_FLAG_VARYINGS)
     static constexpr int BYTES_PER_WARP = PLANES * PLANE * (int)sizeof(float2);
+    // WT_FLAG_CHECKSUM in the bit-faithful kernel (80 registers, every live value counts): the warp's running digest lives
+    // behind the ring — [4][32] 64-bit words (position, normal, shade sums, (min y, max y); one column per lane)
+    static constexpr int CKS_BYTES_PER_WARP = 4 * 32 * (int)sizeof(unsigned long long);
 };
 
 template <int CAP, int R, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY, bool BATCH = false>
@@ -606,7 +624,23 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
     const bool dyn = a.queue != nullptr;
     int item = blockIdx.x;
     if (dyn) item = next_item(a.queue, lane);
+    // The digest accumulators.  Recurrence kernel (128+ registers): in registers.  Bit-faithful kernel: in shared memory, updated
+    // row by row — eight more live registers across the wave loop and the output stage cost it 4.7 % (measured with the sums
+    // themselves stubbed out), the read-modify-write of this lane's own column of the record costs less (profiles/README.md).
+    // The vertex count stays in a register: it is touched once per work item (measured: 3.6 % with it in a register, 4.8 % in the record).
+    constexpr bool CKS_SMEM = CKS && MODE == 0;
     ChecksumAcc acc;
+    unsigned long long* const cks_slot = reinterpret_cast<unsigned long long*>(ring_all + RL::PLANES * RL::PLANE) + lane;
+    auto cks_reset = [&]() {
+        cks_slot[0] = 0; cks_slot[32] = 0; cks_slot[64] = 0;
+        *reinterpret_cast<float2*>(cks_slot + 96) = make_float2(3.402823466e+38f, -3.402823466e+38f);
+    };
+    auto cks_collect = [&]() {
+        acc.pos = cks_slot[0]; acc.nrm = cks_slot[32]; acc.shd = cks_slot[64];
+        const float2 yr = *reinterpret_cast<const float2*>(cks_slot + 96);
+        acc.ymin = yr.x; acc.ymax = yr.y;
+    };
+    if (CKS_SMEM) cks_reset();
   while (item < a.n_items) {
     unsigned long long t_start = 0;
     if (a.trace) t_start = global_ns();
@@ -960,9 +994,24 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                 if (stA) __stcs(pb, make_float4(yn[0].x * yi.x, yn[1].x * yi.x, yn[2].x * yi.x, 0.0f));
                 if (stB) __stcs(pb + 32, make_float4(yn[0].y * yi.y, yn[1].y * yi.y, yn[2].y * yi.y, 0.0f));
             }
-            if (CKS) {
-                if (stA) { acc.add_sums(opA, onA); if (SHADE) acc.add_shade(sA); }
-                if (stB) { acc.add_sums(opB, onB); if (SHADE) acc.add_shade(sB); }
+            if (CKS_SMEM) {
+                auto w = [](float f) { return (unsigned long long)__float_as_uint(f); };
+                float2* const yr = reinterpret_cast<float2*>(cks_slot + 96);
+                if (stA) {
+                    cks_slot[0] += w(opA.x) + w(opA.y) + w(opA.z);
+                    cks_slot[32] += w(onA.x) + w(onA.y) + w(onA.z) + w(onA.w);
+                    if (SHADE) cks_slot[64] += w(sA.x) + w(sA.y) + w(sA.z) + w(sA.w);
+                    *yr = make_float2(fminf(yr->x, opA.y), fmaxf(yr->y, opA.y));
+                }
+                if (stB) {
+                    cks_slot[0] += w(opB.x) + w(opB.y) + w(opB.z);
+                    cks_slot[32] += w(onB.x) + w(onB.y) + w(onB.z) + w(onB.w);
+                    if (SHADE) cks_slot[64] += w(sB.x) + w(sB.y) + w(sB.z) + w(sB.w);
+                    *yr = make_float2(fminf(yr->x, opB.y), fmaxf(yr->y, opB.y));
+                }
+            } else if (CKS && valid) {
+                // `valid` is uniform and the halo lanes are masked, not branched around: no divergence (5.7 % -> 3.9 % of the recurrence kernel)
+                acc.add_pair(opA, onA, sA, stA, opB, onB, sB, stB, SHADE);
             }
         };
         {
@@ -977,7 +1026,11 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         slot_new = slot_new + R >= RL::ROWS ? slot_new + R - RL::ROWS : slot_new + R;
     }
     // every row of [r0, r1) was stored exactly once for each of this lane's in-range columns
-    if (CKS) acc.count += (unsigned long long)max(r1 - r0, 0) * ((outA ? 1 : 0) + (outB ? 1 : 0));
+    if (CKS) {
+        const unsigned long long nv = (unsigned long long)max(r1 - r0, 0) * ((outA ? 1 : 0) + (outB ? 1 : 0));
+        acc.count += nv;
+    }
+    if (BATCH && CKS_SMEM) { cks_collect(); cks_reset(); }
     if (BATCH && CKS) {
         // one digest per FRAME: the frame's own record (armed by the launcher) takes this item's sums; the item that completes the
         // frame decodes the record in place
@@ -1009,6 +1062,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
         if (atomicAdd(a.queue + 1, 1) == (int)gridDim.x - 1) { a.queue[1] = 0; __threadfence(); a.queue[0] = 0; }
     }
     if (CKS && !BATCH) {
+        if (CKS_SMEM) cks_collect();
         acc.flush(a.cks_acc);
         if (lane == 0) {
             __threadfence();

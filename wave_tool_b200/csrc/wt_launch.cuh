@@ -17,7 +17,7 @@ template <int CAP, int MODE, bool SHADE, bool CKS, bool HMP2, bool VARY>
 cudaError_t launch_warp_vary(wt_ctx* ctx, EvalArgs& a, const std::vector<WaveK>& tab, cudaStream_t stream) {
     constexpr int R = MODE == 1 ? (CAP > 64 ? R_RECUR_BIG : R_RECUR) : R_EXACT;
     auto kernel = surface_warp_kernel<CAP, R, MODE, SHADE, CKS, HMP2, VARY>;
-    const int smem = WARPS_PER_CTA * RingLayout<R, VARY>::BYTES_PER_WARP + g_knobs.extra_smem;
+    const int smem = WARPS_PER_CTA * (RingLayout<R, VARY>::BYTES_PER_WARP + (CKS && MODE == 0 ? RingLayout<R, VARY>::CKS_BYTES_PER_WARP : 0)) + g_knobs.extra_smem;
     // per instantiation: occupancy and the segments of the last (grid, row range) seen
     static thread_local struct { int L = -1, r0 = -1, r1 = -1, dev = -1, slots = 0; unsigned gen = 0; EvalArgs seg; } cache;
     if (cache.L != a.L || cache.r0 != a.row_begin || cache.r1 != a.row_end || cache.dev != ctx->device || cache.gen != g_knobs.generation) {
@@ -104,7 +104,7 @@ cudaError_t launch_warp_batch(wt_ctx* ctx, std::vector<EvalArgs>& fa, const std:
     auto kernel = surface_warp_kernel<CAP, R, MODE, false, CKS, HMP2, false, true>;
     const int F = (int)fa.size();
     if (F < 1 || F > BATCH_MAX_FRAMES) return cudaErrorInvalidValue;
-    const int smem = WARPS_PER_CTA * RingLayout<R, false>::BYTES_PER_WARP;
+    const int smem = WARPS_PER_CTA * (RingLayout<R, false>::BYTES_PER_WARP + (CKS && MODE == 0 ? RingLayout<R, false>::CKS_BYTES_PER_WARP : 0));
     static thread_local struct { int dev = -1, slots = 0; } cache;
     if (cache.dev != ctx->device) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
