@@ -30,32 +30,37 @@ struct ComposeArgs {
 
 __device__ __forceinline__ float mix_f(float x, float y, float a) { return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a)); }
 __device__ __forceinline__ float clamp_f(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-__device__ __forceinline__ int clamp_i(int i, int n) { return i < 0 ? 0 : (i > n - 1 ? n - 1 : i); }
 
-// texture(sampler2D, st) of an RGBA8 texture: GL_LINEAR, GL_CLAMP_TO_EDGE, exact fp32 weights, the oracle's operation order
-__device__ __forceinline__ float4 sample_rgba8_clamp_linear(const uchar4* tex, int w, int h, float s, float t) {
-    // s, t in [0, 1] (the callers clamp them): um, vm in [-0.5, w] — floor and the float -> int conversion by the magic-number
-    // add, the byte -> float conversions by a byte permute (none of them on the XU pipe, which bounded this pass)
+// texture(sampler2D, st) of an RGBA8 texture: GL_LINEAR, GL_CLAMP_TO_EDGE, exact fp32 weights, the oracle's operation order.
+// lut[c] = c / 255 exactly (IEEE division, built per block by unorm8f): a table look-up replaces the six-instruction
+// byte -> float -> / 255 sequence, 32 times per vertex — the conversions were 29 % of this pass's instructions.
+__device__ __forceinline__ float4 sample_rgba8_clamp_linear(const uchar4* tex, const float* lut, int w, int h, float s, float t) {
+    // s, t in [0, 1] (the callers clamp them): um, vm in [-0.5, w - 0.5], so floor(um) is in [-1, w - 1] — each of the four
+    // footprint indices needs one clamp only.  floor and the float -> int conversion by the magic-number add (off the XU pipe).
     const float um = __fsub_rn(__fmul_rn(s, (float)w), 0.5f), vm = __fsub_rn(__fmul_rn(t, (float)h), 0.5f);
     int iu, iv;
     const float fu = floor_small(um, iu), fv = floor_small(vm, iv);
     const float a = __fsub_rn(um, fu), b = __fsub_rn(vm, fv);
-    const int i0 = clamp_i(iu, w), i1 = clamp_i(iu + 1, w), j0 = clamp_i(iv, h), j1 = clamp_i(iv + 1, h);
+    const unsigned i0 = (unsigned)max(iu, 0), i1 = (unsigned)min(iu + 1, w - 1), j0 = (unsigned)max(iv, 0), j1 = (unsigned)min(iv + 1, h - 1);
     const unsigned* const tx = reinterpret_cast<const unsigned*>(tex);
-    const unsigned t00 = __ldg(tx + (size_t)j0 * w + i0), t10 = __ldg(tx + (size_t)j0 * w + i1);
-    const unsigned t01 = __ldg(tx + (size_t)j1 * w + i0), t11 = __ldg(tx + (size_t)j1 * w + i1);
+    const unsigned r0 = j0 * (unsigned)w, r1 = j1 * (unsigned)w;        // w, h <= 16384: the texel index fits 32 bits
+    const unsigned t00 = __ldg(tx + (r0 + i0)), t10 = __ldg(tx + (r0 + i1));
+    const unsigned t01 = __ldg(tx + (r1 + i0)), t11 = __ldg(tx + (r1 + i1));
     const float oma = __fsub_rn(1.0f, a), omb = __fsub_rn(1.0f, b);
     const float w00 = __fmul_rn(oma, omb), w10 = __fmul_rn(a, omb), w01 = __fmul_rn(oma, b), w11 = __fmul_rn(a, b);
     auto ch = [&](unsigned k) {
-        float acc = __fmul_rn(w00, unorm8f(byte_f(t00, k)));
-        acc = __fadd_rn(acc, __fmul_rn(w10, unorm8f(byte_f(t10, k))));
-        acc = __fadd_rn(acc, __fmul_rn(w01, unorm8f(byte_f(t01, k))));
-        return __fadd_rn(acc, __fmul_rn(w11, unorm8f(byte_f(t11, k))));
+        float acc = __fmul_rn(w00, lut[(t00 >> (8 * k)) & 255u]);
+        acc = __fadd_rn(acc, __fmul_rn(w10, lut[(t10 >> (8 * k)) & 255u]));
+        acc = __fadd_rn(acc, __fmul_rn(w01, lut[(t01 >> (8 * k)) & 255u]));
+        return __fadd_rn(acc, __fmul_rn(w11, lut[(t11 >> (8 * k)) & 255u]));
     };
     return make_float4(ch(0), ch(1), ch(2), ch(3));
 }
 
 __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = unorm8f((float)threadIdx.x);     // launched with 256 threads per block
+    __syncthreads();
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.n; k += (long long)gridDim.x * blockDim.x) {
         const float4 P = __ldcs(a.pos + k), N = __ldcs(a.nrm + k), S = __ldcs(a.shade + k);
         float4 C, A, B;
@@ -94,8 +99,8 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
         int di, dj;
         floor_small(clamp_f(__fmul_rn(uvx, (float)a.w), -1.0f, (float)a.w), di);
         floor_small(clamp_f(__fmul_rn(uvy, (float)a.h), -1.0f, (float)a.h), dj);
-        di = clamp_i(di, a.w); dj = clamp_i(dj, a.h);
-        const float back = linearize(__ldg(a.depth + (size_t)dj * a.w + di));                                            // frag:84
+        di = min(max(di, 0), a.w - 1); dj = min(max(dj, 0), a.h - 1);
+        const float back = linearize(__ldg(a.depth + ((unsigned)dj * (unsigned)a.w + (unsigned)di)));                                            // frag:84
         const float hack = back > 0.999f ? 0.0f : 1.0f;                                                                 // frag:86
         const float dcl = clamp_f(__fsub_rn(back, linearize(fz)), 0.0f, 1.0f);                                           // frag:87-91
         // frag:118-133 local reflections / refractions
@@ -103,8 +108,8 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
         const float mx = mix_f(uvx, h0x, ds), my = mix_f(uvy, h0y, ds);
         const float rlx = clamp_f(__fadd_rn(mx, __fmul_rn(ds, B.x)), 0.0f, 1.0f), rly = clamp_f(__fadd_rn(my, __fmul_rn(ds, -B.z)), 0.0f, 1.0f);
         const float rrx = clamp_f(__fadd_rn(mx, __fmul_rn(ds, -B.x)), 0.0f, 1.0f), rry = clamp_f(__fadd_rn(my, __fmul_rn(ds, B.z)), 0.0f, 1.0f);
-        const float4 refl = sample_rgba8_clamp_linear(a.refl, a.w, a.h, rlx, rly);
-        const float4 refr = sample_rgba8_clamp_linear(a.refr, a.w, a.h, rrx, rry);
+        const float4 refl = sample_rgba8_clamp_linear(a.refl, lut, a.w, a.h, rlx, rly);
+        const float4 refr = sample_rgba8_clamp_linear(a.refr, lut, a.w, a.h, rrx, rry);
         // frag:136-151 tint, transmission, reflection, Fresnel mix
         const float tint_f = a.tint_threshold == 0.0f ? 0.0f : __fmul_rn(hack, __fsub_rn(1.0f, clamp_f(div_by_uniform(dcl, a.tint_threshold, a.r_tint), 0.0f, 1.0f)));
         const float t_w = __fmul_rn(__fmul_rn(a.clarity, refr.w), __fsub_rn(1.0f, dcl));
