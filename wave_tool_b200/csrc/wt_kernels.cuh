@@ -833,6 +833,10 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             // HM_BATCH rows at a time: all their footprint loads are issued before the first blend
             constexpr int HM_BATCH = R < WT_HM_BATCH ? R : WT_HM_BATCH;
             int slot = slot_new;
+            // The seam entries of the ring.  Measured (profiles/README.md): the branch-free form takes 4-7 % off the small-frame tier
+            // (1024^2 x 8 waves) and is neutral at 8192^2 / 16384^2, but costs the shading instantiations 0.7 % (cfg3): they keep the branches.
+            constexpr bool SEAM_BRANCHLESS = !SHADE;
+            const int seam_a = lane == 31 ? 1 : 0, seam_b = lane == 0 ? 2 * 33 : 2 * 33 + 1;   // float offsets inside a ring row
 #pragma unroll
             for (int j0 = 0; j0 < R; j0 += HM_BATCH) {
                 HmTap tap[HM_BATCH];
@@ -851,11 +855,20 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
                     row[RL::PLANE + 1 + lane] = py[j];
                     row[2 * RL::PLANE + 1 + lane] = pz[j];
 #if !WT_SEAMLESS_RING
-                    if (lane == 31) {
-                        row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
-                    }
-                    if (lane == 0) {
-                        row[33] = make_float2(px[j].y, 0.f); row[RL::PLANE + 33] = make_float2(py[j].y, 0.f); row[2 * RL::PLANE + 33] = make_float2(pz[j].y, 0.f);
+                    if (SEAM_BRANCHLESS) {
+                        // lane 31 puts its A value into entry 0's .y and lane 0 its B value into entry 33's .x; every other lane
+                        // stores into the unused half of the same entry (nobody reads it): no divergent region per row
+                        float* const rowf = reinterpret_cast<float*>(row);
+                        constexpr int PF = 2 * RL::PLANE;
+                        rowf[seam_a] = px[j].x; rowf[PF + seam_a] = py[j].x; rowf[2 * PF + seam_a] = pz[j].x;
+                        rowf[seam_b] = px[j].y; rowf[PF + seam_b] = py[j].y; rowf[2 * PF + seam_b] = pz[j].y;
+                    } else {
+                        if (lane == 31) {
+                            row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
+                        }
+                        if (lane == 0) {
+                            row[33] = make_float2(px[j].y, 0.f); row[RL::PLANE + 33] = make_float2(py[j].y, 0.f); row[2 * RL::PLANE + 33] = make_float2(pz[j].y, 0.f);
+                        }
                     }
 #endif
                     slot = slot + 1 == RL::ROWS ? 0 : slot + 1;
