@@ -15,8 +15,8 @@ struct ComposeArgs {
     const float4 *pos, *nrm, *shade, *clip, *va, *vb;
     float4* colour;
     const float* depth;        // w x h, GL row order, window-space depth
-    const uchar4* refl;        // w x h RGBA8
-    const uchar4* refr;
+    cudaTextureObject_t refl;  // w x h RGBA8 arrays: point sampling, clamp to edge, normalised-float reads (exactly c / 255), gather-able
+    cudaTextureObject_t refr;
     int w, h;
     long long n;
     float fog[4], fog_far, fog_near, soft_edges, tint_threshold, clarity, z_near, z_far, vw, vh;
@@ -32,35 +32,35 @@ __device__ __forceinline__ float mix_f(float x, float y, float a) { return __fad
 __device__ __forceinline__ float clamp_f(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // texture(sampler2D, st) of an RGBA8 texture: GL_LINEAR, GL_CLAMP_TO_EDGE, exact fp32 weights, the oracle's operation order.
-// lut[c] = c / 255 exactly (IEEE division, built per block by unorm8f): a table look-up replaces the six-instruction
-// byte -> float -> / 255 sequence, 32 times per vertex — the conversions were 29 % of this pass's instructions.
-__device__ __forceinline__ float4 sample_rgba8_clamp_linear(const uchar4* tex, const float* lut, int w, int h, float s, float t) {
-    // s, t in [0, 1] (the callers clamp them): um, vm in [-0.5, w - 0.5], so floor(um) is in [-1, w - 1] — each of the four
-    // footprint indices needs one clamp only.  floor and the float -> int conversion by the magic-number add (off the XU pipe).
+// The 2 x 2 footprint comes from the texture unit, one gather per channel: it clamps the footprint to the edge and converts
+// unorm8 to exactly fl(c / 255) (all 256 values checked on the device, tools/probes/probe_unorm.cu) — the byte -> float
+// conversions and the four loads with their index arithmetic were 40 % of this pass's instructions.
+__device__ __forceinline__ float4 sample_rgba8_clamp_linear(cudaTextureObject_t tex, int w, int h, float s, float t) {
+    // s, t in [0, 1] (the callers clamp them): um, vm in [-0.5, w - 0.5]; floor by the magic-number add (off the XU pipe)
     const float um = __fsub_rn(__fmul_rn(s, (float)w), 0.5f), vm = __fsub_rn(__fmul_rn(t, (float)h), 0.5f);
     int iu, iv;
     const float fu = floor_small(um, iu), fv = floor_small(vm, iv);
     const float a = __fsub_rn(um, fu), b = __fsub_rn(vm, fv);
-    const unsigned i0 = (unsigned)max(iu, 0), i1 = (unsigned)min(iu + 1, w - 1), j0 = (unsigned)max(iv, 0), j1 = (unsigned)min(iv + 1, h - 1);
-    const unsigned* const tx = reinterpret_cast<const unsigned*>(tex);
-    const unsigned r0 = j0 * (unsigned)w, r1 = j1 * (unsigned)w;        // w, h <= 16384: the texel index fits 32 bits
-    const unsigned t00 = __ldg(tx + (r0 + i0)), t10 = __ldg(tx + (r0 + i1));
-    const unsigned t01 = __ldg(tx + (r1 + i0)), t11 = __ldg(tx + (r1 + i1));
+    // texels (fu, fu + 1) x (fv, fv + 1): their shared corner (fu + 1, fv + 1) is the gather coordinate (unnormalised, exact in fp32)
+    const float gx = __fadd_rn(fu, 1.0f), gy = __fadd_rn(fv, 1.0f);
     const float oma = __fsub_rn(1.0f, a), omb = __fsub_rn(1.0f, b);
     const float w00 = __fmul_rn(oma, omb), w10 = __fmul_rn(a, omb), w01 = __fmul_rn(oma, b), w11 = __fmul_rn(a, b);
-    auto ch = [&](unsigned k) {
-        float acc = __fmul_rn(w00, lut[(t00 >> (8 * k)) & 255u]);
-        acc = __fadd_rn(acc, __fmul_rn(w10, lut[(t10 >> (8 * k)) & 255u]));
-        acc = __fadd_rn(acc, __fmul_rn(w01, lut[(t01 >> (8 * k)) & 255u]));
-        return __fadd_rn(acc, __fmul_rn(w11, lut[(t11 >> (8 * k)) & 255u]));
+    auto ch = [&](int k) {
+        // gather order: x = (i0, j1), y = (i1, j1), z = (i1, j0), w = (i0, j0)
+        const float4 g = k == 0 ? tex2Dgather<float4>(tex, gx, gy, 0) : k == 1 ? tex2Dgather<float4>(tex, gx, gy, 1)
+                       : k == 2 ? tex2Dgather<float4>(tex, gx, gy, 2) : tex2Dgather<float4>(tex, gx, gy, 3);
+        float acc = __fmul_rn(w00, g.w);
+        acc = __fadd_rn(acc, __fmul_rn(w10, g.z));
+        acc = __fadd_rn(acc, __fmul_rn(w01, g.x));
+        return __fadd_rn(acc, __fmul_rn(w11, g.y));
     };
     return make_float4(ch(0), ch(1), ch(2), ch(3));
 }
 
-__global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
-    __shared__ float lut[256];
-    lut[threadIdx.x] = unorm8f((float)threadIdx.x);     // launched with 256 threads per block
-    __syncthreads();
+#ifndef WT_COMPOSE_MIN_BLOCKS
+#define WT_COMPOSE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, WT_COMPOSE_MIN_BLOCKS) compose_kernel(const ComposeArgs a) {
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.n; k += (long long)gridDim.x * blockDim.x) {
         const float4 P = __ldcs(a.pos + k), N = __ldcs(a.nrm + k), S = __ldcs(a.shade + k);
         float4 C, A, B;
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeArgs a) {
         const float mx = mix_f(uvx, h0x, ds), my = mix_f(uvy, h0y, ds);
         const float rlx = clamp_f(__fadd_rn(mx, __fmul_rn(ds, B.x)), 0.0f, 1.0f), rly = clamp_f(__fadd_rn(my, __fmul_rn(ds, -B.z)), 0.0f, 1.0f);
         const float rrx = clamp_f(__fadd_rn(mx, __fmul_rn(ds, -B.x)), 0.0f, 1.0f), rry = clamp_f(__fadd_rn(my, __fmul_rn(ds, B.z)), 0.0f, 1.0f);
-        const float4 refl = sample_rgba8_clamp_linear(a.refl, lut, a.w, a.h, rlx, rly);
-        const float4 refr = sample_rgba8_clamp_linear(a.refr, lut, a.w, a.h, rrx, rry);
+        const float4 refl = sample_rgba8_clamp_linear(a.refl, a.w, a.h, rlx, rly);
+        const float4 refr = sample_rgba8_clamp_linear(a.refr, a.w, a.h, rrx, rry);
         // frag:136-151 tint, transmission, reflection, Fresnel mix
         const float tint_f = a.tint_threshold == 0.0f ? 0.0f : __fmul_rn(hack, __fsub_rn(1.0f, clamp_f(div_by_uniform(dcl, a.tint_threshold, a.r_tint), 0.0f, 1.0f)));
         const float t_w = __fmul_rn(__fmul_rn(a.clarity, refr.w), __fsub_rn(1.0f, dcl));
@@ -157,17 +157,46 @@ int wt_set_screen_textures(wt_ctx* ctx, const float* depth, const uint8_t* refl,
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
-    ctx->d_depth = nullptr; ctx->d_refl = ctx->d_refr = nullptr;
+    // build into temporaries: the context keeps its previous textures unless every step succeeds
+    float* d_depth = nullptr;
+    cudaArray_t arr[2] = {nullptr, nullptr};
+    cudaTextureObject_t tex[2] = {0, 0};
     const size_t n = (size_t)w * h;
-    cudaError_t e = cudaMalloc(&ctx->d_depth, n * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_refl, n * sizeof(uchar4));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_refr, n * sizeof(uchar4));
-    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_depth, depth, n * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_refl, refl, n * sizeof(uchar4), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_refr, refr, n * sizeof(uchar4), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMalloc(&d_depth, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_depth, depth, n * sizeof(float), cudaMemcpyHostToDevice);
+    const uint8_t* const src[2] = {refl, refr};
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        e = cudaMallocArray(&arr[k], &fmt, (size_t)w, (size_t)h, cudaArrayTextureGather);
+        if (e == cudaSuccess) e = cudaMemcpy2DToArray(arr[k], 0, 0, src[k], (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        cudaResourceDesc res;
+        std::memset(&res, 0, sizeof(res));
+        res.resType = cudaResourceTypeArray;
+        res.res.array.array = arr[k];
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;   // GL_CLAMP_TO_EDGE (render-engine.cpp:138-188)
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 0;
+        e = cudaCreateTextureObject(&tex[k], &res, &td, nullptr);
+    }
+    if (e != cudaSuccess) {
+        for (int k = 0; k < 2; ++k) { if (tex[k]) cudaDestroyTextureObject(tex[k]); if (arr[k]) cudaFreeArray(arr[k]); }
+        cudaFree(d_depth);
+        if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+        return fail(WT_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(ctx->d_depth);
+    if (ctx->refl_tex) cudaDestroyTextureObject(ctx->refl_tex);
+    if (ctx->refr_tex) cudaDestroyTextureObject(ctx->refr_tex);
+    if (ctx->refl_arr) cudaFreeArray(ctx->refl_arr);
+    if (ctx->refr_arr) cudaFreeArray(ctx->refr_arr);
+    ctx->d_depth = d_depth;
+    ctx->refl_arr = arr[0]; ctx->refr_arr = arr[1];
+    ctx->refl_tex = tex[0]; ctx->refr_tex = tex[1];
     if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
-    if (e != cudaSuccess) return fail(WT_ERR_CUDA, cudaGetErrorString(e));
     ctx->screen_w = w; ctx->screen_h = h;
     return WT_OK;
 }
@@ -191,7 +220,7 @@ int wt_compose_frame(wt_ctx* ctx, const wt_frame* frame, const wt_compose_params
     std::memcpy(a.vp, frame->viewProjection, sizeof(a.vp));
     for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) a.vy[3 * c + r] = frame->viewMatOnlyYaw[4 * c + r];
     a.colour = (float4*)d_colour;
-    a.depth = ctx->d_depth; a.refl = ctx->d_refl; a.refr = ctx->d_refr; a.w = ctx->screen_w; a.h = ctx->screen_h;
+    a.depth = ctx->d_depth; a.refl = ctx->refl_tex; a.refr = ctx->refr_tex; a.w = ctx->screen_w; a.h = ctx->screen_h;
     a.n = (long long)(r1 - r0) * L;
     const float sy = std::fmin(std::fmax(frame->sunPosition[1], 0.0f), 1.0f);
     for (int c = 0; c < 3; ++c) a.fog[c] = sy * p->fogColourFarAtNoon[c];   // fogColourFarAtCurrentTime, render-engine.cpp:295

@@ -42,7 +42,9 @@ struct wt_ctx {
     cudaSurfaceObject_t sky_surf = 0;
     // screen-space inputs of the compose pass (wt_set_screen_textures)
     float* d_depth = nullptr;
-    uchar4 *d_refl = nullptr, *d_refr = nullptr;
+    // reflection / refraction colour textures as gather-able arrays (texture unit: footprint fetch + exact c / 255)
+    cudaArray_t refl_arr = nullptr, refr_arr = nullptr;
+    cudaTextureObject_t refl_tex = 0, refr_tex = 0;
     int screen_w = 0, screen_h = 0;
     // scratch for the *_host entry points
     float4 *s_pos = nullptr, *s_nrm = nullptr, *s_shade = nullptr;

@@ -413,7 +413,11 @@ void wt_destroy(wt_ctx* ctx) {
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace); cudaFree(ctx->d_batch_done);
     cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done); cudaFree(ctx->d_step_cks);
-    cudaFree(ctx->d_depth); cudaFree(ctx->d_refl); cudaFree(ctx->d_refr);
+    cudaFree(ctx->d_depth);
+    if (ctx->refl_tex) cudaDestroyTextureObject(ctx->refl_tex);
+    if (ctx->refr_tex) cudaDestroyTextureObject(ctx->refr_tex);
+    if (ctx->refl_arr) cudaFreeArray(ctx->refl_arr);
+    if (ctx->refr_arr) cudaFreeArray(ctx->refr_arr);
     cudaFree(ctx->d_stars); cudaFree(ctx->d_clouds); cudaFree(ctx->d_sky_unsure);
     if (ctx->h_cks_pinned) cudaFreeHost(ctx->h_cks_pinned);
     for (unsigned i = 0; i < STEP_RING; ++i) if (ctx->step_event[i]) cudaEventDestroy(ctx->step_event[i]);
