@@ -49,9 +49,13 @@ extern "C" {
 #define WT_FLAG_REFERENCE_ORDER 0x8u  /* straight transliteration: 5 full evaluations per vertex, libdevice sincosf */
 #define WT_FLAG_VARYINGS 0x10u        /* also write the vertex stage's other outputs (wt_eval_frame_ex): gl_Position,
                                          xyPositionNDCSpaceHeight0, heightmap_colour.r, normalVecInViewSpaceOnlyYaw */
-#define WT_FLAG_STENCIL_ORDER 0x40u    /* the shader's own structure — five full evaluations per vertex, the four stencil neighbours at uv +- du exactly as
-                                         water-grid.vert:164-182 forms them — with the production kernels' trigonometry (Cody-Waite + MUFU): reproduces
-                                         the reference at any animation time, at ~4x the cost of the bit-faithful kernel */
+#define WT_FLAG_STENCIL_ORDER 0x40u    /* the shader's own stencil — the four neighbours evaluated at uv +- du exactly as water-grid.vert:164-182 forms them —
+                                         with the production kernels' trigonometry (Cody-Waite + MUFU): reproduces the reference at any animation
+                                         time.  Those arguments differ from the neighbours' own uv only at the grid indices i where
+                                         fl(fl(i du) +- du) != fl((i +- 1) du) (0.3 % of them at 4096, 19 % at 8192): the bit-faithful kernel runs first,
+                                         then a fix-up pass re-evaluates the stencils of those rows and columns and redoes their normals and shading
+                                         terms (+2 % at 4096^2; positions are the bit-faithful kernel's).  On grid sizes where most indices are flagged (an odd size
+                                         like 700) one kernel evaluates all five points of every vertex instead.  Not available with WT_FLAG_VARYINGS */
 #define WT_FLAG_AUTO_PHASE 0x20u      /* per frame, the fastest kernel whose deviation from the reference wt_fast_phase_report bounds inside the
                                          tolerances: the recurrence kernel, else the bit-faithful kernel, else (late in an animation, where
                                          the shader's own re-evaluation of the stencil neighbours becomes noisy) the stencil-order kernel.
@@ -444,6 +448,10 @@ void wt_debug_reload_env(void);
  * row shards bit-identical to the unsharded evaluation.  Writes (begin, end) pairs to out[0 .. 2 capacity) in launch
  * order and returns the number of chunks (which may exceed capacity: nothing is written then), or < 0. */
 int wt_debug_layout(unsigned grid_len, int rows_per_step, int phase_mode, unsigned row_begin, unsigned row_end, int* out, unsigned capacity);
+/* Diagnostic: which form WT_FLAG_STENCIL_ORDER runs — 0 (default): the cheaper one for the grid size (the fix-up form unless
+ * more than 30 % of the stencil arguments are flagged, e.g. grid_len 700); 1: one kernel with five full evaluations per vertex
+ * (4.5x the bit-faithful kernel); 2: the bit-faithful kernel + fix-up pass.  The tests hold the two against each other. */
+int wt_debug_full_stencil(wt_ctx* ctx, int form);
 
 #ifdef __cplusplus
 }

@@ -340,6 +340,83 @@ def test_row_sharded_equals_unsharded_bit_exact(cfg3, mode):
     assert c["min_y"] == f["min_y"] and c["max_y"] == f["max_y"]
 
 
+def stencil_flags(L):
+    """numpy restatement of the fix-up table (wt_device.cu:ensure_fixup_tables): bit 0 / 1 where the shader's neighbour
+    argument fl(fl(i du) -/+ du) is not the neighbour's own fl((i -/+ 1) du)."""
+    f32 = np.float32
+    du = f32(1.0) / f32(L - 1)
+    i = np.arange(L, dtype=np.float32)
+    u = (i * du).astype(f32)
+    lo, hi = ((i - f32(1)) * du).astype(f32), ((i + f32(1)) * du).astype(f32)
+    return ((u - du).astype(f32) != lo).astype(np.uint8) | (((u + du).astype(f32) != hi).astype(np.uint8) << 1)
+
+
+def words_digest(out, shade):
+    s = lambda a, ncomp: int(a[:, :ncomp].view(np.uint32).astype(np.uint64).sum(dtype=np.uint64))
+    return s(out["pos"], 3), s(out["normal"], 4), (s(out["shade"], 4) if shade else 0)
+
+
+@pytest.mark.parametrize("L,nw,cfg,shade,t", [(1024, 8, 2, False, 3600.0), (700, 64, 3, True, 3600.0), (4096, 64, 3, True, 3600.0), (513, 4, 1, True, 900.0)])
+def test_stencil_fixup_equals_the_five_evaluation_kernel(hm, L, nw, cfg, shade, t):
+    """WT_FLAG_STENCIL_ORDER = the bit-faithful kernel + a fix-up pass over the rows / columns whose stencil arguments differ
+    from their neighbours' own, against the one-kernel form that evaluates all five points of every vertex
+    (wt_debug_full_stencil).  Late in the animation, where the plain bit-faithful kernel is far off on exactly those rows and
+    columns: positions identical; normals and shading terms bit-identical on the flagged rows / columns (same arithmetic, same
+    neighbour positions), untouched elsewhere, where the two forms differ only by their normalisation arithmetic; the digest
+    follows the corrected outputs; row shards reproduce the unsharded bits."""
+    from wave_tool_b200 import shard
+    waves = scenes.default_waves() if cfg == 1 else scenes.seeded_waves(nw, cfg=cfg)
+    p = api.default_params()
+    p.waveAnimationTimeInSeconds = t
+    sc = Scene(waves, scenes.camera(), p, L, hm, skybox=scenes.procedural_skybox(64) if shade else None)
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    fl = api.FLAG_SHADE if shade else 0
+    plain = gpu_eval(ctx, frame, L, flags=fl)
+    ctx.stencil_form(2)
+    fixed = gpu_eval(ctx, frame, L, flags=fl | api.FLAG_STENCIL_ORDER, checksum=True)
+    assert api.PHASE_NAMES[ctx.last_phase_mode()] == "stencil-order"
+    ctx.stencil_form(1)
+    five = gpu_eval(ctx, frame, L, flags=fl | api.FLAG_STENCIL_ORDER, checksum=True)
+    ctx.stencil_form(2)
+    flags = stencil_flags(L)
+    flagged = ((flags[None, :] != 0) | (flags[:, None] != 0)).reshape(-1)       # [row, col]
+    print(f"stencil fix-up L={L}: {int((flags != 0).sum())} flagged indices, {flagged.mean():.4f} of the vertices redone")
+    assert flagged.mean() < 1 and (flagged.any() or L == 513)      # du = 1 / 512 is a power of two: no argument ever differs
+    u32 = lambda a: a.view(np.uint32)
+    assert np.array_equal(u32(fixed["pos"]), u32(plain["pos"])) and np.array_equal(u32(five["pos"]), u32(plain["pos"]))
+    keys = ("normal", "shade") if shade else ("normal",)
+    for k in keys:
+        assert np.array_equal(u32(fixed[k])[flagged], u32(five[k])[flagged]), k            # redone with the five-evaluation arithmetic
+        assert np.array_equal(u32(fixed[k])[~flagged], u32(plain[k])[~flagged]), k          # not touched
+    # the two forms agree everywhere up to the normalisation arithmetic (MUFU rsqrt vs IEEE sqrt / div) ...
+    either = lambda a, b: np.minimum(angle_between(a, b), angle_between(a, -b))    # the view-facing flip may go either way at |dot| ~ 0
+    ang = either(fixed["normal"][:, :3], five["normal"][:, :3])
+    assert ang.max() < 2e-6, ang.max()
+    # ... while the plain bit-faithful kernel, which shares positions between stencils, is off on the flagged vertices by now
+    off = either(plain["normal"][:, :3], five["normal"][:, :3])
+    print(f"  plain vs five-evaluation normals: max {off.max():.2e} rad on flagged vertices, {off[~flagged].max():.2e} elsewhere")
+    assert off[~flagged].max() < 2e-6
+    if t >= 3600.0 and flagged.any():
+        assert off[flagged].max() > 1e-4
+    # digest = the words actually in the buffers, for both forms
+    for out in (fixed, five):
+        c = out["checksum"]
+        assert (int(c["position_bits"]), int(c["normal_bits"]), int(c["shade_bits"])) == words_digest(out, shade)
+        assert int(c["vertices"]) == L * L
+    # row shards: same bits, digests fold
+    parts = []
+    for b, e in [(0, 1), (1, 130), (130, L - 1), (L - 1, L)]:
+        part = gpu_eval(ctx, frame, L, flags=fl | api.FLAG_STENCIL_ORDER, rows=(b, e), checksum=True)
+        for k in ("pos",) + keys:
+            assert np.array_equal(u32(part[k]), u32(fixed[k][b * L:e * L])), (b, e, k)
+        parts.append(part["checksum"])
+    c = shard.combine_checksums(np.array(parts))
+    f = fixed["checksum"]
+    assert (c["position_bits"], c["normal_bits"], c["shade_bits"], c["vertices"]) == (f["position_bits"], f["normal_bits"], f["shade_bits"], f["vertices"])
+
+
 # --------------------------------------------------------------------------------------------------
 # configs[3]: 8192^2 grid, 256 waves (row bands only — 2.15 GB per full frame)
 # --------------------------------------------------------------------------------------------------

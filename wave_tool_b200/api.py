@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
     "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
-    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count", "wt_debug_full_stencil",
 ]
 
 
@@ -169,6 +169,7 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
     L.wt_debug_reload_env.restype = None
     L.wt_debug_layout.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_uint]
+    L.wt_debug_full_stencil.argtypes = [C.c_void_p, C.c_int]
     L.wt_eval_frame_ex.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs), C.c_uint, C.c_void_p]
     L.wt_grid_indices.argtypes = [C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.wt_default_compose_params.argtypes = [C.POINTER(ComposeParams), C.POINTER(Camera), C.c_uint, C.c_uint]
@@ -419,6 +420,10 @@ class Context:
 
     def synthesize_skybox(self, params: "SkyParams", n: int, stream: int = 0):
         return _check(self._lib.wt_synthesize_skybox(self._h, C.byref(params), n, stream or None), self._h)
+
+    def stencil_form(self, form: int):
+        """wt_debug_full_stencil: 0 = automatic, 1 = one kernel with five evaluations per vertex, 2 = bit-faithful kernel + fix-up pass."""
+        _check(self._lib.wt_debug_full_stencil(self._h, int(form)), self._h)
 
     def sky_exact_texels(self) -> int:
         v = C.c_uint64()

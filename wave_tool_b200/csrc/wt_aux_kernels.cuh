@@ -181,6 +181,142 @@ __global__ void __launch_bounds__(128) surface_stencil_order_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stencil fix-up (WT_FLAG_STENCIL_ORDER, what WT_FLAG_AUTO_PHASE runs as its third tier).
+//   The shader evaluates the four stencil neighbours of vertex (row, col) at uv -/+ du (water-grid.vert:164-167).  Those
+//   arguments are the neighbours' OWN uv = fl(index * du) except where fl(fl(i du) -/+ du) != fl((i -/+ 1) du) — a property
+//   of the index i and the grid size alone, the same table for rows and columns (0.3 % of the indices at 4096, 4 % at 1024,
+//   19 % at 8192, 11 % at 16384).  Everywhere else the shader's neighbour positions are bit for bit the positions the
+//   bit-faithful production kernel shares through its ring.  So the shader's structure = the production kernel + this pass
+//   over the flagged columns (every row) and flagged rows (every column): a flagged neighbour is re-evaluated at the
+//   shader's argument (the production kernel's arithmetic, scalar), an unflagged one is read back from the position buffer,
+//   and the vertex's normal and shading terms are redone.  The digest is corrected by (new - old) words.
+// ------------------------------------------------------------------------------------------------
+// one point per half with the bit-faithful production kernel's arithmetic (table = tab_exact; the packed statement of
+// surface_warp_kernel's MODE 0 wave loop and of hm_fetch2 / hm_finish2's scalar twin): same bits as that kernel's positions
+template <int CAP>
+__device__ __forceinline__ void displaced_bit_faithful2(const EvalArgs& a, const WaveTable<CAP>& wt, f2 u, f2 v, P3& lo, P3& hi) {
+    const float one = a.one;
+    const f2 x = make_float2(mix_rn(mix_rn(a.blx, a.brx, u.x), mix_rn(a.tlx, a.trx, u.x), v.x), mix_rn(mix_rn(a.blx, a.brx, u.y), mix_rn(a.tlx, a.trx, u.y), v.y));   // :87-91
+    const f2 z = make_float2(mix_rn(mix_rn(a.blz, a.brz, u.x), mix_rn(a.tlz, a.trz, u.x), v.x), mix_rn(mix_rn(a.blz, a.brz, u.y), mix_rn(a.tlz, a.trz, u.y), v.y));
+    f2 ax = x, ay = bc(0.0f), az = z;
+    for (int i = 0; i < a.n_waves; ++i) {   // :76-82
+        const WaveK wk = wt.w[i];
+        const float pt = mul_rn(wk.phi, a.t);
+        const f2 d = add2x(mul2(bc(wk.Dx), x), mul2(bc(wk.Dz), z), one);
+        const f2 k = add2x(mul2(bc(wk.w), d), bc(pt), one);
+        f2 sn, cs;
+        sincos2(k, sn, cs);
+        ax = fma2(bc(wk.cX), cs, ax);
+        ay = fma2(bc(wk.A), sn, ay);
+        az = fma2(bc(wk.cZ), cs, az);
+    }
+    lo = {ax.x, finish_height(a, ax.x, ay.x, az.x), az.x};
+    hi = {ax.y, finish_height(a, ax.y, ay.y, az.y), az.y};
+}
+
+struct FixupArgs {
+    const unsigned char* flags;   // [L]: bit 0 = the "minus" argument fl(fl(i du) - du) differs from fl((i - 1) du), bit 1 = the "plus" one
+    const int* idx;               // the flagged indices, ascending
+    const int* perm;              // [L]: every index, the unflagged ones first — consecutive threads of a column job then share
+                                  // their up / down pattern too (a warp re-evaluates a neighbour if any of its lanes needs it)
+    int n_idx;
+};
+
+// One warp per CTA and a tile of 64 consecutive jobs per trip, two per lane (the halves of packed evaluations): every loop
+// bound and the decision to re-evaluate a neighbour (a warp vote) are uniform, so the wave loop fetches its constants through
+// the uniform datapath like the production kernel, once per pair of points.  (Per-lane constant loads made the first version
+// of this pass MIO-bound — issue slots 38 % busy, mio_throttle 13.7 — and so did uniform loads amortised over one point.)
+template <int CAP, bool SHADE>
+__global__ void __launch_bounds__(32, 24) stencil_fixup_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ WaveTable<CAP> wt, const FixupArgs f) {
+    const int lane = threadIdx.x;
+    const int plain_cols = a.L - f.n_idx;
+    const long long col_jobs = (long long)f.n_idx * a.L;                  // (flagged column, every row): rows outside the range drop out
+    const long long jobs = col_jobs + (long long)f.n_idx * plain_cols;    // + (flagged row, every unflagged column: a flagged column is a column job)
+    const long long tiles = (jobs + 63) / 64;
+    const float du = a.du;
+    ChecksumAcc fresh, stale;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        bool active[2];
+        int r[2], c[2];
+        long long k[2];
+        unsigned fc[2], fr[2];
+        float u[2], v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long t = tile * 64 + 32 * h + lane;
+            active[h] = t < jobs;
+            r[h] = a.row_begin; c[h] = 0;
+            if (active[h]) {
+                if (t < col_jobs) {
+                    c[h] = f.idx[t / a.L];
+                    r[h] = f.perm[t % a.L];
+                } else {
+                    const long long q = t - col_jobs;
+                    r[h] = f.idx[q / plain_cols];
+                    c[h] = f.perm[q % plain_cols];
+                }
+                active[h] = r[h] >= a.row_begin && r[h] < a.row_end;
+                if (!active[h]) r[h] = a.row_begin;
+            }
+            fc[h] = f.flags[c[h]]; fr[h] = f.flags[r[h]];
+            u[h] = mul_rn((float)c[h], du); v[h] = mul_rn((float)r[h], du);   // :123-125
+            k[h] = (long long)(r[h] - a.row_begin) * a.L + c[h];
+        }
+        // left, right, down, up: read back where the shader's argument is the neighbour's own and the neighbour is in the buffer
+        P3 nb[2][4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            bool shared[2];
+            long long kn[2];
+            float un[2], vn[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                shared[h] = s == 0 ? (!(fc[h] & 1u) && c[h] > 0) : s == 1 ? (!(fc[h] & 2u) && c[h] < a.L - 1)
+                          : s == 2 ? (!(fr[h] & 1u) && r[h] > a.row_begin) : (!(fr[h] & 2u) && r[h] < a.row_end - 1);
+                kn[h] = k[h] + (s == 0 ? -1 : s == 1 ? 1 : s == 2 ? -(long long)a.L : (long long)a.L);
+                un[h] = s == 0 ? sub_rn(u[h], du) : s == 1 ? add_rn(u[h], du) : u[h];
+                vn[h] = s == 2 ? sub_rn(v[h], du) : s == 3 ? add_rn(v[h], du) : v[h];
+            }
+            const bool need0 = active[0] && !shared[0], need1 = active[1] && !shared[1];
+            if (__any_sync(0xffffffffu, need0 || need1)) {
+                // every lane evaluates both halves (the tile's jobs nearly always agree: same column or same row, rows ordered by their flags)
+                P3 e0, e1;
+                displaced_bit_faithful2<CAP>(a, wt, make_float2(un[0], un[1]), make_float2(vn[0], vn[1]), e0, e1);
+                if (need0) nb[0][s] = e0;
+                if (need1) nb[1][s] = e1;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (active[h] && shared[h]) {
+                    const float4 q = a.pos[kn[h]];
+                    nb[h][s] = {q.x, q.y, q.z};
+                }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (active[h]) {
+                const float4 pc = a.pos[k[h]];
+                if (a.cks) {
+                    stale.add(pc, a.nrm[k[h]]);
+                    if (SHADE) stale.add_shade(a.shade[k[h]]);
+                }
+                const P3 centre = {pc.x, pc.y, pc.z};
+                finish_five_eval<SHADE>(a, k[h], centre, nb[h][0], nb[h][1], nb[h][2], nb[h][3], fresh);
+            }
+    }
+    if (a.cks) {
+        // the record already holds the production kernel's finished digest: add (new - old) of the vertices redone here
+        unsigned long long dn = fresh.nrm - stale.nrm, ds = fresh.shd - stale.shd;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { dn += __shfl_xor_sync(0xffffffffu, dn, o); ds += __shfl_xor_sync(0xffffffffu, ds, o); }
+        if (lane == 0 && (dn | ds)) {
+            atomicAdd((unsigned long long*)&a.cks->normal_bits, dn);
+            atomicAdd((unsigned long long*)&a.cks->shade_bits, ds);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Roofline denominators measured on the device itself (wt_measure_peak)
 // ------------------------------------------------------------------------------------------------
 __global__ void peak_mufu_kernel(float* sink, int iters) {

@@ -22,6 +22,12 @@ struct wt_ctx {
     std::vector<wt_wave> waves;     // as handed to wt_set_waves (wt_fast_phase_valid)
     float max_horizontal = 0.0f;    // sum_i |A_i Q_i D_i|_1: the furthest a vertex can move sideways
     int last_phase_mode = -1;       // WT_PHASE_*: what the most recent evaluation launch ran
+    // stencil fix-up tables of the grid size last used with WT_FLAG_STENCIL_ORDER (they depend on grid_len alone)
+    unsigned char* d_fix_flags = nullptr;
+    int *d_fix_idx = nullptr, *d_fix_perm = nullptr;
+    int fix_L = 0, fix_n = 0;
+    float fix_side_rate = 0.0f;     // probability that one of a vertex's four stencil arguments is flagged (set bits / 2 L)
+    int stencil_form = 0;           // wt_debug_full_stencil: 0 = whichever is cheaper for the grid, 1 = five evaluations per vertex, 2 = fix-up form
     uint64_t mode_launches[4] = {0, 0, 0, 0};   // evaluation launches per kernel, indexed by WT_PHASE_* (wt_phase_mode_counts)
     // textures
     float* d_hm_r = nullptr;        // R channel, c/255.0f (reference-order kernel)

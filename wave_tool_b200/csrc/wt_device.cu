@@ -234,6 +234,78 @@ cudaError_t launch_stencil(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t st
     }
 }
 
+// The index table of the stencil fix-up: i is flagged where the shader's neighbour argument fl(fl(i du) -/+ du) is not the
+// neighbour's own fl((i -/+ 1) du) (water-grid.vert:123-125,164-167).  Same table for rows and columns; cached per grid size.
+cudaError_t ensure_fixup_tables(wt_ctx* ctx, int L, float du) {
+    if (ctx->fix_L == L && ctx->d_fix_flags) return cudaSuccess;
+    std::vector<unsigned char> flags((size_t)L);
+    std::vector<int> idx;
+    long long sides = 0;
+    for (int i = 0; i < L; ++i) {
+        const float u = (float)i * du, lo = (float)(i - 1) * du, hi = (float)(i + 1) * du;
+        const float minus = u - du, plus = u + du;
+        flags[i] = (unsigned char)((minus != lo ? 1 : 0) | (plus != hi ? 2 : 0));
+        if (flags[i]) idx.push_back(i);
+        sides += (flags[i] & 1) + (flags[i] >> 1);
+    }
+    std::vector<int> perm;
+    perm.reserve((size_t)L);
+    for (int i = 0; i < L; ++i) if (!flags[i]) perm.push_back(i);
+    perm.insert(perm.end(), idx.begin(), idx.end());
+    auto drop = [&]() {
+        cudaFree(ctx->d_fix_flags); cudaFree(ctx->d_fix_idx); cudaFree(ctx->d_fix_perm);
+        ctx->d_fix_flags = nullptr; ctx->d_fix_idx = ctx->d_fix_perm = nullptr; ctx->fix_L = 0; ctx->fix_n = 0;
+    };
+    drop();
+    cudaError_t e = cudaMalloc(&ctx->d_fix_flags, (size_t)L);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fix_idx, std::max<size_t>(idx.size(), 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fix_perm, (size_t)L * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_fix_flags, flags.data(), (size_t)L, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !idx.empty()) e = cudaMemcpy(ctx->d_fix_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_fix_perm, perm.data(), (size_t)L * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { drop(); return e; }
+    ctx->fix_L = L; ctx->fix_n = (int)idx.size();
+    ctx->fix_side_rate = (float)sides / (2.0f * (float)L);
+    return cudaSuccess;
+}
+
+// Which form of WT_FLAG_STENCIL_ORDER runs on this grid (tables ensured).  The fix-up form costs about one production
+// evaluation plus 1.6 (scalar code) per re-evaluated neighbour, 4 x side_rate of them per vertex; the one-kernel form 4.5.
+// The rate is a property of du = 1 / (L - 1): 0.003 at 4096, 0.04 at 1024, 0.19 at 8192, 0.11 at 16384, ~0.5 for an odd size like 700.
+bool stencil_runs_full(const wt_ctx* ctx) {
+    if (ctx->stencil_form == 1) return true;
+    if (ctx->stencil_form == 2) return false;
+    return ctx->fix_side_rate > 0.3f;
+}
+
+template <int CAP, bool SHADE>
+cudaError_t launch_stencil_fixup(wt_ctx* ctx, EvalArgs& a, cudaStream_t stream) {
+    if (ctx->fix_n == 0) return cudaSuccess;
+    static thread_local WaveTable<CAP> table;
+    fill_table(table, ctx->tab_exact);
+    const long long jobs = (long long)ctx->fix_n * (2LL * a.L - ctx->fix_n);
+    const int blocks = (int)std::min<long long>((jobs + 63) / 64, (long long)ctx->sm_count * 24 * 4);   // one warp per CTA, 4 tiles of 64 jobs or more each
+    const FixupArgs f = {ctx->d_fix_flags, ctx->d_fix_idx, ctx->d_fix_perm, ctx->fix_n};
+    stencil_fixup_kernel<CAP, SHADE><<<std::max(blocks, 1), 32, 0, stream>>>(a, table, f);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+// WT_FLAG_STENCIL_ORDER: the bit-faithful production kernel, then the fix-up pass over the rows and columns whose stencil
+// arguments differ from their neighbours' own (see stencil_fixup_kernel).
+cudaError_t launch_stencil_hybrid(wt_ctx* ctx, EvalArgs& a, bool shade, unsigned flags, cudaStream_t stream) {
+    cudaError_t e = ensure_fixup_tables(ctx, a.L, a.du);
+    if (e != cudaSuccess) return e;
+    const unsigned pflags = flags & ~(WT_FLAG_STENCIL_ORDER | WT_FLAG_FAST_PHASE | WT_FLAG_AUTO_PHASE);
+    e = shade ? launch_production_exact_shade(ctx, a, pflags, stream) : launch_production_exact(ctx, a, pflags, stream);
+    if (e != cudaSuccess) return e;
+    switch (wave_capacity(ctx->n_waves)) {
+        case 64: return shade ? launch_stencil_fixup<64, true>(ctx, a, stream) : launch_stencil_fixup<64, false>(ctx, a, stream);
+        case 256: return shade ? launch_stencil_fixup<256, true>(ctx, a, stream) : launch_stencil_fixup<256, false>(ctx, a, stream);
+        default: return shade ? launch_stencil_fixup<1000, true>(ctx, a, stream) : launch_stencil_fixup<1000, false>(ctx, a, stream);
+    }
+}
+
 cudaError_t launch_reference(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t stream) {
     switch (wave_capacity(ctx->n_waves)) {
         case 64: return shade ? launch_reference_order<64, true>(ctx, a, stream) : launch_reference_order<64, false>(ctx, a, stream);
@@ -327,7 +399,11 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
                            : (flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL;
     ctx->mode_launches[ctx->last_phase_mode]++;
     if (flags & WT_FLAG_REFERENCE_ORDER) return launch_reference(ctx, a, shade, stream);
-    if (flags & WT_FLAG_STENCIL_ORDER) return launch_stencil(ctx, a, shade, stream);
+    if (flags & WT_FLAG_STENCIL_ORDER) {
+        const cudaError_t e = ensure_fixup_tables(ctx, a.L, a.du);
+        if (e != cudaSuccess) return e;
+        return stencil_runs_full(ctx) ? launch_stencil(ctx, a, shade, stream) : launch_stencil_hybrid(ctx, a, shade, flags, stream);
+    }
     if (flags & WT_FLAG_FAST_PHASE)
         return shade ? launch_production_recur_shade(ctx, a, flags, stream) : launch_production_recur(ctx, a, flags, stream);
     return shade ? launch_production_exact_shade(ctx, a, flags, stream) : launch_production_exact(ctx, a, flags, stream);
@@ -337,7 +413,14 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
 // into the digest record — arms the record before and decodes it after (the production kernels do both themselves).
 cudaError_t launch_frame(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t stream) {
     flags = resolve_phase(ctx, a, flags);
-    const bool ref_cks = a.cks && (flags & FIVE_EVAL_FLAGS);
+    // (WT_FLAG_STENCIL_ORDER is the production kernel + the fix-up pass, which corrects the finished record in place)
+    bool accumulates = (flags & WT_FLAG_REFERENCE_ORDER) != 0;
+    if (flags & WT_FLAG_STENCIL_ORDER) {
+        const cudaError_t e = ensure_fixup_tables(ctx, a.L, a.du);
+        if (e != cudaSuccess) return e;
+        accumulates = stencil_runs_full(ctx);
+    }
+    const bool ref_cks = a.cks && accumulates;
     if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
     const cudaError_t e = launch_eval(ctx, a, flags, stream);
     if (e != cudaSuccess) return e;
@@ -413,6 +496,7 @@ void wt_destroy(wt_ctx* ctx) {
     cudaFree(ctx->s_pos); cudaFree(ctx->s_nrm); cudaFree(ctx->s_shade); cudaFree(ctx->s_cks);
     cudaFree(ctx->d_queues); cudaFree(ctx->d_trace); cudaFree(ctx->d_batch_done);
     cudaFree(ctx->d_cks_acc); cudaFree(ctx->d_cks_done); cudaFree(ctx->d_step_cks);
+    cudaFree(ctx->d_fix_flags); cudaFree(ctx->d_fix_idx); cudaFree(ctx->d_fix_perm);
     cudaFree(ctx->d_depth);
     if (ctx->refl_tex) cudaDestroyTextureObject(ctx->refl_tex);
     if (ctx->refr_tex) cudaDestroyTextureObject(ctx->refr_tex);
@@ -871,6 +955,13 @@ uint64_t wt_launch_count(const wt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t wt_batched_frame_count(const wt_ctx* ctx) { return ctx ? ctx->batched_frames : 0; }
 
 void wt_debug_reload_env(void) { g_knobs.load(); }
+
+int wt_debug_full_stencil(wt_ctx* ctx, int on) {
+    if (!ctx) return fail(nullptr, WT_ERR_INVALID_ARGUMENT, "wt_debug_full_stencil: ctx is NULL");
+    if (on < 0 || on > 2) return fail(ctx, WT_ERR_INVALID_ARGUMENT, "wt_debug_full_stencil: 0 (automatic), 1 (five evaluations per vertex) or 2 (fix-up form)");
+    ctx->stencil_form = on;
+    return WT_OK;
+}
 
 int wt_debug_layout(unsigned L, int rows_per_step, int phase_mode, unsigned row_begin, unsigned row_end, int* out, unsigned capacity) {
     if (L < 2 || L > 32768 || rows_per_step < 1 || row_begin >= row_end || row_end > L || !out)
