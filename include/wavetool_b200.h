@@ -219,8 +219,10 @@ typedef struct wt_phase_report {
     /* The bit-faithful kernel reproduces k and the running sums bit for bit but, like the recurrence kernel, shares every
      * displaced position between the stencils of its neighbours, where the shader re-evaluates them at uv +- du
      * (water-grid.vert:164-182).  Once ulp(k) is large (late in an animation) that re-evaluation flips
-     * roundings of k and the SHADER's normals carry noise of A_i ulp(k_i) / spacing that only the five-evaluation kernels
-     * (WT_FLAG_STENCIL_ORDER / WT_FLAG_REFERENCE_ORDER: exactly the shader's arguments) reproduce. */
+     * roundings of k and the SHADER's normals carry noise of A_i ulp(k_i) / spacing that only an evaluation at exactly the
+     * shader's arguments reproduces (WT_FLAG_STENCIL_ORDER / WT_FLAG_REFERENCE_ORDER).  The arguments differ from the
+     * neighbours' own only at some grid indices (see WT_FLAG_STENCIL_ORDER) and at none when 1 / (grid_len - 1) is a power of
+     * two (513, 1025, 2049 ...): the estimate is 0 there, the bit-faithful kernel is valid at any animation time. */
     float est_shared_stencil_normal_error_rad;
     int shared_stencil_valid;                          /* 1: the bit-faithful kernel is inside ITS validity domain */
     /* What one ulp of the fp32 coordinates does to a finite-difference normal on this grid: the floor for ANY evaluation whose

@@ -60,8 +60,9 @@ def test_report_bounds_the_smooth_phase_model(oracle, name, t):
     if t >= 600.0:
         assert rep.valid == 0
     # the bit-faithful (shared-stencil) kernel: inside its domain for the first minutes of an animation on every scene,
-    # outside at the top of the slider, where only the reference-order kernel reproduces the shader's neighbour evaluations
-    assert rep.shared_stencil_valid == (1 if t <= 17.0 else 0 if t >= 3600.0 else rep.shared_stencil_valid)
+    # outside at the top of the slider, where only a kernel that evaluates the shader's own neighbour arguments follows it — except
+    # on the 513^2 grid: du = 1/512 is a power of two, no stencil argument differs from the neighbour's own, the kernel is exact there
+    assert rep.shared_stencil_valid == (1 if t <= 17.0 or name == "cfg1" else 0 if t >= 3600.0 else rep.shared_stencil_valid)
     assert rep.recommended == (api.PHASE_RECURRENCE if rep.valid else api.PHASE_BIT_FAITHFUL if rep.shared_stencil_valid else api.PHASE_STENCIL_ORDER)
     assert rep.coordinate_ulp_normal_error_rad > 0.0
 

@@ -418,6 +418,22 @@ static inline float ulp_of(float x) {
     return std::ldexp(1.0f, e - 24);
 }
 
+// does fl(fl(i du) -/+ du) differ from fl((i -/+ 1) du) for any index of an L-grid (water-grid.vert:123-125,164-167)?  Cached per L.
+static bool stencil_arguments_differ(unsigned L) {
+    static thread_local unsigned last_L = 0;
+    static thread_local bool last = true;
+    if (L == last_L) return last;
+    const float du = 1.0f / (float)(L - 1);
+    bool any = false;
+    for (unsigned i = 0; i < L && !any; ++i) {
+        const float u = (float)i * du;
+        const float minus = u - du, plus = u + du;
+        any = minus != (float)((int)i - 1) * du || plus != (float)(i + 1) * du;
+    }
+    last_L = L; last = any;
+    return any;
+}
+
 int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f, unsigned L, wt_phase_report* out) {
     if ((count && !waves) || !f || L < 2) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_fast_phase_report: bad argument");
     const float* c[4] = {f->bottomLeftGridPointInWorld, f->bottomRightGridPointInWorld, f->topLeftGridPointInWorld, f->topRightGridPointInWorld};
@@ -487,6 +503,9 @@ int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f
         a_ulp = std::fmax(a_ulp, (double)waves[i].amplitude_A * ulp_of((float)K));
     }
     r.est_shared_stencil_normal_error_rad = (float)(WT_PHASE_K_STENCIL * a_ulp * gain);
+    // ... unless no stencil argument of this grid size differs from its neighbour's own at all (du a power of two: 513, 1025, 2049 ...):
+    // the bit-faithful kernel then evaluates exactly what the shader does, at any animation time
+    if (!stencil_arguments_differ(L)) r.est_shared_stencil_normal_error_rad = 0.0f;
     // what ONE ulp of the fp32 coordinates does to a finite-difference normal: the floor of every evaluation whose sin / cos are
     // not bit-identical to the reference's libm (one flipped rounding of the running sum moves a neighbour by ulp(coord))
     r.coordinate_ulp_normal_error_rad = (float)(0.5 * uc * gain);
