@@ -585,7 +585,7 @@ def run_ours(args):
                                  "bit-faithful": "bit-faithful fp32 phase (the reference's own rounding of k), Cody-Waite reduction, MUFU sin/cos pair per vertex-wave, "
                                                  "every displaced position evaluated once and shared by the stencils of its neighbours",
                                  "reference-order": "straight transliteration of the shader: 5 full evaluations per vertex at the shader's own uv +- du arguments, libdevice sincosf",
-                                 "stencil-order": "the shader's structure (5 full evaluations per vertex at its own uv +- du arguments) with Cody-Waite + MUFU sin/cos"}[timed_kernel],
+                                 "stencil-order": "the bit-faithful kernel + a fix-up pass that re-evaluates, at the shader's own uv +- du arguments, the stencils of the rows / columns where those differ from the neighbours' own uv"}[timed_kernel],
                       "why": "WT_FLAG_AUTO_PHASE: wt_fast_phase_valid decides per frame (see parity_margin.fast_phase_report)" if phase == "auto" else "forced by --phase"},
             "ms_per_frame": ms_per_step,
             "roofline": primary,
