@@ -55,7 +55,8 @@ extern "C" {
                                          fl(fl(i du) +- du) != fl((i +- 1) du) (0.3 % of them at 4096, 19 % at 8192): the bit-faithful kernel runs first,
                                          then a fix-up pass re-evaluates the stencils of those rows and columns and redoes their normals and shading
                                          terms (+2 % at 4096^2; positions are the bit-faithful kernel's).  On grid sizes where most indices are flagged (an odd size
-                                         like 700) one kernel evaluates all five points of every vertex instead.  Not available with WT_FLAG_VARYINGS */
+                                         like 700) one kernel evaluates all five points of every vertex instead (never with WT_FLAG_VARYINGS, which only the
+                                         production kernel writes: the fix-up pass then also redoes normalVecInViewSpaceOnlyYaw) */
 #define WT_FLAG_AUTO_PHASE 0x20u      /* per frame, the fastest kernel whose deviation from the reference wt_fast_phase_report bounds inside the
                                          tolerances: the recurrence kernel, else the bit-faithful kernel, else (late in an animation, where
                                          the shader's own re-evaluation of the stencil neighbours becomes noisy) the stencil-order kernel.

@@ -628,6 +628,46 @@ def test_varyings_clip_ndc_yaw_normal(oracle, hm, mode, shade):
     print("varyings", mode, shade, stats, float(clip_err.max()), float(ndc_err.max()), float(hm_err.max()))
 
 
+def test_varyings_with_the_stencil_fixup(hm):
+    """WT_FLAG_VARYINGS with WT_FLAG_STENCIL_ORDER (what WT_FLAG_AUTO_PHASE picks late in an animation): gl_Position and the
+    height-0 NDC position are the production kernel's, normalVecInViewSpaceOnlyYaw follows the redone normal on the rows /
+    columns the fix-up pass touches and is the production kernel's elsewhere."""
+    torch = torch_mod()
+    L = 1024
+    p = api.default_params()
+    p.waveAnimationTimeInSeconds = 3600.0
+    sc = Scene(scenes.seeded_waves(8, cfg=2), scenes.camera(pos=(3.0, 11.0, 60.0), yaw=-75.0, pitch=-17.0, aspect=1.6), p, L, hm, skybox=scenes.procedural_skybox(32))
+    st, frame = sc.frame()
+    assert st == api.WT_OK
+    ctx = sc.make_context()
+    n = L * L
+
+    def run(flags):
+        bufs = {k: torch.empty((n, 4), dtype=torch.float32, device="cuda") for k in ("pos", "normal", "shade", "clip", "va", "vb")}
+        out = api.Outputs(bufs["pos"].data_ptr(), bufs["normal"].data_ptr(), bufs["shade"].data_ptr(), bufs["clip"].data_ptr(), bufs["va"].data_ptr(), bufs["vb"].data_ptr(), None)
+        assert ctx.eval_frame_ex(frame, L, out, flags=flags, stream=torch.cuda.current_stream().cuda_stream) == api.WT_OK
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in bufs.items()}
+    base = api.FLAG_SHADE | api.FLAG_VARYINGS
+    plain, fixed, auto = run(base), run(base | api.FLAG_STENCIL_ORDER), run(base | api.FLAG_AUTO_PHASE)
+    assert api.PHASE_NAMES[ctx.last_phase_mode()] == "stencil-order"             # AUTO at t = 3600 s on this grid
+    flags = stencil_flags(L)
+    flagged = ((flags[None, :] != 0) | (flags[:, None] != 0)).reshape(-1)
+    u32 = lambda a: a.view(np.uint32)
+    for k in ("pos", "clip", "va"):
+        assert np.array_equal(u32(fixed[k]), u32(plain[k])), k
+    for k in ("normal", "shade", "vb"):
+        assert np.array_equal(u32(fixed[k])[~flagged], u32(plain[k])[~flagged]), k
+        assert np.array_equal(u32(fixed[k]), u32(auto[k])), k
+    assert not np.array_equal(u32(fixed["normal"])[flagged], u32(plain["normal"])[flagged])
+    # the yaw-only view-space normal of the redone vertices is the rotation of their (new) normal
+    m = np.array(frame.viewMatOnlyYaw[:], np.float64).reshape(4, 4).T[:3, :3]
+    want = fixed["normal"][flagged, :3].astype(np.float64) @ m.T
+    want /= np.linalg.norm(want, axis=1, keepdims=True)
+    assert angle_between(fixed["vb"][flagged, :3], want).max() < 2e-6
+    assert np.all(fixed["vb"][:, 3] == 0.0)
+
+
 def test_varyings_argument_checks(hm):
     torch = torch_mod()
     sc = Scene(scenes.default_waves(), scenes.camera(), scenes.animation_params(0), 64, hm)

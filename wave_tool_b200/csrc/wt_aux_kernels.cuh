@@ -64,8 +64,8 @@ __device__ __forceinline__ P3 displaced_reference_order(const EvalArgs& a, const
 // Normal, view-facing flip, shading terms and the stores of one vertex from its five evaluated points (:164-190, frag:71-111),
 // with IEEE sqrt / div like the CPU reference.  Shared by the two five-evaluation kernels.
 template <bool SHADE>
-__device__ __forceinline__ void finish_five_eval(const EvalArgs& a, long long k, const P3& c, const P3& left, const P3& right, const P3& down, const P3& up,
-                                                 ChecksumAcc& acc) {
+__device__ __forceinline__ float4 finish_five_eval(const EvalArgs& a, long long k, const P3& c, const P3& left, const P3& right, const P3& down, const P3& up,
+                                                   ChecksumAcc& acc) {
     float ux = sub_rn(right.x, left.x), uy = sub_rn(right.y, left.y), uz = sub_rn(right.z, left.z);
     float vx = sub_rn(up.x, down.x), vy = sub_rn(up.y, down.y), vz = sub_rn(up.z, down.z);
     float nx = sub_rn(mul_rn(uy, vz), mul_rn(vy, uz));
@@ -102,6 +102,7 @@ __device__ __forceinline__ void finish_five_eval(const EvalArgs& a, long long k,
     a.nrm[k] = on;
     if (SHADE) a.shade[k] = os;
     if (a.cks) { acc.add(op, on); if (SHADE) acc.add_shade(os); }
+    return on;
 }
 
 template <int CAP, bool SHADE>
@@ -301,7 +302,17 @@ __global__ void __launch_bounds__(32, 24) stencil_fixup_kernel(const __grid_cons
                     if (SHADE) stale.add_shade(a.shade[k[h]]);
                 }
                 const P3 centre = {pc.x, pc.y, pc.z};
-                finish_five_eval<SHADE>(a, k[h], centre, nb[h][0], nb[h][1], nb[h][2], nb[h][3], fresh);
+                const float4 n = finish_five_eval<SHADE>(a, k[h], centre, nb[h][0], nb[h][1], nb[h][2], nb[h][3], fresh);
+                if (a.vary_b) {
+                    // WT_FLAG_VARYINGS: normalVecInViewSpaceOnlyYaw follows the normal (:193; the production kernel's operations);
+                    // gl_Position and the height-0 NDC position depend on the position alone and stay
+                    const float* const y = a.vy;
+                    float yn[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) yn[q] = __fmaf_rn(y[6 + q], n.z, __fmaf_rn(y[3 + q], n.y, __fmul_rn(y[q], n.x)));
+                    const float yi = rsq_approx(__fmaf_rn(yn[0], yn[0], __fmaf_rn(yn[1], yn[1], __fmul_rn(yn[2], yn[2]))));
+                    a.vary_b[k[h]] = make_float4(yn[0] * yi, yn[1] * yi, yn[2] * yi, 0.0f);
+                }
             }
     }
     if (a.cks) {

@@ -272,7 +272,8 @@ cudaError_t ensure_fixup_tables(wt_ctx* ctx, int L, float du) {
 // Which form of WT_FLAG_STENCIL_ORDER runs on this grid (tables ensured).  The fix-up form costs about one production
 // evaluation plus 1.6 (scalar code) per re-evaluated neighbour, 4 x side_rate of them per vertex; the one-kernel form 4.5.
 // The rate is a property of du = 1 / (L - 1): 0.003 at 4096, 0.04 at 1024, 0.19 at 8192, 0.11 at 16384, ~0.5 for an odd size like 700.
-bool stencil_runs_full(const wt_ctx* ctx) {
+bool stencil_runs_full(const wt_ctx* ctx, const EvalArgs& a) {
+    if (a.clip) return false;               // WT_FLAG_VARYINGS: only the production kernel writes them
     if (ctx->stencil_form == 1) return true;
     if (ctx->stencil_form == 2) return false;
     return ctx->fix_side_rate > 0.3f;
@@ -372,8 +373,7 @@ EvalArgs make_args(const wt_ctx* ctx, const wt_frame& f, unsigned L, unsigned r0
 }
 
 // WT_FLAG_AUTO_PHASE for one frame: the fastest kernel whose deviation from the reference wt_fast_phase_report bounds inside
-// the tolerances (this frame's corners and time): recurrence, else bit-faithful, else reference-order.  The reference-order
-// kernel has no WT_FLAG_VARYINGS variant: with that flag the bit-faithful kernel is the last resort.
+// the tolerances (this frame's corners and time): recurrence, else bit-faithful, else the stencil-order form.
 unsigned resolve_phase(const wt_ctx* ctx, const EvalArgs& a, unsigned flags) {
     if (!(flags & WT_FLAG_AUTO_PHASE)) return flags;
     flags &= ~WT_FLAG_AUTO_PHASE;
@@ -389,7 +389,7 @@ unsigned resolve_phase(const wt_ctx* ctx, const EvalArgs& a, unsigned flags) {
     if (wt_fast_phase_report(ctx->waves.data(), (unsigned)ctx->waves.size(), &f, (unsigned)a.L, &rep) < 0) return flags & ~WT_FLAG_FAST_PHASE;
     flags &= ~WT_FLAG_FAST_PHASE;
     if (rep.recommended == WT_PHASE_RECURRENCE) flags |= WT_FLAG_FAST_PHASE;
-    else if (rep.recommended == WT_PHASE_STENCIL_ORDER && !(flags & WT_FLAG_VARYINGS)) flags |= WT_FLAG_STENCIL_ORDER;
+    else if (rep.recommended == WT_PHASE_STENCIL_ORDER) flags |= WT_FLAG_STENCIL_ORDER;
     return flags;
 }
 
@@ -402,7 +402,7 @@ cudaError_t launch_eval(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t s
     if (flags & WT_FLAG_STENCIL_ORDER) {
         const cudaError_t e = ensure_fixup_tables(ctx, a.L, a.du);
         if (e != cudaSuccess) return e;
-        return stencil_runs_full(ctx) ? launch_stencil(ctx, a, shade, stream) : launch_stencil_hybrid(ctx, a, shade, flags, stream);
+        return stencil_runs_full(ctx, a) ? launch_stencil(ctx, a, shade, stream) : launch_stencil_hybrid(ctx, a, shade, flags, stream);
     }
     if (flags & WT_FLAG_FAST_PHASE)
         return shade ? launch_production_recur_shade(ctx, a, flags, stream) : launch_production_recur(ctx, a, flags, stream);
@@ -418,7 +418,7 @@ cudaError_t launch_frame(wt_ctx* ctx, EvalArgs& a, unsigned flags, cudaStream_t 
     if (flags & WT_FLAG_STENCIL_ORDER) {
         const cudaError_t e = ensure_fixup_tables(ctx, a.L, a.du);
         if (e != cudaSuccess) return e;
-        accumulates = stencil_runs_full(ctx);
+        accumulates = stencil_runs_full(ctx, a);
     }
     const bool ref_cks = a.cks && accumulates;
     if (ref_cks) { checksum_init_kernel<<<1, 32, 0, stream>>>(a.cks, 1); ctx->launches++; }
@@ -645,8 +645,8 @@ int wt_eval_frame_ex(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0
     const bool vary = flags & WT_FLAG_VARYINGS;
     if (vary && (!out->clip_position || !out->varyings_a || !out->varyings_b))
         return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS needs the clip_position, varyings_a and varyings_b buffers");
-    if (vary && (flags & FIVE_EVAL_FLAGS))
-        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS is not available with WT_FLAG_REFERENCE_ORDER / WT_FLAG_STENCIL_ORDER");
+    if (vary && (flags & WT_FLAG_REFERENCE_ORDER))
+        return fail(ctx, WT_ERR_INVALID_ARGUMENT, "WT_FLAG_VARYINGS is not available with WT_FLAG_REFERENCE_ORDER");
     DeviceGuard g(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     EvalArgs a = make_args(ctx, *frame, L, r0, r1, out->position, out->normal, out->shade, out->checksum, flags);

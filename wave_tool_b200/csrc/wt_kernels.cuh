@@ -608,7 +608,8 @@ struct RingLayout {
     static constexpr int ROWS = R + 2;
     static constexpr int PLANE = ROWS * RING_COLS;                   // float2 entries per component
     static constexpr int PLANES = VARY ? 4 : 3;                      // x, y, z (+ the heightmap sample with WT_FLAG_VARYINGS)
-    static constexpr int BYTES_PER_WARP = PLANES * PLANE * (int)sizeof(float2);
+    static constexpr int SEAM_SCRATCH = 16;                          // float2 entries behind the planes: one float per lane (see the seam stores)
+    static constexpr int BYTES_PER_WARP = (PLANES * PLANE + SEAM_SCRATCH) * (int)sizeof(float2);
     // WT_FLAG_CHECKSUM in the bit-faithful kernel (80 registers, every live value counts): the warp's running digest lives
     // behind the ring — [4][32] 64-bit words (position, normal, shade sums, (min y, max y); one column per lane)
     static constexpr int CKS_BYTES_PER_WARP = 4 * 32 * (int)sizeof(unsigned long long);
@@ -630,7 +631,7 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
     // The vertex count stays in a register: it is touched once per work item (measured: 3.6 % with it in a register, 4.8 % in the record).
     constexpr bool CKS_SMEM = CKS && MODE == 0;
     ChecksumAcc acc;
-    unsigned long long* const cks_slot = reinterpret_cast<unsigned long long*>(ring_all + RL::PLANES * RL::PLANE) + lane;
+    unsigned long long* const cks_slot = reinterpret_cast<unsigned long long*>(ring_all + RL::PLANES * RL::PLANE + RL::SEAM_SCRATCH) + lane;
     auto cks_reset = [&]() {
         cks_slot[0] = 0; cks_slot[32] = 0; cks_slot[64] = 0;
         *reinterpret_cast<float2*>(cks_slot + 96) = make_float2(3.402823466e+38f, -3.402823466e+38f);
@@ -833,10 +834,11 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
             // HM_BATCH rows at a time: all their footprint loads are issued before the first blend
             constexpr int HM_BATCH = R < WT_HM_BATCH ? R : WT_HM_BATCH;
             int slot = slot_new;
-            // The seam entries of the ring.  Measured (profiles/README.md): the branch-free form takes 4-7 % off the small-frame tier
-            // (1024^2 x 8 waves) and is neutral at 8192^2 / 16384^2, but costs the shading instantiations 0.7 % (cfg3): they keep the branches.
+            // The seam entries of the ring.  Measured (profiles/README.md): the branch-free form takes 6 % off the small-frame tier with
+            // digests (1024^2 x 8 waves) and is neutral at 8192^2 / 16384^2, but costs the shading instantiations 0.7 % (cfg3): they keep the branches.
             constexpr bool SEAM_BRANCHLESS = !SHADE;
-            const int seam_a = lane == 31 ? 1 : 0, seam_b = lane == 0 ? 2 * 33 : 2 * 33 + 1;   // float offsets inside a ring row
+            float* const seam_scratch = reinterpret_cast<float*>(ring_all + RL::PLANES * RL::PLANE) + lane;
+            const int seam_sa = lane == 31 ? 2 * RL::PLANE : 0, seam_sb = lane == 0 ? 2 * RL::PLANE : 0;   // plane stride of the seam entry / none in the scratch word
 #pragma unroll
             for (int j0 = 0; j0 < R; j0 += HM_BATCH) {
                 HmTap tap[HM_BATCH];
@@ -857,11 +859,12 @@ surface_warp_kernel(const __grid_constant__ EvalArgs a, const __grid_constant__ 
 #if !WT_SEAMLESS_RING
                     if (SEAM_BRANCHLESS) {
                         // lane 31 puts its A value into entry 0's .y and lane 0 its B value into entry 33's .x; every other lane
-                        // stores into the unused half of the same entry (nobody reads it): no divergent region per row
+                        // stores into its own scratch word behind the ring (nobody reads it): no divergent region per row
                         float* const rowf = reinterpret_cast<float*>(row);
-                        constexpr int PF = 2 * RL::PLANE;
-                        rowf[seam_a] = px[j].x; rowf[PF + seam_a] = py[j].x; rowf[2 * PF + seam_a] = pz[j].x;
-                        rowf[seam_b] = px[j].y; rowf[PF + seam_b] = py[j].y; rowf[2 * PF + seam_b] = pz[j].y;
+                        float* const pa = lane == 31 ? rowf + 1 : seam_scratch;
+                        float* const pb = lane == 0 ? rowf + 2 * 33 : seam_scratch;
+                        pa[0] = px[j].x; pa[seam_sa] = py[j].x; pa[2 * seam_sa] = pz[j].x;
+                        pb[0] = px[j].y; pb[seam_sb] = py[j].y; pb[2 * seam_sb] = pz[j].y;
                     } else {
                         if (lane == 31) {
                             row[0] = make_float2(0.f, px[j].x); row[RL::PLANE] = make_float2(0.f, py[j].x); row[2 * RL::PLANE] = make_float2(0.f, pz[j].x);
