@@ -236,6 +236,8 @@ typedef struct wt_phase_report {
 #define WT_PHASE_REFERENCE_ORDER 2
 #define WT_PHASE_STENCIL_ORDER 3
 #define WT_PHASE_MARGIN 1.0f        /* valid iff estimate x margin <= tolerance */
+#define WT_PHASE_MARGIN_STENCIL 1.5f /* the same for the shared-stencil term: the measured deviation reaches 0.97 of the estimate (16384^2 seen from
+                                       above, t = 600 s) and the next tier costs the bit-faithful kernel + 5 % at 4096^2, so it is taken early */
 #define WT_PHASE_K_POSITION 4.5     /* extreme of the position noise in modelled sigmas */
 #define WT_PHASE_K_NORMAL 3.7       /* height-noise term of the normal estimate: envelope 2.85 x 1.27 (the kernel's own MUFU / recurrence noise) */
 #define WT_PHASE_K_FLIP 0.35        /* flipped-rounding term: envelope 0.274 x 1.27 */

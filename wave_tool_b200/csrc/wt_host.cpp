@@ -509,7 +509,7 @@ int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f
     // what ONE ulp of the fp32 coordinates does to a finite-difference normal: the floor of every evaluation whose sin / cos are
     // not bit-identical to the reference's libm (one flipped rounding of the running sum moves a neighbour by ulp(coord))
     r.coordinate_ulp_normal_error_rad = (float)(0.5 * uc * gain);
-    r.shared_stencil_valid = (count == 0) || (r.est_shared_stencil_normal_error_rad * WT_PHASE_MARGIN <= r.normal_tolerance_rad);
+    r.shared_stencil_valid = (count == 0) || (r.est_shared_stencil_normal_error_rad * WT_PHASE_MARGIN_STENCIL <= r.normal_tolerance_rad);
     r.recommended = r.valid ? WT_PHASE_RECURRENCE : (r.shared_stencil_valid ? WT_PHASE_BIT_FAITHFUL : WT_PHASE_STENCIL_ORDER);
     if (out) *out = r;
     return r.valid ? 1 : 0;
