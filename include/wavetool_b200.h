@@ -453,6 +453,10 @@ void wt_debug_reload_env(void);
  * row shards bit-identical to the unsharded evaluation.  Writes (begin, end) pairs to out[0 .. 2 capacity) in launch
  * order and returns the number of chunks (which may exceed capacity: nothing is written then), or < 0. */
 int wt_debug_layout(unsigned grid_len, int rows_per_step, int phase_mode, unsigned row_begin, unsigned row_end, int* out, unsigned capacity);
+/* Host only: the fraction of the stencil arguments of a grid_len-grid that differ from their neighbours' own uv —
+ * fl(fl(i du) -/+ du) != fl((i -/+ 1) du), du = 1 / (grid_len - 1) (water-grid.vert:123-125,164-167): 0.003 at 4096, 0.04 at
+ * 1024, 0.19 at 8192, 0.11 at 16384, 0 where du is a power of two.  What the fix-up pass of WT_FLAG_STENCIL_ORDER re-evaluates. */
+float wt_stencil_flag_rate(unsigned grid_len);
 /* Diagnostic: which form WT_FLAG_STENCIL_ORDER runs — 0 (default): the cheaper one for the grid size (the fix-up form unless
  * more than 30 % of the stencil arguments are flagged, e.g. grid_len 700); 1: one kernel with five full evaluations per vertex
  * (4.5x the bit-faithful kernel); 2: the bit-faithful kernel + fix-up pass.  The tests hold the two against each other. */

@@ -98,3 +98,19 @@ def test_report_is_monotone_in_time_and_resolution(oracle):
     assert api.fast_phase_report(waves, high, 4096).valid == 1
     # no waves: nothing to deviate
     assert api.fast_phase_report(np.zeros((0, 6), np.float32), frame, 4096).valid == 1
+
+
+def test_stencil_flag_rate_matches_its_restatement():
+    """wt_stencil_flag_rate: where the shader's neighbour argument fl(fl(i du) -/+ du) is not the neighbour's own fl((i -/+ 1) du)
+    (water-grid.vert:123-125,164-167) — the table the fix-up pass of WT_FLAG_STENCIL_ORDER works from — against numpy."""
+    f32 = np.float32
+    for L, expect in ((513, 0.0), (1025, 0.0), (1024, None), (4096, None), (8192, None), (700, None), (2, None), (3, None)):
+        du = f32(1.0) / f32(L - 1)
+        i = np.arange(L, dtype=np.float32)
+        u = (i * du).astype(f32)
+        sides = int(((u - du).astype(f32) != ((i - f32(1)) * du).astype(f32)).sum() + ((u + du).astype(f32) != ((i + f32(1)) * du).astype(f32)).sum())
+        got = api.stencil_flag_rate(L)
+        assert abs(got - sides / (2.0 * L)) < 1e-6, (L, got, sides)
+        if expect is not None:
+            assert got == expect
+    assert 0.001 < api.stencil_flag_rate(4096) < 0.005 and 0.15 < api.stencil_flag_rate(8192) < 0.25

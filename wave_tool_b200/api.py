@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
     "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
-    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count", "wt_debug_full_stencil",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count", "wt_debug_full_stencil", "wt_stencil_flag_rate",
 ]
 
 
@@ -170,6 +170,8 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     L.wt_debug_reload_env.restype = None
     L.wt_debug_layout.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_uint]
     L.wt_debug_full_stencil.argtypes = [C.c_void_p, C.c_int]
+    L.wt_stencil_flag_rate.argtypes = [C.c_uint]
+    L.wt_stencil_flag_rate.restype = C.c_float
     L.wt_eval_frame_ex.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_uint, C.c_uint, C.c_uint, C.POINTER(Outputs), C.c_uint, C.c_void_p]
     L.wt_grid_indices.argtypes = [C.c_uint, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.wt_default_compose_params.argtypes = [C.POINTER(ComposeParams), C.POINTER(Camera), C.c_uint, C.c_uint]
@@ -311,6 +313,11 @@ def fast_phase_report(waves: np.ndarray, frame: Frame, grid_len: int) -> PhaseRe
     rep = PhaseReport()
     _check(lib().wt_fast_phase_report(w.ctypes.data, len(w), C.byref(frame), grid_len, C.byref(rep)))
     return rep
+
+
+def stencil_flag_rate(grid_len: int) -> float:
+    """wt_stencil_flag_rate (host only): fraction of the stencil arguments that differ from their neighbours' own uv."""
+    return float(lib().wt_stencil_flag_rate(grid_len))
 
 
 def debug_layout(grid_len: int, rows_per_step: int, phase_mode: int, rows=None) -> np.ndarray:

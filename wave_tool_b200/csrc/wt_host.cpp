@@ -434,6 +434,18 @@ static bool stencil_arguments_differ(unsigned L) {
     return any;
 }
 
+float wt_stencil_flag_rate(unsigned L) {
+    if (L < 2) return 0.0f;
+    const float du = 1.0f / (float)(L - 1);
+    unsigned long long sides = 0;
+    for (unsigned i = 0; i < L; ++i) {
+        const float u = (float)i * du;
+        const float minus = u - du, plus = u + du;
+        sides += (minus != (float)((int)i - 1) * du) + (plus != (float)(i + 1) * du);
+    }
+    return (float)((double)sides / (2.0 * (double)L));
+}
+
 int wt_fast_phase_report(const wt_wave* waves, unsigned count, const wt_frame* f, unsigned L, wt_phase_report* out) {
     if ((count && !waves) || !f || L < 2) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_fast_phase_report: bad argument");
     const float* c[4] = {f->bottomLeftGridPointInWorld, f->bottomRightGridPointInWorld, f->topLeftGridPointInWorld, f->topRightGridPointInWorld};
