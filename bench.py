@@ -274,7 +274,8 @@ def oracle_margin(api, scenes, ctx, waves, cam, params, L, hm, flags, shade_flag
                      **{k: stats[k] for k in ("pos_max", "pos_tol", "pos_margin", "normal_max", "normal_tol", "normal_margin", "flip_band")}}
     rep = ctx.fast_phase_valid(frame, L)
     return {"vertices_compared": int(len(ids)), "rows": f"{len(rows)} rows: 0-7, every {max(1, L // 20)}th, the last two",
-            "frame_time_s": float(params.waveAnimationTimeInSeconds), "modes": out, "fast_phase_report": rep.as_dict()}
+            "frame_time_s": float(params.waveAnimationTimeInSeconds), "modes": out, "fast_phase_report": rep.as_dict(),
+            "stencil_flag_rate": api.stencil_flag_rate(L)}
 
 
 def run_ours(args):
