@@ -348,10 +348,13 @@ def run_ours(args):
                        cks.data_ptr() + 40 * lo if with_cks else 0, flags=f | (api.FLAG_CHECKSUM if with_cks else 0), rows=rows, stream=sp)
 
     # ---- device-timed region: W warm-up steps, then exactly K steps ------------------------------
-    launch(0, Wm)
-    barrier()
+    # (the clock sampler is started BEFORE the warm-up: nothing but the barrier sits between the warm-up and the timed steps,
+    # so the GPU does not idle its clocks down in between)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.15 if sampler else 0.0)
+    barrier()
+    launch(0, Wm)
+    barrier()
     l0 = ctx.launch_count()
     m0 = ctx.phase_mode_counts()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
