@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128) surface_stencil_order_kernel(const __grid
 //   19 % at 8192, 11 % at 16384).  Everywhere else the shader's neighbour positions are bit for bit the positions the
 //   bit-faithful production kernel shares through its ring.  So the shader's structure = the production kernel + this pass
 //   over the flagged columns (every row) and flagged rows (every column): a flagged neighbour is re-evaluated at the
-//   shader's argument (the production kernel's arithmetic, scalar), an unflagged one is read back from the position buffer,
+//   shader's argument (the production kernel's arithmetic), an unflagged one is read back from the position buffer,
 //   and the vertex's normal and shading terms are redone.  The digest is corrected by (new - old) words.
 // ------------------------------------------------------------------------------------------------
 // one point per half with the bit-faithful production kernel's arithmetic (table = tab_exact; the packed statement of

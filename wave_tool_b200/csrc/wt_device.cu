@@ -315,7 +315,7 @@ cudaError_t launch_reference(wt_ctx* ctx, EvalArgs& a, bool shade, cudaStream_t 
     }
 }
 
-constexpr unsigned FIVE_EVAL_FLAGS = WT_FLAG_REFERENCE_ORDER | WT_FLAG_STENCIL_ORDER;   // one thread per vertex, the shader's own five evaluations
+constexpr unsigned FIVE_EVAL_FLAGS = WT_FLAG_REFERENCE_ORDER | WT_FLAG_STENCIL_ORDER;   // the shader's own stencil arguments: more than one launch per frame, never grouped; digest in a device record
 
 int validate_eval(wt_ctx* ctx, const wt_frame* frame, unsigned L, unsigned r0, unsigned r1, void* d_pos, void* d_nrm, void* d_shade,
                   void* d_cks, unsigned flags) {
