@@ -382,6 +382,10 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* params, int n, void* 
 /* Diagnostic: how many texels of the most recent wt_synthesize_skybox were recomputed on the exact path (IEEE division, libdevice
  * powf) because the approximate path (MUFU lg2 / ex2, reciprocal multiply) could not exclude a different byte.  Synchronises. */
 int wt_debug_sky_exact_texels(wt_ctx* ctx, uint64_t* out);
+/* Diagnostic (host only): the per-byte table the synthesis kernel applies for the fog quad (screen-space-quad.frag:45 blended
+ * with GL_SRC_ALPHA / GL_ONE_MINUS_SRC_ALPHA into RGBA8): byte c of out[d] = the byte channel c holds after the quad when it
+ * held d before, for the fog colour / alpha given (already scaled by the sun height as render-engine.cpp:295 does). */
+int wt_debug_fog_table(const float fog_rgba[4], uint32_t out[256]);
 /* Copies the context's current skybox faces (6 * n * n RGBA8) to HOST memory; out may be NULL to query n.  Synchronises. */
 int wt_get_skybox_rgba8(wt_ctx* ctx, uint8_t* out, int* n_out);
 

@@ -275,3 +275,24 @@ def test_division_by_a_uniform_divisor_is_ieee_division():
             want = rn(Fraction(float(x)) / Fraction(float(c)))
             bad += int(q2 != want)
     assert bad == 0, bad
+
+
+def test_fog_quad_table_is_the_gl_blend_per_byte():
+    """wt_debug_fog_table — the table the skybox synthesis applies for the fog quad — against a numpy restatement of the GL
+    blend (GL_SRC_ALPHA, GL_ONE_MINUS_SRC_ALPHA on an RGBA8 attachment: operands clamped, Cs As + Cd (1 - As) on all four
+    channels, round to nearest on the way back to unorm8; GL 4.1 sections 4.1.7, 2.1.5), one fp32 operation at a time."""
+    f32 = np.float32
+    d = np.arange(256, dtype=np.float32)
+    for fog in ((1.0, 1.0, 1.0, 0.1), (0.3, 0.8, 0.9, 0.35), (0.0, 0.0, 0.0, 1.0), (0.7, 0.2, 0.1, 0.0), (1.5, -0.2, 0.5, 0.999), (0.25, 0.5, 0.75, 0.5)):
+        src = np.clip(np.array(fog, f32), f32(0), f32(1))
+        a_s = src[3]
+        oma = f32(1.0) - a_s
+        want = np.zeros((256, 4), np.uint8)
+        for c in range(4):
+            t0 = f32(src[c] * a_s)
+            t1 = ((d / f32(255.0)).astype(f32) * oma).astype(f32)
+            v = np.clip((t0 + t1).astype(f32), f32(0), f32(1))
+            want[:, c] = np.floor(((v * f32(255.0)).astype(f32) + f32(0.5)).astype(f32)).astype(np.uint8)
+        got = api.fog_table(fog)
+        assert np.array_equal(got, want), fog
+    assert np.array_equal(api.fog_table((0.4, 0.5, 0.6, 0.0)), np.repeat(np.arange(256, dtype=np.uint8)[:, None], 4, 1))   # alpha 0: identity

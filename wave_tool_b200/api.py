@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "wt_default_compose_params", "wt_set_screen_textures", "wt_compose_frame",
     "wt_step_host", "wt_step_submit", "wt_step_wait", "wt_default_sky_params", "wt_set_sky_layers", "wt_synthesize_skybox", "wt_get_skybox_rgba8",
     "wt_wave_from_wavelength_speed", "wt_wave_clamp_ui", "wt_params_clamp_ui", "wt_animation_clamp_ui", "wt_sky_params_clamp_ui",
-    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count", "wt_debug_full_stencil", "wt_stencil_flag_rate",
+    "wt_compose_params_clamp_ui", "wt_ui_ranges", "wt_fast_phase_report", "wt_fast_phase_valid", "wt_last_phase_mode", "wt_phase_mode_counts", "wt_debug_sky_exact_texels", "wt_batched_frame_count", "wt_debug_full_stencil", "wt_stencil_flag_rate", "wt_debug_fog_table",
 ]
 
 
@@ -313,6 +313,14 @@ def fast_phase_report(waves: np.ndarray, frame: Frame, grid_len: int) -> PhaseRe
     rep = PhaseReport()
     _check(lib().wt_fast_phase_report(w.ctypes.data, len(w), C.byref(frame), grid_len, C.byref(rep)))
     return rep
+
+
+def fog_table(fog_rgba) -> np.ndarray:
+    """wt_debug_fog_table (host only): (256, 4) uint8 — the byte each channel holds after the fog quad, per byte before it."""
+    f = (C.c_float * 4)(*[float(v) for v in fog_rgba])
+    out = np.zeros(256, np.uint32)
+    _check(lib().wt_debug_fog_table(f, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return out.view(np.uint8).reshape(256, 4)
 
 
 def stencil_flag_rate(grid_len: int) -> float:

@@ -472,6 +472,14 @@ int wt_synthesize_skybox(wt_ctx* ctx, const wt_sky_params* p, int n, void* strea
     return WT_OK;
 }
 
+int wt_debug_fog_table(const float fog_rgba[4], uint32_t out[256]) {
+    if (!fog_rgba || !out) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_debug_fog_table: NULL argument");
+    unsigned lut[256];
+    fog_table(fog_rgba, lut);
+    for (int d = 0; d < 256; ++d) out[d] = lut[d];
+    return WT_OK;
+}
+
 int wt_debug_sky_exact_texels(wt_ctx* ctx, uint64_t* out) {
     if (!ctx || !out) return set_thread_error(WT_ERR_INVALID_ARGUMENT, "wt_debug_sky_exact_texels: NULL argument");
     *out = 0;
