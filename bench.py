@@ -662,7 +662,7 @@ def extra_workloads(torch, dist, api, scenes, shard, rank, world, local_rank, de
         ctx = api.Context(local_rank)
         ctx.set_waves(waves); ctx.set_heightmap(hm)
         n = L * L
-        ring = 8                    # frames in flight: wt_run_animation groups up to ring-depth small frames into one persistent launch
+        ring = 16                   # frames in flight: wt_run_animation groups up to ring-depth (at most 16) small frames into one persistent launch
         pos = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
         nrm = torch.empty((ring * n, 4), dtype=torch.float32, device=dev)
         total_frames = 1000
@@ -684,8 +684,8 @@ def extra_workloads(torch, dist, api, scenes, shard, rank, world, local_rank, de
         out["cfg2_animation"] = {"workload": WORKLOADS["cfg2"][4], "frames": total_frames, "ms_per_frame": ms / total_frames * world, "ms_total": ms,
                                  "vertex_waves_per_sec": total_frames * n * W / (ms * 1e-3), "hbm_gbs_written": gbs, "hbm_frac_of_measured_peak": gbs / hbm_peak / world,
                                  "kernel": kernel_name(ctx, before), "n_gpus": world,
-                                 "what": "wt_run_animation (native frame loop: advance state, build frame, grouped launches of up to 8 frames), t from 0 to 16.7 s, "
-                                         "8-deep ring, digest per frame; 33.5 MB written per frame: hbm_frac is per GPU against MEASURED_PEAKS hbm_gbs — at 8 waves "
+                                 "what": "wt_run_animation (native frame loop: advance state, build frame, grouped launches of up to 16 frames), t from 0 to 16.7 s, "
+                                         "16-deep ring, digest per frame; 33.5 MB written per frame: hbm_frac is per GPU against MEASURED_PEAKS hbm_gbs — at 8 waves "
                                          "the per-vertex stage's issue rate, not HBM, bounds this tier (DESIGN.md)"}
         del pos, nrm, cks, ctx
         torch.cuda.empty_cache()

@@ -21,7 +21,7 @@ ls -la gpurun_out | tail -12
 for c in cfg4 cfg5; do timeout 300 python bench.py --workload $c --steps 10 --no-cpu-baseline --no-readback > gpurun_out/${T}_bench_$c.json 2>> gpurun_out/${T}_bench.err; done
 timeout 300 python bench.py --workload cfg2 --steps 200 --no-cpu-baseline --no-readback > gpurun_out/${T}_bench_cfg2.json 2>> gpurun_out/${T}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
-python tools/time_sky.py 2048 2048 > gpurun_out/${T}_sky.log 2>&1; python tools/time_sky.py 2048 1024 >> gpurun_out/${T}_sky.log 2>&1; python tools/time_compose.py > gpurun_out/${T}_compose.log 2>&1; RING=8 python tools/time_animation.py 1024 8 1000 > gpurun_out/${T}_anim.log 2>&1
+python tools/time_sky.py 2048 2048 > gpurun_out/${T}_sky.log 2>&1; python tools/time_sky.py 2048 1024 >> gpurun_out/${T}_sky.log 2>&1; python tools/time_compose.py > gpurun_out/${T}_compose.log 2>&1; RING=16 python tools/time_animation.py 1024 8 1000 > gpurun_out/${T}_anim.log 2>&1
 python tools/time_variants.py 4096:64:shade 4096:64:shade,fast 4096:64:shade,stencil 4096:64:shade,ref 8192:256: 8192:256:fast 16384:32: 16384:32:fast 1024:8:fast 1024:8: > gpurun_out/${T}_kernels.log 2>&1
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "not cfg3_full_grid and not large_grid and not maximum_grid and not cfg5" 2>&1 | tail -4 > gpurun_out/${T}_memcheck.log
 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "wave_count_tiers or varyings or cfg2_animation or stream_ordering" 2>&1 | tail -4 > gpurun_out/${T}_racecheck.log

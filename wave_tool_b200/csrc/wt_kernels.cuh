@@ -56,7 +56,12 @@ struct WaveTable {
 };
 
 struct EvalArgs;
-constexpr int BATCH_MAX_FRAMES = 8;   // frames per grouped launch: 8 x (680 + 256) bytes of kernel parameters
+#ifndef WT_BATCH_MAX_FRAMES
+#define WT_BATCH_MAX_FRAMES 16
+#endif
+// frames per grouped launch: 16 x (680 + 256) bytes of kernel parameters (the limit is 32 KB).  Measured on 1024^2 x 8 waves:
+// 8 frames per launch 8.48 us / frame, 16 frames 7.87 (9.84 -> 9.02 with digests)
+constexpr int BATCH_MAX_FRAMES = WT_BATCH_MAX_FRAMES;
 struct NoBatch { int unused; };
 constexpr int STRIP_COLS = 62;   // output columns per warp: 64 held columns minus the two halo columns
 
