@@ -392,8 +392,9 @@ int wt_get_skybox_rgba8(wt_ctx* ctx, uint8_t* out, int* n_out);
 /* A batch of n_frames independent frames (animation; frame sharding takes a subset per GPU).
  * Frame f writes slot (f % ring_depth) of each ring buffer (slot stride = (row_end-row_begin)*grid_len
  * float4) and, with WT_FLAG_CHECKSUM, d_checksums[f].  Stream-ordered, returns without synchronising.
- * Small frames without shading terms / extra varyings are grouped: up to min(ring_depth, 16) consecutive frames run as ONE
- * persistent launch over one work queue (1024^2 x 8 waves: 7.9 us per frame on a 16-deep ring, 8.5 on an 8-deep one). */
+ * Small frames without shading terms / extra varyings are grouped: up to min(ring_depth / 2, 16) consecutive frames run as ONE
+ * persistent launch over one work queue, the groups of the two halves of the ring on two internal streams forked off and joined
+ * back into cuda_stream (1024^2 x 8 waves: 7.5 us per frame on a ring of 8 or more). */
 int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsigned grid_len, unsigned row_begin,
                   unsigned row_end, void* d_position_ring, void* d_normal_ring, void* d_shade_ring, unsigned ring_depth,
                   void* d_checksums, unsigned flags, void* cuda_stream);

@@ -725,42 +725,56 @@ struct FrameBatcher {
     cudaStream_t stream;
     unsigned ring_depth;
     bool enabled;
+    // Two lanes: the groups of the lower and of the upper half of the ring go to two internal streams, so that the tail of one
+    // group (a persistent grid running dry) overlaps the head of the next.  A group never straddles the halves and a ring slot is
+    // always written from the same lane: every slot is still written in frame order.  half == 0: one lane, the caller's stream.
+    unsigned half = 0;
+    FanOut* fan = nullptr;
     std::vector<EvalArgs> group;
-    unsigned group_flags = 0;
+    unsigned group_flags = 0, group_slot0 = 0;
     FrameBatcher(wt_ctx* c, cudaStream_t s, unsigned ring, unsigned n_frames, unsigned L, unsigned rows, unsigned flags)
         : ctx(c), stream(s), ring_depth(ring),
           enabled(ring >= 2 && n_frames >= 2 && c->n_waves <= 64 && (unsigned long long)L * rows <= (1ull << 22) && g_knobs.fanout != 1 &&
-                  !(flags & (FIVE_EVAL_FLAGS | WT_FLAG_SHADE | WT_FLAG_VARYINGS))) {}
+                  !(flags & (FIVE_EVAL_FLAGS | WT_FLAG_SHADE | WT_FLAG_VARYINGS))) {
+        if (enabled && ring >= 4 && ring % 2 == 0 && n_frames > ring / 2) half = ring / 2;
+    }
+    int lanes() const { return half ? 2 : 1; }
+    cudaStream_t lane_stream(unsigned slot) const { return half && fan ? fan->stream_for(slot / half) : stream; }
     cudaError_t flush() {
         if (group.empty()) return cudaSuccess;
         cudaError_t e;
+        const cudaStream_t lane = lane_stream(group_slot0);
         if (group.size() == 1) {
-            e = launch_frame(ctx, group[0], group_flags, stream);
+            e = launch_frame(ctx, group[0], group_flags, lane);
         } else {
             const int mode = (group_flags & WT_FLAG_FAST_PHASE) ? WT_PHASE_RECURRENCE : WT_PHASE_BIT_FAITHFUL;
             if (group[0].cks) {   // the frames' digest records are consecutive: arm them (zero sums, min / max keys at their identities)
-                checksum_init_kernel<<<1, 32, 0, stream>>>(group[0].cks, (int)group.size());
+                checksum_init_kernel<<<1, 32, 0, lane>>>(group[0].cks, (int)group.size());
                 ctx->launches++;
             }
             ctx->last_phase_mode = mode;
             ctx->mode_launches[mode] += group.size();
             ctx->batched_frames += group.size();
-            e = mode == WT_PHASE_RECURRENCE ? launch_production_batch_recur(ctx, group, stream) : launch_production_batch_exact(ctx, group, stream);
+            e = mode == WT_PHASE_RECURRENCE ? launch_production_batch_recur(ctx, group, lane) : launch_production_batch_exact(ctx, group, lane);
         }
         group.clear();
         return e;
     }
-    // `a` with flags as the caller passed them (WT_FLAG_AUTO_PHASE unresolved); other_stream: where a frame that cannot be grouped goes
-    cudaError_t add(EvalArgs& a, unsigned flags, cudaStream_t other_stream) {
+    // `a` with flags as the caller passed them (WT_FLAG_AUTO_PHASE unresolved); slot: the frame's ring slot; other_stream: where a
+    // frame that cannot be grouped goes when nothing is grouped at all
+    cudaError_t add(EvalArgs& a, unsigned flags, unsigned slot, cudaStream_t other_stream) {
         const unsigned rflags = resolve_phase(ctx, a, flags);
         const bool groupable = enabled && !(rflags & (FIVE_EVAL_FLAGS | WT_FLAG_SHADE | WT_FLAG_VARYINGS));
         cudaError_t e;
         if (!groupable) {
             if ((e = flush()) != cudaSuccess) return e;
-            return launch_frame(ctx, a, rflags, enabled ? stream : other_stream);
+            return launch_frame(ctx, a, rflags, enabled ? lane_stream(slot) : other_stream);
         }
-        if (!group.empty() && (group.size() >= ring_depth || group.size() >= (size_t)BATCH_MAX_FRAMES || ((rflags ^ group_flags) & WT_FLAG_FAST_PHASE) || (group[0].cks && a.cks != group[0].cks + group.size())))
+        const size_t cap = std::min<size_t>(half ? half : ring_depth, (size_t)BATCH_MAX_FRAMES);
+        if (!group.empty() && (group.size() >= cap || (half && slot % half == 0) || ((rflags ^ group_flags) & WT_FLAG_FAST_PHASE) ||
+                               (group[0].cks && a.cks != group[0].cks + group.size())))
             if ((e = flush()) != cudaSuccess) return e;
+        if (group.empty()) group_slot0 = slot;
         group.push_back(a);
         group_flags = rflags;
         return cudaSuccess;
@@ -781,7 +795,9 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
     const bool cks = flags & WT_FLAG_CHECKSUM;
     const size_t slot = (size_t)(r1 - r0) * L;
     FrameBatcher batcher(ctx, stream, ring_depth, n_frames, L, r1 - r0, flags);
-    FanOut fan(ctx, stream, batcher.enabled ? 1 : ring_depth, n_frames, L, r1 - r0);   // grouped frames need no fan-out
+    FanOut fan(ctx, stream, batcher.enabled ? batcher.lanes() : ring_depth, n_frames, L, r1 - r0);   // grouped frames: one stream per lane
+    batcher.fan = &fan;
+    if (fan.k != batcher.lanes()) batcher.half = 0;
     WT_CUDA(ctx, fan.begin());
     for (unsigned f = 0; f <= n_frames; ++f) {
         cudaError_t e;
@@ -789,7 +805,7 @@ int wt_eval_batch(wt_ctx* ctx, const wt_frame* frames, unsigned n_frames, unsign
             const size_t off = (size_t)(f % ring_depth) * slot;
             EvalArgs a = make_args(ctx, frames[f], L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + f : nullptr, flags);
-            e = batcher.add(a, flags, fan.stream_for(f));
+            e = batcher.add(a, flags, f % ring_depth, fan.stream_for(f));
         } else {
             e = batcher.flush();
         }
@@ -821,7 +837,9 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
     const size_t slot = (size_t)(r1 - r0) * L;
     unsigned drawn = 0;
     FrameBatcher batcher(ctx, stream, ring_depth, n_frames, L, r1 - r0, flags);
-    FanOut fan(ctx, stream, batcher.enabled ? 1 : ring_depth, n_frames, L, r1 - r0);   // grouped frames need no fan-out
+    FanOut fan(ctx, stream, batcher.enabled ? batcher.lanes() : ring_depth, n_frames, L, r1 - r0);   // grouped frames: one stream per lane
+    batcher.fan = &fan;
+    if (fan.k != batcher.lanes()) batcher.half = 0;
     WT_CUDA(ctx, fan.begin());
     // after begin() the internal streams have been forked off the caller's: every exit path joins them again
     auto bail = [&](int code, const std::string& msg) { fan.end(); return fail(ctx, code, msg); };
@@ -833,7 +851,7 @@ int wt_run_animation(wt_ctx* ctx, const wt_camera* cam, wt_params* params, const
             const size_t off = (size_t)(k % ring_depth) * slot;
             EvalArgs a = make_args(ctx, frame, L, r0, r1, (float4*)d_pos_ring + off, (float4*)d_nrm_ring + off,
                                    d_shade_ring ? (float4*)d_shade_ring + off : nullptr, cks ? (wt_checksum*)d_checksums + k : nullptr, flags);
-            const cudaError_t e = batcher.add(a, flags, fan.stream_for(k));
+            const cudaError_t e = batcher.add(a, flags, k % ring_depth, fan.stream_for(k));
             if (e != cudaSuccess) return bail(WT_ERR_CUDA, std::string("wt_run_animation: ") + cudaGetErrorString(e));
             ++drawn;
         } else if (cks) {   // nothing drawn: zero digest (after the pending group, which may hold the neighbouring records)
