@@ -420,7 +420,11 @@ int wt_step_host(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, flo
 
 /* The same round trip split in two so that frames overlap: wt_step_submit builds and enqueues a frame and returns a
  * ticket; wt_step_wait blocks until that frame's digest has arrived in host memory (WT_NO_GRID: zero digest).  Up to 4
- * frames may be in flight — the host prepares frame k+1 while the GPU evaluates frame k, as a render loop does. */
+ * frames may be in flight — the host prepares frame k+1 while the GPU evaluates frame k, as a render loop does.
+ * Ordering: a submitted frame sees everything enqueued on `cuda_stream` before the call; its outputs are complete when
+ * wt_step_wait returns for its ticket (NOT merely in `cuda_stream` order): consecutive frames run on two internal streams so
+ * that one frame's tail overlaps the next frame's head.  A frame that writes the position buffer of a pending frame waits
+ * for that frame first, so reusing buffers is safe; give consecutive frames different buffers (a ring of 2) to let them overlap. */
 int wt_step_submit(wt_ctx* ctx, const wt_camera* cam, const wt_params* params, float total_wave_amplitude, unsigned grid_len,
                    unsigned row_begin, unsigned row_end, void* d_position, void* d_normal, void* d_shade, unsigned flags,
                    void* cuda_stream, unsigned* ticket);

@@ -61,6 +61,8 @@ struct wt_ctx {
     cudaEvent_t step_event[4] = {nullptr, nullptr, nullptr, nullptr};
     int step_status[4] = {0, 0, 0, 0};
     unsigned step_next = 0;
+    const void* step_buffer[4] = {nullptr, nullptr, nullptr, nullptr};   // position buffer each pending step writes (lane hazards, wt_step_submit)
+    cudaEvent_t ev_step_fork = nullptr;
     uint64_t launches = 0;
     uint64_t batched_frames = 0;    // frames evaluated inside grouped launches (wt_launch.cuh: launch_warp_batch)
     // dynamic work distribution: a ring of self re-arming {next item, warps done} counters, one per launch in flight
