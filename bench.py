@@ -573,6 +573,10 @@ def run_ours(args):
         if pipes:
             primary = dict(primary)
             primary["pipes_ncu"] = pipes          # what the binding pipe was actually doing (ncu capture of the same kernel, profiles/)
+        primary = dict(primary)
+        primary["launch_duration"] = ("timed region / launches (CUDA events on the launching stream around the K steps): consecutive frames of a batch run on two "
+                                      "internal streams forked off and joined back into that stream, so one launch's tail overlaps the next launch's head; a launch "
+                                      "alone (ncu: profiles/r2_launches_cfg3.csv) takes ~4 % longer")
         line = {
             "metric": "vertex_waves_per_sec", "value": value, "unit": "vertex-waves/s", "n_gpus": n_gpus, "steps": K, "warmup": Wm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if row_sharded else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
